@@ -1,0 +1,594 @@
+/*
+ * acm_core.c -- Aho-Corasick automaton builder (host, plain C).
+ *
+ * Produces what the reference's acsm_compile()/acsm_gen_state_table() produce
+ * (reference acsmx.c:552-671; ushort twin AC_ushorts/iacsmx.c:357-520) -- a dense
+ * DFA plus per-state match information -- but built for the sm_100a kernels:
+ *
+ *   - array based, no per-node or per-queue-entry malloc (the reference mallocs
+ *     every queue node, acsmx.c:166-186, and every match-list copy,
+ *     acsmx.c:283-294);
+ *   - states renumbered breadth-first so that shallow (hot) rows are contiguous
+ *     and "is this edge a trie edge" is a compare against level_start[];
+ *   - the match list of a state is not materialised: each state keeps the
+ *     patterns that end exactly there (own list) and a link to the nearest
+ *     proper suffix that has any (olink); the union along olink is exactly the
+ *     reference's per-state match_list set (acsmx.c:417-429);
+ *   - for byte automata, the entry filters of the scan kernels.
+ *
+ * The trie is still grown in the reference's order (last added pattern first,
+ * one new state per byte, acsmx.c:318-349,579-580) so that node creation order
+ * IS the reference's state numbering; acm_core_export_ref() uses that to emit a
+ * table that can be compared bit for bit with the reference's h_trans.
+ */
+#define _GNU_SOURCE
+#include <malloc.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include "acm_core.h"
+#include "../../include/acm.h"
+
+static __thread char acm_errbuf[512];
+
+void
+acm_set_error(const char *fmt, ...)
+{
+	va_list ap;
+
+	va_start(ap, fmt);
+	vsnprintf(acm_errbuf, sizeof(acm_errbuf), fmt, ap);
+	va_end(ap);
+}
+
+const char *
+acm_last_error(void)
+{
+	return acm_errbuf;
+}
+
+struct acm_core *
+acm_core_new(int alpha)
+{
+	struct acm_core *c = calloc(1, sizeof(*c));
+
+	if (!c) {
+		acm_set_error("acm_core_new: out of memory");
+		return NULL;
+	}
+	c->alpha = alpha;
+	c->sym_size = (alpha <= 256) ? 1 : 2;
+	c->min_len = 0;
+	return c;
+}
+
+int
+acm_core_add(struct acm_core *c, const void *syms, int n, int nocase, int offset,
+    int depth, void *id, int iid)
+{
+	struct acm_pat *p;
+
+	if (c->compiled) {
+		acm_set_error("add_pattern after compile");
+		return c->status = ACM_ERR_STATE;
+	}
+	if (n < 0 || (n > 0 && !syms)) {
+		acm_set_error("add_pattern: bad length %d", n);
+		return c->status = ACM_ERR_ARG;
+	}
+	if (c->npats >= (int)ACM_KEY_PAT_MASK) {
+		acm_set_error("add_pattern: more than %u patterns", ACM_KEY_PAT_MASK);
+		return c->status = ACM_ERR_LIMIT;
+	}
+	if (c->npats == c->cap_pats) {
+		int nc = c->cap_pats ? c->cap_pats * 2 : 1024;
+		void *np = realloc(c->pats, (size_t)nc * sizeof(*c->pats));
+		if (!np) {
+			acm_set_error("add_pattern: out of memory");
+			return c->status = ACM_ERR_NOMEM;
+		}
+		c->pats = np;
+		c->cap_pats = nc;
+	}
+	p = &c->pats[c->npats];
+	memset(p, 0, sizeof(*p));
+	p->syms = malloc((size_t)(n ? n : 1) * c->sym_size);
+	if (!p->syms) {
+		acm_set_error("add_pattern: out of memory");
+		return c->status = ACM_ERR_NOMEM;
+	}
+	if (n)
+		memcpy(p->syms, syms, (size_t)n * c->sym_size);
+	if (c->sym_size == 2) {
+		const unsigned short *s = syms;
+		for (int k = 0; k < n; k++)
+			if (s[k] >= c->alpha) {
+				free(p->syms);
+				acm_set_error("add_pattern: symbol %u outside alphabet %d",
+				    s[k], c->alpha);
+				return c->status = ACM_ERR_ARG;
+			}
+	}
+	p->n = n;
+	p->nocase = nocase;
+	p->offset = offset;
+	p->depth = depth;
+	p->id = id;
+	p->iid = iid;
+	c->npats++;
+	if (n > c->max_len)
+		c->max_len = n;
+	if (n > 0 && (c->min_len == 0 || n < c->min_len))
+		c->min_len = n;
+	if (n == 0) {
+		/* kept so later indices agree with the reference; can never match */
+		acm_set_error("add_pattern: zero-length pattern %d ignored", c->npats - 1);
+		return c->status = ACM_ERR_EMPTY_PATTERN;
+	}
+	return ACM_OK;
+}
+
+static inline unsigned
+sym_at(const struct acm_core *c, const struct acm_pat *p, int k)
+{
+	return c->sym_size == 1 ? ((const unsigned char *)p->syms)[k]
+	                        : ((const unsigned short *)p->syms)[k];
+}
+
+void
+acm_tables_free(struct acm_tables *t)
+{
+	free(t->T); free(t->level_start); free(t->own_begin); free(t->own_pat);
+	free(t->olink); free(t->fail); free(t->pat_len); free(t->pat_iid);
+	free(t->bfs_to_ref); free(t->f1); free(t->f2); free(t->grams); free(t->b2);
+	memset(t, 0, sizeof(*t));
+}
+
+size_t
+acm_tables_device_bytes(const struct acm_tables *t)
+{
+	size_t b = (size_t)t->num_states * t->alpha * 4;
+
+	b += (size_t)(t->num_states + 1) * 4 + (size_t)t->own_total * 4;
+	b += (size_t)t->num_states * 4 + (size_t)t->num_patterns * 4;
+	b += (size_t)(t->max_depth + 2) * 4;
+	if (t->f1)
+		b += (1u << ACM_F1_BITS_LOG2) / 8 + (1u << ACM_F2_BITS_LOG2) / 8 +
+		    (size_t)t->gram_slots * sizeof(struct acm_gram_slot);
+	if (t->b2)
+		b += 65536 / 8;
+	return b;
+}
+
+/* ------------------------------------------------------------------------- */
+
+struct trie {
+	uint32_t  n;           /* nodes, creation order == reference state ids */
+	uint32_t *parent;
+	uint16_t *sym;
+	uint32_t *first_child;
+	uint32_t *next_sib;
+	uint32_t *root_child;  /* [alpha], 0 = none                            */
+	int32_t  *own_head;    /* per node: first own entry or -1               */
+	int32_t  *own_next;    /* per pattern: next own entry of the same node  */
+};
+
+static void
+trie_free(struct trie *t)
+{
+	free(t->parent); free(t->sym); free(t->first_child); free(t->next_sib);
+	free(t->root_child); free(t->own_head); free(t->own_next);
+}
+
+static uint32_t
+trie_child(const struct trie *t, uint32_t u, unsigned a)
+{
+	uint32_t c;
+
+	if (u == 0)
+		return t->root_child[a];
+	for (c = t->first_child[u]; c; c = t->next_sib[c])
+		if (t->sym[c] == a)
+			return c;
+	return 0;
+}
+
+static int
+build_filters(struct acm_core *c)
+{
+	struct acm_tables *t = &c->tab;
+	uint32_t s, k;
+
+	/* exact 2-byte start bitmap: "a walk from this position can report" */
+	t->b2 = calloc(65536 / 32, 4);
+	if (!t->b2)
+		return ACM_ERR_NOMEM;
+	if (t->max_depth >= 1) {
+		for (unsigned b0 = 0; b0 < 256; b0++) {
+			uint32_t e1 = t->T[b0];
+			uint32_t s1 = e1 & ACM_T_MASK;
+			if (s1 < t->level_start[1])
+				continue;                 /* no depth-1 node */
+			if (e1 & ACM_T_OWN) {             /* 1-byte pattern  */
+				for (unsigned b1 = 0; b1 < 256; b1++) {
+					uint32_t idx = b0 | (b1 << 8);
+					t->b2[idx >> 5] |= 0x80000000u >> (idx & 31);
+				}
+				continue;
+			}
+			if (t->max_depth < 2)
+				continue;
+			for (unsigned b1 = 0; b1 < 256; b1++) {
+				uint32_t s2 = t->T[(size_t)s1 * 256 + b1] & ACM_T_MASK;
+				if (s2 >= t->level_start[2]) {
+					uint32_t idx = b0 | (b1 << 8);
+					t->b2[idx >> 5] |= 0x80000000u >> (idx & 31);
+				}
+			}
+		}
+	}
+
+	if (t->min_pattern_len < 7)
+		return ACM_OK;
+
+	/* hashed 4-gram filters over pattern offsets 0..3 */
+	t->f1 = calloc((1u << ACM_F1_BITS_LOG2) / 32, 4);
+	t->f2 = calloc((1u << ACM_F2_BITS_LOG2) / 32, 4);
+	if (!t->f1 || !t->f2)
+		return ACM_ERR_NOMEM;
+	{
+		uint64_t want = (uint64_t)c->npats * 4 * 2;
+		uint32_t slots = 1024, lg = 10;
+		while (slots < want) {
+			slots <<= 1;
+			lg++;
+		}
+		t->gram_slots = slots;
+		t->grams = calloc(slots, sizeof(*t->grams));
+		if (!t->grams)
+			return ACM_ERR_NOMEM;
+		for (k = 0; k < (uint32_t)c->npats; k++) {
+			const unsigned char *p = c->pats[k].syms;
+			if (c->pats[k].n == 0)
+				continue;
+			for (int j = 0; j < 4; j++) {
+				uint32_t g = (uint32_t)p[j] | ((uint32_t)p[j + 1] << 8) |
+				    ((uint32_t)p[j + 2] << 16) | ((uint32_t)p[j + 3] << 24);
+				uint32_t h1 = g * ACM_HASH1_MUL;
+				uint32_t h2 = g * ACM_HASH2_MUL;
+				uint32_t h3 = (g * ACM_HASH3_MUL) >> (32 - lg);
+				t->f1[h1 >> (32 - (ACM_F1_BITS_LOG2 - 5))] |=
+				    0x80000000u >> (h1 & 31);
+				t->f2[h2 >> (32 - (ACM_F2_BITS_LOG2 - 5))] |=
+				    0x80000000u >> (h2 & 31);
+				for (s = h3;; s = (s + 1) & (slots - 1)) {
+					if (t->grams[s].jmask == 0) {
+						t->grams[s].gram = g;
+						t->grams[s].jmask = 1u << j;
+						t->gram_count++;
+						break;
+					}
+					if (t->grams[s].gram == g) {
+						t->grams[s].jmask |= 1u << j;
+						break;
+					}
+				}
+			}
+		}
+	}
+	return ACM_OK;
+}
+
+int
+acm_core_compile(struct acm_core *c)
+{
+	struct acm_tables *t = &c->tab;
+	struct trie tr;
+	const int A = c->alpha;
+	uint32_t total = 1, last = 0, i, u, qt;
+	uint32_t *order = NULL, *bfs_id = NULL, *depth = NULL;
+	uint32_t *cbuf = NULL;
+	int k, rc = ACM_OK;
+
+	if (c->compiled)
+		return ACM_OK;
+	memset(&tr, 0, sizeof(tr));
+	for (k = 0; k < c->npats; k++)
+		total += (uint32_t)c->pats[k].n;
+	if (total >= ACM_T_MASK) {
+		acm_set_error("compile: too many states");
+		return c->status = ACM_ERR_LIMIT;
+	}
+
+	tr.parent      = calloc(total, 4);
+	tr.sym         = calloc(total, 2);
+	tr.first_child = calloc(total, 4);
+	tr.next_sib    = calloc(total, 4);
+	tr.root_child  = calloc(A, 4);
+	tr.own_head    = malloc((size_t)total * 4);
+	tr.own_next    = malloc((size_t)(c->npats + 1) * 4);
+	if (!tr.parent || !tr.sym || !tr.first_child || !tr.next_sib ||
+	    !tr.root_child || !tr.own_head || !tr.own_next) {
+		rc = ACM_ERR_NOMEM;
+		goto out;
+	}
+	memset(tr.own_head, 0xff, (size_t)total * 4);
+
+	/* 1. trie, reference insertion order: last added pattern first */
+	for (k = c->npats - 1; k >= 0; k--) {
+		const struct acm_pat *p = &c->pats[k];
+		uint32_t state = 0, nx;
+		int pos = 0;
+
+		if (p->n == 0) {
+			tr.own_next[k] = -1;
+			continue;
+		}
+		for (; pos < p->n; pos++) {
+			nx = trie_child(&tr, state, sym_at(c, p, pos));
+			if (!nx)
+				break;
+			state = nx;
+		}
+		for (; pos < p->n; pos++) {
+			unsigned a = sym_at(c, p, pos);
+			last++;
+			tr.parent[last] = state;
+			tr.sym[last] = (uint16_t)a;
+			if (state == 0) {
+				tr.root_child[a] = last;
+			} else {
+				tr.next_sib[last] = tr.first_child[state];
+				tr.first_child[state] = last;
+			}
+			state = last;
+		}
+		/* prepend: the own list ends up in ascending pattern index */
+		tr.own_next[k] = tr.own_head[state];
+		tr.own_head[state] = k;
+	}
+	tr.n = last + 1;
+
+	/* 2. breadth-first numbering, children visited in symbol order
+	 *    (the reference's BFS loops i = 0..ALPHABET_SIZE-1, acsmx.c:376-395) */
+	order  = malloc((size_t)tr.n * 4);
+	bfs_id = malloc((size_t)tr.n * 4);
+	depth  = malloc((size_t)tr.n * 4);
+	cbuf   = malloc((size_t)(A > 256 ? A : 256) * 4);
+	t->level_start = calloc((size_t)c->max_len + 3, 4);
+	if (!order || !bfs_id || !depth || !cbuf || !t->level_start) {
+		rc = ACM_ERR_NOMEM;
+		goto out;
+	}
+	order[0] = 0;
+	bfs_id[0] = 0;
+	depth[0] = 0;
+	qt = 1;
+	for (i = 0; i < qt; i++) {
+		uint32_t nc = 0, x, y;
+
+		u = order[i];
+		if (u == 0) {
+			for (x = 0; x < (uint32_t)A; x++)
+				if (tr.root_child[x])
+					cbuf[nc++] = tr.root_child[x];
+		} else {
+			for (x = tr.first_child[u]; x; x = tr.next_sib[x])
+				cbuf[nc++] = x;
+			for (x = 1; x < nc; x++) {       /* insertion sort by symbol */
+				uint32_t v = cbuf[x];
+				for (y = x; y > 0 && tr.sym[cbuf[y - 1]] > tr.sym[v]; y--)
+					cbuf[y] = cbuf[y - 1];
+				cbuf[y] = v;
+			}
+		}
+		for (x = 0; x < nc; x++) {
+			uint32_t ch = cbuf[x];
+			depth[ch] = depth[u] + 1;
+			bfs_id[ch] = qt;
+			order[qt++] = ch;
+		}
+	}
+	t->alpha = A;
+	t->num_states = tr.n;
+	t->num_patterns = (uint32_t)c->npats;
+	t->max_pattern_len = c->max_len;
+	t->min_pattern_len = c->min_len;
+	t->max_depth = c->max_len;
+	{
+		int d = 0;
+		for (i = 0; i < tr.n; i++)
+			while ((int)depth[order[i]] >= d)
+				t->level_start[d++] = i;
+		for (; d <= c->max_len + 1; d++)
+			t->level_start[d] = tr.n;
+	}
+
+	/* 3. dense DFA rows + fail links, in BFS order */
+	t->T          = malloc((size_t)tr.n * A * 4);
+	t->fail       = calloc(tr.n, 4);
+	t->olink      = calloc(tr.n, 4);
+	t->own_begin  = calloc((size_t)tr.n + 1, 4);
+	t->own_pat    = malloc((size_t)(c->npats + 1) * 4);
+	t->pat_len    = malloc((size_t)(c->npats + 1) * 4);
+	t->pat_iid    = malloc((size_t)(c->npats + 1) * 4);
+	t->bfs_to_ref = malloc((size_t)tr.n * 4);
+	if (!t->T || !t->fail || !t->olink || !t->own_begin || !t->own_pat ||
+	    !t->pat_len || !t->pat_iid || !t->bfs_to_ref) {
+		rc = ACM_ERR_NOMEM;
+		goto out;
+	}
+	for (k = 0; k < c->npats; k++) {
+		t->pat_len[k] = (uint32_t)c->pats[k].n;
+		t->pat_iid[k] = c->pats[k].iid;
+	}
+	memset(t->T, 0, (size_t)A * 4);
+	for (i = 0; i < tr.n; i++) {
+		uint32_t *row = t->T + (size_t)i * A;
+		const uint32_t *frow = t->T + (size_t)t->fail[i] * A;
+		uint32_t x;
+
+		u = order[i];
+		t->bfs_to_ref[i] = u;
+		if (i)
+			memcpy(row, frow, (size_t)A * 4);
+		if (u == 0) {
+			for (x = 0; x < (uint32_t)A; x++)
+				if (tr.root_child[x]) {
+					uint32_t cid = bfs_id[tr.root_child[x]];
+					row[x] = cid;
+					t->fail[cid] = 0;
+				}
+		} else {
+			for (x = tr.first_child[u]; x; x = tr.next_sib[x]) {
+				uint32_t cid = bfs_id[x];
+				t->fail[cid] = frow[tr.sym[x]];
+				row[tr.sym[x]] = cid;
+			}
+		}
+	}
+
+	/* 4. own lists (CSR, BFS order) and output links */
+	{
+		uint32_t w = 0;
+		for (i = 0; i < tr.n; i++) {
+			int32_t e;
+			t->own_begin[i] = w;
+			for (e = tr.own_head[order[i]]; e != -1; e = tr.own_next[e])
+				t->own_pat[w++] = (uint32_t)e;
+		}
+		t->own_begin[tr.n] = w;
+		t->own_total = w;
+		for (i = 1; i < tr.n; i++) {
+			uint32_t f = t->fail[i];
+			t->olink[i] = (t->own_begin[f + 1] > t->own_begin[f]) ? f
+			                                                     : t->olink[f];
+		}
+	}
+
+	/* 5. flag every edge with what its target reports */
+	{
+		uint8_t *flag = malloc(tr.n);
+		size_t z, cells = (size_t)tr.n * A;
+
+		if (!flag) {
+			rc = ACM_ERR_NOMEM;
+			goto out;
+		}
+		for (i = 0; i < tr.n; i++) {
+			int own = t->own_begin[i + 1] > t->own_begin[i];
+			flag[i] = (uint8_t)((own ? 2 : 0) | ((own || t->olink[i]) ? 1 : 0));
+		}
+		for (z = 0; z < cells; z++) {
+			uint32_t v = t->T[z];
+			uint8_t f = flag[v];
+			if (f)
+				t->T[z] = v | ((f & 2) ? ACM_T_OWN : 0) | ACM_T_ANY;
+		}
+		free(flag);
+	}
+
+	if (A == 256)
+		rc = build_filters(c);
+
+out:
+	trie_free(&tr);
+	free(order); free(bfs_id); free(depth); free(cbuf);
+	if (rc != ACM_OK) {
+		acm_tables_free(t);
+		acm_set_error("compile failed (%d)", rc);
+		return c->status = rc;
+	}
+	c->compiled = 1;
+	return ACM_OK;
+}
+
+/*
+ * Reference-layout table (reference acsmx.c:640-659): row stride 2*alpha ints,
+ * first half = +/- next state (negative: target has a match list), second half =
+ * index (bytes) or iid (ushorts, iacsmx.c:504) of the HEAD of the target's list.
+ *
+ * The reference's list for state s is reverse(list(fail s)) followed by the own
+ * entries in ascending index (inherited copies are prepended one by one,
+ * acsmx.c:417-429; own entries were prepended at insertion, acsmx.c:300-312,
+ * in descending index order).  So
+ *     head(s) = list(fail s) non-empty ? last(fail s) : min own index
+ *     last(s) = own non-empty ? max own index : head(fail s)
+ * States use the reference's numbering (trie creation order).
+ */
+int
+acm_core_export_ref(struct acm_core *c, int **out)
+{
+	const struct acm_tables *t = &c->tab;
+	const int A = c->alpha;
+	const size_t row = 2 * (size_t)A;
+	int32_t *head, *lastp;
+	int *tab;
+	uint32_t i;
+
+	if (!c->compiled || !t->T) {
+		acm_set_error("export_ref_table: automaton not compiled or already cleaned up");
+		return ACM_ERR_STATE;
+	}
+	head = malloc((size_t)t->num_states * 4);
+	lastp = malloc((size_t)t->num_states * 4);
+	tab = memalign(4096, (size_t)t->num_states * row * sizeof(int));
+	if (!head || !lastp || !tab) {
+		free(head); free(lastp); free(tab);
+		acm_set_error("export_ref_table: out of memory");
+		return ACM_ERR_NOMEM;
+	}
+	head[0] = lastp[0] = -1;
+	for (i = 1; i < t->num_states; i++) {
+		uint32_t f = t->fail[i];
+		int own = t->own_begin[i + 1] > t->own_begin[i];
+		int inh = head[f] != -1;
+
+		head[i] = inh ? lastp[f] : (own ? (int32_t)t->own_pat[t->own_begin[i]] : -1);
+		lastp[i] = own ? (int32_t)t->own_pat[t->own_begin[i + 1] - 1]
+		               : (inh ? head[f] : -1);
+	}
+	memset(tab, 0, (size_t)t->num_states * row * sizeof(int));
+	for (i = 0; i < t->num_states; i++) {
+		int *r = tab + (size_t)t->bfs_to_ref[i] * row;
+		const uint32_t *src = t->T + (size_t)i * A;
+		for (int a = 0; a < A; a++) {
+			uint32_t nx = src[a] & ACM_T_MASK;
+			int ref = (int)t->bfs_to_ref[nx];
+			if (head[nx] != -1) {
+				r[a] = -ref;
+				r[A + a] = (A == 256) ? head[nx] : t->pat_iid[head[nx]];
+			} else {
+				r[a] = ref;
+			}
+		}
+	}
+	free(head);
+	free(lastp);
+	*out = tab;
+	return ACM_OK;
+}
+
+void
+acm_core_cleanup(struct acm_core *c)
+{
+	int k;
+
+	for (k = 0; k < c->npats; k++) {
+		free(c->pats[k].syms);
+		c->pats[k].syms = NULL;
+	}
+	acm_tables_free(&c->tab);
+}
+
+void
+acm_core_free(struct acm_core *c)
+{
+	if (!c)
+		return;
+	acm_core_cleanup(c);
+	free(c->pats);
+	free(c);
+}

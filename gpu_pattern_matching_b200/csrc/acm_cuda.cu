@@ -1,0 +1,1096 @@
+/*
+ * acm_cuda.cu -- device objects, kernel launchers and the native C ABI of acm.h.
+ *
+ * Compiled for sm_100a only.  There is no CPU fallback anywhere in this file: every
+ * entry point that needs a GPU returns ACM_ERR_NO_DEVICE / ACM_ERR_CUDA when there
+ * is none.
+ */
+#include <cuda_runtime.h>
+
+#include <stdarg.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include "../../include/acm.h"
+#include "acm_core.h"
+#include "acm_tables.h"
+#include "k1_scan.cuh"
+#include "k234_post.cuh"
+
+#define CUDA_TRY(expr)                                                              \
+	do {                                                                            \
+		cudaError_t e_ = (expr);                                                    \
+		if (e_ != cudaSuccess) {                                                    \
+			acm_set_error("%s:%d: %s: %s", __FILE__, __LINE__, #expr,              \
+			    cudaGetErrorString(e_));                                            \
+			return ACM_ERR_CUDA;                                                    \
+		}                                                                           \
+	} while (0)
+
+struct acm_device {
+	int          ordinal;
+	int          sm_count;
+	cudaStream_t own_stream;
+	cudaStream_t stream;        /* own_stream or an adopted one */
+	cudaStream_t copy_stream;   /* H2D staging for acm_scan_host */
+	/* scratch for the stand-alone scan / sort entry points */
+	uint64_t    *tile_state;
+	uint32_t    *tile_counter;
+	uint32_t     tile_cap;
+	uint32_t    *hist;
+	uint64_t     hist_cap;
+};
+
+struct acm_automaton {
+	struct acm_device *dev;
+	AutDev    d;                /* device pointers */
+	uint32_t  num_states, num_patterns, gram_count;
+	int       alpha, max_len, min_len;
+	size_t    bytes;
+	uint32_t *h_pat_len;        /* host copies that outlive acsm_cleanup() */
+	int32_t  *h_pat_iid;
+	void     *allocs[16];
+	int       n_allocs;
+};
+
+struct acm_scanner {
+	struct acm_device    *dev;
+	struct acm_automaton *aut;
+	struct acm_scan_params p;
+	uint64_t  max_bytes;
+	uint32_t  shift, cap, max_buckets;
+	uint64_t *buckets;
+	uint32_t *counts, *offsets;
+	uint32_t *flags;            /* [0] overflow, [1] total, [2] final state, [3] tile counter */
+	uint64_t *tile_state;
+	uint32_t  max_tiles;
+	uint64_t *out;              /* sorted keys of the last scan */
+	uint64_t  out_cap;
+	uint64_t *tmp;              /* radix sort ping-pong (fallback only) */
+	uint64_t  tmp_cap;
+	uint32_t *hist;             /* radix histograms (fallback only) */
+	uint64_t  hist_cap;
+	uint32_t *h_flags;          /* pinned, 4 words */
+	uint64_t  last_n;           /* matches of the last scan */
+	cudaEvent_t ev[4];
+	/* acm_scan_host staging */
+	uint8_t  *stage[2];
+	uint64_t  stage_bytes;
+	cudaEvent_t ev_copied[2], ev_free[2];
+	uint64_t *h_keys;           /* pinned bounce buffer for results */
+	uint64_t  h_keys_cap;
+};
+
+/* ------------------------------------------------------------------------- */
+/* device                                                                    */
+/* ------------------------------------------------------------------------- */
+
+extern "C" int
+acm_device_count(void)
+{
+	int n = 0;
+	if (cudaGetDeviceCount(&n) != cudaSuccess) {
+		cudaGetLastError();
+		return 0;
+	}
+	return n;
+}
+
+static int g_attr_done[64];
+
+static int
+set_kernel_attrs(int ordinal)
+{
+	if (ordinal < 64 && g_attr_done[ordinal])
+		return ACM_OK;
+	CUDA_TRY(cudaFuncSetAttribute(k_scan_sampled4, cudaFuncAttributeMaxDynamicSharedMemorySize,
+	    S4_SMEM_BYTES));
+	CUDA_TRY(cudaFuncSetAttribute(k_scan_start2, cudaFuncAttributeMaxDynamicSharedMemorySize,
+	    S2_SMEM_BYTES));
+	CUDA_TRY(cudaFuncSetAttribute(k_bucket_sort_compact, cudaFuncAttributeMaxDynamicSharedMemorySize,
+	    65536));
+	if (ordinal < 64)
+		g_attr_done[ordinal] = 1;
+	return ACM_OK;
+}
+
+extern "C" int
+acm_device_open(int ordinal, struct acm_device **out)
+{
+	int n = acm_device_count();
+	struct acm_device *d;
+	cudaDeviceProp prop;
+	int rc;
+
+	*out = NULL;
+	if (n <= 0) {
+		acm_set_error("no CUDA device visible; this library has no CPU fallback");
+		return ACM_ERR_NO_DEVICE;
+	}
+	if (ordinal < 0 || ordinal >= n) {
+		acm_set_error("device ordinal %d out of range (0..%d)", ordinal, n - 1);
+		return ACM_ERR_ARG;
+	}
+	CUDA_TRY(cudaSetDevice(ordinal));
+	CUDA_TRY(cudaGetDeviceProperties(&prop, ordinal));
+	if (prop.major < 10) {
+		acm_set_error("device %d is sm_%d%d; this build carries sm_100a code only", ordinal,
+		    prop.major, prop.minor);
+		return ACM_ERR_NO_DEVICE;
+	}
+	d = (struct acm_device *)calloc(1, sizeof(*d));
+	if (!d)
+		return ACM_ERR_NOMEM;
+	d->ordinal = ordinal;
+	d->sm_count = prop.multiProcessorCount;
+	CUDA_TRY(cudaStreamCreateWithFlags(&d->own_stream, cudaStreamNonBlocking));
+	CUDA_TRY(cudaStreamCreateWithFlags(&d->copy_stream, cudaStreamNonBlocking));
+	d->stream = d->own_stream;
+	if ((rc = set_kernel_attrs(ordinal)) != ACM_OK) {
+		free(d);
+		return rc;
+	}
+	*out = d;
+	return ACM_OK;
+}
+
+extern "C" void
+acm_device_close(struct acm_device *d)
+{
+	if (!d)
+		return;
+	cudaSetDevice(d->ordinal);
+	cudaStreamSynchronize(d->stream);
+	cudaFree(d->tile_state);
+	cudaFree(d->tile_counter);
+	cudaFree(d->hist);
+	cudaStreamDestroy(d->own_stream);
+	cudaStreamDestroy(d->copy_stream);
+	free(d);
+}
+
+extern "C" int acm_device_ordinal(struct acm_device *d) { return d->ordinal; }
+extern "C" void *acm_device_stream(struct acm_device *d) { return (void *)d->stream; }
+
+extern "C" int
+acm_device_set_stream(struct acm_device *d, void *s)
+{
+	d->stream = s ? (cudaStream_t)s : d->own_stream;
+	return ACM_OK;
+}
+
+extern "C" int
+acm_device_sync(struct acm_device *d)
+{
+	CUDA_TRY(cudaSetDevice(d->ordinal));
+	CUDA_TRY(cudaStreamSynchronize(d->stream));
+	return ACM_OK;
+}
+
+static struct acm_device *g_default_dev;
+
+extern "C" struct acm_device *
+acm_default_device(void)
+{
+	if (!g_default_dev) {
+		const char *e = getenv("ACM_DEVICE");
+		int ord = e ? atoi(e) : 0;
+		if (!e && getenv("LOCAL_RANK") && acm_device_count() > 1)
+			ord = atoi(getenv("LOCAL_RANK")) % acm_device_count();
+		if (acm_device_open(ord, &g_default_dev) != ACM_OK)
+			return NULL;
+	}
+	return g_default_dev;
+}
+
+extern "C" int
+acm_dev_alloc(struct acm_device *d, size_t bytes, void **p)
+{
+	CUDA_TRY(cudaSetDevice(d->ordinal));
+	CUDA_TRY(cudaMalloc(p, bytes ? bytes : 16));
+	return ACM_OK;
+}
+
+extern "C" void
+acm_dev_free(struct acm_device *d, void *p)
+{
+	if (!p)
+		return;
+	cudaSetDevice(d->ordinal);
+	cudaFree(p);
+}
+
+extern "C" int
+acm_host_alloc_pinned(size_t bytes, void **p)
+{
+	CUDA_TRY(cudaHostAlloc(p, bytes ? bytes : 16, cudaHostAllocDefault));
+	return ACM_OK;
+}
+
+extern "C" void
+acm_host_free_pinned(void *p)
+{
+	if (p)
+		cudaFreeHost(p);
+}
+
+extern "C" int
+acm_memcpy_h2d(struct acm_device *d, void *dst, const void *src, size_t bytes)
+{
+	CUDA_TRY(cudaSetDevice(d->ordinal));
+	CUDA_TRY(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, d->stream));
+	return ACM_OK;
+}
+
+extern "C" int
+acm_memcpy_d2h(struct acm_device *d, void *dst, const void *src, size_t bytes)
+{
+	CUDA_TRY(cudaSetDevice(d->ordinal));
+	CUDA_TRY(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, d->stream));
+	return ACM_OK;
+}
+
+extern "C" int
+acm_memcpy_d2d(struct acm_device *d, void *dst, const void *src, size_t bytes)
+{
+	CUDA_TRY(cudaSetDevice(d->ordinal));
+	CUDA_TRY(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToDevice, d->stream));
+	return ACM_OK;
+}
+
+/* ------------------------------------------------------------------------- */
+/* automaton                                                                 */
+/* ------------------------------------------------------------------------- */
+
+static int
+upload(struct acm_automaton *a, const void *src, size_t bytes, const void **dst)
+{
+	void *p = NULL;
+	size_t padded = (bytes + 255) & ~(size_t)255;
+
+	*dst = NULL;
+	if (a->n_allocs >= 16)
+		return ACM_ERR_LIMIT;
+	CUDA_TRY(cudaMalloc(&p, padded ? padded : 256));
+	a->allocs[a->n_allocs++] = p;
+	if (bytes)
+		CUDA_TRY(cudaMemcpyAsync(p, src, bytes, cudaMemcpyHostToDevice, a->dev->stream));
+	a->bytes += padded;
+	*dst = p;
+	return ACM_OK;
+}
+
+extern "C" void
+acm_automaton_free(struct acm_automaton *a)
+{
+	if (!a)
+		return;
+	cudaSetDevice(a->dev->ordinal);
+	cudaStreamSynchronize(a->dev->stream);
+	for (int i = 0; i < a->n_allocs; i++)
+		cudaFree(a->allocs[i]);
+	free(a->h_pat_len);
+	free(a->h_pat_iid);
+	free(a);
+}
+
+extern "C" int
+acm_automaton_upload(struct acm_device *dev, const struct acm_tables *t, struct acm_automaton **out)
+{
+	struct acm_automaton *a;
+	int rc = ACM_OK;
+
+	*out = NULL;
+	if (!dev) {
+		acm_set_error("automaton_upload: no device");
+		return ACM_ERR_NO_DEVICE;
+	}
+	if (!t || !t->T) {
+		acm_set_error("automaton_upload: automaton not compiled");
+		return ACM_ERR_STATE;
+	}
+	CUDA_TRY(cudaSetDevice(dev->ordinal));
+	a = (struct acm_automaton *)calloc(1, sizeof(*a));
+	if (!a)
+		return ACM_ERR_NOMEM;
+	a->dev = dev;
+	a->num_states = t->num_states;
+	a->num_patterns = t->num_patterns;
+	a->alpha = t->alpha;
+	a->max_len = t->max_pattern_len;
+	a->min_len = t->min_pattern_len;
+	a->gram_count = t->gram_count;
+	a->h_pat_len = (uint32_t *)malloc((size_t)(t->num_patterns + 1) * 4);
+	a->h_pat_iid = (int32_t *)malloc((size_t)(t->num_patterns + 1) * 4);
+	if (!a->h_pat_len || !a->h_pat_iid) {
+		acm_automaton_free(a);
+		return ACM_ERR_NOMEM;
+	}
+	memcpy(a->h_pat_len, t->pat_len, (size_t)t->num_patterns * 4);
+	memcpy(a->h_pat_iid, t->pat_iid, (size_t)t->num_patterns * 4);
+
+#define UP(field, src, bytes)                                                       \
+	if (rc == ACM_OK)                                                               \
+		rc = upload(a, (src), (bytes), (const void **)&a->d.field)
+	UP(T, t->T, (size_t)t->num_states * t->alpha * 4);
+	UP(level_start, t->level_start, (size_t)(t->max_depth + 2) * 4);
+	UP(own_begin, t->own_begin, (size_t)(t->num_states + 1) * 4);
+	UP(own_pat, t->own_pat, (size_t)t->own_total * 4);
+	UP(olink, t->olink, (size_t)t->num_states * 4);
+	if (t->b2)
+		UP(b2, t->b2, 65536 / 8);
+	if (t->f1) {
+		UP(f1, t->f1, (1u << ACM_F1_BITS_LOG2) / 8);
+		UP(f2, t->f2, (1u << ACM_F2_BITS_LOG2) / 8);
+		UP(grams, t->grams, (size_t)t->gram_slots * sizeof(struct acm_gram_slot));
+		a->d.gram_mask = t->gram_slots - 1;
+		uint32_t lg = 0;
+		while ((1u << lg) < t->gram_slots)
+			lg++;
+		a->d.gram_shift = 32 - lg;
+	}
+#undef UP
+	a->d.num_states = t->num_states;
+	a->d.alpha = t->alpha;
+	a->d.max_len = t->max_pattern_len;
+	if (rc == ACM_OK && cudaStreamSynchronize(dev->stream) != cudaSuccess) {
+		acm_set_error("automaton_upload: %s", cudaGetErrorString(cudaGetLastError()));
+		rc = ACM_ERR_CUDA;
+	}
+	if (rc != ACM_OK) {
+		acm_automaton_free(a);
+		return rc;
+	}
+	*out = a;
+	return ACM_OK;
+}
+
+extern "C" uint32_t acm_automaton_states(const struct acm_automaton *a) { return a->num_states; }
+extern "C" uint32_t acm_automaton_patterns(const struct acm_automaton *a) { return a->num_patterns; }
+extern "C" int acm_automaton_max_pattern_len(const struct acm_automaton *a) { return a->max_len; }
+extern "C" int acm_automaton_min_pattern_len(const struct acm_automaton *a) { return a->min_len; }
+extern "C" int acm_automaton_alphabet(const struct acm_automaton *a) { return a->alpha; }
+extern "C" size_t acm_automaton_device_bytes(const struct acm_automaton *a) { return a->bytes; }
+extern "C" uint32_t acm_automaton_gram_count(const struct acm_automaton *a) { return a->gram_count; }
+
+extern "C" int
+acm_automaton_default_mode(const struct acm_automaton *a)
+{
+	if (a->alpha != 256)
+		return ACM_MODE_DFA;
+	if (a->d.f1 && a->min_len >= 7)
+		return ACM_MODE_SAMPLED4;
+	return ACM_MODE_START2;
+}
+
+/* ------------------------------------------------------------------------- */
+/* stand-alone post-pass primitives                                          */
+/* ------------------------------------------------------------------------- */
+
+static int
+launch_exclusive_scan(cudaStream_t st, const uint32_t *in, uint32_t *out, uint32_t n,
+    uint64_t *tile_state, uint32_t *tile_counter, uint32_t *total)
+{
+	const uint32_t tiles = (n + SCAN_TILE - 1) / SCAN_TILE;
+
+	if (n == 0) {
+		if (total)
+			CUDA_TRY(cudaMemsetAsync(total, 0, 4, st));
+		return ACM_OK;
+	}
+	CUDA_TRY(cudaMemsetAsync(tile_state, 0, (size_t)tiles * 8, st));
+	CUDA_TRY(cudaMemsetAsync(tile_counter, 0, 4, st));
+	k_scan_lookback<<<tiles, SCAN_THREADS, 0, st>>>(in, out, n, tile_state, tile_counter, total);
+	CUDA_TRY(cudaGetLastError());
+	return ACM_OK;
+}
+
+static int
+dev_scan_scratch(struct acm_device *d, uint32_t tiles)
+{
+	if (tiles > d->tile_cap) {
+		cudaFree(d->tile_state);
+		d->tile_state = NULL;
+		d->tile_cap = 0;
+		CUDA_TRY(cudaMalloc(&d->tile_state, (size_t)tiles * 8));
+		d->tile_cap = tiles;
+	}
+	if (!d->tile_counter)
+		CUDA_TRY(cudaMalloc(&d->tile_counter, 16));
+	return ACM_OK;
+}
+
+extern "C" int
+acm_exclusive_scan_u32(struct acm_device *d, const uint32_t *in, uint32_t *out, uint32_t n,
+    uint32_t *total)
+{
+	int rc;
+
+	CUDA_TRY(cudaSetDevice(d->ordinal));
+	if ((rc = dev_scan_scratch(d, (n + SCAN_TILE - 1) / SCAN_TILE + 1)) != ACM_OK)
+		return rc;
+	return launch_exclusive_scan(d->stream, in, out, n, d->tile_state, d->tile_counter, total);
+}
+
+extern "C" int
+acm_compact_columns_i32(struct acm_device *d, int32_t *dst, const int32_t *src, const int32_t *prefix,
+    int32_t len, int32_t max_results)
+{
+	CUDA_TRY(cudaSetDevice(d->ordinal));
+	if (len <= 0)
+		return ACM_OK;
+	k_compact_columns<<<(len + 255) / 256, 256, 0, d->stream>>>(dst, src, prefix, len, max_results);
+	CUDA_TRY(cudaGetLastError());
+	return ACM_OK;
+}
+
+/* sorts keys[0..n) on bits [b0, b1); result ends in `keys`; hist has 256 * nblocks + scratch */
+static int
+radix_sort_impl(cudaStream_t st, uint64_t *keys, uint64_t *tmp, uint64_t n, int b0, int b1, int desc,
+    uint32_t *hist, uint64_t *tile_state, uint32_t *tile_counter, uint32_t *launches)
+{
+	const uint32_t nblocks = (uint32_t)((n + RS_TILE - 1) / RS_TILE);
+	uint64_t *src = keys, *dst = tmp;
+	int rc;
+
+	if (n <= 1 || b1 <= b0)
+		return ACM_OK;
+	for (int shift = b0; shift < b1; shift += 8) {
+		const uint64_t flip = desc ? ~0ull : 0ull;
+		k_radix_hist<<<nblocks, RS_THREADS, 0, st>>>(src, n, shift, flip, hist, nblocks);
+		CUDA_TRY(cudaGetLastError());
+		rc = launch_exclusive_scan(st, hist, hist, 256u * nblocks, tile_state, tile_counter, NULL);
+		if (rc != ACM_OK)
+			return rc;
+		k_radix_scatter<<<nblocks, RS_THREADS, 0, st>>>(src, dst, n, shift, flip, hist, nblocks);
+		CUDA_TRY(cudaGetLastError());
+		if (launches)
+			*launches += 3;
+		uint64_t *t = src;
+		src = dst;
+		dst = t;
+	}
+	if (src != keys)
+		CUDA_TRY(cudaMemcpyAsync(keys, src, n * 8, cudaMemcpyDeviceToDevice, st));
+	return ACM_OK;
+}
+
+static int
+dev_sort_scratch(struct acm_device *d, uint64_t n)
+{
+	const uint64_t nblocks = (n + RS_TILE - 1) / RS_TILE;
+	const uint64_t need = 256 * nblocks + 256;
+	int rc;
+
+	if (need > d->hist_cap) {
+		cudaFree(d->hist);
+		d->hist = NULL;
+		d->hist_cap = 0;
+		CUDA_TRY(cudaMalloc(&d->hist, need * 4));
+		d->hist_cap = need;
+	}
+	if ((rc = dev_scan_scratch(d, (uint32_t)((need + SCAN_TILE - 1) / SCAN_TILE + 1))) != ACM_OK)
+		return rc;
+	return ACM_OK;
+}
+
+extern "C" int
+acm_radix_sort_u64(struct acm_device *d, uint64_t *keys, uint64_t *tmp, uint64_t n, int b0, int b1,
+    int desc)
+{
+	int rc;
+
+	if (b0 < 0 || b1 > 64 || n >= (1ull << 32)) {
+		acm_set_error("radix_sort: bad arguments");
+		return ACM_ERR_ARG;
+	}
+	CUDA_TRY(cudaSetDevice(d->ordinal));
+	if ((rc = dev_sort_scratch(d, n)) != ACM_OK)
+		return rc;
+	return radix_sort_impl(d->stream, keys, tmp, n, b0, b1, desc, d->hist, d->tile_state,
+	    d->tile_counter, NULL);
+}
+
+extern "C" int
+acm_sort_pairs_u32(struct acm_device *d, uint32_t *dk, uint32_t *dv, const uint32_t *sk,
+    const uint32_t *sv, uint32_t n, int desc)
+{
+	uint64_t *buf = NULL;
+	int rc;
+
+	if (n == 0)
+		return ACM_OK;
+	CUDA_TRY(cudaSetDevice(d->ordinal));
+	CUDA_TRY(cudaMalloc(&buf, (size_t)n * 16));
+	k_pack_pairs<<<(n + 255) / 256, 256, 0, d->stream>>>(sk, sv, buf, n);
+	rc = acm_radix_sort_u64(d, buf, buf + n, n, 0, 64, desc);
+	if (rc == ACM_OK) {
+		k_unpack_pairs<<<(n + 255) / 256, 256, 0, d->stream>>>(buf, dk, dv, n);
+		if (cudaStreamSynchronize(d->stream) != cudaSuccess) {
+			acm_set_error("sort_pairs: %s", cudaGetErrorString(cudaGetLastError()));
+			rc = ACM_ERR_CUDA;
+		}
+	}
+	cudaFree(buf);
+	return rc;
+}
+
+/* ------------------------------------------------------------------------- */
+/* scanner                                                                   */
+/* ------------------------------------------------------------------------- */
+
+static uint32_t
+next_pow2(uint32_t v)
+{
+	uint32_t p = 1;
+	while (p < v)
+		p <<= 1;
+	return p;
+}
+
+extern "C" void
+acm_scanner_free(struct acm_scanner *s)
+{
+	if (!s)
+		return;
+	cudaSetDevice(s->dev->ordinal);
+	cudaStreamSynchronize(s->dev->stream);
+	cudaStreamSynchronize(s->dev->copy_stream);
+	cudaFree(s->buckets); cudaFree(s->counts); cudaFree(s->offsets); cudaFree(s->flags);
+	cudaFree(s->tile_state); cudaFree(s->out); cudaFree(s->tmp); cudaFree(s->hist);
+	cudaFree(s->stage[0]); cudaFree(s->stage[1]);
+	if (s->h_flags)
+		cudaFreeHost(s->h_flags);
+	if (s->h_keys)
+		cudaFreeHost(s->h_keys);
+	for (int i = 0; i < 4; i++)
+		if (s->ev[i])
+			cudaEventDestroy(s->ev[i]);
+	for (int i = 0; i < 2; i++) {
+		if (s->ev_copied[i])
+			cudaEventDestroy(s->ev_copied[i]);
+		if (s->ev_free[i])
+			cudaEventDestroy(s->ev_free[i]);
+	}
+	free(s);
+}
+
+extern "C" int
+acm_scanner_create(struct acm_device *dev, struct acm_automaton *aut, uint64_t max_bytes,
+    const struct acm_scan_params *params, struct acm_scanner **out)
+{
+	struct acm_scanner *s;
+	int mode;
+
+	*out = NULL;
+	if (!dev || !aut) {
+		acm_set_error("scanner_create: device and automaton required");
+		return ACM_ERR_ARG;
+	}
+	if (max_bytes == 0 || max_bytes > (1ull << 40)) {
+		acm_set_error("scanner_create: max_bytes must be in 1 .. 2^40");
+		return ACM_ERR_LIMIT;
+	}
+	CUDA_TRY(cudaSetDevice(dev->ordinal));
+	s = (struct acm_scanner *)calloc(1, sizeof(*s));
+	if (!s)
+		return ACM_ERR_NOMEM;
+	s->dev = dev;
+	s->aut = aut;
+	if (params)
+		s->p = *params;
+	mode = s->p.mode ? s->p.mode : acm_automaton_default_mode(aut);
+	if (aut->alpha != 256 && mode != ACM_MODE_DFA) {
+		acm_set_error("scanner_create: ushort automata run in DFA mode only");
+		free(s);
+		return ACM_ERR_ARG;
+	}
+	if (mode == ACM_MODE_SAMPLED4 && (!aut->d.f1 || aut->min_len < 7)) {
+		acm_set_error("scanner_create: sampled mode needs every pattern >= 7 bytes (shortest is %d)",
+		    aut->min_len);
+		free(s);
+		return ACM_ERR_ARG;
+	}
+	s->p.mode = mode;
+	s->max_bytes = max_bytes;
+	s->shift = s->p.bucket_shift ? (uint32_t)s->p.bucket_shift : 15u;
+	if (s->shift < 8 || s->shift > 30) {
+		acm_set_error("scanner_create: bucket_shift must be in 8..30");
+		free(s);
+		return ACM_ERR_ARG;
+	}
+	s->cap = s->p.bucket_cap ? (uint32_t)s->p.bucket_cap
+	                         : (mode == ACM_MODE_SAMPLED4 ? 256u : 1024u);
+	if (s->cap < 32)
+		s->cap = 32;
+	if (s->cap > 8192)
+		s->cap = 8192;
+	s->cap = next_pow2(s->cap);
+	s->max_buckets = (uint32_t)((max_bytes + (1ull << s->shift) - 1) >> s->shift) + 1;
+	s->max_tiles = (s->max_buckets + SCAN_TILE - 1) / SCAN_TILE + 1;
+
+#define SALLOC(ptr, bytes)                                                          \
+	do {                                                                            \
+		cudaError_t e_ = cudaMalloc((void **)&(ptr), (bytes));                      \
+		if (e_ != cudaSuccess) {                                                    \
+			acm_set_error("scanner_create: cudaMalloc(%zu): %s", (size_t)(bytes),  \
+			    cudaGetErrorString(e_));                                            \
+			acm_scanner_free(s);                                                    \
+			return ACM_ERR_CUDA;                                                    \
+		}                                                                           \
+	} while (0)
+	SALLOC(s->buckets, (size_t)s->max_buckets * s->cap * 8);
+	SALLOC(s->counts, (size_t)s->max_buckets * 4);
+	SALLOC(s->offsets, (size_t)s->max_buckets * 4);
+	SALLOC(s->flags, 64);
+	SALLOC(s->tile_state, (size_t)s->max_tiles * 8);
+	s->out_cap = 1u << 16;
+	SALLOC(s->out, s->out_cap * 8);
+#undef SALLOC
+	if (cudaHostAlloc((void **)&s->h_flags, 64, cudaHostAllocDefault) != cudaSuccess) {
+		acm_set_error("scanner_create: cudaHostAlloc failed");
+		acm_scanner_free(s);
+		return ACM_ERR_CUDA;
+	}
+	for (int i = 0; i < 4; i++)
+		cudaEventCreate(&s->ev[i]);
+	for (int i = 0; i < 2; i++) {
+		cudaEventCreateWithFlags(&s->ev_copied[i], cudaEventDisableTiming);
+		cudaEventCreateWithFlags(&s->ev_free[i], cudaEventDisableTiming);
+	}
+	*out = s;
+	return ACM_OK;
+}
+
+static int
+grow(uint64_t **buf, uint64_t *cap, uint64_t need, const char *what)
+{
+	if (need <= *cap)
+		return ACM_OK;
+	uint64_t nc = *cap ? *cap : 1024;
+	while (nc < need)
+		nc *= 2;
+	cudaFree(*buf);
+	*buf = NULL;
+	*cap = 0;
+	if (cudaMalloc((void **)buf, nc * 8) != cudaSuccess) {
+		acm_set_error("scan: cannot allocate %llu bytes for %s", (unsigned long long)(nc * 8), what);
+		cudaGetLastError();
+		return ACM_ERR_CUDA;
+	}
+	*cap = nc;
+	return ACM_OK;
+}
+
+static int
+launch_k1(struct acm_scanner *s, cudaStream_t st, const void *d_data, uint64_t n, const EmitCtx &E)
+{
+	const struct acm_automaton *a = s->aut;
+	const uint64_t limit = E.emit_hi < n ? E.emit_hi : n;
+	const uint64_t halo = a->max_len > 0 ? (uint64_t)(a->max_len - 1) : 0;
+	uint64_t scan_lo = E.emit_lo > halo ? E.emit_lo - halo : 0;
+	if (scan_lo < E.valid_lo)
+		scan_lo = E.valid_lo;
+	const uint64_t vec_lo = scan_lo >> 4, vec_hi = (limit + 15) >> 4;
+
+	if (limit <= E.emit_lo)
+		return ACM_OK;
+	if (s->p.mode == ACM_MODE_SAMPLED4) {
+		const uint64_t tile = (uint64_t)S4_THREADS * S4_UNROLL;
+		uint64_t blocks = (vec_hi - vec_lo + tile - 1) / tile;
+		if (blocks > (uint64_t)s->dev->sm_count)
+			blocks = s->dev->sm_count;
+		k_scan_sampled4<<<(unsigned)blocks, S4_THREADS, S4_SMEM_BYTES, st>>>(a->d, E,
+		    (const uint8_t *)d_data, n, vec_lo, vec_hi, limit);
+	} else if (s->p.mode == ACM_MODE_START2) {
+		const uint64_t tile = (uint64_t)S2_THREADS * S2_UNROLL;
+		uint64_t blocks = (vec_hi - vec_lo + tile - 1) / tile;
+		if (blocks > (uint64_t)s->dev->sm_count * 2)
+			blocks = (uint64_t)s->dev->sm_count * 2;
+		k_scan_start2<<<(unsigned)blocks, S2_THREADS, S2_SMEM_BYTES, st>>>(a->d, E,
+		    (const uint8_t *)d_data, n, vec_lo, vec_hi, limit);
+	} else {
+		const uint64_t chunk = s->p.dfa_chunk > 0 ? (uint64_t)s->p.dfa_chunk : 4096;
+		const uint64_t nthreads = (limit - E.emit_lo + chunk - 1) / chunk;
+		const uint64_t blocks = (nthreads + 1 + 255) / 256;
+		if (a->alpha == 256)
+			k_scan_dfa<uint8_t><<<(unsigned)blocks, 256, 0, st>>>(a->d, E, (const uint8_t *)d_data, n,
+			    chunk, nthreads, s->flags + 2);
+		else
+			k_scan_dfa<uint16_t><<<(unsigned)blocks, 256, 0, st>>>(a->d, E, (const uint16_t *)d_data,
+			    n, chunk, nthreads, s->flags + 2);
+	}
+	CUDA_TRY(cudaGetLastError());
+	return ACM_OK;
+}
+
+static int
+scan_on_stream(struct acm_scanner *s, cudaStream_t st, const void *d_data, uint64_t n, uint64_t valid_lo,
+    uint64_t emit_lo, uint64_t emit_hi, struct acm_scan_result *res)
+{
+	const struct acm_automaton *a = s->aut;
+	EmitCtx E;
+	uint32_t nb, launches = 0;
+	int rc, timing = s->p.timing;
+
+	if (emit_hi > n)
+		emit_hi = n;
+	if (res)
+		memset(res, 0, sizeof(*res));
+	s->last_n = 0;
+	if (emit_lo >= emit_hi)
+		return ACM_OK;
+	if (emit_hi - emit_lo > s->max_bytes) {
+		acm_set_error("scan: %llu bytes exceed the scanner's max_bytes %llu",
+		    (unsigned long long)(emit_hi - emit_lo), (unsigned long long)s->max_bytes);
+		return ACM_ERR_ARG;
+	}
+	if (((uintptr_t)d_data & 15) != 0) {
+		acm_set_error("scan: device buffer must be 16-byte aligned");
+		return ACM_ERR_ARG;
+	}
+	if (n >= (1ull << 40)) {
+		acm_set_error("scan: more than 2^40 symbols in one call");
+		return ACM_ERR_LIMIT;
+	}
+	CUDA_TRY(cudaSetDevice(s->dev->ordinal));
+	nb = (uint32_t)((emit_hi - emit_lo + (1ull << s->shift) - 1) >> s->shift);
+
+	memset(&E, 0, sizeof(E));
+	E.buckets = s->buckets;
+	E.counts = s->counts;
+	E.overflow = s->flags;
+	E.emit_lo = emit_lo;
+	E.emit_hi = emit_hi;
+	E.valid_lo = valid_lo;
+	E.cap = s->cap;
+	E.shift = s->shift;
+
+	CUDA_TRY(cudaMemsetAsync(s->counts, 0, (size_t)nb * 4, st));
+	CUDA_TRY(cudaMemsetAsync(s->flags, 0, 64, st));
+	if (timing)
+		CUDA_TRY(cudaEventRecord(s->ev[0], st));
+	if ((rc = launch_k1(s, st, d_data, n, E)) != ACM_OK)
+		return rc;
+	launches++;
+	if (timing)
+		CUDA_TRY(cudaEventRecord(s->ev[1], st));
+	if ((rc = launch_exclusive_scan(st, s->counts, s->offsets, nb, s->tile_state, s->flags + 3,
+	    s->flags + 1)) != ACM_OK)
+		return rc;
+	launches++;
+	if (timing)
+		CUDA_TRY(cudaEventRecord(s->ev[2], st));
+	CUDA_TRY(cudaMemcpyAsync(s->h_flags, s->flags, 16, cudaMemcpyDeviceToHost, st));
+	CUDA_TRY(cudaStreamSynchronize(st));
+
+	const uint32_t overflow = s->h_flags[0];
+	const uint64_t total = s->h_flags[1];
+	if ((rc = grow(&s->out, &s->out_cap, total, "the match list")) != ACM_OK)
+		return rc;
+	if (total && !overflow) {
+		const uint32_t warps = K3_THREADS / 32;
+		k_bucket_sort_compact<<<(nb + warps - 1) / warps, K3_THREADS, (size_t)s->cap * 8, st>>>(
+		    s->buckets, s->counts, s->offsets, s->out, s->cap, nb);
+		CUDA_TRY(cudaGetLastError());
+		launches++;
+	} else if (total) {
+		/* exact two-pass path: counts are exact, refill straight into place, then sort */
+		int bits = ACM_KEY_PAT_BITS;
+		uint64_t span = emit_hi;
+		const uint64_t nblocks = (total + RS_TILE - 1) / RS_TILE;
+		uint64_t hist_need = (256 * nblocks + 256 + 1) / 2;   /* in u64 units for grow() */
+
+		while (span) {
+			bits++;
+			span >>= 1;
+		}
+		if ((rc = grow(&s->tmp, &s->tmp_cap, total, "the sort buffer")) != ACM_OK)
+			return rc;
+		if ((rc = grow((uint64_t **)&s->hist, &s->hist_cap, hist_need, "sort histograms")) != ACM_OK)
+			return rc;
+		const uint32_t scan_tiles = (uint32_t)((256 * nblocks + SCAN_TILE - 1) / SCAN_TILE) + 1;
+		if (scan_tiles > s->max_tiles) {
+			cudaFree(s->tile_state);
+			s->tile_state = NULL;
+			CUDA_TRY(cudaMalloc((void **)&s->tile_state, (size_t)scan_tiles * 8));
+			s->max_tiles = scan_tiles;
+		}
+		E.direct = 1;
+		E.offsets = s->offsets;
+		E.out = s->out;
+		CUDA_TRY(cudaMemsetAsync(s->counts, 0, (size_t)nb * 4, st));
+		if ((rc = launch_k1(s, st, d_data, n, E)) != ACM_OK)
+			return rc;
+		launches++;
+		if ((rc = radix_sort_impl(st, s->out, s->tmp, total, 0, bits, 0, s->hist, s->tile_state,
+		    s->flags + 3, &launches)) != ACM_OK)
+			return rc;
+	}
+	if (timing) {
+		CUDA_TRY(cudaEventRecord(s->ev[3], st));
+		CUDA_TRY(cudaStreamSynchronize(st));
+	}
+	s->last_n = total;
+	if (res) {
+		res->n_matches = total;
+		res->n_bytes = emit_hi - emit_lo;
+		res->mode = s->p.mode;
+		res->fallback = overflow ? 1 : 0;
+		res->final_state = s->h_flags[2];
+		res->n_buckets = nb;
+		res->launches = launches;
+		if (timing) {
+			cudaEventElapsedTime(&res->ms_scan, s->ev[0], s->ev[1]);
+			cudaEventElapsedTime(&res->ms_prefix, s->ev[1], s->ev[2]);
+			cudaEventElapsedTime(&res->ms_compact, s->ev[2], s->ev[3]);
+			cudaEventElapsedTime(&res->ms_total, s->ev[0], s->ev[3]);
+		}
+	}
+	(void)a;
+	return ACM_OK;
+}
+
+extern "C" int
+acm_scan_device(struct acm_scanner *s, const void *d_data, uint64_t n, uint64_t emit_lo, uint64_t emit_hi,
+    struct acm_scan_result *res)
+{
+	return scan_on_stream(s, s->dev->stream, d_data, n, 0, emit_lo, emit_hi, res);
+}
+
+extern "C" int
+acm_scan_device_ex(struct acm_scanner *s, const void *d_data, uint64_t n, uint64_t valid_lo,
+    uint64_t emit_lo, uint64_t emit_hi, struct acm_scan_result *res)
+{
+	if (valid_lo > emit_lo) {
+		acm_set_error("scan: valid_lo must not exceed emit_lo");
+		return ACM_ERR_ARG;
+	}
+	return scan_on_stream(s, s->dev->stream, d_data, n, valid_lo, emit_lo, emit_hi, res);
+}
+
+extern "C" const uint64_t *
+acm_scan_keys(struct acm_scanner *s)
+{
+	return s->out;
+}
+
+static int
+ensure_h_keys(struct acm_scanner *s, uint64_t n)
+{
+	if (n <= s->h_keys_cap)
+		return ACM_OK;
+	uint64_t nc = s->h_keys_cap ? s->h_keys_cap : (1u << 16);
+	while (nc < n)
+		nc *= 2;
+	if (s->h_keys)
+		cudaFreeHost(s->h_keys);
+	s->h_keys = NULL;
+	s->h_keys_cap = 0;
+	if (cudaHostAlloc((void **)&s->h_keys, nc * 8, cudaHostAllocDefault) != cudaSuccess) {
+		acm_set_error("scan_fetch: cannot pin %llu bytes", (unsigned long long)(nc * 8));
+		cudaGetLastError();
+		return ACM_ERR_CUDA;
+	}
+	s->h_keys_cap = nc;
+	return ACM_OK;
+}
+
+/* D2H of the last scan's keys on stream st, unpacked into h_off/h_pat with a signed shift */
+static int64_t
+fetch_on_stream(struct acm_scanner *s, cudaStream_t st, uint64_t base, int64_t rel_shift, uint64_t *h_off,
+    uint32_t *h_pat, uint64_t cap)
+{
+	const uint64_t n = s->last_n < cap ? s->last_n : cap;
+	int rc;
+
+	if (n == 0)
+		return 0;
+	if ((rc = ensure_h_keys(s, n)) != ACM_OK)
+		return rc;
+	CUDA_TRY(cudaMemcpyAsync(s->h_keys, s->out, n * 8, cudaMemcpyDeviceToHost, st));
+	CUDA_TRY(cudaStreamSynchronize(st));
+	for (uint64_t i = 0; i < n; i++) {
+		const uint64_t k = s->h_keys[i];
+		h_off[i] = base + (uint64_t)((int64_t)(k >> ACM_KEY_PAT_BITS) + rel_shift);
+		h_pat[i] = (uint32_t)(k & ACM_KEY_PAT_MASK);
+	}
+	return (int64_t)n;
+}
+
+extern "C" int64_t
+acm_scan_fetch(struct acm_scanner *s, uint64_t base, uint64_t *h_off, uint32_t *h_pat, uint64_t cap)
+{
+	CUDA_TRY(cudaSetDevice(s->dev->ordinal));
+	return fetch_on_stream(s, s->dev->stream, base, 0, h_off, h_pat, cap);
+}
+
+extern "C" int
+acm_scan_histogram(struct acm_scanner *s, uint64_t *d_counts)
+{
+	CUDA_TRY(cudaSetDevice(s->dev->ordinal));
+	if (s->last_n == 0)
+		return ACM_OK;
+	uint64_t blocks = (s->last_n + 255) / 256;
+	if (blocks > 1184)
+		blocks = 1184;
+	k_histogram<<<(unsigned)blocks, 256, 0, s->dev->stream>>>(s->out, s->last_n,
+	    (unsigned long long *)d_counts);
+	CUDA_TRY(cudaGetLastError());
+	return ACM_OK;
+}
+
+/*
+ * Host-buffer scan: double-buffered H2D on the copy stream, scan on the device
+ * stream.  Segment i is copied together with the Lmax-1 bytes before it, so each
+ * segment is an independent halo scan and the concatenation of
+ * the per-segment sorted lists is the sorted list of the whole stream.
+ */
+extern "C" int64_t
+acm_scan_host(struct acm_scanner *s, const void *h_data, uint64_t n, uint64_t base, uint64_t *h_off,
+    uint32_t *h_pat, uint64_t cap, struct acm_scan_result *res)
+{
+	const uint8_t *src = (const uint8_t *)h_data;
+	const uint64_t sym = s->aut->alpha == 256 ? 1 : 2;
+	const uint64_t halo = s->aut->max_len > 0 ? (uint64_t)(s->aut->max_len - 1) : 0;
+	uint64_t seg = s->max_bytes;
+	uint64_t written = 0, found = 0, launches = 0;
+	cudaStream_t ks = s->dev->stream, cs = s->dev->copy_stream;
+	struct acm_scan_result r1;
+	int rc, fallback = 0;
+
+	CUDA_TRY(cudaSetDevice(s->dev->ordinal));
+	if (res)
+		memset(res, 0, sizeof(*res));
+	if (n == 0)
+		return 0;
+	if (seg > n)
+		seg = n;
+	const uint64_t nseg = (n + seg - 1) / seg;
+	const uint64_t need = (halo + seg) * sym + 64;
+	if (need > s->stage_bytes) {
+		for (int i = 0; i < 2; i++) {
+			cudaFree(s->stage[i]);
+			s->stage[i] = NULL;
+		}
+		s->stage_bytes = 0;
+		for (int i = 0; i < 2; i++)
+			CUDA_TRY(cudaMalloc((void **)&s->stage[i], need));
+		s->stage_bytes = need;
+	}
+
+	/* segment i travels with its `lead` symbols of context: [lo - lead, hi) -> stage[i & 1] */
+	auto enqueue_copy = [&](uint64_t i) -> int {
+		const uint64_t lo = i * seg, hi = (lo + seg < n) ? lo + seg : n;
+		const uint64_t lead = lo < halo ? lo : halo;
+		const int b = (int)(i & 1);
+		if (i >= 2)
+			CUDA_TRY(cudaStreamWaitEvent(cs, s->ev_free[b], 0));
+		CUDA_TRY(cudaMemcpyAsync(s->stage[b], src + (lo - lead) * sym, (hi - lo + lead) * sym,
+		    cudaMemcpyHostToDevice, cs));
+		CUDA_TRY(cudaEventRecord(s->ev_copied[b], cs));
+		return ACM_OK;
+	};
+
+	if ((rc = enqueue_copy(0)) != ACM_OK)
+		return rc;
+	for (uint64_t i = 0; i < nseg; i++) {
+		const uint64_t lo = i * seg, hi = (lo + seg < n) ? lo + seg : n;
+		const uint64_t lead = lo < halo ? lo : halo;
+		const int b = (int)(i & 1);
+
+		if (i + 1 < nseg && (rc = enqueue_copy(i + 1)) != ACM_OK)
+			return rc;
+		CUDA_TRY(cudaStreamWaitEvent(ks, s->ev_copied[b], 0));
+		rc = scan_on_stream(s, ks, s->stage[b], lead + (hi - lo), 0, lead, lead + (hi - lo), &r1);
+		if (rc != ACM_OK)
+			return rc;
+		/* K1 has finished (scan_on_stream synchronised): the staging buffer is free again */
+		CUDA_TRY(cudaEventRecord(s->ev_free[b], ks));
+		found += r1.n_matches;
+		launches += r1.launches;
+		fallback |= r1.fallback;
+		if (written < cap) {
+			int64_t got = fetch_on_stream(s, ks, base + lo, -(int64_t)lead, h_off + written,
+			    h_pat + written, cap - written);
+			if (got < 0)
+				return got;
+			written += (uint64_t)got;
+		}
+	}
+	if (res) {
+		res->n_matches = found;
+		res->n_bytes = n;
+		res->mode = s->p.mode;
+		res->fallback = fallback;
+		res->launches = (uint32_t)launches;
+	}
+	return (int64_t)found;
+}
+
+/* ------------------------------------------------------------------------- */
+/* synthetic streams                                                         */
+/* ------------------------------------------------------------------------- */
+
+extern "C" void
+acm_synth_fill_host(void *dst, uint64_t n, uint64_t seed, uint64_t offset)
+{
+	uint8_t *p = (uint8_t *)dst;
+	uint64_t i = 0;
+
+	while (i < n) {
+		const uint64_t g = offset + i;
+		const uint64_t w = acm_mix64(seed, g >> 3);
+		if ((g & 7) == 0 && n - i >= 8) {
+			memcpy(p + i, &w, 8);
+			i += 8;
+		} else {
+			p[i] = (uint8_t)(w >> (8 * (g & 7)));
+			i++;
+		}
+	}
+}
+
+extern "C" int
+acm_synth_fill_device(struct acm_device *d, void *dst, uint64_t n, uint64_t seed, uint64_t offset)
+{
+	if (((uintptr_t)dst & 7) || (offset & 7) || (n & 7)) {
+		acm_set_error("synth_fill_device: pointer, offset and size must be multiples of 8");
+		return ACM_ERR_ARG;
+	}
+	CUDA_TRY(cudaSetDevice(d->ordinal));
+	if (n == 0)
+		return ACM_OK;
+	k_synth_fill<<<d->sm_count * 8, 256, 0, d->stream>>>((uint64_t *)dst, n >> 3, seed, offset >> 3);
+	CUDA_TRY(cudaGetLastError());
+	return ACM_OK;
+}
+
+extern "C" int
+acm_plant_device(struct acm_device *d, void *buf, uint64_t n, uint64_t buf_offset, const uint64_t *h_pos,
+    const uint32_t *h_blob_off, const uint32_t *h_len, uint32_t count, const uint8_t *h_blob,
+    uint32_t blob_bytes)
+{
+	uint8_t *mem = NULL;
+	const size_t a = (size_t)count * 8, b = (size_t)count * 4;
+	int rc = ACM_OK;
+
+	if (count == 0)
+		return ACM_OK;
+	CUDA_TRY(cudaSetDevice(d->ordinal));
+	CUDA_TRY(cudaMalloc((void **)&mem, a + 2 * b + blob_bytes + 64));
+	cudaMemcpyAsync(mem, h_pos, a, cudaMemcpyHostToDevice, d->stream);
+	cudaMemcpyAsync(mem + a, h_blob_off, b, cudaMemcpyHostToDevice, d->stream);
+	cudaMemcpyAsync(mem + a + b, h_len, b, cudaMemcpyHostToDevice, d->stream);
+	cudaMemcpyAsync(mem + a + 2 * b, h_blob, blob_bytes, cudaMemcpyHostToDevice, d->stream);
+	k_plant<<<(count * 32 + 255) / 256, 256, 0, d->stream>>>((uint8_t *)buf, n, buf_offset,
+	    (const uint64_t *)mem, (const uint32_t *)(mem + a), (const uint32_t *)(mem + a + b), count,
+	    mem + a + 2 * b);
+	if (cudaStreamSynchronize(d->stream) != cudaSuccess) {
+		acm_set_error("plant_device: %s", cudaGetErrorString(cudaGetLastError()));
+		rc = ACM_ERR_CUDA;
+	}
+	cudaFree(mem);
+	return rc;
+}

@@ -1,0 +1,83 @@
+/*
+ * acm_tables.h -- host-side compiled automaton, shared between the C builder
+ * (acsm_build.c) and the CUDA side (acm_cuda.cu).  Private to the library.
+ *
+ * States are numbered breadth-first, so ids are sorted by depth and
+ * level_start[d] is the first id at depth d.  A DFA edge T[s][c] leads to a trie
+ * child of s exactly when its target id is >= level_start[depth(s) + 1].
+ */
+#ifndef ACM_TABLES_H
+#define ACM_TABLES_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* transition entry: low 30 bits = next state id */
+#define ACM_T_OWN   0x80000000u   /* target ends >= 1 pattern exactly here     */
+#define ACM_T_ANY   0x40000000u   /* target's full match list is non-empty     */
+#define ACM_T_MASK  0x3FFFFFFFu
+
+/* record key: (end offset relative to the scan base) << 24 | pattern index */
+#define ACM_KEY_PAT_BITS 24
+#define ACM_KEY_PAT_MASK 0xFFFFFFu
+
+/* scan kernels */
+enum {
+	ACM_MODE_AUTO     = 0,
+	ACM_MODE_SAMPLED4 = 1,   /* aligned 4-gram entry filter, needs min len >= 7 */
+	ACM_MODE_START2   = 2,   /* 2-byte start filter, any pattern length        */
+	ACM_MODE_DFA      = 3    /* plain per-chunk DFA walk with leading halo     */
+};
+
+#define ACM_F1_BITS_LOG2   20              /* level-1 gram bitmap: 128 KiB smem */
+#define ACM_F2_BITS_LOG2   19              /* level-2 gram bitmap:  64 KiB smem */
+#define ACM_HASH1_MUL 0x9E3779B1u
+#define ACM_HASH2_MUL 0x85EBCA6Bu
+#define ACM_HASH3_MUL 0xC2B2AE35u
+
+struct acm_gram_slot {     /* exact 4-gram table, open addressing in HBM/L2 */
+	uint32_t gram;         /* little-endian 4 bytes of the pattern          */
+	uint32_t jmask;        /* bit j set: some pattern has this gram at byte offset j (j < 4); 0 = empty */
+};
+
+struct acm_tables {
+	int       alpha;             /* 256 (bytes) or 2048 (ushort symbols)        */
+	uint32_t  num_states;
+	uint32_t  num_patterns;
+	int       max_pattern_len;
+	int       min_pattern_len;
+	int       max_depth;         /* == max_pattern_len                           */
+
+	uint32_t *T;                 /* [num_states][alpha]                          */
+	uint32_t *level_start;       /* [max_depth + 2]; level_start[max_depth+1] == num_states */
+	uint32_t *own_begin;         /* [num_states + 1] CSR into own_pat            */
+	uint32_t *own_pat;           /* pattern indices ending exactly at the state  */
+	uint32_t  own_total;
+	uint32_t *olink;             /* [num_states] nearest proper suffix state with own patterns, 0 = none */
+	uint32_t *fail;              /* [num_states] (host only)                     */
+	uint32_t *pat_len;           /* [num_patterns]                               */
+	int32_t  *pat_iid;           /* [num_patterns]                               */
+	uint32_t *bfs_to_ref;        /* [num_states] id in the reference's numbering  */
+
+	/* --- byte alphabet only: scan filters --- */
+	uint32_t *f1;                /* 2^20-bit bitmap of hashed pattern 4-grams at offsets 0..3 (bit-reversed words) */
+	uint32_t *f2;                /* 2^19-bit second hash of the same grams        */
+	struct acm_gram_slot *grams; /* exact gram table                              */
+	uint32_t  gram_slots;        /* power of two                                  */
+	uint32_t  gram_count;
+	uint32_t *b2;                /* 2^16-bit exact start bitmap: bit (b0 | b1<<8) */
+	uint16_t *h2;                /* [65536] depth-2 node for (b0,b1): 0 = none, else (id - level_start[2] + 1) | 0x8000 if terminal; 0xFFFF = look it up */
+	int       h2_valid;          /* 0 when there are more than 32766 depth-2 nodes */
+};
+
+void acm_tables_free(struct acm_tables *t);
+size_t acm_tables_device_bytes(const struct acm_tables *t);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

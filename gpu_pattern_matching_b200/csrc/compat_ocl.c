@@ -1,0 +1,210 @@
+/*
+ * compat_ocl.c -- the ocl_* entry points of the reference, over acm.h.
+ *
+ *   clinitctx            reference ocl_context.c:19
+ *   ocl_aho_match*       reference ocl_aho_match.c:13-131, AC_ushorts/ocl_aho_match.c
+ *   ocl_prefix_sum*      reference ocl_prefix_sum.c:70-498
+ *   ocl_compact_array*   reference ocl_compact_array.c:14-172
+ *   ocl_bitonic_sort*    reference ocl_bitonic_sort.c:24-251
+ */
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include "../../include/acm.h"
+#include "../../include/ocl_aho_match.h"
+#include "../../include/ocl_bitonic_sort.h"
+#include "../../include/ocl_compact_array.h"
+#include "../../include/ocl_context.h"
+#include "../../include/ocl_prefix_sum.h"
+#include "acm_core.h"
+#include "acm_queue.h"
+#include "databuf_priv.h"
+
+/* cudaMemcpy D2D without pulling the CUDA headers into C code */
+int acm_memcpy_d2d(struct acm_device *, void *d_dst, const void *d_src, size_t bytes);
+
+void
+clinitctx(struct clconf *c, int pos, int subpos)
+{
+	struct acm_device *dev = NULL;
+	struct acm_queue *q;
+
+	(void)subpos;
+	memset(c, 0, sizeof(*c));
+	if (acm_device_open(pos, &dev) != ACM_OK)
+		return;
+	q = calloc(1, sizeof(*q));
+	if (!q) {
+		acm_device_close(dev);
+		acm_set_error("clinitctx: out of memory");
+		return;
+	}
+	q->dev = dev;
+	c->ctx = (cl_context)dev;
+	c->queue = q;
+	c->type = CL_DEVICE_TYPE_GPU;
+}
+
+void
+clfreectx(struct clconf *c)
+{
+	if (!c)
+		return;
+	if (c->ctx)
+		acm_device_close((struct acm_device *)c->ctx);
+	free(c->queue);
+	memset(c, 0, sizeof(*c));
+}
+
+void ocl_aho_match_init(struct clconf *c) { (void)c; }
+void ocl_aho_match_close(struct clconf *c) { (void)c; }
+void ocl_prefix_sum_init(struct clconf *c) { (void)c; }
+void ocl_prefix_sum_close(struct clconf *c) { (void)c; }
+void ocl_compact_array_init(struct clconf *c) { (void)c; }
+void ocl_compact_array_close(struct clconf *c) { (void)c; }
+int  ocl_bitonic_sort_init(struct clconf *c) { (void)c; return 0; }
+int  ocl_bitonic_sort_close(struct clconf *c) { (void)c; return 0; }
+
+static void
+match_common(struct databuf *db, struct acm_automaton *aut, int sym_size, int stream)
+{
+	struct databuf_priv *pv = (struct databuf_priv *)db->priv;
+	const uint64_t carry_cap = DATABUF_CARRY_CAP / (uint64_t)sym_size;
+	const uint64_t nsym = db->bytes / (uint64_t)sym_size;
+	struct acm_scan_result res;
+	uint64_t halo, keep;
+	int rc;
+
+	pv->n_matches = 0;
+	pv->fetched = 0;
+	if (!aut) {
+		acm_set_error("ocl_aho_match: automaton has no device tables (acsm_gen_state_table not called or failed)");
+		pv->status = ACM_ERR_STATE;
+		return;
+	}
+	pv->sym_size = sym_size;
+	if (pv->scanner && pv->scanner_aut != aut) {
+		acm_scanner_free(pv->scanner);
+		pv->scanner = NULL;
+		pv->carry_len = 0;
+	}
+	if (!pv->scanner) {
+		struct acm_scan_params p;
+		memset(&p, 0, sizeof(p));
+		/* db->max_results is per max_chunk_size bytes in the reference; scale it to a bucket */
+		p.bucket_shift = 15;
+		rc = acm_scanner_create(pv->dev, aut, db->size / (uint64_t)sym_size + 1, &p, &pv->scanner);
+		if (rc != ACM_OK) {
+			pv->status = rc;
+			return;
+		}
+		pv->scanner_aut = aut;
+	}
+	halo = (uint64_t)(acm_automaton_max_pattern_len(aut) > 0 ? acm_automaton_max_pattern_len(aut) - 1 : 0);
+	if (halo > carry_cap)
+		halo = carry_cap;
+	if (!stream)
+		pv->carry_len = 0;
+	if (nsym == 0)
+		return;
+	rc = acm_scan_device_ex(pv->scanner, pv->d_base, carry_cap + nsym, carry_cap - pv->carry_len,
+	    carry_cap, carry_cap + nsym, &res);
+	if (rc != ACM_OK) {
+		pv->status = rc;
+		return;
+	}
+	pv->n_matches = res.n_matches;
+
+	/* new carry = last `halo` symbols of (old carry + this buffer), right-aligned before d_data */
+	keep = pv->carry_len + nsym;
+	if (keep > halo)
+		keep = halo;
+	if (stream && keep) {
+		unsigned char *data = pv->d_base + DATABUF_CARRY_CAP;
+		const size_t kb = (size_t)keep * sym_size, nb = (size_t)nsym * sym_size;
+		/* source range [data + nb - kb, data + nb) may reach back into the old carry */
+		rc = acm_memcpy_d2d(pv->dev, pv->d_carry_tmp, data + nb - kb, kb);
+		if (rc == ACM_OK)
+			rc = acm_memcpy_d2d(pv->dev, data - kb, pv->d_carry_tmp, kb);
+		if (rc != ACM_OK) {
+			pv->status = rc;
+			return;
+		}
+	}
+	pv->carry_len = stream ? keep : 0;
+	/* the reference blocks in clFinish (ocl_aho_match.c:128) */
+	pv->status = acm_device_sync(pv->dev);
+}
+
+void
+ocl_aho_match(struct clconf *cl, struct databuf *db, acsm_t *acsm, size_t local_ws, int stream)
+{
+	(void)cl;
+	(void)local_ws;
+	match_common(db, acsm_device_automaton(acsm), 1, stream);
+}
+
+void
+ocl_aho_match_ushort(struct clconf *cl, struct databuf *db, iacsm_t *iacsm, size_t local_ws)
+{
+	(void)cl;
+	(void)local_ws;
+	match_common(db, iacsm_device_automaton(iacsm), 2, 1);
+}
+
+void
+ocl_prefix_sum(struct clconf *cl, struct databuf *db, unsigned int n)
+{
+	struct databuf_priv *pv = (struct databuf_priv *)db->priv;
+
+	(void)cl;
+	if (databuf_alloc_postpass(db) != ACM_OK)
+		return;
+	pv->status = acm_exclusive_scan_u32(pv->dev, (const uint32_t *)db->d_results,
+	    (uint32_t *)db->d_prefixsum, n, NULL);
+	if (pv->status == ACM_OK)
+		pv->status = acm_device_sync(pv->dev);
+}
+
+void
+ocl_compact_array(struct clconf *cl, struct databuf *db, size_t local)
+{
+	struct databuf_priv *pv = (struct databuf_priv *)db->priv;
+
+	(void)cl;
+	(void)local;
+	if (databuf_alloc_postpass(db) != ACM_OK || db->chunks == 0)
+		return;
+	pv->status = acm_compact_columns_i32(pv->dev, (int32_t *)db->d_results_comp,
+	    (const int32_t *)db->d_results, (const int32_t *)db->d_prefixsum, (int32_t)db->chunks,
+	    db->max_results);
+	if (pv->status == ACM_OK)
+		pv->status = acm_compact_columns_i32(pv->dev, (int32_t *)db->d_results2_comp,
+		    (const int32_t *)db->d_results2, (const int32_t *)db->d_prefixsum, (int32_t)db->chunks,
+		    db->max_results);
+	if (pv->status == ACM_OK)
+		pv->status = acm_device_sync(pv->dev);
+}
+
+int
+ocl_bitonic_sort(struct clconf *cl, cl_mem dst_key, cl_mem dst_val, cl_mem src_key, cl_mem src_val,
+    unsigned int batch, unsigned int len, unsigned int dir)
+{
+	struct acm_device *dev = acm_queue_device(cl ? cl->ctx : NULL, cl ? cl->queue : NULL);
+	unsigned int b;
+	int rc;
+
+	if (!dev)
+		return -1;
+	if (len < 2)
+		return -2;              /* reference ocl_bitonic_sort.c:146-148 */
+	for (b = 0; b < batch; b++) {
+		const size_t o = (size_t)b * len;
+		rc = acm_sort_pairs_u32(dev, (uint32_t *)dst_key + o, (uint32_t *)dst_val + o,
+		    (const uint32_t *)src_key + o, (const uint32_t *)src_val + o, len, dir == 0);
+		if (rc != ACM_OK)
+			return rc;
+	}
+	return 0;
+}

@@ -1,0 +1,428 @@
+/*
+ * databuf.c -- chunked input buffer and result decoding (host side, plain C).
+ *
+ * Replaces reference databuf.c:77-843.  The chunk bookkeeping (fixed-size chunks
+ * read straight into the host buffer, zero-padded tail chunk, one chunk per line
+ * in text mode, the return codes) follows the reference function by function; the
+ * device side is one contiguous stream with a byte carry in front of it, scanned
+ * through acm.h.
+ */
+#define _GNU_SOURCE
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include <unistd.h>
+
+#include "../../include/acm.h"
+#include "../../include/databuf.h"
+#include "acm_core.h"
+#include "acm_queue.h"
+#include "databuf_priv.h"
+
+#define ROUNDUP16(x) (((x) + 15) & ~(size_t)15)
+#define MIN(a, b) ((a) < (b) ? (a) : (b))
+
+static struct databuf_priv *
+priv_of(struct databuf *db)
+{
+	return (struct databuf_priv *)db->priv;
+}
+
+struct databuf *
+databuf_new(size_t max_chunks, size_t max_chunk_size, int max_results, int mapped, struct clconf *conf)
+{
+	struct databuf *db;
+	struct databuf_priv *pv;
+	struct acm_device *dev = acm_queue_device(conf ? conf->ctx : NULL, conf ? conf->queue : NULL);
+	size_t i, nres;
+	void *p;
+
+	if (!dev || max_chunks == 0 || max_chunk_size == 0 || max_results < 2) {
+		if (dev)
+			acm_set_error("databuf_new: bad shape (%zu chunks x %zu bytes, %d results)",
+			    max_chunks, max_chunk_size, max_results);
+		return NULL;
+	}
+	if (max_chunks * max_chunk_size > (size_t)0x7fffffff) {
+		acm_set_error("databuf_new: buffer larger than 2 GiB (int offsets, as in the reference)");
+		return NULL;
+	}
+	db = calloc(1, sizeof(*db));
+	pv = calloc(1, sizeof(*pv));
+	if (!db || !pv)
+		goto fail;
+	db->priv = pv;
+	pv->dev = dev;
+	pv->sym_size = 1;
+	db->cl = conf;
+	db->mapped = mapped;
+	db->max_results = max_results;
+	db->max_chunks = max_chunks;
+	db->max_chunk_size = max_chunk_size;
+	db->size = max_chunks * max_chunk_size;
+	nres = (size_t)max_results * max_chunks + 1;
+
+	if (acm_host_alloc_pinned(db->size + 64, &p) != ACM_OK)
+		goto fail;
+	db->h_data = p;
+	if (acm_dev_alloc(dev, DATABUF_CARRY_CAP + db->size + 64, &p) != ACM_OK)
+		goto fail;
+	pv->d_base = p;
+	db->d_data = pv->d_base + DATABUF_CARRY_CAP;
+	if (acm_dev_alloc(dev, DATABUF_CARRY_CAP, &p) != ACM_OK)
+		goto fail;
+	pv->d_carry_tmp = p;
+
+	db->h_indices = malloc(max_chunks * sizeof(int));
+	db->h_sizes = malloc(max_chunks * sizeof(int));
+	db->file_ids = malloc(max_chunks * sizeof(int));
+	db->h_results = calloc(nres, sizeof(int));
+	db->h_results2 = calloc(nres, sizeof(int));
+	db->h_prefixsum = calloc(max_chunks, sizeof(int));
+	db->results_comp_size = db->results2_comp_size = MIN(db->size + 2, (size_t)1 << 16);
+	db->h_results_comp = calloc(db->results_comp_size, sizeof(int));
+	db->h_results2_comp = calloc(db->results2_comp_size, sizeof(int));
+	if (!db->h_indices || !db->h_sizes || !db->file_ids || !db->h_results || !db->h_results2 ||
+	    !db->h_prefixsum || !db->h_results_comp || !db->h_results2_comp) {
+		acm_set_error("databuf_new: out of memory");
+		goto fail;
+	}
+	/* reference databuf.c:312-316 */
+	for (i = 0; i < max_chunks; i++) {
+		db->h_sizes[i] = (int)max_chunk_size;
+		db->h_indices[i] = (int)(max_chunk_size * i);
+		db->file_ids[i] = -1;
+	}
+	return db;
+fail:
+	if (db)
+		databuf_free(db, mapped, conf ? conf->queue : NULL);
+	else
+		free(pv);
+	return NULL;
+}
+
+/* reference databuf.c:327-407 */
+int
+databuf_add_fd(struct databuf *db, int fd, int id, size_t *rd_bytes)
+{
+	size_t i, cur_chunks, tail;
+	ssize_t got;
+
+	*rd_bytes = 0;
+	if (db->chunks >= db->max_chunks)
+		return -1;
+	/* chunks are fixed size in this mode: chunk k starts at k * max_chunk_size */
+	got = read(fd, db->h_data + db->chunks * db->max_chunk_size,
+	    (db->max_chunks - db->chunks) * db->max_chunk_size);
+	if (got <= 0)
+		return 0;
+	*rd_bytes = (size_t)got;
+
+	cur_chunks = (size_t)got / db->max_chunk_size;
+	for (i = db->chunks; i < db->chunks + cur_chunks; i++) {
+		db->h_indices[i] = (int)(i * db->max_chunk_size);
+		db->h_sizes[i] = (int)db->max_chunk_size;
+		db->file_ids[i] = id;
+	}
+	db->chunks += cur_chunks;
+	tail = (size_t)got % db->max_chunk_size;
+	if (tail) {
+		db->h_indices[db->chunks] = (int)(db->chunks * db->max_chunk_size);
+		db->h_sizes[db->chunks] = (int)tail;
+		memset(db->h_data + db->chunks * db->max_chunk_size + tail, 0, db->max_chunk_size - tail);
+		db->file_ids[db->chunks] = id;
+		db->chunks++;
+	}
+	db->bytes = db->chunks * db->max_chunk_size;
+	if (db->chunks == db->max_chunks)
+		return -1;
+	if ((size_t)got == db->size)
+		return -2;
+	return (int)got;
+}
+
+/* reference databuf.c:413-481 */
+int
+databuf_add_fp(struct databuf *db, FILE *fp, int id, int aligned, size_t *rd_bytes, size_t *rd_lines)
+{
+	char *buf;
+	size_t toread, len, adv;
+
+	*rd_bytes = *rd_lines = 0;
+	if (db->chunks >= db->max_chunks)
+		return -1;
+	if (db->bytes >= db->size)
+		return -2;
+	buf = (char *)db->h_data + db->bytes;
+	toread = MIN(db->size - db->bytes, db->max_chunk_size);
+	/* fgets needs room for its NUL: a line longer than the chunk is split, as in the reference */
+	while (toread >= 2 && fgets(buf, (int)toread, fp) != NULL) {
+		len = strnlen(buf, toread);
+		*rd_bytes += len;
+		if (len && buf[len - 1] == '\n')
+			*rd_lines += 1;
+		db->h_indices[db->chunks] = (int)db->bytes;
+		db->h_sizes[db->chunks] = (int)len;
+		db->file_ids[db->chunks] = id;
+		db->chunks += 1;
+		adv = aligned ? ROUNDUP16(len) : len;
+		if (db->bytes + adv > db->size)
+			adv = db->size - db->bytes;
+		/* zero the padding (and fgets' NUL) so stale bytes cannot match */
+		if (adv > len)
+			memset(buf + len, 0, adv - len);
+		db->bytes += adv;
+		if (db->chunks >= db->max_chunks)
+			return -1;
+		if (db->bytes >= db->size)
+			return -2;
+		buf = (char *)db->h_data + db->bytes;
+		toread = MIN(db->size - db->bytes, db->max_chunk_size);
+	}
+	if (toread < 2 && !feof(fp))
+		return -2;
+	return (int)(db->size - db->bytes);
+}
+
+/* reference databuf.c:488-528 */
+int
+databuf_add_chunk(struct databuf *db, char *chunk, size_t len, int id, char aligned)
+{
+	size_t adv;
+
+	if (len > db->max_chunk_size)
+		return -3;
+	if (db->chunks >= db->max_chunks)
+		return -1;
+	if (db->bytes + len >= db->size)
+		return -2;
+	memcpy(db->h_data + db->bytes, chunk, len);
+	db->h_indices[db->chunks] = (int)db->bytes;
+	db->h_sizes[db->chunks] = (int)len;
+	db->file_ids[db->chunks] = id;
+	db->chunks += 1;
+	adv = aligned ? ROUNDUP16(len) : len;
+	if (db->bytes + adv > db->size)
+		adv = db->size - db->bytes;
+	if (adv > len)
+		memset(db->h_data + db->bytes + len, 0, adv - len);
+	db->bytes += adv;
+	return (int)(db->size - db->bytes);
+}
+
+void
+databuf_reset(struct databuf *db)
+{
+	db->chunks = 0;
+	db->bytes = 0;
+}
+
+void
+databuf_clear(struct databuf *db)
+{
+	struct databuf_priv *pv = priv_of(db);
+	size_t nres = (size_t)db->max_results * db->max_chunks + 1;
+
+	memset(db->h_data, 0, db->size);
+	memset(db->h_indices, 0, db->max_chunks * sizeof(int));
+	memset(db->h_sizes, 0, db->max_chunks * sizeof(int));
+	memset(db->h_results, 0, nres * sizeof(int));
+	memset(db->h_results2, 0, nres * sizeof(int));
+	memset(db->h_results_comp, 0, db->results_comp_size * sizeof(int));
+	memset(db->h_results2_comp, 0, db->results2_comp_size * sizeof(int));
+	memset(db->file_ids, 0, db->max_chunks * sizeof(int));
+	pv->carry_len = 0;
+	pv->n_matches = 0;
+	db->last_state = 0;
+	databuf_reset(db);
+}
+
+void
+databuf_copy_host_to_device(struct databuf *db, cl_command_queue queue)
+{
+	struct databuf_priv *pv = priv_of(db);
+
+	(void)queue;
+	if (db->bytes == 0)
+		return;
+	pv->status = acm_memcpy_h2d(pv->dev, db->d_data, db->h_data, db->bytes);
+}
+
+static int
+chunk_of(const struct databuf *db, long off)
+{
+	size_t lo = 0, hi = db->chunks;
+
+	/* last chunk whose start is <= off */
+	while (hi - lo > 1) {
+		size_t mid = (lo + hi) / 2;
+		if ((long)db->h_indices[mid] <= off)
+			lo = mid;
+		else
+			hi = mid;
+	}
+	return (int)lo;
+}
+
+void
+databuf_copy_device_to_host(struct databuf *db, cl_command_queue queue)
+{
+	struct databuf_priv *pv = priv_of(db);
+	const size_t R = (size_t)db->max_results, C = db->chunks;
+	uint64_t n = pv->n_matches, i;
+	int64_t got;
+
+	(void)queue;
+	memset(db->h_results, 0, (R * db->max_chunks + 1) * sizeof(int));
+	memset(db->h_results2, 0, (R * db->max_chunks + 1) * sizeof(int));
+	if (n + 2 > db->results_comp_size) {
+		size_t nc = db->results_comp_size;
+		int *a, *b;
+		while (nc < n + 2)
+			nc *= 2;
+		a = realloc(db->h_results_comp, nc * sizeof(int));
+		b = realloc(db->h_results2_comp, nc * sizeof(int));
+		if (a)
+			db->h_results_comp = a;
+		if (b)
+			db->h_results2_comp = b;
+		if (!a || !b) {
+			acm_set_error("databuf_copy_device_to_host: out of memory");
+			pv->status = ACM_ERR_NOMEM;
+			return;
+		}
+		db->results_comp_size = db->results2_comp_size = nc;
+	}
+	if (n > pv->h_cap) {
+		free(pv->h_off);
+		free(pv->h_pat);
+		pv->h_off = malloc(n * sizeof(uint64_t));
+		pv->h_pat = malloc(n * sizeof(uint32_t));
+		pv->h_cap = (pv->h_off && pv->h_pat) ? n : 0;
+		if (!pv->h_cap) {
+			acm_set_error("databuf_copy_device_to_host: out of memory");
+			pv->status = ACM_ERR_NOMEM;
+			return;
+		}
+	}
+	got = n ? acm_scan_fetch(pv->scanner, 0, pv->h_off, pv->h_pat, n) : 0;
+	if (got < 0) {
+		pv->status = (int)got;
+		return;
+	}
+	db->h_results_comp[0] = db->h_results2_comp[0] = (int)n;
+	for (i = 0; i < n; i++) {
+		const long off = (long)(pv->h_off[i] - DATABUF_CARRY_CAP / pv->sym_size);
+		const int pat = (int)pv->h_pat[i];
+		const int c = chunk_of(db, off * pv->sym_size);
+		int k;
+
+		db->h_results_comp[i + 1] = pat;
+		db->h_results2_comp[i + 1] = (int)off;
+		/* reference bucket layout, ahomatch.cl:67-73: row 0 = counts, row k = k-th match */
+		k = ++db->h_results[c];
+		db->h_results2[c] = k;
+		if ((size_t)k < R) {
+			db->h_results[(size_t)k * C + c] = pat;
+			db->h_results2[(size_t)k * C + c] = (int)off;
+		}
+	}
+	db->h_results_comp[n + 1] = db->h_results2_comp[n + 1] = (int)db->last_state;
+	db->h_results[C * R] = (int)db->last_state;
+	{
+		int run = 0;
+		for (i = 0; i < C; i++) {
+			db->h_prefixsum[i] = run;
+			run += db->h_results[i];
+		}
+	}
+	pv->fetched = 1;
+}
+
+int
+databuf_process_results(struct databuf *db,
+    int (*cb)(int file_idx, int patrn_idx, int chunk_idx, int offset, void *uarg), void *uarg)
+{
+	const int n = db->h_results_comp[0];
+	struct databuf_priv *pv = priv_of(db);
+	int i;
+
+	if (cb) {
+		for (i = 0; i < n; i++) {
+			const int off = db->h_results2_comp[i + 1];
+			const int c = chunk_of(db, (long)off * pv->sym_size);
+			cb(db->file_ids[c], db->h_results_comp[i + 1], c, off + 1, uarg);
+		}
+	}
+	return n;
+}
+
+void
+databuf_free(struct databuf *db, int mapped, cl_command_queue queue)
+{
+	struct databuf_priv *pv;
+
+	(void)mapped;
+	(void)queue;
+	if (!db)
+		return;
+	pv = priv_of(db);
+	if (pv) {
+		if (pv->scanner)
+			acm_scanner_free(pv->scanner);
+		if (pv->dev) {
+			acm_dev_free(pv->dev, pv->d_base);
+			acm_dev_free(pv->dev, pv->d_carry_tmp);
+			acm_dev_free(pv->dev, db->d_results);
+			acm_dev_free(pv->dev, db->d_results2);
+			acm_dev_free(pv->dev, db->d_prefixsum);
+			acm_dev_free(pv->dev, db->d_results_comp);
+			acm_dev_free(pv->dev, db->d_results2_comp);
+		}
+		free(pv->h_off);
+		free(pv->h_pat);
+		free(pv);
+	}
+	acm_host_free_pinned(db->h_data);
+	free(db->h_indices); free(db->h_sizes); free(db->file_ids);
+	free(db->h_results); free(db->h_results2); free(db->h_prefixsum);
+	free(db->h_results_comp); free(db->h_results2_comp);
+	free(db);
+}
+
+int
+databuf_status(struct databuf *db)
+{
+	return priv_of(db)->status;
+}
+
+size_t
+databuf_match_count(struct databuf *db)
+{
+	return (size_t)priv_of(db)->n_matches;
+}
+
+int
+databuf_alloc_postpass(struct databuf *db)
+{
+	struct databuf_priv *pv = priv_of(db);
+	const size_t nres = ((size_t)db->max_results * db->max_chunks + 1) * sizeof(int);
+	const size_t ncomp = (db->size + 2) * sizeof(int);
+	void *p;
+	int rc;
+
+	if (db->d_results)
+		return ACM_OK;
+#define PP(field, bytes)                                                            \
+	if ((rc = acm_dev_alloc(pv->dev, (bytes), &p)) != ACM_OK)                     \
+		return pv->status = rc;                                                     \
+	db->field = p
+	PP(d_results, nres);
+	PP(d_results2, nres);
+	PP(d_prefixsum, db->max_chunks * sizeof(int) + 16);
+	PP(d_results_comp, ncomp);
+	PP(d_results2_comp, ncomp);
+#undef PP
+	return ACM_OK;
+}

@@ -1,0 +1,415 @@
+/*
+ * k1_scan.cuh -- K1: the Aho-Corasick scan kernels for sm_100a.
+ *
+ * Replaces the reference's `ahomatch` OpenCL kernel (reference ahomatch.cl:1-165
+ * and its ushort twin AC_ushorts/ahomatch.cl:1-148).  The reference gives every
+ * work-item one chunk and does one dependent, uncoalesced 4-byte global load per
+ * input byte into a table of up to 1.29 GiB (ahomatch.cl:56-65).  Here:
+ *
+ *   k_scan_sampled4  (all patterns >= 7 bytes, e.g. the ClamAV sets)
+ *       Every occurrence of a pattern of length >= 7 contains a 4-byte window
+ *       that starts at a multiple of 4.  The kernel streams the input once with
+ *       coalesced 16-byte loads and tests only those aligned windows against a
+ *       hashed bitmap of all pattern 4-grams at byte offsets 0..3 (128 KiB,
+ *       shared memory, loaded with TMA bulk copies).  Survivors (a few %) are
+ *       re-tested against a second 64 KiB shared-memory bitmap, then against an
+ *       exact gram table in L2, and only then is the automaton entered: a walk of
+ *       the DFA table from the candidate start, following trie edges, reporting
+ *       the patterns that end at each node.  0.25 shared-memory lookups per
+ *       input byte instead of one table gather per byte.
+ *
+ *   k_scan_start2    (any pattern length)
+ *       Same structure with an exact 64-Kbit bitmap over (byte, next byte) tested
+ *       at every position: "can an automaton walk started here report anything".
+ *
+ *   k_scan_dfa       (bytes or ushort symbols; cross-check and AC_ushorts path)
+ *       The textbook form: one thread per chunk, cold start Lmax-1 symbols early
+ *       (SURVEY.md A.5), one table lookup per symbol, matches reported through the
+ *       output links.
+ *
+ * All three report exactly the set { (end offset, pattern index) } that a serial
+ * walk of the reference's automaton reports with full match lists (SURVEY.md
+ * A.3): an occurrence is found from its start position by following trie edges,
+ * and a trie edge is a DFA edge whose target lies one level deeper.
+ *
+ * Match emission: records go to the bucket of their END offset
+ * ((end - emit_lo) >> shift); lanes of a warp that emit into the same bucket at
+ * the same time are aggregated with match.any/popc into one atomicAdd.
+ */
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "acm_tables.h"
+
+struct AutDev {
+	const uint32_t *T;
+	const uint32_t *level_start;
+	const uint32_t *own_begin;
+	const uint32_t *own_pat;
+	const uint32_t *olink;
+	const uint32_t *f1;
+	const uint32_t *f2;
+	const acm_gram_slot *grams;
+	const uint32_t *b2;
+	uint32_t gram_mask;
+	uint32_t gram_shift;     /* 32 - log2(slots) */
+	uint32_t num_states;
+	int      alpha;
+	int      max_len;
+};
+
+struct EmitCtx {
+	uint64_t *buckets;       /* [n_buckets][cap] record keys                         */
+	uint32_t *counts;        /* [n_buckets] records produced (exact, may exceed cap) */
+	uint32_t *overflow;      /* set to 1 when any bucket exceeded cap               */
+	const uint32_t *offsets; /* direct mode: exclusive scan of counts               */
+	uint64_t *out;           /* direct mode: dense output                           */
+	uint64_t  emit_lo, emit_hi;
+	uint64_t  valid_lo;      /* positions before this are never read nor used as walk starts */
+	uint32_t  cap;
+	uint32_t  shift;
+	int       direct;
+};
+
+#define F1_WORDS (1u << (ACM_F1_BITS_LOG2 - 5))
+#define F2_WORDS (1u << (ACM_F2_BITS_LOG2 - 5))
+
+__device__ __forceinline__ uint32_t smem_u32(const void *p)
+{
+	return (uint32_t)__cvta_generic_to_shared(p);
+}
+
+__device__ __forceinline__ uint32_t lanemask_lt()
+{
+	uint32_t m;
+	asm("mov.u32 %0, %%lanemask_lt;" : "=r"(m));
+	return m;
+}
+
+/* ---- TMA bulk copy + mbarrier (global -> shared) ---- */
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count)
+{
+	asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+	asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes)
+{
+	asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;"
+	    ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+
+__device__ __forceinline__ void bulk_g2s(void *dst, const void *src, uint32_t bytes, uint64_t *bar)
+{
+	asm volatile(
+	    "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+	    ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity)
+{
+	asm volatile(
+	    "{\n"
+	    ".reg .pred p;\n"
+	    "WAIT_%=:\n"
+	    "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+	    "@p bra DONE_%=;\n"
+	    "bra WAIT_%=;\n"
+	    "DONE_%=:\n"
+	    "}\n" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+
+/* ---- emission ---- */
+__device__ __forceinline__ void emit_record(const EmitCtx &E, uint64_t end, uint32_t pat)
+{
+	if (end < E.emit_lo || end >= E.emit_hi)
+		return;
+	const uint32_t b = (uint32_t)((end - E.emit_lo) >> E.shift);
+	const unsigned act = __activemask();
+	const unsigned peers = __match_any_sync(act, b);
+	const int leader = __ffs(peers) - 1;
+	const int lane = threadIdx.x & 31;
+	uint32_t base = 0;
+	if (lane == leader)
+		base = atomicAdd(&E.counts[b], (uint32_t)__popc(peers));
+	base = __shfl_sync(peers, base, leader);
+	const uint32_t slot = base + (uint32_t)__popc(peers & lanemask_lt());
+	const uint64_t key = (end << ACM_KEY_PAT_BITS) | pat;
+	if (E.direct) {
+		E.out[(uint64_t)E.offsets[b] + slot] = key;
+	} else if (slot < E.cap) {
+		E.buckets[(uint64_t)b * E.cap + slot] = key;
+	} else {
+		*E.overflow = 1u;
+	}
+}
+
+__device__ __forceinline__ void emit_own(const AutDev &A, const EmitCtx &E, uint32_t state, uint64_t end)
+{
+	const uint32_t lo = __ldg(&A.own_begin[state]);
+	const uint32_t hi = __ldg(&A.own_begin[state + 1]);
+	for (uint32_t k = lo; k < hi; ++k)
+		emit_record(E, end, __ldg(&A.own_pat[k]));
+}
+
+/*
+ * Enter the automaton at position s: follow trie edges while they exist, report
+ * the patterns ending at every node passed.  `limit` is exclusive.
+ */
+__device__ __noinline__ void walk_from(const AutDev A, const EmitCtx E, const uint8_t *__restrict__ data,
+    uint64_t s, uint64_t limit)
+{
+	uint32_t state = 0;
+	uint32_t d = 0;
+	for (uint64_t pos = s; pos < limit; ++pos) {
+		const uint32_t e = __ldg(&A.T[(size_t)state * 256 + __ldg(&data[pos])]);
+		const uint32_t nx = e & ACM_T_MASK;
+		if (nx < __ldg(&A.level_start[d + 1]))
+			break;
+		state = nx;
+		++d;
+		if (e & ACM_T_OWN)
+			emit_own(A, E, state, pos);
+	}
+}
+
+/* 16 bytes at vector index idx; the last, partial vector is assembled bytewise */
+__device__ __forceinline__ uint4 load_vec(const uint8_t *__restrict__ data, uint64_t idx, uint64_t nvec_full,
+    uint64_t n)
+{
+	if (idx < nvec_full)
+		return __ldcs(reinterpret_cast<const uint4 *>(data) + idx);
+	uint32_t w[4] = {0, 0, 0, 0};
+	const uint64_t base = idx * 16;
+	for (int k = 0; k < 16; ++k)
+		if (base + k < n)
+			w[k >> 2] |= (uint32_t)data[base + k] << (8 * (k & 3));
+	return make_uint4(w[0], w[1], w[2], w[3]);
+}
+
+/* ------------------------------------------------------------------------- */
+/* sampled 4-gram entry filter                                               */
+/* ------------------------------------------------------------------------- */
+
+#define S4_THREADS 1024
+#define S4_UNROLL  4
+#define S4_SMEM_BYTES ((F1_WORDS + F2_WORDS) * 4 + 16)
+
+__device__ __noinline__ void s4_confirm(const AutDev A, const EmitCtx E, const uint8_t *__restrict__ data,
+    uint32_t g, uint64_t e, uint64_t limit)
+{
+	uint32_t s = (g * ACM_HASH3_MUL) >> A.gram_shift;
+	for (;;) {
+		const uint2 slot = __ldg(reinterpret_cast<const uint2 *>(A.grams) + s);
+		if (slot.y == 0)
+			return;
+		if (slot.x == g) {
+			uint32_t jm = slot.y;
+			while (jm) {
+				const uint32_t j = __ffs(jm) - 1;
+				jm &= jm - 1;
+				if (e >= j && e - j >= E.valid_lo)
+					walk_from(A, E, data, e - j, limit);
+			}
+			return;
+		}
+		s = (s + 1) & A.gram_mask;
+	}
+}
+
+__global__ void __launch_bounds__(S4_THREADS, 1)
+k_scan_sampled4(const AutDev A, const EmitCtx E, const uint8_t *__restrict__ data, uint64_t n,
+    uint64_t vec_lo, uint64_t vec_hi, uint64_t limit)
+{
+	extern __shared__ __align__(128) uint32_t s4_smem[];
+	uint32_t *f1 = s4_smem;
+	uint32_t *f2 = s4_smem + F1_WORDS;
+	uint64_t *bar = reinterpret_cast<uint64_t *>(s4_smem + F1_WORDS + F2_WORDS);
+
+	/* stage both bitmaps with TMA bulk copies, 32 KiB each */
+	if (threadIdx.x == 0) {
+		mbar_init(bar, 1);
+		mbar_expect_tx(bar, (F1_WORDS + F2_WORDS) * 4);
+		for (uint32_t off = 0; off < F1_WORDS; off += 8192)
+			bulk_g2s(f1 + off, A.f1 + off, 32768, bar);
+		for (uint32_t off = 0; off < F2_WORDS; off += 8192)
+			bulk_g2s(f2 + off, A.f2 + off, 32768, bar);
+	}
+	__syncthreads();
+	mbar_wait(bar, 0);
+
+	const uint64_t nvec_full = n >> 4;
+	const uint64_t tile_vecs = (uint64_t)S4_THREADS * S4_UNROLL;
+
+	for (uint64_t first = vec_lo + (uint64_t)blockIdx.x * tile_vecs; first < vec_hi;
+	     first += (uint64_t)gridDim.x * tile_vecs) {
+		uint4 v[S4_UNROLL];
+#pragma unroll
+		for (int u = 0; u < S4_UNROLL; ++u) {
+			const uint64_t idx = first + (uint64_t)u * S4_THREADS + threadIdx.x;
+			v[u] = (idx < vec_hi) ? load_vec(data, idx, nvec_full, n) : make_uint4(0, 0, 0, 0);
+		}
+		uint32_t hits = 0;
+#pragma unroll
+		for (int u = 0; u < S4_UNROLL; ++u) {
+			const uint32_t w[4] = {v[u].x, v[u].y, v[u].z, v[u].w};
+#pragma unroll
+			for (int k = 0; k < 4; ++k) {
+				const uint32_t h = w[k] * ACM_HASH1_MUL;
+				const uint32_t word = f1[h >> (32 - (ACM_F1_BITS_LOG2 - 5))];
+				/* bitmap words are bit-reversed: the tested bit lands in the MSB */
+				const uint32_t t = __funnelshift_l(0u, word, h);
+				hits = __funnelshift_l(t, hits, 1);
+			}
+		}
+		/* bit (15 - q) of hits belongs to window q = u * 4 + k */
+		while (hits) {
+			const int p = 31 - __clz(hits);
+			hits &= ~(1u << p);
+			const int q = 15 - p;
+			const uint4 x = (q & 8) ? ((q & 4) ? v[3] : v[2]) : ((q & 4) ? v[1] : v[0]);
+			const uint32_t g = (q & 2) ? ((q & 1) ? x.w : x.z) : ((q & 1) ? x.y : x.x);
+			const uint32_t h2 = g * ACM_HASH2_MUL;
+			const uint32_t word2 = f2[h2 >> (32 - (ACM_F2_BITS_LOG2 - 5))];
+			if (!(__funnelshift_l(0u, word2, h2) & 0x80000000u))
+				continue;
+			const uint64_t idx = first + (uint64_t)(q >> 2) * S4_THREADS + threadIdx.x;
+			if (idx >= vec_hi)
+				continue;
+			s4_confirm(A, E, data, g, idx * 16 + (uint64_t)(q & 3) * 4, limit);
+		}
+	}
+}
+
+/* ------------------------------------------------------------------------- */
+/* exact 2-byte start filter                                                 */
+/* ------------------------------------------------------------------------- */
+
+#define S2_THREADS 512
+#define S2_UNROLL  2
+#define S2_SMEM_BYTES (65536 / 8 + 16)
+
+__global__ void __launch_bounds__(S2_THREADS, 2)
+k_scan_start2(const AutDev A, const EmitCtx E, const uint8_t *__restrict__ data, uint64_t n,
+    uint64_t vec_lo, uint64_t vec_hi, uint64_t limit)
+{
+	extern __shared__ __align__(128) uint32_t s2_smem[];
+	uint32_t *b2 = s2_smem;
+	uint64_t *bar = reinterpret_cast<uint64_t *>(s2_smem + 2048);
+
+	if (threadIdx.x == 0) {
+		mbar_init(bar, 1);
+		mbar_expect_tx(bar, 8192);
+		bulk_g2s(b2, A.b2, 8192, bar);
+	}
+	__syncthreads();
+	mbar_wait(bar, 0);
+
+	const uint64_t nvec_full = n >> 4;
+	const uint64_t tile_vecs = (uint64_t)S2_THREADS * S2_UNROLL;
+	const int lane = threadIdx.x & 31;
+
+	for (uint64_t first = vec_lo + (uint64_t)blockIdx.x * tile_vecs; first < vec_hi;
+	     first += (uint64_t)gridDim.x * tile_vecs) {
+#pragma unroll
+		for (int u = 0; u < S2_UNROLL; ++u) {
+			const uint64_t idx = first + (uint64_t)u * S2_THREADS + threadIdx.x;
+			/* whole warps fall off the end together except in the last tile */
+			const bool live = idx < vec_hi;
+			uint4 v = live ? load_vec(data, idx, nvec_full, n) : make_uint4(0, 0, 0, 0);
+			/* first word of the next vector: the neighbour lane has it */
+			uint32_t nxt = __shfl_down_sync(0xffffffffu, v.x, 1);
+			if (lane == 31) {
+				nxt = 0;
+				if (live) {
+					const uint64_t b = (idx + 1) * 16;
+					if (b + 4 <= n)
+						nxt = __ldg(reinterpret_cast<const uint32_t *>(data + b));
+					else
+						for (int k = 0; k < 4; ++k)
+							if (b + k < n)
+								nxt |= (uint32_t)data[b + k] << (8 * k);
+				}
+			}
+			const uint32_t w[5] = {v.x, v.y, v.z, v.w, nxt};
+			uint32_t hits = 0;
+#pragma unroll
+			for (int p = 0; p < 16; ++p) {
+				/* low 16 bits: bytes p, p+1 */
+				const uint32_t x = __funnelshift_r(w[p >> 2], w[(p >> 2) + 1], 8 * (p & 3));
+				const uint32_t word = b2[(x >> 5) & 0x7FF];
+				const uint32_t t = __funnelshift_l(0u, word, x);
+				hits = __funnelshift_l(t, hits, 1);
+			}
+			if (!live)
+				hits = 0;
+			while (hits) {
+				const int p = 31 - __clz(hits);
+				hits &= ~(1u << p);
+				const uint64_t s = idx * 16 + (uint64_t)(15 - p);
+				if (s >= E.valid_lo && s < limit)
+					walk_from(A, E, data, s, limit);
+			}
+		}
+	}
+}
+
+/* ------------------------------------------------------------------------- */
+/* plain DFA walk, one thread per chunk, leading halo                        */
+/* ------------------------------------------------------------------------- */
+
+template <typename SYM>
+__global__ void __launch_bounds__(256)
+k_scan_dfa(const AutDev A, const EmitCtx E, const SYM *__restrict__ data, uint64_t n, uint64_t chunk,
+    uint64_t nthreads, uint32_t *final_state)
+{
+	const uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+	const uint32_t alpha = (uint32_t)A.alpha;
+	const uint64_t limit = E.emit_hi < n ? E.emit_hi : n;
+
+	if (t == nthreads) {
+		/* the true state after the last symbol: the longest suffix that is a
+		 * pattern prefix fits in the last Lmax symbols */
+		const uint64_t back = (uint64_t)A.max_len;
+		uint32_t state = 0;
+		uint64_t p0 = n > back ? n - back : 0;
+		if (p0 < E.valid_lo)
+			p0 = E.valid_lo;
+		for (uint64_t pos = p0; pos < n; ++pos) {
+			const uint32_t c = data[pos];
+			state = (c < alpha) ? (__ldg(&A.T[(size_t)state * alpha + c]) & ACM_T_MASK) : 0u;
+		}
+		*final_state = state;
+		return;
+	}
+	if (t > nthreads)
+		return;
+
+	const uint64_t a = E.emit_lo + t * chunk;
+	uint64_t b = a + chunk;
+	if (b > limit)
+		b = limit;
+	if (a >= b)
+		return;
+	const uint64_t halo = A.max_len > 0 ? (uint64_t)(A.max_len - 1) : 0;
+	uint32_t state = 0;
+	uint64_t pos0 = a > halo ? a - halo : 0;
+	if (pos0 < E.valid_lo)
+		pos0 = E.valid_lo;
+	for (uint64_t pos = pos0; pos < b; ++pos) {
+		const uint32_t c = data[pos];
+		if (c >= alpha) {
+			state = 0;
+			continue;
+		}
+		const uint32_t e = __ldg(&A.T[(size_t)state * alpha + c]);
+		state = e & ACM_T_MASK;
+		if ((e & ACM_T_ANY) && pos >= a) {
+			/* full match list = own lists along the output links */
+			for (uint32_t v = state; v; v = __ldg(&A.olink[v]))
+				emit_own(A, E, v, pos);
+		}
+	}
+}

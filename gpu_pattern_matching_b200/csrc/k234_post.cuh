@@ -1,0 +1,386 @@
+/*
+ * k234_post.cuh -- the post-passes that turn per-bucket match records into one
+ * canonical, sorted list.
+ *
+ *   K2  k_scan_lookback      single-pass exclusive prefix sum with decoupled
+ *                            look-back and warp-shuffle scans.  Replaces the five
+ *                            Blelloch kernels of reference scan_kernel.cl:307-415
+ *                            driven by PreScanBufferRecursive
+ *                            (reference ocl_prefix_sum.c:389-498).
+ *   K3  k_bucket_sort_compact
+ *                            stream compaction fused with a per-bucket bitonic
+ *                            sort in shared memory.  Replaces reference
+ *                            compactarray.cl:40-68 (and, for the normal case, the
+ *                            sort).
+ *       k_compact_columns    the reference's own column-major bucket format,
+ *                            for the ocl_compact_array() entry point.
+ *   K4  k_radix_hist / k_radix_scatter
+ *                            stable LSD radix sort of 64-bit keys, 8 bits a pass.
+ *                            Replaces reference BitonicSort.cl:50-249
+ *                            (power-of-two lengths only there).
+ */
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "acm_tables.h"
+
+/* ------------------------------------------------------------------------- */
+/* K2: decoupled look-back exclusive scan                                    */
+/* ------------------------------------------------------------------------- */
+
+#define SCAN_THREADS 256
+#define SCAN_ITEMS   8
+#define SCAN_TILE    (SCAN_THREADS * SCAN_ITEMS)
+
+#define TS_EMPTY     0u
+#define TS_AGGREGATE 1u
+#define TS_INCLUSIVE 2u
+
+__device__ __forceinline__ uint64_t ts_load(const uint64_t *p)
+{
+	uint64_t v;
+	asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+	return v;
+}
+
+__device__ __forceinline__ void ts_store(uint64_t *p, uint32_t flag, uint32_t value)
+{
+	const uint64_t v = ((uint64_t)flag << 32) | value;
+	asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+
+/*
+ * tile_state[t] = (flag << 32) | value, zeroed before launch; tile_counter hands
+ * out tile ids in launch order so a tile only ever waits on tiles already running.
+ */
+__global__ void __launch_bounds__(SCAN_THREADS)
+k_scan_lookback(const uint32_t *__restrict__ in, uint32_t *__restrict__ out, uint32_t n,
+    uint64_t *tile_state, uint32_t *tile_counter, uint32_t *total)
+{
+	__shared__ uint32_t s_tile;
+	__shared__ uint32_t s_warp[SCAN_THREADS / 32];
+	__shared__ uint32_t s_prefix;
+
+	if (threadIdx.x == 0)
+		s_tile = atomicAdd(tile_counter, 1u);
+	__syncthreads();
+	const uint32_t tile = s_tile;
+	const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+	const uint32_t base = tile * SCAN_TILE + threadIdx.x * SCAN_ITEMS;
+
+	uint32_t x[SCAN_ITEMS];
+	uint32_t sum = 0;
+#pragma unroll
+	for (int k = 0; k < SCAN_ITEMS; ++k) {
+		x[k] = (base + k < n) ? in[base + k] : 0u;
+		sum += x[k];
+	}
+	/* warp inclusive scan of the per-thread sums */
+	uint32_t inc = sum;
+#pragma unroll
+	for (int d = 1; d < 32; d <<= 1) {
+		const uint32_t y = __shfl_up_sync(0xffffffffu, inc, d);
+		if (lane >= (uint32_t)d)
+			inc += y;
+	}
+	if (lane == 31)
+		s_warp[warp] = inc;
+	__syncthreads();
+	uint32_t warp_off = 0, block_sum = 0;
+#pragma unroll
+	for (int w = 0; w < SCAN_THREADS / 32; ++w) {
+		const uint32_t v = s_warp[w];
+		if ((uint32_t)w < warp)
+			warp_off += v;
+		block_sum += v;
+	}
+
+	/* publish, then look back (warp 0) */
+	if (warp == 0) {
+		uint32_t excl = 0;
+		if (tile == 0) {
+			if (lane == 0)
+				ts_store(&tile_state[0], TS_INCLUSIVE, block_sum);
+		} else {
+			if (lane == 0)
+				ts_store(&tile_state[tile], TS_AGGREGATE, block_sum);
+			int32_t pred = (int32_t)tile - 1;
+			for (;;) {
+				const int32_t idx = pred - (int32_t)lane;
+				uint64_t st = ((uint64_t)TS_INCLUSIVE << 32);   /* before tile 0: prefix 0 */
+				if (idx >= 0) {
+					do {
+						st = ts_load(&tile_state[idx]);
+					} while ((uint32_t)(st >> 32) == TS_EMPTY);
+				}
+				const uint32_t flag = (uint32_t)(st >> 32);
+				const uint32_t val = (uint32_t)st;
+				const uint32_t inc_mask = __ballot_sync(0xffffffffu, flag == TS_INCLUSIVE);
+				/* nearest inclusive predecessor = lowest lane with the flag */
+				const int stop = inc_mask ? (__ffs(inc_mask) - 1) : 32;
+				uint32_t contrib = ((int)lane <= stop && (int)lane < 32) ? val : 0u;
+				if ((int)lane > stop)
+					contrib = 0;
+#pragma unroll
+				for (int d = 16; d > 0; d >>= 1)
+					contrib += __shfl_xor_sync(0xffffffffu, contrib, d);
+				excl += contrib;
+				if (inc_mask)
+					break;
+				pred -= 32;
+			}
+			if (lane == 0)
+				ts_store(&tile_state[tile], TS_INCLUSIVE, excl + block_sum);
+		}
+		if (lane == 0)
+			s_prefix = excl;
+	}
+	__syncthreads();
+	uint32_t run = s_prefix + warp_off + (inc - sum);
+#pragma unroll
+	for (int k = 0; k < SCAN_ITEMS; ++k) {
+		if (base + k < n)
+			out[base + k] = run;
+		run += x[k];
+	}
+	if (total && tile == (n - 1) / SCAN_TILE && threadIdx.x == SCAN_THREADS - 1)
+		*total = s_prefix + block_sum;
+}
+
+/* ------------------------------------------------------------------------- */
+/* K3: compaction + per-bucket sort                                          */
+/* ------------------------------------------------------------------------- */
+
+#define K3_THREADS 128
+
+__global__ void __launch_bounds__(K3_THREADS)
+k_bucket_sort_compact(const uint64_t *__restrict__ buckets, const uint32_t *__restrict__ counts,
+    const uint32_t *__restrict__ offsets, uint64_t *__restrict__ out, uint32_t cap, uint32_t n_buckets)
+{
+	extern __shared__ uint64_t k3_keys[];
+	const uint32_t lane = threadIdx.x & 31;
+
+	/* buckets with at most 32 records: one warp each, sorted in registers */
+	const uint32_t warps = K3_THREADS / 32;
+	const uint32_t b0 = blockIdx.x * warps + (threadIdx.x >> 5);
+	uint32_t cnt = 0;
+	if (b0 < n_buckets)
+		cnt = min(__ldg(&counts[b0]), cap);
+	const uint32_t big = __syncthreads_or(cnt > 32);
+
+	if (cnt > 0 && cnt <= 32) {
+		uint64_t key = (lane < cnt) ? buckets[(uint64_t)b0 * cap + lane] : ~0ull;
+		/* bitonic network across the warp */
+#pragma unroll
+		for (int k = 2; k <= 32; k <<= 1) {
+#pragma unroll
+			for (int j = k >> 1; j > 0; j >>= 1) {
+				const uint64_t other = __shfl_xor_sync(0xffffffffu, key, j);
+				const bool up = ((lane & k) == 0);
+				const bool lower = ((lane & j) == 0);
+				const bool take_min = (up == lower);
+				key = take_min ? (key < other ? key : other) : (key > other ? key : other);
+			}
+		}
+		if (lane < cnt)
+			out[(uint64_t)__ldg(&offsets[b0]) + lane] = key;
+	}
+	if (!big)
+		return;
+
+	/* the rare larger buckets of this block: whole block, shared memory */
+	for (uint32_t w = 0; w < warps; ++w) {
+		const uint32_t b = blockIdx.x * warps + w;
+		if (b >= n_buckets)
+			break;
+		const uint32_t c = min(__ldg(&counts[b]), cap);
+		if (c <= 32)
+			continue;
+		uint32_t P = 64;
+		while (P < c)
+			P <<= 1;
+		for (uint32_t i = threadIdx.x; i < P; i += K3_THREADS)
+			k3_keys[i] = (i < c) ? buckets[(uint64_t)b * cap + i] : ~0ull;
+		__syncthreads();
+		for (uint32_t k = 2; k <= P; k <<= 1) {
+			for (uint32_t j = k >> 1; j > 0; j >>= 1) {
+				for (uint32_t i = threadIdx.x; i < P; i += K3_THREADS) {
+					const uint32_t ixj = i ^ j;
+					if (ixj > i) {
+						const uint64_t a = k3_keys[i], bb = k3_keys[ixj];
+						const bool up = ((i & k) == 0);
+						if ((a > bb) == up) {
+							k3_keys[i] = bb;
+							k3_keys[ixj] = a;
+						}
+					}
+				}
+				__syncthreads();
+			}
+		}
+		const uint64_t o = __ldg(&offsets[b]);
+		for (uint32_t i = threadIdx.x; i < c; i += K3_THREADS)
+			out[o + i] = k3_keys[i];
+		__syncthreads();
+	}
+}
+
+/* reference bucket format -> [total, values..., tail]  (reference compactarray.cl:40-68) */
+__global__ void k_compact_columns(int32_t *__restrict__ dst, const int32_t *__restrict__ src,
+    const int32_t *__restrict__ prefix, int32_t len, int32_t max_results)
+{
+	const int64_t gid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+	if (gid == 0) {
+		const int32_t total = prefix[len - 1] + src[len - 1];
+		dst[0] = total;
+		dst[(int64_t)total + 1] = src[(int64_t)max_results * len];
+	}
+	if (gid >= len)
+		return;
+	const int32_t off = prefix[gid];
+	const int32_t m = src[gid];
+	for (int32_t i = 0; i < m && i < max_results - 1; ++i)
+		dst[(int64_t)off + 1 + i] = src[(int64_t)len * (i + 1) + gid];
+}
+
+/* ------------------------------------------------------------------------- */
+/* K4: LSD radix sort, 8 bits per pass                                       */
+/* ------------------------------------------------------------------------- */
+
+#define RS_THREADS 256
+#define RS_ROUNDS  16
+#define RS_TILE    (RS_THREADS * RS_ROUNDS)
+
+/* hist is digit-major: hist[digit * nblocks + block] */
+__global__ void __launch_bounds__(RS_THREADS)
+k_radix_hist(const uint64_t *__restrict__ keys, uint64_t n, int shift, uint64_t flip,
+    uint32_t *__restrict__ hist, uint32_t nblocks)
+{
+	__shared__ uint32_t s_h[256];
+	s_h[threadIdx.x] = 0;
+	__syncthreads();
+	const uint64_t base = (uint64_t)blockIdx.x * RS_TILE;
+	for (int r = 0; r < RS_ROUNDS; ++r) {
+		const uint64_t i = base + (uint64_t)r * RS_THREADS + threadIdx.x;
+		if (i < n)
+			atomicAdd(&s_h[((keys[i] ^ flip) >> shift) & 0xFF], 1u);
+	}
+	__syncthreads();
+	hist[(uint64_t)threadIdx.x * nblocks + blockIdx.x] = s_h[threadIdx.x];
+}
+
+/* stable scatter: item order within a block is (round, thread) */
+__global__ void __launch_bounds__(RS_THREADS)
+k_radix_scatter(const uint64_t *__restrict__ keys, uint64_t *__restrict__ out, uint64_t n, int shift,
+    uint64_t flip, const uint32_t *__restrict__ hist_scan, uint32_t nblocks)
+{
+	__shared__ uint32_t s_run[256];                     /* next free slot per digit   */
+	__shared__ uint32_t s_wc[RS_THREADS / 32][256];     /* per-warp digit counts      */
+	const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+
+	s_run[threadIdx.x] = hist_scan[(uint64_t)threadIdx.x * nblocks + blockIdx.x];
+	const uint64_t base = (uint64_t)blockIdx.x * RS_TILE;
+	for (int r = 0; r < RS_ROUNDS; ++r) {
+		for (int w = 0; w < RS_THREADS / 32; ++w)
+			s_wc[w][threadIdx.x] = 0;
+		__syncthreads();
+		const uint64_t i = base + (uint64_t)r * RS_THREADS + threadIdx.x;
+		const bool live = i < n;
+		uint64_t key = 0;
+		uint32_t digit = 0, rank = 0;
+		if (live) {
+			key = keys[i];
+			digit = (uint32_t)(((key ^ flip) >> shift) & 0xFF);
+		}
+		const unsigned act = __ballot_sync(0xffffffffu, live);
+		if (live) {
+			const unsigned peers = __match_any_sync(act, digit);
+			rank = __popc(peers & ((1u << lane) - 1));
+			if (rank == 0)
+				s_wc[warp][digit] = __popc(peers);
+		}
+		__syncthreads();
+		if (live) {
+			uint32_t pos = s_run[digit] + rank;
+			for (uint32_t w = 0; w < warp; ++w)
+				pos += s_wc[w][digit];
+			out[pos] = key;
+		}
+		__syncthreads();
+		{
+			uint32_t add = 0;
+			for (int w = 0; w < RS_THREADS / 32; ++w)
+				add += s_wc[w][threadIdx.x];
+			s_run[threadIdx.x] += add;
+		}
+		__syncthreads();
+	}
+}
+
+/* (key, value) u32 pairs <-> u64 keys for acm_sort_pairs_u32 */
+__global__ void k_pack_pairs(const uint32_t *__restrict__ k, const uint32_t *__restrict__ v,
+    uint64_t *__restrict__ out, uint32_t n)
+{
+	const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+	if (i < n)
+		out[i] = ((uint64_t)k[i] << 32) | v[i];
+}
+
+__global__ void k_unpack_pairs(const uint64_t *__restrict__ in, uint32_t *__restrict__ k,
+    uint32_t *__restrict__ v, uint32_t n)
+{
+	const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+	if (i < n) {
+		k[i] = (uint32_t)(in[i] >> 32);
+		v[i] = (uint32_t)in[i];
+	}
+}
+
+/* per-pattern counts of a key list */
+__global__ void k_histogram(const uint64_t *__restrict__ keys, uint64_t n, unsigned long long *counts)
+{
+	for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n;
+	     i += (uint64_t)gridDim.x * blockDim.x)
+		atomicAdd(&counts[keys[i] & ACM_KEY_PAT_MASK], 1ull);
+}
+
+/* ------------------------------------------------------------------------- */
+/* synthetic streams                                                         */
+/* ------------------------------------------------------------------------- */
+
+__host__ __device__ __forceinline__ uint64_t acm_mix64(uint64_t seed, uint64_t i)
+{
+	uint64_t z = (i + 1) * 0x9E3779B97F4A7C15ull + seed * 0xD1B54A32D192ED03ull;
+	z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+	z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+	return z ^ (z >> 31);
+}
+
+/* dst must be 8-byte aligned and offset a multiple of 8 for the fast path; the host wrapper guarantees it */
+__global__ void k_synth_fill(uint64_t *__restrict__ dst, uint64_t nwords, uint64_t seed, uint64_t word0)
+{
+	for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < nwords;
+	     i += (uint64_t)gridDim.x * blockDim.x)
+		dst[i] = acm_mix64(seed, word0 + i);
+}
+
+__global__ void k_plant(uint8_t *__restrict__ buf, uint64_t n, uint64_t buf_offset,
+    const uint64_t *__restrict__ pos, const uint32_t *__restrict__ blob_off,
+    const uint32_t *__restrict__ len, uint32_t count, const uint8_t *__restrict__ blob)
+{
+	/* one warp per plant; plants are disjoint by construction */
+	const uint32_t w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+	const uint32_t lane = threadIdx.x & 31;
+	if (w >= count)
+		return;
+	const uint64_t p = pos[w];
+	const uint32_t L = len[w];
+	const uint8_t *src = blob + blob_off[w];
+	for (uint32_t k = lane; k < L; k += 32) {
+		const uint64_t g = p + k;
+		if (g >= buf_offset && g - buf_offset < n)
+			buf[g - buf_offset] = src[k];
+	}
+}

@@ -1,0 +1,179 @@
+/*
+ * acm.h -- native C ABI of the B200 Aho-Corasick matcher.
+ *
+ * Everything the reference-compatible entry points (acsmx.h, iacsmx.h, databuf.h,
+ * ocl_aho_match.h, ocl_worker.h, ocl_prefix_sum.h, ocl_compact_array.h,
+ * ocl_bitonic_sort.h) do on the device goes through the functions declared
+ * here; language bindings (ctypes, cgo, JNI ...) can bind either layer.  Plain
+ * pointers and sizes only.  Functions return ACM_OK (0) or a negative ACM_ERR_*;
+ * acm_last_error() gives the text for the calling thread.  Nothing exit()s.
+ *
+ * The hot path these functions replace in the reference is the five-call
+ * sequence of cpu_worker() (reference ocl_aho_grep.c:116-137):
+ *   databuf_copy_host_to_device -> ocl_aho_match -> databuf_copy_device_to_host
+ *   -> databuf_process_results -> databuf_reset
+ * plus the optional post-passes ocl_prefix_sum / ocl_compact_array /
+ * ocl_bitonic_sort (reference databuf.c:633-706, ocl_bitonic_sort.c:140).
+ */
+#ifndef ACM_H
+#define ACM_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define ACM_OK                  0
+#define ACM_ERR_CUDA          -10   /* a CUDA runtime call failed              */
+#define ACM_ERR_NOMEM         -11
+#define ACM_ERR_ARG           -12
+#define ACM_ERR_STATE         -13   /* call made in the wrong order            */
+#define ACM_ERR_LIMIT         -14   /* > 2^24-1 patterns, > 2^30 states, > 2^40 bytes per scan */
+#define ACM_ERR_EMPTY_PATTERN -15   /* zero-length pattern (kept, never matches) */
+#define ACM_ERR_IO            -16
+#define ACM_ERR_NO_DEVICE     -17   /* no CUDA device: there is no CPU fallback */
+
+const char *acm_last_error(void);
+
+struct acm_device;      /* one GPU: ordinal, stream, events                    */
+struct acm_automaton;   /* device-resident automaton + filters                 */
+struct acm_scanner;     /* scratch and result buffers for scans up to a size   */
+struct acm_tables;      /* host-side compiled automaton (private layout)       */
+
+/* ---- device ---- */
+int   acm_device_count(void);
+int   acm_device_open(int ordinal, struct acm_device **out);
+void  acm_device_close(struct acm_device *);
+int   acm_device_ordinal(struct acm_device *);
+/* the cudaStream_t all work of this device object is ordered on */
+void *acm_device_stream(struct acm_device *);
+/* adopt an external stream (e.g. torch.cuda.current_stream().cuda_stream); NULL restores the own stream */
+int   acm_device_set_stream(struct acm_device *, void *cuda_stream);
+int   acm_device_sync(struct acm_device *);
+/* process-wide default device object for the compat layer (ordinal from ACM_DEVICE, default 0) */
+struct acm_device *acm_default_device(void);
+
+/* raw memory helpers (bindings that cannot call the CUDA runtime themselves) */
+int   acm_dev_alloc(struct acm_device *, size_t bytes, void **d_ptr);
+void  acm_dev_free(struct acm_device *, void *d_ptr);
+int   acm_host_alloc_pinned(size_t bytes, void **h_ptr);
+void  acm_host_free_pinned(void *h_ptr);
+int   acm_memcpy_h2d(struct acm_device *, void *d_dst, const void *h_src, size_t bytes);  /* async on the stream */
+int   acm_memcpy_d2h(struct acm_device *, void *h_dst, const void *d_src, size_t bytes);  /* async on the stream */
+
+/* ---- automaton ---- */
+int   acm_automaton_upload(struct acm_device *, const struct acm_tables *, struct acm_automaton **out);
+void  acm_automaton_free(struct acm_automaton *);
+uint32_t acm_automaton_states(const struct acm_automaton *);
+uint32_t acm_automaton_patterns(const struct acm_automaton *);
+int      acm_automaton_max_pattern_len(const struct acm_automaton *);
+int      acm_automaton_min_pattern_len(const struct acm_automaton *);
+int      acm_automaton_alphabet(const struct acm_automaton *);
+size_t   acm_automaton_device_bytes(const struct acm_automaton *);
+/* which kernel ACM_MODE_AUTO picks: 1 = sampled 4-gram, 2 = 2-byte start filter, 3 = DFA */
+int      acm_automaton_default_mode(const struct acm_automaton *);
+uint32_t acm_automaton_gram_count(const struct acm_automaton *);
+
+/* ---- scan ---- */
+struct acm_scan_params {
+	int      mode;          /* 0 auto, 1 sampled4, 2 start2, 3 dfa                        */
+	int      bucket_shift;  /* log2 bytes of input per result bucket; 0 = default (15)   */
+	int      bucket_cap;    /* records per bucket before the exact 2-pass fallback; 0 = default */
+	int      timing;        /* record CUDA events around each kernel                      */
+	int      dfa_chunk;     /* bytes per thread in DFA mode; 0 = default (4096)          */
+	int      reserved[3];
+};
+
+struct acm_scan_result {
+	uint64_t n_matches;     /* records in the sorted list                                  */
+	uint64_t n_bytes;       /* bytes whose matches were kept (emit_hi - emit_lo)           */
+	int      mode;          /* kernel that ran                                              */
+	int      fallback;      /* 1 if a bucket overflowed and the exact 2-pass path ran       */
+	uint32_t final_state;   /* DFA mode only: state after the last byte (BFS numbering)    */
+	uint32_t n_buckets;
+	float    ms_scan;       /* timing != 0: kernel times, this call                         */
+	float    ms_prefix;
+	float    ms_compact;
+	float    ms_total;
+	uint32_t launches;      /* kernels launched by this call                                */
+	uint32_t reserved;
+};
+
+int  acm_scanner_create(struct acm_device *, struct acm_automaton *, uint64_t max_bytes,
+         const struct acm_scan_params *, struct acm_scanner **out);
+void acm_scanner_free(struct acm_scanner *);
+
+/*
+ * Scan n symbols that are already in device memory (bytes, or ushorts for a
+ * 2048-symbol automaton).  Only matches whose END offset e (in symbols, relative
+ * to d_data) satisfies emit_lo <= e < emit_hi are kept, so a caller that shards a
+ * stream passes Lmax-1 symbols of leading context and emit_lo = that length
+ * (SURVEY.md A.5).  d_data must be 16-byte aligned.  The sorted result stays on
+ * the device (acm_scan_keys) until the next scan on this scanner.
+ */
+int  acm_scan_device(struct acm_scanner *, const void *d_data, uint64_t n,
+         uint64_t emit_lo, uint64_t emit_hi, struct acm_scan_result *res);
+
+/*
+ * Same, for a buffer whose first valid_lo symbols are not part of the stream
+ * (stale bytes in front of an aligned carry area): nothing before valid_lo is
+ * read or used as a match start.  valid_lo <= emit_lo.
+ */
+int  acm_scan_device_ex(struct acm_scanner *, const void *d_data, uint64_t n, uint64_t valid_lo,
+         uint64_t emit_lo, uint64_t emit_hi, struct acm_scan_result *res);
+
+/* device pointer to the sorted u64 keys of the last scan: (end offset relative to d_data) << 24 | pattern index */
+const uint64_t *acm_scan_keys(struct acm_scanner *);
+
+/*
+ * Copy the last scan's matches to the host in canonical order (end offset, then
+ * pattern index): h_off[i] = base + end offset relative to d_data, h_pat[i] =
+ * pattern index (add order).  Returns the number of matches written (<= cap) or a
+ * negative error.
+ */
+int64_t acm_scan_fetch(struct acm_scanner *, uint64_t base, uint64_t *h_off,
+            uint32_t *h_pat, uint64_t cap);
+
+/* add the last scan's per-pattern match counts into d_counts[num_patterns] (u64, device) */
+int  acm_scan_histogram(struct acm_scanner *, uint64_t *d_counts);
+
+/*
+ * End-to-end: scan a HOST buffer.  The stream is cut into segments, each copied
+ * with its Lmax-1 bytes of leading context into one of two device staging
+ * buffers while the previous segment is being scanned; sorted matches are
+ * appended to h_off/h_pat (absolute offsets = base + position in h_data).
+ * h_data should be pinned (acm_host_alloc_pinned) for full PCIe rate.
+ * Returns the number of matches (may exceed cap; only cap are written).
+ */
+int64_t acm_scan_host(struct acm_scanner *, const void *h_data, uint64_t n, uint64_t base,
+            uint64_t *h_off, uint32_t *h_pat, uint64_t cap, struct acm_scan_result *res);
+
+/* ---- post-pass primitives (reference ocl_prefix_sum / ocl_compact_array / ocl_bitonic_sort) ---- */
+/* exclusive prefix sum, single-pass decoupled look-back; d_total may be NULL */
+int  acm_exclusive_scan_u32(struct acm_device *, const uint32_t *d_in, uint32_t *d_out,
+         uint32_t n, uint32_t *d_total);
+/* column-major bucket compaction (reference compactarray.cl:40-68): dst = [total, values..., tail] */
+int  acm_compact_columns_i32(struct acm_device *, int32_t *d_dst, const int32_t *d_src,
+         const int32_t *d_prefix, int32_t len, int32_t max_results);
+/* LSD radix sort of u64 keys on bits [begin_bit, end_bit); d_tmp has n entries */
+int  acm_radix_sort_u64(struct acm_device *, uint64_t *d_keys, uint64_t *d_tmp, uint64_t n,
+         int begin_bit, int end_bit, int descending);
+/* key/value u32 sort built on it; in-place when dst == src */
+int  acm_sort_pairs_u32(struct acm_device *, uint32_t *d_dst_key, uint32_t *d_dst_val,
+         const uint32_t *d_src_key, const uint32_t *d_src_val, uint32_t n, int descending);
+
+/* ---- synthetic streams (bench / tests): counter-based, identical on CPU and GPU ---- */
+/* byte i of the stream = byte (i & 7) of splitmix64(seed, i >> 3); fills d_dst[0..n) with stream[offset..offset+n) */
+int  acm_synth_fill_device(struct acm_device *, void *d_dst, uint64_t n, uint64_t seed, uint64_t offset);
+void acm_synth_fill_host(void *h_dst, uint64_t n, uint64_t seed, uint64_t offset);
+/* overwrite d_buf[pos[i] - buf_offset ...] with blob[blob_off[i] .. +len[i]) for every plant that intersects the buffer */
+int  acm_plant_device(struct acm_device *, void *d_buf, uint64_t n, uint64_t buf_offset,
+         const uint64_t *h_pos, const uint32_t *h_blob_off, const uint32_t *h_len, uint32_t count,
+         const uint8_t *h_blob, uint32_t blob_bytes);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ACM_H */

@@ -1,0 +1,175 @@
+"""GPU parity: every scan kernel, through the C ABI, against the CPU oracle on the same
+bytes.  Bar: identical sorted (end offset, pattern index) lists -- bit exact."""
+import numpy as np
+import pytest
+
+import gpu_pattern_matching_b200 as g
+from gpu_pattern_matching_b200 import synth
+from helpers import (HAND_PATTERNS, HAND_TEXT, KAT_CASES, assert_same, build_oracle, build_product,
+                     clamav_pats, gpu_scan, load_patterns, modes_for, planted_stream)
+from oracle_lib import read_fixture
+
+pytestmark = pytest.mark.gpu
+
+
+def test_hand_case(device):
+    pats = [(p, i) for i, p in enumerate(HAND_PATTERNS)]
+    o, a = build_oracle(pats), build_product(pats)
+    eo, ep, _, _ = o.search(HAND_TEXT)
+    assert list(zip(eo.tolist(), ep.tolist())) == [(2, 5), (3, 0), (3, 1), (3, 2), (3, 3), (6, 1),
+                                                  (6, 2), (6, 4), (8, 5)]
+    for mode in modes_for(a):
+        off, pat, res = gpu_scan(device, a, np.frombuffer(HAND_TEXT, dtype=np.uint8), mode)
+        assert_same(off, pat, eo, ep, f"hand mode {mode}")
+
+
+@pytest.mark.parametrize("pf,hexp,tf", KAT_CASES)
+def test_reference_fixtures(device, pf, hexp, tf):
+    pats = load_patterns(pf, hexp)
+    text = np.frombuffer(read_fixture(tf), dtype=np.uint8)
+    o, a = build_oracle(pats), build_product(pats)
+    eo, ep, _, _ = o.search(text)
+    for mode in modes_for(a):
+        off, pat, res = gpu_scan(device, a, text, mode)
+        assert res.mode == mode
+        assert_same(off, pat, eo, ep, f"{pf} x {tf} mode {mode}")
+
+
+@pytest.mark.parametrize("nsig,nbytes,plants", [(2000, 4 << 20, 512), (10000, 2 << 20, 256)])
+def test_clamav_planted(device, nsig, nbytes, plants):
+    pats = clamav_pats(nsig)
+    o, a = build_oracle(pats), build_product(pats)
+    assert a.get_min_pattern_size() >= 7
+    lmax = a.get_max_pattern_size()
+    forced = [(0, 3), (nbytes - len(pats[5][0]), 5),            # first and last byte
+              ((1 << 15) - 7, 11), ((1 << 16) - 1, 12),          # across result buckets
+              ((1 << 20) - 3, 13)]
+    buf, pl = planted_stream(pats, nbytes, seed=7, plants=plants, forced=forced)
+    eo, ep, _, _ = o.search(buf)
+    assert eo.size >= plants        # every plant is found (plus chance overlaps)
+    for mode in modes_for(a):
+        off, pat, res = gpu_scan(device, a, buf, mode)
+        assert_same(off, pat, eo, ep, f"clamav{nsig} mode {mode}")
+        assert not res.fallback
+
+
+def test_unaligned_lengths_and_tails(device):
+    pats = clamav_pats(2000)
+    o, a = build_oracle(pats), build_product(pats)
+    for n in (1, 3, 15, 16, 17, 31, 33, 64, 4095, 65537):
+        buf = synth.stream(max(n, 256), 11)[:n].copy()
+        # a signature that ends exactly at the last byte whenever it fits
+        sig = pats[17][0]
+        if n >= len(sig):
+            buf[n - len(sig):] = np.frombuffer(sig, dtype=np.uint8)
+        eo, ep, _, _ = o.search(buf)
+        for mode in modes_for(a):
+            off, pat, _ = gpu_scan(device, a, buf, mode)
+            assert_same(off, pat, eo, ep, f"n={n} mode {mode}")
+
+
+def test_emit_window_sharding(device):
+    """Contiguous shards with Lmax-1 bytes of leading halo reproduce the whole-stream list."""
+    pats = clamav_pats(2000)
+    o, a = build_oracle(pats), build_product(pats)
+    n = 1 << 20
+    cuts = [0, 300001, 300002 + 4096, 777777, n]
+    forced = [(c - 20, 40 + k) for k, c in enumerate(cuts[1:-1])]     # straddle every cut
+    buf, _ = planted_stream(pats, n, seed=3, plants=128, forced=forced)
+    eo, ep, _, _ = o.search(buf)
+    halo = a.get_max_pattern_size() - 1
+    for mode in modes_for(a):
+        offs, pts = [], []
+        for lo, hi in zip(cuts[:-1], cuts[1:]):
+            start = max(0, lo - halo) & ~15       # device buffers are 16-byte aligned
+            off, pat, _ = gpu_scan(device, a, buf[start:hi], mode, emit_lo=lo - start, emit_hi=hi - start)
+            offs.append(off + np.uint64(start))
+            pts.append(pat)
+        assert_same(np.concatenate(offs), np.concatenate(pts), eo, ep, f"sharded mode {mode}")
+
+
+def test_valid_lo_hides_stale_prefix(device):
+    pats = [(b"needle", 0), (b"dle", 1)]
+    o, a = build_oracle(pats), build_product(pats)
+    body = b"xxneedlexx needle"
+    buf = np.frombuffer(b"nee" + b"dle....." + body, dtype=np.uint8)   # "needle" straddles valid_lo
+    valid = 3
+    eo, ep, _, _ = o.search(buf[valid:])
+    for mode in modes_for(a):
+        off, pat, _ = gpu_scan(device, a, buf, mode, emit_lo=valid, valid_lo=valid)
+        assert_same(off - np.uint64(valid), pat, eo, ep, f"valid_lo mode {mode}")
+
+
+def test_dense_matches_overflow_fallback(device):
+    """Every byte matches several patterns: buckets overflow, the exact two-pass path runs."""
+    pats = [(b"a", 0), (b"aa", 1), (b"aaa", 2), (b"ab", 3), (b"b", 4)]
+    o, a = build_oracle(pats), build_product(pats)
+    rng = np.random.default_rng(5)
+    buf = rng.choice(np.frombuffer(b"aab", dtype=np.uint8), size=200000)
+    eo, ep, _, _ = o.search(buf)
+    for mode in modes_for(a):
+        off, pat, res = gpu_scan(device, a, buf, mode, bucket_cap=32, bucket_shift=12)
+        assert res.fallback == 1
+        assert_same(off, pat, eo, ep, f"dense mode {mode}")
+        off, pat, res = gpu_scan(device, a, buf, mode, bucket_cap=8192, bucket_shift=10)
+        assert res.fallback == 0
+        assert_same(off, pat, eo, ep, f"dense mode {mode} (buckets)")
+
+
+def test_sentiment_text(device):
+    pats = load_patterns("sentiment_categorical.pat.gz")
+    o, a = build_oracle(pats), build_product(pats)
+    words = [l.split(b"\t")[0] for l in read_fixture("english_top5000.txt.gz").split(b"\n") if l]
+    text = synth.english_like(words, 1 << 20, seed=4)
+    eo, ep, _, _ = o.search(text)
+    assert eo.size > 5000
+    for mode in modes_for(a):
+        off, pat, res = gpu_scan(device, a, text, mode)
+        assert_same(off, pat, eo, ep, f"sentiment mode {mode}")
+
+
+def test_scan_host_pipeline(device):
+    pats = clamav_pats(2000)
+    o, a = build_oracle(pats), build_product(pats)
+    n = (3 << 20) + 12345
+    seg = 1 << 20
+    forced = [(seg - 9, 21), (2 * seg - 30, 22), (3 * seg - 1, 23)]
+    buf, _ = planted_stream(pats, n, seed=9, plants=300, forced=forced)
+    eo, ep, _, _ = o.search(buf)
+    sc = g.Scanner(device, a.automaton, seg)        # forces 4 segments
+    off, pat, res = sc.scan_host(buf, base=1000)
+    assert_same(off - np.uint64(1000), pat, eo, ep, "scan_host")
+    sc.close()
+
+
+def test_histogram(device):
+    pats = clamav_pats(2000)
+    o, a = build_oracle(pats), build_product(pats)
+    buf, _ = planted_stream(pats, 1 << 20, seed=13, plants=400)
+    eo, ep, _, _ = o.search(buf)
+    d = device.alloc(buf.size + 64)
+    device.h2d(d, buf)
+    sc = g.Scanner(device, a.automaton, buf.size)
+    sc.scan_device(d, buf.size)
+    dc = device.alloc(8 * len(pats))
+    device.h2d(dc, np.zeros(len(pats), dtype=np.uint64))
+    sc.histogram_into(dc)
+    counts = device.d2h(dc, 8 * len(pats), np.uint64)
+    assert np.array_equal(counts, np.bincount(ep, minlength=len(pats)).astype(np.uint64))
+    device.free(d)
+    device.free(dc)
+    sc.close()
+
+
+def test_device_synth_matches_host(device):
+    n = 1 << 16
+    d = device.alloc(n)
+    device.synth_fill(d, n, seed=99, offset=4096)
+    device.sync()
+    got = device.d2h(d, n)
+    assert np.array_equal(got, synth.stream(n, 99, 4096))
+    host = np.empty(1000, dtype=np.uint8)
+    import ctypes as C
+    g.lib().acm_synth_fill_host(host.ctypes.data_as(C.c_void_p), 1000, 99, 4099)
+    assert np.array_equal(host, synth.stream(1000, 99, 4099))
+    device.free(d)
