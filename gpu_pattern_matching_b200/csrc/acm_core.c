@@ -143,6 +143,7 @@ acm_tables_free(struct acm_tables *t)
 	free(t->T); free(t->level_start); free(t->own_begin); free(t->own_pat);
 	free(t->olink); free(t->fail); free(t->pat_len); free(t->pat_iid);
 	free(t->bfs_to_ref); free(t->f1); free(t->f2); free(t->grams); free(t->b2);
+	free(t->cand); free(t->pat_blob); free(t->pat_off);
 	memset(t, 0, sizeof(*t));
 }
 
@@ -156,7 +157,8 @@ acm_tables_device_bytes(const struct acm_tables *t)
 	b += (size_t)(t->max_depth + 2) * 4;
 	if (t->f1)
 		b += (1u << ACM_F1_BITS_LOG2) / 8 + (1u << ACM_F2_BITS_LOG2) / 8 +
-		    (size_t)t->gram_slots * sizeof(struct acm_gram_slot);
+		    (size_t)t->gram_slots * sizeof(struct acm_gram_slot) + (size_t)t->cand_count * 4 +
+		    t->pat_blob_bytes + (size_t)t->num_patterns * 4;
 	if (t->b2)
 		b += 65536 / 8;
 	return b;
@@ -193,6 +195,15 @@ trie_child(const struct trie *t, uint32_t u, unsigned a)
 		if (t->sym[c] == a)
 			return c;
 	return 0;
+}
+
+static int
+cmp_gtrip(const void *a, const void *b)
+{
+	const uint32_t *x = a, *y = b;
+	if (x[0] != y[0])
+		return x[0] < y[0] ? -1 : 1;
+	return x[1] < y[1] ? -1 : (x[1] > y[1]);
 }
 
 static int
@@ -233,50 +244,81 @@ build_filters(struct acm_core *c)
 	if (t->min_pattern_len < 7)
 		return ACM_OK;
 
-	/* hashed 4-gram filters over pattern offsets 0..3 */
+	/* hashed 4-gram filters over pattern offsets 0..3, exact gram table, candidate lists */
 	t->f1 = calloc((1u << ACM_F1_BITS_LOG2) / 32, 4);
 	t->f2 = calloc((1u << ACM_F2_BITS_LOG2) / 32, 4);
 	if (!t->f1 || !t->f2)
 		return ACM_ERR_NOMEM;
 	{
+		struct gtrip { uint32_t gram, cand; } *tr;
 		uint64_t want = (uint64_t)c->npats * 4 * 2;
-		uint32_t slots = 1024, lg = 10;
+		uint32_t slots = 1024, lg = 10, ntr = 0, blob = 0;
+
 		while (slots < want) {
 			slots <<= 1;
 			lg++;
 		}
 		t->gram_slots = slots;
 		t->grams = calloc(slots, sizeof(*t->grams));
-		if (!t->grams)
+		tr = malloc(((size_t)c->npats * 4 + 1) * sizeof(*tr));
+		t->pat_off = calloc((size_t)c->npats + 1, 4);
+		if (!t->grams || !tr || !t->pat_off) {
+			free(tr);
 			return ACM_ERR_NOMEM;
+		}
+		for (k = 0; k < (uint32_t)c->npats; k++) {
+			t->pat_off[k] = blob;
+			blob += ((uint32_t)c->pats[k].n + 3u + 4u) & ~3u;   /* >= 4 zero bytes after each */
+		}
+		t->pat_blob_bytes = blob + 16;
+		t->pat_blob = calloc(t->pat_blob_bytes, 1);
+		if (!t->pat_blob) {
+			free(tr);
+			return ACM_ERR_NOMEM;
+		}
 		for (k = 0; k < (uint32_t)c->npats; k++) {
 			const unsigned char *p = c->pats[k].syms;
 			if (c->pats[k].n == 0)
 				continue;
-			for (int j = 0; j < 4; j++) {
+			memcpy(t->pat_blob + t->pat_off[k], p, (size_t)c->pats[k].n);
+			for (uint32_t j = 0; j < 4; j++) {
 				uint32_t g = (uint32_t)p[j] | ((uint32_t)p[j + 1] << 8) |
 				    ((uint32_t)p[j + 2] << 16) | ((uint32_t)p[j + 3] << 24);
 				uint32_t h1 = g * ACM_HASH1_MUL;
 				uint32_t h2 = g * ACM_HASH2_MUL;
-				uint32_t h3 = (g * ACM_HASH3_MUL) >> (32 - lg);
 				t->f1[h1 >> (32 - (ACM_F1_BITS_LOG2 - 5))] |=
 				    0x80000000u >> (h1 & 31);
 				t->f2[h2 >> (32 - (ACM_F2_BITS_LOG2 - 5))] |=
 				    0x80000000u >> (h2 & 31);
-				for (s = h3;; s = (s + 1) & (slots - 1)) {
-					if (t->grams[s].jmask == 0) {
+				tr[ntr].gram = g;
+				tr[ntr].cand = k | (j << ACM_CAND_J_SHIFT);
+				ntr++;
+			}
+		}
+		/* group by gram (stable order inside a gram is irrelevant: results get sorted) */
+		qsort(tr, ntr, sizeof(*tr), cmp_gtrip);
+		t->cand = malloc(((size_t)ntr + 1) * 4);
+		if (!t->cand) {
+			free(tr);
+			return ACM_ERR_NOMEM;
+		}
+		t->cand_count = ntr;
+		for (k = 0; k < ntr; k++) {
+			const int first = (k == 0) || tr[k - 1].gram != tr[k].gram;
+			const int lastc = (k + 1 == ntr) || tr[k + 1].gram != tr[k].gram;
+			t->cand[k] = tr[k].cand | (lastc ? ACM_CAND_LAST : 0);
+			if (first) {
+				uint32_t g = tr[k].gram;
+				for (s = (g * ACM_HASH3_MUL) >> (32 - lg);; s = (s + 1) & (slots - 1))
+					if (t->grams[s].begin1 == 0) {
 						t->grams[s].gram = g;
-						t->grams[s].jmask = 1u << j;
+						t->grams[s].begin1 = k + 1;
 						t->gram_count++;
 						break;
 					}
-					if (t->grams[s].gram == g) {
-						t->grams[s].jmask |= 1u << j;
-						break;
-					}
-				}
 			}
 		}
+		free(tr);
 	}
 	return ACM_OK;
 }

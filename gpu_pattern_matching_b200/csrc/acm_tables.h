@@ -41,8 +41,13 @@ enum {
 
 struct acm_gram_slot {     /* exact 4-gram table, open addressing in HBM/L2 */
 	uint32_t gram;         /* little-endian 4 bytes of the pattern          */
-	uint32_t jmask;        /* bit j set: some pattern has this gram at byte offset j (j < 4); 0 = empty */
+	uint32_t begin1;       /* 1 + index of the gram's first candidate in cand[]; 0 = empty slot */
 };
+
+/* candidate: pattern `id` has the gram at byte offset j; LAST marks the end of a gram's list */
+#define ACM_CAND_ID_MASK 0x00FFFFFFu
+#define ACM_CAND_J_SHIFT 24
+#define ACM_CAND_LAST    0x80000000u
 
 struct acm_tables {
 	int       alpha;             /* 256 (bytes) or 2048 (ushort symbols)        */
@@ -68,10 +73,13 @@ struct acm_tables {
 	uint32_t *f2;                /* 2^19-bit second hash of the same grams        */
 	struct acm_gram_slot *grams; /* exact gram table                              */
 	uint32_t  gram_slots;        /* power of two                                  */
-	uint32_t  gram_count;
+	uint32_t  gram_count;        /* distinct grams                                */
+	uint32_t *cand;              /* candidate lists, grouped by gram              */
+	uint32_t  cand_count;
+	uint8_t  *pat_blob;          /* pattern bytes, each pattern 4-byte aligned, zero padded */
+	uint32_t  pat_blob_bytes;
+	uint32_t *pat_off;           /* [num_patterns] byte offset into pat_blob      */
 	uint32_t *b2;                /* 2^16-bit exact start bitmap: bit (b0 | b1<<8) */
-	uint16_t *h2;                /* [65536] depth-2 node for (b0,b1): 0 = none, else (id - level_start[2] + 1) | 0x8000 if terminal; 0xFFFF = look it up */
-	int       h2_valid;          /* 0 when there are more than 32766 depth-2 nodes */
 };
 
 void acm_tables_free(struct acm_tables *t);

@@ -52,6 +52,10 @@ struct AutDev {
 	const uint32_t *f1;
 	const uint32_t *f2;
 	const acm_gram_slot *grams;
+	const uint32_t *cand;
+	const uint8_t  *pat_blob;
+	const uint32_t *pat_off;
+	const uint32_t *pat_len;
 	const uint32_t *b2;
 	uint32_t gram_mask;
 	uint32_t gram_shift;     /* 32 - log2(slots) */
@@ -175,18 +179,15 @@ __device__ __noinline__ void walk_from(const AutDev A, const EmitCtx E, const ui
 	}
 }
 
-/* 16 bytes at vector index idx; the last, partial vector is assembled bytewise */
-__device__ __forceinline__ uint4 load_vec(const uint8_t *__restrict__ data, uint64_t idx, uint64_t nvec_full,
-    uint64_t n)
+/*
+ * 16 bytes at vector index idx.  The caller guarantees idx * 16 < n, and device buffers
+ * are 16-byte aligned and readable up to the next multiple of 16 (acm.h), so the last,
+ * partial vector is a plain load too; whatever lies beyond n can only raise a filter hit
+ * that the exact stages then reject.
+ */
+__device__ __forceinline__ uint4 load_vec(const uint8_t *__restrict__ data, uint64_t idx)
 {
-	if (idx < nvec_full)
-		return __ldcs(reinterpret_cast<const uint4 *>(data) + idx);
-	uint32_t w[4] = {0, 0, 0, 0};
-	const uint64_t base = idx * 16;
-	for (int k = 0; k < 16; ++k)
-		if (base + k < n)
-			w[k >> 2] |= (uint32_t)data[base + k] << (8 * (k & 3));
-	return make_uint4(w[0], w[1], w[2], w[3]);
+	return __ldcs(reinterpret_cast<const uint4 *>(data) + idx);
 }
 
 /* ------------------------------------------------------------------------- */
@@ -196,27 +197,43 @@ __device__ __forceinline__ uint4 load_vec(const uint8_t *__restrict__ data, uint
 #define S4_THREADS 1024
 #define S4_UNROLL  4
 #define S4_SMEM_BYTES ((F1_WORDS + F2_WORDS) * 4 + 16)
+#define FULL_MASK 0xffffffffu
 
-__device__ __noinline__ void s4_confirm(const AutDev A, const EmitCtx E, const uint8_t *__restrict__ data,
-    uint32_t g, uint64_t e, uint64_t limit)
+/*
+ * Whole-warp verification of one candidate: does pattern `pid` occur at text position s?
+ * Lane l compares bytes [4l, 4l+4) of each 128-byte round; all arguments are warp-uniform.
+ */
+__device__ __forceinline__ void s4_verify(const AutDev &A, const EmitCtx &E, const uint8_t *__restrict__ data,
+    uint32_t pid, uint64_t s, uint64_t limit, int lane)
 {
-	uint32_t s = (g * ACM_HASH3_MUL) >> A.gram_shift;
-	for (;;) {
-		const uint2 slot = __ldg(reinterpret_cast<const uint2 *>(A.grams) + s);
-		if (slot.y == 0)
-			return;
-		if (slot.x == g) {
-			uint32_t jm = slot.y;
-			while (jm) {
-				const uint32_t j = __ffs(jm) - 1;
-				jm &= jm - 1;
-				if (e >= j && e - j >= E.valid_lo)
-					walk_from(A, E, data, e - j, limit);
-			}
-			return;
+	const uint32_t len = __ldg(&A.pat_len[pid]);
+	if (s + len > limit)            /* would end beyond the kept range (or the data) */
+		return;
+	const uint32_t *pw = reinterpret_cast<const uint32_t *>(A.pat_blob + __ldg(&A.pat_off[pid]));
+	const uint32_t *tw = reinterpret_cast<const uint32_t *>(data + (s & ~3ull));
+	const uint32_t sh = (uint32_t)(s & 3) * 8;
+	bool ok = true;
+	for (uint32_t r = 0; r < len; r += 128) {
+		const uint32_t k = r + 4 * (uint32_t)lane;        /* byte offset inside the pattern */
+		uint32_t diff = 0;
+		if (k < len) {
+			/* aligned words around the unaligned text position; both contain valid bytes */
+			const uint32_t rem = len - k;
+			const uint32_t w0 = __ldg(tw + (k >> 2));
+			/* the second word only when this lane's bytes really reach into it */
+			const bool need1 = ((uint32_t)(s & 3) + (rem < 4 ? rem : 4u)) > 4u;
+			const uint32_t w1 = need1 ? __ldg(tw + (k >> 2) + 1) : 0u;
+			const uint32_t t = __funnelshift_r(w0, w1, sh);
+			const uint32_t p = __ldg(pw + (k >> 2));
+			const uint32_t mask = rem >= 4 ? 0xffffffffu : ((1u << (8 * rem)) - 1u);
+			diff = (t ^ p) & mask;
 		}
-		s = (s + 1) & A.gram_mask;
+		ok = __all_sync(FULL_MASK, diff == 0);
+		if (!ok)
+			break;
 	}
+	if (ok && lane == 0)
+		emit_record(E, s + len - 1, pid);
 }
 
 __global__ void __launch_bounds__(S4_THREADS, 1)
@@ -227,6 +244,7 @@ k_scan_sampled4(const AutDev A, const EmitCtx E, const uint8_t *__restrict__ dat
 	uint32_t *f1 = s4_smem;
 	uint32_t *f2 = s4_smem + F1_WORDS;
 	uint64_t *bar = reinterpret_cast<uint64_t *>(s4_smem + F1_WORDS + F2_WORDS);
+	const int lane = threadIdx.x & 31;
 
 	/* stage both bitmaps with TMA bulk copies, 32 KiB each */
 	if (threadIdx.x == 0) {
@@ -238,18 +256,32 @@ k_scan_sampled4(const AutDev A, const EmitCtx E, const uint8_t *__restrict__ dat
 			bulk_g2s(f2 + off, A.f2 + off, 32768, bar);
 	}
 	__syncthreads();
+
+	const uint64_t tile_vecs = (uint64_t)S4_THREADS * S4_UNROLL;
+	const uint64_t stride = (uint64_t)gridDim.x * tile_vecs;
+	uint64_t first = vec_lo + (uint64_t)blockIdx.x * tile_vecs;
+
+	/* the first tile's loads fly while the bitmaps land */
+	uint4 v[S4_UNROLL], nx[S4_UNROLL];
+#pragma unroll
+	for (int u = 0; u < S4_UNROLL; ++u) {
+		const uint64_t idx = first + (uint64_t)u * S4_THREADS + threadIdx.x;
+		nx[u] = (idx < vec_hi) ? load_vec(data, idx) : make_uint4(0, 0, 0, 0);
+	}
 	mbar_wait(bar, 0);
 
-	const uint64_t nvec_full = n >> 4;
-	const uint64_t tile_vecs = (uint64_t)S4_THREADS * S4_UNROLL;
-
-	for (uint64_t first = vec_lo + (uint64_t)blockIdx.x * tile_vecs; first < vec_hi;
-	     first += (uint64_t)gridDim.x * tile_vecs) {
-		uint4 v[S4_UNROLL];
+	for (; first < vec_hi; first += stride) {
 #pragma unroll
-		for (int u = 0; u < S4_UNROLL; ++u) {
-			const uint64_t idx = first + (uint64_t)u * S4_THREADS + threadIdx.x;
-			v[u] = (idx < vec_hi) ? load_vec(data, idx, nvec_full, n) : make_uint4(0, 0, 0, 0);
+		for (int u = 0; u < S4_UNROLL; ++u)
+			v[u] = nx[u];
+		/* software pipeline: next tile's 64 bytes per thread are in flight during this one */
+		{
+			const uint64_t nfirst = first + stride;
+#pragma unroll
+			for (int u = 0; u < S4_UNROLL; ++u) {
+				const uint64_t idx = nfirst + (uint64_t)u * S4_THREADS + threadIdx.x;
+				nx[u] = (idx < vec_hi) ? load_vec(data, idx) : make_uint4(0, 0, 0, 0);
+			}
 		}
 		uint32_t hits = 0;
 #pragma unroll
@@ -264,21 +296,52 @@ k_scan_sampled4(const AutDev A, const EmitCtx E, const uint8_t *__restrict__ dat
 				hits = __funnelshift_l(t, hits, 1);
 			}
 		}
-		/* bit (15 - q) of hits belongs to window q = u * 4 + k */
-		while (hits) {
-			const int p = 31 - __clz(hits);
-			hits &= ~(1u << p);
-			const int q = 15 - p;
-			const uint4 x = (q & 8) ? ((q & 4) ? v[3] : v[2]) : ((q & 4) ? v[1] : v[0]);
-			const uint32_t g = (q & 2) ? ((q & 1) ? x.w : x.z) : ((q & 1) ? x.y : x.x);
-			const uint32_t h2 = g * ACM_HASH2_MUL;
-			const uint32_t word2 = f2[h2 >> (32 - (ACM_F2_BITS_LOG2 - 5))];
-			if (!(__funnelshift_l(0u, word2, h2) & 0x80000000u))
-				continue;
-			const uint64_t idx = first + (uint64_t)(q >> 2) * S4_THREADS + threadIdx.x;
-			if (idx >= vec_hi)
-				continue;
-			s4_confirm(A, E, data, g, idx * 16 + (uint64_t)(q & 3) * 4, limit);
+		/* bit (15 - q) of hits belongs to window q = u * 4 + k.  Survivors are rare: from
+		 * here on control flow is warp-uniform and verification is done by the whole warp. */
+		while (__any_sync(FULL_MASK, hits != 0)) {
+			uint32_t cbegin = 0;
+			uint64_t e = 0;
+			if (hits) {
+				const int p = 31 - __clz(hits);
+				hits &= ~(1u << p);
+				const int q = 15 - p;
+				const uint4 x = (q & 8) ? ((q & 4) ? v[3] : v[2]) : ((q & 4) ? v[1] : v[0]);
+				const uint32_t g = (q & 2) ? ((q & 1) ? x.w : x.z) : ((q & 1) ? x.y : x.x);
+				const uint32_t h2 = g * ACM_HASH2_MUL;
+				const uint32_t word2 = f2[h2 >> (32 - (ACM_F2_BITS_LOG2 - 5))];
+				if (__funnelshift_l(0u, word2, h2) & 0x80000000u) {
+					/* exact gram table (L2 resident) */
+					uint32_t sl = (g * ACM_HASH3_MUL) >> A.gram_shift;
+					for (;;) {
+						const uint2 slot = __ldg(reinterpret_cast<const uint2 *>(A.grams) + sl);
+						if (slot.y == 0)
+							break;
+						if (slot.x == g) {
+							cbegin = slot.y;
+							break;
+						}
+						sl = (sl + 1) & A.gram_mask;
+					}
+					e = (first + (uint64_t)(q >> 2) * S4_THREADS + threadIdx.x) * 16 +
+					    (uint64_t)(q & 3) * 4;
+				}
+			}
+			uint32_t pend = __ballot_sync(FULL_MASK, cbegin != 0);
+			while (pend) {
+				const int src = __ffs(pend) - 1;
+				pend &= pend - 1;
+				uint32_t ci = __shfl_sync(FULL_MASK, cbegin, src) - 1;
+				const uint64_t ew = __shfl_sync(FULL_MASK, e, src);
+				for (;;) {
+					const uint32_t c = __ldg(&A.cand[ci]);
+					const uint32_t j = (c >> ACM_CAND_J_SHIFT) & 3u;
+					if (ew >= j && ew - j >= E.valid_lo)
+						s4_verify(A, E, data, c & ACM_CAND_ID_MASK, ew - j, limit, lane);
+					if (c & ACM_CAND_LAST)
+						break;
+					++ci;
+				}
+			}
 		}
 	}
 }
@@ -307,7 +370,6 @@ k_scan_start2(const AutDev A, const EmitCtx E, const uint8_t *__restrict__ data,
 	__syncthreads();
 	mbar_wait(bar, 0);
 
-	const uint64_t nvec_full = n >> 4;
 	const uint64_t tile_vecs = (uint64_t)S2_THREADS * S2_UNROLL;
 	const int lane = threadIdx.x & 31;
 
@@ -318,7 +380,7 @@ k_scan_start2(const AutDev A, const EmitCtx E, const uint8_t *__restrict__ data,
 			const uint64_t idx = first + (uint64_t)u * S2_THREADS + threadIdx.x;
 			/* whole warps fall off the end together except in the last tile */
 			const bool live = idx < vec_hi;
-			uint4 v = live ? load_vec(data, idx, nvec_full, n) : make_uint4(0, 0, 0, 0);
+			uint4 v = live ? load_vec(data, idx) : make_uint4(0, 0, 0, 0);
 			/* first word of the next vector: the neighbour lane has it */
 			uint32_t nxt = __shfl_down_sync(0xffffffffu, v.x, 1);
 			if (lane == 31) {

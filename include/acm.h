@@ -110,7 +110,9 @@ void acm_scanner_free(struct acm_scanner *);
  * 2048-symbol automaton).  Only matches whose END offset e (in symbols, relative
  * to d_data) satisfies emit_lo <= e < emit_hi are kept, so a caller that shards a
  * stream passes Lmax-1 symbols of leading context and emit_lo = that length
- * (SURVEY.md A.5).  d_data must be 16-byte aligned.  The sorted result stays on
+ * (SURVEY.md A.5).  d_data must be 16-byte aligned and readable up to the next
+ * multiple of 16 bytes past its end (true of any cudaMalloc / torch allocation; the
+ * kernels load whole 16-byte vectors).  The sorted result stays on
  * the device (acm_scan_keys) until the next scan on this scanner.
  */
 int  acm_scan_device(struct acm_scanner *, const void *d_data, uint64_t n,

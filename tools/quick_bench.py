@@ -49,10 +49,23 @@ def run(dev, name, pats, n, modes, text=None, plants=0, iters=5):
 if __name__ == "__main__":
     dev = g.Device(0)
     n = int(sys.argv[1]) << 20 if len(sys.argv) > 1 else 1 << 30
-    run(dev, "clamav2k", clamav_pats(2000), n, [1, 2], plants=4096)
-    run(dev, "clamav10k", clamav_pats(10000), n, [1, 2], plants=100000)
-    run(dev, "clamav15k", clamav_pats(15000), n, [1, 2], plants=100000)
-    run(dev, "clamav10k-dfa", clamav_pats(10000), n >> 3, [3], plants=10000)
-    words = [l.split(b"\t")[0] for l in read_fixture("english_top5000.txt.gz").split(b"\n") if l]
-    text = synth.english_like(words, 16 << 20, seed=4)
-    run(dev, "sentiment", load_patterns("sentiment_categorical.pat.gz"), n >> 2, [2, 3], text=text)
+    which = sys.argv[2].split(",") if len(sys.argv) > 2 else ["2k", "10k", "15k", "dfa", "sent"]
+    iters = int(sys.argv[3]) if len(sys.argv) > 3 else 5
+    per_gib = n / float(1 << 30)
+    if "2k" in which:
+        run(dev, "clamav2k", clamav_pats(2000), n, [1, 2], plants=int(4096 * per_gib * 32), iters=iters)
+    if "2k-s4" in which:
+        run(dev, "clamav2k", clamav_pats(2000), n, [1], plants=int(4096 * per_gib * 32), iters=iters)
+    if "10k" in which:
+        run(dev, "clamav10k", clamav_pats(10000), n, [1, 2], plants=int(100000 * per_gib), iters=iters)
+    if "10k-s4" in which:
+        run(dev, "clamav10k", clamav_pats(10000), n, [1], plants=int(100000 * per_gib), iters=iters)
+    if "15k" in which:
+        run(dev, "clamav15k", clamav_pats(15000), n, [1, 2], plants=int(100000 * per_gib), iters=iters)
+    if "dfa" in which:
+        run(dev, "clamav10k-dfa", clamav_pats(10000), n >> 3, [3], plants=int(12500 * per_gib), iters=iters)
+    if "sent" in which:
+        words = [l.split(b"\t")[0] for l in read_fixture("english_top5000.txt.gz").split(b"\n") if l]
+        text = synth.english_like(words, 16 << 20, seed=4)
+        run(dev, "sentiment", load_patterns("sentiment_categorical.pat.gz"), n >> 2, [2, 3], text=text,
+            iters=iters)
