@@ -157,7 +157,8 @@ acm_tables_device_bytes(const struct acm_tables *t)
 	b += (size_t)(t->max_depth + 2) * 4;
 	if (t->f1)
 		b += (1u << ACM_F1_BITS_LOG2) / 8 + (1u << ACM_F2_BITS_LOG2) / 8 +
-		    (size_t)t->gram_slots * sizeof(struct acm_gram_slot) + (size_t)t->cand_count * 4 +
+		    (size_t)t->gram_slots * sizeof(struct acm_gram_slot) +
+		    ((size_t)t->cand_count + ACM_CAND_PAD) * sizeof(struct acm_cand) +
 		    t->pat_blob_bytes + (size_t)t->num_patterns * 4;
 	if (t->b2)
 		b += 65536 / 8;
@@ -297,7 +298,7 @@ build_filters(struct acm_core *c)
 		}
 		/* group by gram (stable order inside a gram is irrelevant: results get sorted) */
 		qsort(tr, ntr, sizeof(*tr), cmp_gtrip);
-		t->cand = malloc(((size_t)ntr + 1) * 4);
+		t->cand = calloc((size_t)ntr + ACM_CAND_PAD, sizeof(*t->cand));
 		if (!t->cand) {
 			free(tr);
 			return ACM_ERR_NOMEM;
@@ -306,7 +307,14 @@ build_filters(struct acm_core *c)
 		for (k = 0; k < ntr; k++) {
 			const int first = (k == 0) || tr[k - 1].gram != tr[k].gram;
 			const int lastc = (k + 1 == ntr) || tr[k + 1].gram != tr[k].gram;
-			t->cand[k] = tr[k].cand | (lastc ? ACM_CAND_LAST : 0);
+			const uint32_t pid = tr[k].cand & ACM_CAND_ID_MASK;
+			const unsigned char *pb = t->pat_blob + t->pat_off[pid];   /* zero padded */
+			t->cand[k].info = tr[k].cand | (lastc ? ACM_CAND_LAST : 0);
+			t->cand[k].pre0 = (uint32_t)pb[0] | ((uint32_t)pb[1] << 8) | ((uint32_t)pb[2] << 16) |
+			    ((uint32_t)pb[3] << 24);
+			t->cand[k].pre1 = (uint32_t)pb[4] | ((uint32_t)pb[5] << 8) | ((uint32_t)pb[6] << 16) |
+			    ((uint32_t)pb[7] << 24);
+			t->cand[k].len = (uint32_t)c->pats[pid].n;
 			if (first) {
 				uint32_t g = tr[k].gram;
 				for (s = (g * ACM_HASH3_MUL) >> (32 - lg);; s = (s + 1) & (slots - 1))

@@ -344,7 +344,7 @@ acm_automaton_upload(struct acm_device *dev, const struct acm_tables *t, struct 
 		UP(f1, t->f1, (1u << ACM_F1_BITS_LOG2) / 8);
 		UP(f2, t->f2, (1u << ACM_F2_BITS_LOG2) / 8);
 		UP(grams, t->grams, (size_t)t->gram_slots * sizeof(struct acm_gram_slot));
-		UP(cand, t->cand, (size_t)t->cand_count * 4);
+		UP(cand, t->cand, ((size_t)t->cand_count + ACM_CAND_PAD) * sizeof(struct acm_cand));
 		UP(pat_blob, t->pat_blob, t->pat_blob_bytes);
 		UP(pat_off, t->pat_off, (size_t)t->num_patterns * 4);
 		UP(pat_len, t->pat_len, (size_t)t->num_patterns * 4);

@@ -44,10 +44,20 @@ struct acm_gram_slot {     /* exact 4-gram table, open addressing in HBM/L2 */
 	uint32_t begin1;       /* 1 + index of the gram's first candidate in cand[]; 0 = empty slot */
 };
 
-/* candidate: pattern `id` has the gram at byte offset j; LAST marks the end of a gram's list */
+/*
+ * candidate: pattern `id` has the gram at byte offset j; LAST marks the end of a gram's
+ * list.  pre0/pre1 are the pattern's first 8 bytes (zero padded) for a quick reject.
+ */
 #define ACM_CAND_ID_MASK 0x00FFFFFFu
 #define ACM_CAND_J_SHIFT 24
 #define ACM_CAND_LAST    0x80000000u
+#define ACM_CAND_PAD     32          /* zeroed entries after the last list */
+
+struct acm_cand {
+	uint32_t info;         /* id | j << 24 | LAST */
+	uint32_t pre0, pre1;
+	uint32_t len;
+};
 
 struct acm_tables {
 	int       alpha;             /* 256 (bytes) or 2048 (ushort symbols)        */
@@ -74,7 +84,7 @@ struct acm_tables {
 	struct acm_gram_slot *grams; /* exact gram table                              */
 	uint32_t  gram_slots;        /* power of two                                  */
 	uint32_t  gram_count;        /* distinct grams                                */
-	uint32_t *cand;              /* candidate lists, grouped by gram              */
+	struct acm_cand *cand;       /* candidate lists, grouped by gram, + ACM_CAND_PAD */
 	uint32_t  cand_count;
 	uint8_t  *pat_blob;          /* pattern bytes, each pattern 4-byte aligned, zero padded */
 	uint32_t  pat_blob_bytes;

@@ -52,7 +52,7 @@ struct AutDev {
 	const uint32_t *f1;
 	const uint32_t *f2;
 	const acm_gram_slot *grams;
-	const uint32_t *cand;
+	const acm_cand *cand;
 	const uint8_t  *pat_blob;
 	const uint32_t *pat_off;
 	const uint32_t *pat_len;
@@ -204,11 +204,8 @@ __device__ __forceinline__ uint4 load_vec(const uint8_t *__restrict__ data, uint
  * Lane l compares bytes [4l, 4l+4) of each 128-byte round; all arguments are warp-uniform.
  */
 __device__ __forceinline__ void s4_verify(const AutDev &A, const EmitCtx &E, const uint8_t *__restrict__ data,
-    uint32_t pid, uint64_t s, uint64_t limit, int lane)
+    uint32_t pid, uint32_t len, uint64_t s, int lane)
 {
-	const uint32_t len = __ldg(&A.pat_len[pid]);
-	if (s + len > limit)            /* would end beyond the kept range (or the data) */
-		return;
 	const uint32_t *pw = reinterpret_cast<const uint32_t *>(A.pat_blob + __ldg(&A.pat_off[pid]));
 	const uint32_t *tw = reinterpret_cast<const uint32_t *>(data + (s & ~3ull));
 	const uint32_t sh = (uint32_t)(s & 3) * 8;
@@ -332,14 +329,36 @@ k_scan_sampled4(const AutDev A, const EmitCtx E, const uint8_t *__restrict__ dat
 				pend &= pend - 1;
 				uint32_t ci = __shfl_sync(FULL_MASK, cbegin, src) - 1;
 				const uint64_t ew = __shfl_sync(FULL_MASK, e, src);
+				/* the aligned words around the window: enough for any candidate's first 8 bytes */
+				const uint32_t *wp = reinterpret_cast<const uint32_t *>(data + ew);
+				const uint64_t wm = ew >= 4 ? __ldg(wp - 1) : 0u;
+				const uint64_t w0 = __ldg(wp);
+				const uint64_t w1 = (ew + 4 < n) ? __ldg(wp + 1) : 0u;
 				for (;;) {
-					const uint32_t c = __ldg(&A.cand[ci]);
-					const uint32_t j = (c >> ACM_CAND_J_SHIFT) & 3u;
-					if (ew >= j && ew - j >= E.valid_lo)
-						s4_verify(A, E, data, c & ACM_CAND_ID_MASK, ew - j, limit, lane);
-					if (c & ACM_CAND_LAST)
+					/* one candidate per lane (lists are padded, lanes past LAST are ignored) */
+					const uint4 c = __ldg(reinterpret_cast<const uint4 *>(A.cand) + ci + lane);
+					const uint32_t lastm = __ballot_sync(FULL_MASK, (c.x & ACM_CAND_LAST) != 0);
+					const int nvalid = lastm ? __ffs(lastm) : 32;
+					const uint32_t j = (c.x >> ACM_CAND_J_SHIFT) & 3u;
+					const uint32_t len = c.w;
+					const uint32_t t0 = (uint32_t)(((w0 << 32) | wm) >> (32 - 8 * j));
+					const uint32_t t1 = (uint32_t)(((w1 << 32) | w0) >> (32 - 8 * j));
+					const uint32_t m1 = len >= 8 ? 0xffffffffu : ((1u << (8 * (len - 4))) - 1u);
+					const uint64_t s = ew - j;
+					const bool ok = lane < nvalid && ew >= j && s >= E.valid_lo && s + len <= limit &&
+					    t0 == c.y && ((t1 ^ c.z) & m1) == 0;
+					if (ok && len <= 8)
+						emit_record(E, s + len - 1, c.x & ACM_CAND_ID_MASK);
+					uint32_t surv = __ballot_sync(FULL_MASK, ok && len > 8);
+					while (surv) {
+						const int l = __ffs(surv) - 1;
+						surv &= surv - 1;
+						s4_verify(A, E, data, __shfl_sync(FULL_MASK, c.x, l) & ACM_CAND_ID_MASK,
+						    __shfl_sync(FULL_MASK, len, l), __shfl_sync(FULL_MASK, s, l), lane);
+					}
+					if (lastm)
 						break;
-					++ci;
+					ci += 32;
 				}
 			}
 		}
