@@ -315,6 +315,11 @@ build_filters(struct acm_core *c)
 			t->cand[k].pre1 = (uint32_t)pb[4] | ((uint32_t)pb[5] << 8) | ((uint32_t)pb[6] << 16) |
 			    ((uint32_t)pb[7] << 24);
 			t->cand[k].len = (uint32_t)c->pats[pid].n;
+			{
+				const unsigned char *pe = pb + c->pats[pid].n - 4;   /* n >= 7 here */
+				t->cand[k].tail = (uint32_t)pe[0] | ((uint32_t)pe[1] << 8) | ((uint32_t)pe[2] << 16) |
+				    ((uint32_t)pe[3] << 24);
+			}
 			if (first) {
 				uint32_t g = tr[k].gram;
 				for (s = (g * ACM_HASH3_MUL) >> (32 - lg);; s = (s + 1) & (slots - 1))

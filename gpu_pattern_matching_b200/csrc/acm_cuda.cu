@@ -78,6 +78,7 @@ struct acm_scanner {
 	uint8_t  *stage[2];
 	uint64_t  stage_bytes;
 	cudaEvent_t ev_copied[2], ev_free[2];
+	uint64_t *trace;            /* ACM_TRACE=1: per-CTA timestamps of the last K1 launch */
 	uint64_t *h_keys;           /* pinned bounce buffer for results */
 	uint64_t  h_keys_cap;
 };
@@ -563,7 +564,7 @@ acm_scanner_free(struct acm_scanner *s)
 	cudaStreamSynchronize(s->dev->copy_stream);
 	cudaFree(s->buckets); cudaFree(s->counts); cudaFree(s->offsets); cudaFree(s->flags);
 	cudaFree(s->tile_state); cudaFree(s->out); cudaFree(s->tmp); cudaFree(s->hist);
-	cudaFree(s->stage[0]); cudaFree(s->stage[1]);
+	cudaFree(s->stage[0]); cudaFree(s->stage[1]); cudaFree(s->trace);
 	if (s->h_flags)
 		cudaFreeHost(s->h_flags);
 	if (s->h_keys)
@@ -651,6 +652,8 @@ acm_scanner_create(struct acm_device *dev, struct acm_automaton *aut, uint64_t m
 	SALLOC(s->tile_state, (size_t)s->max_tiles * 8);
 	s->out_cap = 1u << 16;
 	SALLOC(s->out, s->out_cap * 8);
+	if (getenv("ACM_TRACE"))
+		SALLOC(s->trace, 1024 * 4 * 8);
 #undef SALLOC
 	if (cudaHostAlloc((void **)&s->h_flags, 64, cudaHostAllocDefault) != cudaSuccess) {
 		acm_set_error("scanner_create: cudaHostAlloc failed");
@@ -701,12 +704,16 @@ launch_k1(struct acm_scanner *s, cudaStream_t st, const void *d_data, uint64_t n
 	if (limit <= E.emit_lo)
 		return ACM_OK;
 	if (s->p.mode == ACM_MODE_SAMPLED4) {
-		const uint64_t tile = (uint64_t)S4_THREADS * S4_UNROLL;
-		uint64_t blocks = (vec_hi - vec_lo + tile - 1) / tile;
+		/* persistent: one CTA per SM, warps pull 16 KiB units from flags[4] */
+		const uint64_t unit = 32ull * S4_UNROLL * S4_UNIT_CHUNKS * (S4_THREADS / 32);
+		uint64_t blocks = (vec_hi - vec_lo + unit - 1) / unit;
 		if (blocks > (uint64_t)s->dev->sm_count)
 			blocks = s->dev->sm_count;
+		CUDA_TRY(cudaMemsetAsync(s->flags + 4, 0, 8, st));
+		/* the last two chunks per resident warp are handed out singly */
 		k_scan_sampled4<<<(unsigned)blocks, S4_THREADS, S4_SMEM_BYTES, st>>>(a->d, E,
-		    (const uint8_t *)d_data, n, vec_lo, vec_hi, limit);
+		    (const uint8_t *)d_data, n, vec_lo, vec_hi, limit, s->flags + 4,
+		    (uint32_t)(blocks * (S4_THREADS / 32) * 2));
 	} else if (s->p.mode == ACM_MODE_START2) {
 		const uint64_t tile = (uint64_t)S2_THREADS * S2_UNROLL;
 		uint64_t blocks = (vec_hi - vec_lo + tile - 1) / tile;
@@ -768,6 +775,9 @@ scan_on_stream(struct acm_scanner *s, cudaStream_t st, const void *d_data, uint6
 	E.emit_lo = emit_lo;
 	E.emit_hi = emit_hi;
 	E.valid_lo = valid_lo;
+	E.trace = s->trace;
+	if (s->trace)
+		CUDA_TRY(cudaMemsetAsync(s->trace, 0, 1024 * 4 * 8, st));
 	E.cap = s->cap;
 	E.shift = s->shift;
 
@@ -872,6 +882,21 @@ acm_scan_device_ex(struct acm_scanner *s, const void *d_data, uint64_t n, uint64
 		return ACM_ERR_ARG;
 	}
 	return scan_on_stream(s, s->dev->stream, d_data, n, valid_lo, emit_lo, emit_hi, res);
+}
+
+/* ACM_TRACE=1: copies {t_entry, t_ready, t_exit, chunks} x n_ctas (ns, globaltimer) of the last scan kernel */
+extern "C" int
+acm_scan_trace(struct acm_scanner *s, uint64_t *h_out, uint32_t n_ctas)
+{
+	if (!s->trace) {
+		acm_set_error("scan_trace: set ACM_TRACE=1 before creating the scanner");
+		return ACM_ERR_STATE;
+	}
+	if (n_ctas > 1024)
+		n_ctas = 1024;
+	CUDA_TRY(cudaSetDevice(s->dev->ordinal));
+	CUDA_TRY(cudaMemcpy(h_out, s->trace, (size_t)n_ctas * 32, cudaMemcpyDeviceToHost));
+	return ACM_OK;
 }
 
 extern "C" const uint64_t *

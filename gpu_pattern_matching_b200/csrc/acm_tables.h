@@ -46,7 +46,8 @@ struct acm_gram_slot {     /* exact 4-gram table, open addressing in HBM/L2 */
 
 /*
  * candidate: pattern `id` has the gram at byte offset j; LAST marks the end of a gram's
- * list.  pre0/pre1 are the pattern's first 8 bytes (zero padded) for a quick reject.
+ * list.  pre0/pre1 (first 8 bytes, zero padded) and tail (last 4 bytes) give a quick reject
+ * before the full compare; 32 bytes per record = two 16-byte loads.
  */
 #define ACM_CAND_ID_MASK 0x00FFFFFFu
 #define ACM_CAND_J_SHIFT 24
@@ -55,8 +56,10 @@ struct acm_gram_slot {     /* exact 4-gram table, open addressing in HBM/L2 */
 
 struct acm_cand {
 	uint32_t info;         /* id | j << 24 | LAST */
-	uint32_t pre0, pre1;
+	uint32_t pre0, pre1;   /* pattern bytes 0..7 */
 	uint32_t len;
+	uint32_t tail;         /* pattern bytes len-4 .. len-1 */
+	uint32_t pad[3];
 };
 
 struct acm_tables {

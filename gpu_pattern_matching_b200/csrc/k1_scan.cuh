@@ -72,6 +72,7 @@ struct EmitCtx {
 	uint64_t *out;           /* direct mode: dense output                           */
 	uint64_t  emit_lo, emit_hi;
 	uint64_t  valid_lo;      /* positions before this are never read nor used as walk starts */
+	uint64_t *trace;         /* optional: per CTA {t_entry, t_ready, t_exit, chunks} (globaltimer ns) */
 	uint32_t  cap;
 	uint32_t  shift;
 	int       direct;
@@ -83,6 +84,13 @@ struct EmitCtx {
 __device__ __forceinline__ uint32_t smem_u32(const void *p)
 {
 	return (uint32_t)__cvta_generic_to_shared(p);
+}
+
+__device__ __forceinline__ uint64_t globaltimer_ns()
+{
+	uint64_t t;
+	asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+	return t;
 }
 
 __device__ __forceinline__ uint32_t lanemask_lt()
@@ -196,6 +204,7 @@ __device__ __forceinline__ uint4 load_vec(const uint8_t *__restrict__ data, uint
 
 #define S4_THREADS 1024
 #define S4_UNROLL  4
+#define S4_UNIT_CHUNKS 8
 #define S4_SMEM_BYTES ((F1_WORDS + F2_WORDS) * 4 + 16)
 #define FULL_MASK 0xffffffffu
 
@@ -235,14 +244,17 @@ __device__ __forceinline__ void s4_verify(const AutDev &A, const EmitCtx &E, con
 
 __global__ void __launch_bounds__(S4_THREADS, 1)
 k_scan_sampled4(const AutDev A, const EmitCtx E, const uint8_t *__restrict__ data, uint64_t n,
-    uint64_t vec_lo, uint64_t vec_hi, uint64_t limit)
+    uint64_t vec_lo, uint64_t vec_hi, uint64_t limit, uint32_t *work_counter, uint32_t tail_chunks)
 {
 	extern __shared__ __align__(128) uint32_t s4_smem[];
 	uint32_t *f1 = s4_smem;
 	uint32_t *f2 = s4_smem + F1_WORDS;
 	uint64_t *bar = reinterpret_cast<uint64_t *>(s4_smem + F1_WORDS + F2_WORDS);
 	const int lane = threadIdx.x & 31;
+	uint32_t trace_chunks = 0;
 
+	if (E.trace && threadIdx.x == 0)
+		E.trace[blockIdx.x * 4 + 0] = globaltimer_ns();
 	/* stage both bitmaps with TMA bulk copies, 32 KiB each */
 	if (threadIdx.x == 0) {
 		mbar_init(bar, 1);
@@ -254,31 +266,76 @@ k_scan_sampled4(const AutDev A, const EmitCtx E, const uint8_t *__restrict__ dat
 	}
 	__syncthreads();
 
-	const uint64_t tile_vecs = (uint64_t)S4_THREADS * S4_UNROLL;
-	const uint64_t stride = (uint64_t)gridDim.x * tile_vecs;
-	uint64_t first = vec_lo + (uint64_t)blockIdx.x * tile_vecs;
+	/*
+	 * Work distribution.  The range is cut into chunks of 32 lanes x S4_UNROLL vectors
+	 * (2 KiB; a lane reads vectors chunk_base + u * 32 + lane, so each load instruction
+	 * covers 512 contiguous bytes).  Warps pull runs of S4_UNIT_CHUNKS chunks from
+	 * work_counter[0], one run ahead of use, so SMs that run slower (far-die L2,
+	 * verification-heavy regions) simply take fewer; the last tail_chunks chunks are handed
+	 * out one at a time from work_counter[1] so that no warp is left holding 32 KiB of
+	 * work when the others have run dry.
+	 */
+	const uint64_t chunk_vecs = 32ull * S4_UNROLL;
+	const uint64_t n_chunks = (vec_hi - vec_lo + chunk_vecs - 1) / chunk_vecs;
+	const uint64_t n_big = (n_chunks > tail_chunks ? n_chunks - tail_chunks : 0) / S4_UNIT_CHUNKS;
+	const uint64_t tail0 = n_big * S4_UNIT_CHUNKS;            /* first chunk of the tail zone */
+	/* a run is (first chunk, number of chunks); count 0 = nothing left */
+	auto grab = [&](uint64_t &start, uint32_t &count) {
+		start = 0;
+		count = 0;
+		if (lane == 0) {
+			const uint64_t u = atomicAdd(&work_counter[0], 1u);
+			if (u < n_big) {
+				start = u * S4_UNIT_CHUNKS;
+				count = S4_UNIT_CHUNKS;
+			} else {
+				const uint64_t t = tail0 + atomicAdd(&work_counter[1], 1u);
+				if (t < n_chunks) {
+					start = t;
+					count = 1;
+				}
+			}
+		}
+	};
+	uint64_t run_start, next_start;
+	uint32_t run_count, next_count;
+	grab(run_start, run_count);
+	grab(next_start, next_count);
+	run_start = __shfl_sync(FULL_MASK, run_start, 0);
+	run_count = __shfl_sync(FULL_MASK, run_count, 0);
 
-	/* the first tile's loads fly while the bitmaps land */
+	/* the first chunk's loads fly while the bitmaps land */
 	uint4 v[S4_UNROLL], nx[S4_UNROLL];
+	uint64_t first = vec_lo + run_start * chunk_vecs;        /* first vector of the chunk in nx */
 #pragma unroll
 	for (int u = 0; u < S4_UNROLL; ++u) {
-		const uint64_t idx = first + (uint64_t)u * S4_THREADS + threadIdx.x;
-		nx[u] = (idx < vec_hi) ? load_vec(data, idx) : make_uint4(0, 0, 0, 0);
+		const uint64_t idx = first + (uint64_t)u * 32 + lane;
+		nx[u] = (run_count && idx < vec_hi) ? load_vec(data, idx) : make_uint4(0, 0, 0, 0);
 	}
 	mbar_wait(bar, 0);
+	if (E.trace && threadIdx.x == 0)
+		E.trace[blockIdx.x * 4 + 1] = globaltimer_ns();
 
-	for (; first < vec_hi; first += stride) {
+	while (run_count) {
+		++trace_chunks;
 #pragma unroll
 		for (int u = 0; u < S4_UNROLL; ++u)
 			v[u] = nx[u];
-		/* software pipeline: next tile's 64 bytes per thread are in flight during this one */
-		{
-			const uint64_t nfirst = first + stride;
+		/* software pipeline: the next chunk's 64 bytes per lane are in flight during this one */
+		const uint64_t cur_first = first;
+		if (--run_count == 0) {
+			run_start = __shfl_sync(FULL_MASK, next_start, 0);
+			run_count = __shfl_sync(FULL_MASK, next_count, 0);
+			if (run_count)
+				grab(next_start, next_count);
+			first = vec_lo + run_start * chunk_vecs;
+		} else {
+			first += chunk_vecs;
+		}
 #pragma unroll
-			for (int u = 0; u < S4_UNROLL; ++u) {
-				const uint64_t idx = nfirst + (uint64_t)u * S4_THREADS + threadIdx.x;
-				nx[u] = (idx < vec_hi) ? load_vec(data, idx) : make_uint4(0, 0, 0, 0);
-			}
+		for (int u = 0; u < S4_UNROLL; ++u) {
+			const uint64_t idx = first + (uint64_t)u * 32 + lane;
+			nx[u] = (run_count && idx < vec_hi) ? load_vec(data, idx) : make_uint4(0, 0, 0, 0);
 		}
 		uint32_t hits = 0;
 #pragma unroll
@@ -319,8 +376,7 @@ k_scan_sampled4(const AutDev A, const EmitCtx E, const uint8_t *__restrict__ dat
 						}
 						sl = (sl + 1) & A.gram_mask;
 					}
-					e = (first + (uint64_t)(q >> 2) * S4_THREADS + threadIdx.x) * 16 +
-					    (uint64_t)(q & 3) * 4;
+					e = (cur_first + (uint64_t)(q >> 2) * 32 + lane) * 16 + (uint64_t)(q & 3) * 4;
 				}
 			}
 			uint32_t pend = __ballot_sync(FULL_MASK, cbegin != 0);
@@ -336,7 +392,8 @@ k_scan_sampled4(const AutDev A, const EmitCtx E, const uint8_t *__restrict__ dat
 				const uint64_t w1 = (ew + 4 < n) ? __ldg(wp + 1) : 0u;
 				for (;;) {
 					/* one candidate per lane (lists are padded, lanes past LAST are ignored) */
-					const uint4 c = __ldg(reinterpret_cast<const uint4 *>(A.cand) + ci + lane);
+					const uint4 *cp = reinterpret_cast<const uint4 *>(A.cand) + 2 * (size_t)(ci + lane);
+					const uint4 c = __ldg(cp);
 					const uint32_t lastm = __ballot_sync(FULL_MASK, (c.x & ACM_CAND_LAST) != 0);
 					const int nvalid = lastm ? __ffs(lastm) : 32;
 					const uint32_t j = (c.x >> ACM_CAND_J_SHIFT) & 3u;
@@ -345,8 +402,18 @@ k_scan_sampled4(const AutDev A, const EmitCtx E, const uint8_t *__restrict__ dat
 					const uint32_t t1 = (uint32_t)(((w1 << 32) | w0) >> (32 - 8 * j));
 					const uint32_t m1 = len >= 8 ? 0xffffffffu : ((1u << (8 * (len - 4))) - 1u);
 					const uint64_t s = ew - j;
-					const bool ok = lane < nvalid && ew >= j && s >= E.valid_lo && s + len <= limit &&
+					bool ok = lane < nvalid && ew >= j && s >= E.valid_lo && s + len <= limit &&
 					    t0 == c.y && ((t1 ^ c.z) & m1) == 0;
+					if (ok && len > 8) {
+						/* the pattern's last 4 bytes against the text: repetitive text makes many
+						 * candidates share their first 8 bytes, very few also share their end */
+						const uint64_t ta = s + len - 4;
+						const uint32_t *tp = reinterpret_cast<const uint32_t *>(data + (ta & ~3ull));
+						const uint32_t sh = (uint32_t)(ta & 3) * 8;
+						const uint32_t a0 = __ldg(tp);
+						const uint32_t a1 = sh ? __ldg(tp + 1) : 0u;
+						ok = __funnelshift_r(a0, a1, sh) == __ldg(reinterpret_cast<const uint32_t *>(cp + 1));
+					}
 					if (ok && len <= 8)
 						emit_record(E, s + len - 1, c.x & ACM_CAND_ID_MASK);
 					uint32_t surv = __ballot_sync(FULL_MASK, ok && len > 8);
@@ -362,6 +429,10 @@ k_scan_sampled4(const AutDev A, const EmitCtx E, const uint8_t *__restrict__ dat
 				}
 			}
 		}
+	}
+	if (E.trace && lane == 0) {
+		atomicMax((unsigned long long *)&E.trace[blockIdx.x * 4 + 2], (unsigned long long)globaltimer_ns());
+		atomicAdd((unsigned long long *)&E.trace[blockIdx.x * 4 + 3], (unsigned long long)trace_chunks);
 	}
 }
 

@@ -138,6 +138,10 @@ const uint64_t *acm_scan_keys(struct acm_scanner *);
 int64_t acm_scan_fetch(struct acm_scanner *, uint64_t base, uint64_t *h_off,
             uint32_t *h_pat, uint64_t cap);
 
+/* tracing: with ACM_TRACE=1 in the environment at scanner creation, the scan kernel records per-CTA
+ * {t_entry, t_ready, t_exit, chunks} (globaltimer ns); this copies n_ctas x 4 u64 to h_out */
+int  acm_scan_trace(struct acm_scanner *, uint64_t *h_out, uint32_t n_ctas);
+
 /* add the last scan's per-pattern match counts into d_counts[num_patterns] (u64, device) */
 int  acm_scan_histogram(struct acm_scanner *, uint64_t *d_counts);
 

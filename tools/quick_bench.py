@@ -41,6 +41,16 @@ def run(dev, name, pats, n, modes, text=None, plants=0, iters=5):
               f"fallback={best.fallback} scan {best.ms_scan:.3f} ms = {gbs:.1f} GB/s "
               f"({gbs / 6531.6 * 100:.1f}% of measured HBM) prefix {best.ms_prefix:.3f} ms "
               f"compact {best.ms_compact:.3f} ms total {best.ms_total:.3f} ms", flush=True)
+        if os.environ.get("ACM_TRACE") and mode == 1:
+            import ctypes as C
+            tr = np.zeros(148 * 4, dtype=np.uint64)
+            g.lib().acm_scan_trace(sc._h, tr.ctypes.data_as(g._lib.u64p), 148)
+            tr = tr.reshape(148, 4).astype(np.int64)
+            t0 = tr[:, 0].min()
+            print("  trace(us): entry min/max %.1f/%.1f ready min/max %.1f/%.1f exit min/max %.1f/%.1f chunks/CTA min/max %d/%d" % (
+                (tr[:, 0].min() - t0) / 1e3, (tr[:, 0].max() - t0) / 1e3, (tr[:, 1].min() - t0) / 1e3,
+                (tr[:, 1].max() - t0) / 1e3, (tr[:, 2].min() - t0) / 1e3, (tr[:, 2].max() - t0) / 1e3,
+                tr[:, 3].min(), tr[:, 3].max()), flush=True)
         sc.close()
     dev.free(d)
     a.free()
