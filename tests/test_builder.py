@@ -1,0 +1,141 @@
+"""Host side of the product (no GPU): the C builder behind acsmx.h / iacsmx.h reproduces the
+reference's automaton bit for bit (via acsm_export_ref_table), the pattern-file loader follows
+the reference grammar, error paths return codes instead of exiting."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+import gpu_pattern_matching_b200 as g
+from gpu_pattern_matching_b200 import _lib
+from helpers import HAND_PATTERNS, build_oracle, build_product, clamav_pats, load_patterns
+from oracle_lib import (Oracle, RefAcsm, materialize, parse_pattern_file, read_fixture,
+                        ref_available)
+
+
+def _same_table(at, ot, alpha=256):
+    neg = ot[:, :alpha] < 0
+    return (at.shape == ot.shape and np.array_equal(ot[:, :alpha], at[:, :alpha]) and
+            np.array_equal(ot[:, alpha:][neg], at[:, alpha:][neg]))
+
+
+@pytest.mark.parametrize("name", ["hand", "kat_pat_a.txt", "kat_pat_b.txt", "kat_pat_c.txt",
+                                  "kat_pat_two_words.txt", "kat_pat_categorical_small.txt",
+                                  "sentiment_categorical.pat.gz", "clamav2000"])
+def test_exported_table_equals_oracle(name):
+    if name == "hand":
+        pats = [(p, i) for i, p in enumerate(HAND_PATTERNS)]
+    elif name.startswith("clamav"):
+        pats = clamav_pats(int(name[6:]))
+    else:
+        pats = load_patterns(name)
+    o, a = build_oracle(pats), build_product(pats, upload=False)
+    assert a.get_states() == o.num_states - 1       # highest id before gen_state_table (acsmx.c:615)
+    assert a.get_max_pattern_size() == o.max_pattern_len
+    assert _same_table(a.export_ref_table(), o.ref_table())
+    a.free()
+    o.close()
+
+
+@pytest.mark.slow
+def test_exported_table_equals_oracle_15000():
+    pats = clamav_pats(15000)
+    o, a = build_oracle(pats), build_product(pats, upload=False)
+    assert o.num_states == 661298
+    assert _same_table(a.export_ref_table(), o.ref_table())
+
+
+@pytest.mark.skipif(not ref_available(), reason="oracle/_ref not built")
+def test_exported_table_equals_compiled_reference():
+    pats = clamav_pats(2000)
+    r = RefAcsm()
+    for p, iid in pats:
+        r.add(p, iid)
+    r.compile()
+    a = build_product(pats, upload=False)
+    assert _same_table(a.export_ref_table(), r.h_trans())
+    r.close()
+
+
+def test_ushort_builder_table():
+    sigs = [[666, 676], [7, 6, 5], [1, 2, 3], [6, 5], [2047, 0, 2047]]
+    o = Oracle(2048)
+    m = g.Iacsm()
+    for k, s in enumerate(sigs):
+        o.add(s, 100 + k)
+        m.add_pattern(s, 100 + k)
+    m.add_fullpattern("40,32,287", 7)
+    o.add_csv("40,32,287", 7)
+    o.compile()
+    m.compile()
+    assert m.get_states() == o.num_states - 1 and m.get_max_pattern_size() == 3
+    assert _same_table(m.export_ref_table(), o.ref_table(), 2048)
+    with pytest.raises(g.AcmError):
+        g.Iacsm().add_pattern([1, 2048], 0)          # symbol outside the alphabet
+
+
+def test_patterns_table_and_indices():
+    a = g.Acsm()
+    a.add_pattern(b"one", 11)
+    a.add_pattern(b"tw\x00o", -5)                     # embedded NUL survives (reference truncates)
+    a.add_pattern(b"one", 12)
+    a.compile()
+    tab = a.get_patterns_table()
+    assert tab == [(b"one", 11, 0), (b"tw\x00o", -5, 1), (b"one", 12, 2)]
+    assert a.num_patterns == 3 and a.get_min_pattern_size() == 3 and a.get_max_pattern_size() == 4
+
+
+def test_pattern_file_loader_follows_reference_grammar(tmp_path):
+    for name, hexp, limit in (("kat_pat_a.txt", False, -1), ("kat_pat_categorical_small.txt", False, -1),
+                              ("sentiment_categorical.pat.gz", False, -1),
+                              ("sentiment_categorical.pat.gz", False, 3),
+                              ("clamav_sigs_15000.hex.gz", True, -1), ("clamav_sigs_15000.hex.gz", True, 12)):
+        path = materialize(name, tmp_path)
+        a = g.Acsm()
+        n = a.load_pattern_file(path, hexp, limit)
+        want = parse_pattern_file(read_fixture(name), hexp, limit)
+        assert n == len(want)
+        a.compile()
+        got = a.get_patterns_table()
+        assert [(p, i) for p, i, _ in got] == want
+        a.free()
+
+
+def test_pattern_file_errors(tmp_path):
+    a = g.Acsm()
+    with pytest.raises(g.AcmError):
+        a.load_pattern_file(tmp_path / "missing.txt")
+    bad = tmp_path / "odd.hex"
+    bad.write_text("4d5a9\n")
+    with pytest.raises(g.AcmError):
+        a.load_pattern_file(bad, hex_pat=True)        # the reference exit()s here (utils.c:39-42)
+    quoted = tmp_path / "q.txt"
+    quoted.write_text('7 "a b"\n-3 " spaced "\n+12 plain\n')
+    b = g.Acsm()
+    assert b.load_pattern_file(quoted) == 3
+    b.compile()
+    assert [(p, i) for p, i, _ in b.get_patterns_table()] == [(b"a b", 7), (b" spaced ", -3), (b"plain", 12)]
+
+
+def test_error_codes_instead_of_exit():
+    L = g.lib()
+    a = g.Acsm()
+    a.add_pattern(b"", 1)                             # zero length: kept, flagged, never matches
+    assert a.status() == -15                          # ACM_ERR_EMPTY_PATTERN
+    a.add_pattern(b"ok", 2)
+    a.compile()
+    assert a.num_patterns == 2 and a.get_states() == 2
+    with pytest.raises(g.AcmError):
+        a.gen_state_table()                           # no GPU here: must fail loudly, not fall back
+    h = L.printable_hex_to_bytes(b"4D5a90")
+    assert h and bytes((C.c_ubyte * 3).from_address(h)) == b"\x4d\x5a\x90"
+    assert not L.printable_hex_to_bytes(b"4d5")
+    assert not L.printable_hex_to_bytes(b"zz")
+
+
+def test_filter_tables_cover_every_pattern():
+    """Every pattern's four leading 4-grams must be present in both bitmaps: checked through the
+    exported reference table indirectly by test_gpu_parity; here: builder statistics."""
+    pats = clamav_pats(2000)
+    a = build_product(pats, upload=False)
+    assert a.get_min_pattern_size() == 10 and a.get_max_pattern_size() == 159
