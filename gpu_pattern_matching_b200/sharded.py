@@ -1,0 +1,127 @@
+"""One process per GPU: contiguous byte-range shards with a leading halo, a replicated
+automaton, and torch.distributed (NCCL on GPUs, gloo in the CPU tests) used only for the
+small exchange that follows the scan: an all-gather of the per-rank match counts and a
+gather of the sorted key lists to rank 0.
+
+Because every rank keeps only matches that END inside its own range and sorts locally, the
+global canonical list is the concatenation of the per-rank lists in rank order: no merge.
+Nothing here touches the scan itself; the per-rank scan is libacmatch_b200.so.
+"""
+import numpy as np
+import torch
+import torch.distributed as dist
+
+KEY_PAT_BITS = 24
+KEY_PAT_MASK = (1 << KEY_PAT_BITS) - 1
+
+
+def shard_bounds(total_bytes, world, rank, align=16):
+    """[lo, hi) of rank's shard; cuts are multiples of `align` (device buffers are 16-byte
+    aligned and the scan windows are aligned to the buffer)."""
+    def cut(r):
+        if r >= world:
+            return total_bytes
+        return (total_bytes * r // world) // align * align
+    return cut(rank), cut(rank + 1)
+
+
+def shard_window(total_bytes, world, rank, max_pattern_len, align=16):
+    """(read_lo, lo, hi): the shard reads [read_lo, hi) and keeps matches ending in [lo, hi).
+    read_lo is `lo` minus the halo of Lmax-1 bytes, rounded down to `align`."""
+    lo, hi = shard_bounds(total_bytes, world, rank, align)
+    halo = max(0, max_pattern_len - 1)
+    read_lo = max(0, lo - halo) // align * align
+    return read_lo, lo, hi
+
+
+def exchange_counts(n_local, device):
+    """All-gather of the per-rank match counts -> python list (one small collective)."""
+    world = dist.get_world_size()
+    mine = torch.tensor([int(n_local)], dtype=torch.int64, device=device)
+    outs = [torch.empty(1, dtype=torch.int64, device=device) for _ in range(world)]
+    dist.all_gather(outs, mine)
+    return [int(x.item()) for x in outs]
+
+
+def gather_keys(keys, counts, dst=0):
+    """Variable-length gather of the per-rank sorted key tensors (int64, already offset to
+    global positions) to rank `dst`.  Returns the concatenated tensor on dst, None elsewhere."""
+    rank, world = dist.get_rank(), dist.get_world_size()
+    if rank != dst:
+        if counts[rank]:
+            dist.send(keys[:counts[rank]].contiguous(), dst=dst)
+        return None
+    out = torch.empty(sum(counts), dtype=torch.int64, device=keys.device)
+    pos = 0
+    for r in range(world):
+        n = counts[r]
+        if n:
+            if r == dst:
+                out[pos:pos + n] = keys[:n]
+            else:
+                dist.recv(out[pos:pos + n], src=r)
+        pos += n
+    return out
+
+
+def allreduce_histogram(hist):
+    """Per-pattern counts over all shards (int64 tensor, summed in place)."""
+    dist.all_reduce(hist, op=dist.ReduceOp.SUM)
+    return hist
+
+
+def unpack_keys(keys):
+    """int64 key tensor / array -> (end offsets u64, pattern indices u32) numpy arrays."""
+    k = keys.cpu().numpy().astype(np.uint64) if isinstance(keys, torch.Tensor) else \
+        np.asarray(keys, dtype=np.uint64)
+    return k >> np.uint64(KEY_PAT_BITS), (k & np.uint64(KEY_PAT_MASK)).astype(np.uint32)
+
+
+def pack_keys(off, pat):
+    return (np.asarray(off, dtype=np.uint64) << np.uint64(KEY_PAT_BITS)) | np.asarray(pat, dtype=np.uint64)
+
+
+class ShardedScan:
+    """Per-rank state for scanning one shard of a stream that lives in this rank's HBM.
+
+    data_ptr / n describe the device buffer holding stream bytes [read_lo, hi)."""
+
+    def __init__(self, device, automaton, total_bytes, max_pattern_len, scanner_kwargs=None):
+        from .matcher import Scanner
+        self.rank, self.world = dist.get_rank(), dist.get_world_size()
+        self.read_lo, self.lo, self.hi = shard_window(total_bytes, self.world, self.rank, max_pattern_len)
+        self.scanner = Scanner(device, automaton, max(1, self.hi - self.lo), **(scanner_kwargs or {}))
+        self.device = device
+        self.tdev = torch.device("cuda", device.ordinal)
+
+    def scan(self, data_ptr):
+        """Scan the shard; returns the ScanResult (matches stay on the device)."""
+        n = self.hi - self.read_lo
+        return self.scanner.scan_device(data_ptr, n, emit_lo=self.lo - self.read_lo, emit_hi=n)
+
+    def local_keys(self, res):
+        """The sorted keys of the last scan as an int64 torch view shifted to stream offsets."""
+        n = int(res.n_matches)
+        if n == 0:
+            return torch.empty(0, dtype=torch.int64, device=self.tdev)
+        ptr = self.scanner.keys_ptr()
+        arr = _as_tensor(ptr, n, self.tdev)
+        return arr + (self.read_lo << KEY_PAT_BITS)
+
+    def gather(self, res, dst=0):
+        """Count exchange + key gather.  Returns (offsets, patterns) numpy arrays on dst."""
+        counts = exchange_counts(res.n_matches, self.tdev)
+        out = gather_keys(self.local_keys(res), counts, dst)
+        if out is None:
+            return None
+        return unpack_keys(out)
+
+
+class _CudaArrayView:
+    def __init__(self, ptr, n):
+        self.__cuda_array_interface__ = {"shape": (n,), "typestr": "<i8", "data": (ptr, False),
+                                         "version": 3, "strides": None}
+
+
+def _as_tensor(ptr, n, tdev):
+    return torch.as_tensor(_CudaArrayView(ptr, n), device=tdev)
