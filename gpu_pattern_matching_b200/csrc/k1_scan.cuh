@@ -350,6 +350,14 @@ k_scan_sampled4(const AutDev A, const EmitCtx E, const uint8_t *__restrict__ dat
 				hits = __funnelshift_l(t, hits, 1);
 			}
 		}
+		/* the last chunk may stick out past vec_hi: those vectors were not loaded (zeros) and
+		 * must not be tested -- an all-zero window is a real, and popular, pattern gram */
+		if (cur_first + chunk_vecs > vec_hi) {
+#pragma unroll
+			for (int u = 0; u < S4_UNROLL; ++u)
+				if (cur_first + (uint64_t)u * 32 + lane >= vec_hi)
+					hits &= ~(0xF000u >> (4 * u));
+		}
 		/* bit (15 - q) of hits belongs to window q = u * 4 + k.  Survivors are rare: from
 		 * here on control flow is warp-uniform and verification is done by the whole warp. */
 		while (__any_sync(FULL_MASK, hits != 0)) {
