@@ -120,6 +120,12 @@ __device__ __forceinline__ void bulk_g2s(void *dst, const void *src, uint32_t by
 	    ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
 }
 
+/* pull [p, p + bytes) into L2; p 16-byte aligned, bytes a multiple of 16 */
+__device__ __forceinline__ void prefetch_l2_bulk(const void *p, uint32_t bytes)
+{
+	asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p), "r"(bytes) : "memory");
+}
+
 __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity)
 {
 	asm volatile(
@@ -304,25 +310,28 @@ k_scan_sampled4(const AutDev A, const EmitCtx E, const uint8_t *__restrict__ dat
 	run_start = __shfl_sync(FULL_MASK, run_start, 0);
 	run_count = __shfl_sync(FULL_MASK, run_count, 0);
 
-	/* the first chunk's loads fly while the bitmaps land */
-	uint4 v[S4_UNROLL], nx[S4_UNROLL];
-	uint64_t first = vec_lo + run_start * chunk_vecs;        /* first vector of the chunk in nx */
-#pragma unroll
-	for (int u = 0; u < S4_UNROLL; ++u) {
-		const uint64_t idx = first + (uint64_t)u * 32 + lane;
-		nx[u] = (run_count && idx < vec_hi) ? load_vec(data, idx) : make_uint4(0, 0, 0, 0);
-	}
+	/*
+	 * Latency hiding without a register double buffer (the slow path below needs the
+	 * registers): while a chunk is processed, the next one is pulled into L2 with one bulk
+	 * prefetch per warp, so the loads at the top of the next iteration are L2 hits, and the
+	 * seven other warps of the scheduler cover those.
+	 */
+	uint4 v[S4_UNROLL];
+	uint64_t first = vec_lo + run_start * chunk_vecs;        /* first vector of the next chunk */
+	if (run_count && lane == 0)
+		prefetch_l2_bulk(data + first * 16, (uint32_t)chunk_vecs * 16);
 	mbar_wait(bar, 0);
 	if (E.trace && threadIdx.x == 0)
 		E.trace[blockIdx.x * 4 + 1] = globaltimer_ns();
 
 	while (run_count) {
 		++trace_chunks;
-#pragma unroll
-		for (int u = 0; u < S4_UNROLL; ++u)
-			v[u] = nx[u];
-		/* software pipeline: the next chunk's 64 bytes per lane are in flight during this one */
 		const uint64_t cur_first = first;
+#pragma unroll
+		for (int u = 0; u < S4_UNROLL; ++u) {
+			const uint64_t idx = cur_first + (uint64_t)u * 32 + lane;
+			v[u] = (idx < vec_hi) ? load_vec(data, idx) : make_uint4(0, 0, 0, 0);
+		}
 		if (--run_count == 0) {
 			run_start = __shfl_sync(FULL_MASK, next_start, 0);
 			run_count = __shfl_sync(FULL_MASK, next_count, 0);
@@ -332,11 +341,8 @@ k_scan_sampled4(const AutDev A, const EmitCtx E, const uint8_t *__restrict__ dat
 		} else {
 			first += chunk_vecs;
 		}
-#pragma unroll
-		for (int u = 0; u < S4_UNROLL; ++u) {
-			const uint64_t idx = first + (uint64_t)u * 32 + lane;
-			nx[u] = (run_count && idx < vec_hi) ? load_vec(data, idx) : make_uint4(0, 0, 0, 0);
-		}
+		if (run_count && lane == 0)
+			prefetch_l2_bulk(data + first * 16, (uint32_t)chunk_vecs * 16);
 		uint32_t hits = 0;
 #pragma unroll
 		for (int u = 0; u < S4_UNROLL; ++u) {
