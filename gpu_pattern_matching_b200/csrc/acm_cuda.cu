@@ -796,19 +796,40 @@ scan_on_stream(struct acm_scanner *s, cudaStream_t st, const void *d_data, uint6
 	launches++;
 	if (timing)
 		CUDA_TRY(cudaEventRecord(s->ev[2], st));
-	CUDA_TRY(cudaMemcpyAsync(s->h_flags, s->flags, 16, cudaMemcpyDeviceToHost, st));
+	/*
+	 * K3 goes out right behind K2, before the host knows the total: it guards itself against
+	 * an overflowed scan (flags[0]) and against an output buffer that is too small (flags[5]);
+	 * one synchronisation per step instead of two.
+	 */
+	const uint32_t k3_warps = K3_THREADS / 32;
+	uint32_t k3_blocks = (nb + k3_warps - 1) / k3_warps;
+	if (k3_blocks > (uint32_t)s->dev->sm_count * 16)
+		k3_blocks = (uint32_t)s->dev->sm_count * 16;
+	k_bucket_sort_compact<<<k3_blocks, K3_THREADS, (size_t)s->cap * 8, st>>>(s->buckets, s->counts,
+	    s->offsets, s->out, s->cap, nb, s->out_cap, s->flags);
+	CUDA_TRY(cudaGetLastError());
+	launches++;
+	if (timing)
+		CUDA_TRY(cudaEventRecord(s->ev[3], st));
+	CUDA_TRY(cudaMemcpyAsync(s->h_flags, s->flags, 32, cudaMemcpyDeviceToHost, st));
 	CUDA_TRY(cudaStreamSynchronize(st));
 
 	const uint32_t overflow = s->h_flags[0];
 	const uint64_t total = s->h_flags[1];
-	if ((rc = grow(&s->out, &s->out_cap, total, "the match list")) != ACM_OK)
-		return rc;
+	if (total > s->out_cap) {
+		if ((rc = grow(&s->out, &s->out_cap, total, "the match list")) != ACM_OK)
+			return rc;
+		if (!overflow) {
+			k_bucket_sort_compact<<<k3_blocks, K3_THREADS, (size_t)s->cap * 8, st>>>(s->buckets,
+			    s->counts, s->offsets, s->out, s->cap, nb, s->out_cap, s->flags);
+			CUDA_TRY(cudaGetLastError());
+			launches++;
+			if (timing)
+				CUDA_TRY(cudaEventRecord(s->ev[3], st));
+		}
+	}
 	if (total && !overflow) {
-		const uint32_t warps = K3_THREADS / 32;
-		k_bucket_sort_compact<<<(nb + warps - 1) / warps, K3_THREADS, (size_t)s->cap * 8, st>>>(
-		    s->buckets, s->counts, s->offsets, s->out, s->cap, nb);
-		CUDA_TRY(cudaGetLastError());
-		launches++;
+		/* the sorted list is in place */
 	} else if (total) {
 		/* exact two-pass path: counts are exact, refill straight into place, then sort */
 		int bits = ACM_KEY_PAT_BITS;
@@ -841,11 +862,11 @@ scan_on_stream(struct acm_scanner *s, cudaStream_t st, const void *d_data, uint6
 		if ((rc = radix_sort_impl(st, s->out, s->tmp, total, 0, bits, 0, s->hist, s->tile_state,
 		    s->flags + 3, &launches)) != ACM_OK)
 			return rc;
+		if (timing)
+			CUDA_TRY(cudaEventRecord(s->ev[3], st));
 	}
-	if (timing) {
-		CUDA_TRY(cudaEventRecord(s->ev[3], st));
+	if (timing)
 		CUDA_TRY(cudaStreamSynchronize(st));
-	}
 	s->last_n = total;
 	if (res) {
 		res->n_matches = total;

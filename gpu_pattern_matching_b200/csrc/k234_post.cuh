@@ -155,75 +155,94 @@ k_scan_lookback(const uint32_t *__restrict__ in, uint32_t *__restrict__ out, uin
 
 #define K3_THREADS 128
 
+/*
+ * Launched right after K2 without waiting for the host to learn the total: `flags[0]`
+ * (a bucket overflowed -> the exact two-pass path will run instead) makes it a no-op, and a
+ * bucket whose output would not fit `out_cap` is skipped and reported in flags[5] (the host
+ * then grows the buffer and relaunches).  Persistent over buckets: 4 buckets per block-step.
+ */
 __global__ void __launch_bounds__(K3_THREADS)
 k_bucket_sort_compact(const uint64_t *__restrict__ buckets, const uint32_t *__restrict__ counts,
-    const uint32_t *__restrict__ offsets, uint64_t *__restrict__ out, uint32_t cap, uint32_t n_buckets)
+    const uint32_t *__restrict__ offsets, uint64_t *__restrict__ out, uint32_t cap, uint32_t n_buckets,
+    uint64_t out_cap, uint32_t *flags)
 {
 	extern __shared__ uint64_t k3_keys[];
 	const uint32_t lane = threadIdx.x & 31;
-
-	/* buckets with at most 32 records: one warp each, sorted in registers */
 	const uint32_t warps = K3_THREADS / 32;
-	const uint32_t b0 = blockIdx.x * warps + (threadIdx.x >> 5);
-	uint32_t cnt = 0;
-	if (b0 < n_buckets)
-		cnt = min(__ldg(&counts[b0]), cap);
-	const uint32_t big = __syncthreads_or(cnt > 32);
 
-	if (cnt > 0 && cnt <= 32) {
-		uint64_t key = (lane < cnt) ? buckets[(uint64_t)b0 * cap + lane] : ~0ull;
-		/* bitonic network across the warp */
-#pragma unroll
-		for (int k = 2; k <= 32; k <<= 1) {
-#pragma unroll
-			for (int j = k >> 1; j > 0; j >>= 1) {
-				const uint64_t other = __shfl_xor_sync(0xffffffffu, key, j);
-				const bool up = ((lane & k) == 0);
-				const bool lower = ((lane & j) == 0);
-				const bool take_min = (up == lower);
-				key = take_min ? (key < other ? key : other) : (key > other ? key : other);
+	if (*(volatile uint32_t *)flags)        /* overflow: buckets are incomplete */
+		return;
+	for (uint32_t blk = blockIdx.x; blk * warps < n_buckets; blk += gridDim.x) {
+		/* buckets with at most 32 records: one warp each, sorted in registers */
+		const uint32_t b0 = blk * warps + (threadIdx.x >> 5);
+		uint32_t cnt = 0;
+		uint64_t o0 = 0;
+		if (b0 < n_buckets) {
+			cnt = min(__ldg(&counts[b0]), cap);
+			o0 = __ldg(&offsets[b0]);
+			if (cnt && o0 + cnt > out_cap) {
+				if (lane == 0)
+					flags[5] = 1u;
+				cnt = 0;
 			}
 		}
-		if (lane < cnt)
-			out[(uint64_t)__ldg(&offsets[b0]) + lane] = key;
-	}
-	if (!big)
-		return;
+		const uint32_t big = __syncthreads_or(cnt > 32);
 
-	/* the rare larger buckets of this block: whole block, shared memory */
-	for (uint32_t w = 0; w < warps; ++w) {
-		const uint32_t b = blockIdx.x * warps + w;
-		if (b >= n_buckets)
-			break;
-		const uint32_t c = min(__ldg(&counts[b]), cap);
-		if (c <= 32)
+		if (cnt > 0 && cnt <= 32) {
+			uint64_t key = (lane < cnt) ? buckets[(uint64_t)b0 * cap + lane] : ~0ull;
+			/* bitonic network across the warp */
+#pragma unroll
+			for (int k = 2; k <= 32; k <<= 1) {
+#pragma unroll
+				for (int j = k >> 1; j > 0; j >>= 1) {
+					const uint64_t other = __shfl_xor_sync(0xffffffffu, key, j);
+					const bool up = ((lane & k) == 0);
+					const bool lower = ((lane & j) == 0);
+					const bool take_min = (up == lower);
+					key = take_min ? (key < other ? key : other) : (key > other ? key : other);
+				}
+			}
+			if (lane < cnt)
+				out[o0 + lane] = key;
+		}
+		if (!big)
 			continue;
-		uint32_t P = 64;
-		while (P < c)
-			P <<= 1;
-		for (uint32_t i = threadIdx.x; i < P; i += K3_THREADS)
-			k3_keys[i] = (i < c) ? buckets[(uint64_t)b * cap + i] : ~0ull;
-		__syncthreads();
-		for (uint32_t k = 2; k <= P; k <<= 1) {
-			for (uint32_t j = k >> 1; j > 0; j >>= 1) {
-				for (uint32_t i = threadIdx.x; i < P; i += K3_THREADS) {
-					const uint32_t ixj = i ^ j;
-					if (ixj > i) {
-						const uint64_t a = k3_keys[i], bb = k3_keys[ixj];
-						const bool up = ((i & k) == 0);
-						if ((a > bb) == up) {
-							k3_keys[i] = bb;
-							k3_keys[ixj] = a;
+
+		/* the rare larger buckets of this step: whole block, shared memory */
+		for (uint32_t w = 0; w < warps; ++w) {
+			const uint32_t b = blk * warps + w;
+			if (b >= n_buckets)
+				break;
+			const uint32_t c = min(__ldg(&counts[b]), cap);
+			const uint64_t o = __ldg(&offsets[b]);
+			if (c <= 32 || o + c > out_cap)
+				continue;
+			uint32_t P = 64;
+			while (P < c)
+				P <<= 1;
+			for (uint32_t i = threadIdx.x; i < P; i += K3_THREADS)
+				k3_keys[i] = (i < c) ? buckets[(uint64_t)b * cap + i] : ~0ull;
+			__syncthreads();
+			for (uint32_t k = 2; k <= P; k <<= 1) {
+				for (uint32_t j = k >> 1; j > 0; j >>= 1) {
+					for (uint32_t i = threadIdx.x; i < P; i += K3_THREADS) {
+						const uint32_t ixj = i ^ j;
+						if (ixj > i) {
+							const uint64_t a = k3_keys[i], bb = k3_keys[ixj];
+							const bool up = ((i & k) == 0);
+							if ((a > bb) == up) {
+								k3_keys[i] = bb;
+								k3_keys[ixj] = a;
+							}
 						}
 					}
+					__syncthreads();
 				}
-				__syncthreads();
 			}
+			for (uint32_t i = threadIdx.x; i < c; i += K3_THREADS)
+				out[o + i] = k3_keys[i];
+			__syncthreads();
 		}
-		const uint64_t o = __ldg(&offsets[b]);
-		for (uint32_t i = threadIdx.x; i < c; i += K3_THREADS)
-			out[o + i] = k3_keys[i];
-		__syncthreads();
 	}
 }
 
