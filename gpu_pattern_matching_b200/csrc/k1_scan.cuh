@@ -248,8 +248,57 @@ __device__ __forceinline__ void s4_verify(const AutDev &A, const EmitCtx &E, con
 		emit_record(E, s + len - 1, pid);
 }
 
+/*
+ * Dense-hit fallback.  On repetitive input (zero pages, period-4/8 fills) almost every
+ * aligned window is a pattern gram with a long candidate list, and filter + verify would
+ * degenerate to (windows x candidates).  A chunk whose level-1 hit count says "this is not
+ * random-looking data" is handed to the automaton instead, which is linear whatever the
+ * text: lane l owns the starts whose first aligned window lies in its 64 bytes,
+ * s in [lo - 3, lo + 60], walks the DFA cold from the first of them until no match that
+ * started there can still be open, and keeps a match iff its start is one of its own.
+ */
+#define S4_DENSE_HITS 128      /* of 512 windows per chunk; random data sees ~4..6 % */
+
+__device__ __noinline__ void s4_chunk_dfa(const AutDev *__restrict__ Ap, const EmitCtx *__restrict__ Ep,
+    const uint8_t *__restrict__ data, uint64_t chunk_lo, uint64_t limit, int lane)
+{
+	const AutDev &A = *Ap;
+	const EmitCtx &E = *Ep;
+	const uint64_t lo = chunk_lo + 64ull * (uint64_t)lane;
+	uint64_t s_min = lo >= 3 ? lo - 3 : 0;
+	if (s_min < E.valid_lo)
+		s_min = E.valid_lo;
+	const uint64_t s_max = lo + 60;
+	uint64_t end = s_max + (uint64_t)A.max_len;
+	if (end > limit)
+		end = limit;
+	uint32_t state = 0;
+	for (uint64_t pos = s_min; pos < end; ++pos) {
+		const uint32_t e = __ldg(&A.T[(size_t)state * 256 + __ldg(&data[pos])]);
+		state = e & ACM_T_MASK;
+		if (e & ACM_T_ANY) {
+			for (uint32_t v = state; v; v = __ldg(&A.olink[v])) {
+				const uint32_t b = __ldg(&A.own_begin[v]), t = __ldg(&A.own_begin[v + 1]);
+				for (uint32_t k = b; k < t; ++k) {
+					const uint32_t pid = __ldg(&A.own_pat[k]);
+					const uint64_t len = __ldg(&A.pat_len[pid]);
+					if (pos + 1 >= len + s_min && pos + 1 - len <= s_max)
+						emit_record(E, pos, pid);
+				}
+			}
+		}
+		/* past the last owned start: stop once the longest open prefix began after it */
+		if (pos >= s_max) {
+			const uint64_t d = pos - s_max;          /* symbols read beyond s_max */
+			if (state < __ldg(&A.level_start[d + 1 <= (uint64_t)A.max_len ? d + 1 : (uint64_t)A.max_len]))
+				break;
+		}
+	}
+}
+
 __global__ void __launch_bounds__(S4_THREADS, 1)
-k_scan_sampled4(const AutDev A, const EmitCtx E, const uint8_t *__restrict__ data, uint64_t n,
+k_scan_sampled4(const __grid_constant__ AutDev A, const __grid_constant__ EmitCtx E,
+    const uint8_t *__restrict__ data, uint64_t n,
     uint64_t vec_lo, uint64_t vec_hi, uint64_t limit, uint32_t *work_counter, uint32_t tail_chunks)
 {
 	extern __shared__ __align__(128) uint32_t s4_smem[];
@@ -363,6 +412,10 @@ k_scan_sampled4(const AutDev A, const EmitCtx E, const uint8_t *__restrict__ dat
 			for (int u = 0; u < S4_UNROLL; ++u)
 				if (cur_first + (uint64_t)u * 32 + lane >= vec_hi)
 					hits &= ~(0xF000u >> (4 * u));
+		}
+		if (__reduce_add_sync(FULL_MASK, (uint32_t)__popc(hits)) >= S4_DENSE_HITS) {
+			s4_chunk_dfa(&A, &E, data, cur_first * 16, limit, lane);
+			continue;
 		}
 		/* bit (15 - q) of hits belongs to window q = u * 4 + k.  Survivors are rare: from
 		 * here on control flow is warp-uniform and verification is done by the whole warp. */

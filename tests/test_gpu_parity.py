@@ -173,3 +173,26 @@ def test_device_synth_matches_host(device):
     g.lib().acm_synth_fill_host(host.ctypes.data_as(C.c_void_p), 1000, 99, 4099)
     assert np.array_equal(host, synth.stream(1000, 99, 4099))
     device.free(d)
+
+
+def test_repetitive_input_dense_hit_fallback(device):
+    """Zero pages and short-period fills make almost every aligned window a pattern gram; the
+    sampled kernel hands such chunks to the automaton walk.  Results must not change."""
+    pats = clamav_pats(10000)
+    o, a = build_oracle(pats), build_product(pats)
+    n = 1 << 19
+    buf = synth.stream(n, 31)
+    sig = lambda i: np.frombuffer(pats[i][0], dtype=np.uint8)
+    buf[4096:4096 + 40000] = 0                                     # zero run
+    buf[100000:100000 + 30000] = np.tile(np.frombuffer(bytes.fromhex("e800005d"), np.uint8), 7500)
+    buf[200000:200000 + 16384] = np.tile(np.frombuffer(bytes.fromhex("b440cd21e8c2045a"), np.uint8), 2048)
+    # real signatures inside, next to and straddling the dense regions
+    for pos, i in ((5000, 504), (44090, 4385), (4096 - 30, 17), (99990, 23), (129990, 4390), (207000, 99),
+                   (300000, 504), (300200, 4385)):
+        s = sig(i)
+        buf[pos:pos + s.size] = s
+    eo, ep, _, _ = o.search(buf)
+    assert eo.size >= 8
+    for mode in modes_for(a):
+        off, pat, res = gpu_scan(device, a, buf, mode)
+        assert_same(off, pat, eo, ep, f"repetitive mode {mode}")
