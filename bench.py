@@ -213,23 +213,41 @@ def main():
     scanner = g.Scanner(dev, acsm.automaton, hi - lo, timing=True)
     emit_lo = lo - read_lo
 
+    pinned_out = torch.empty(1 << 22, dtype=torch.int64).pin_memory() if (world > 1 and rank == 0) else None
+    prof = {"scan": 0.0, "counts": 0.0, "gather": 0.0, "d2h": 0.0} if os.environ.get("BENCH_PROFILE") else None
+
     def step():
         """scan + (N > 1) count exchange and gather to rank 0 + D2H of the list on rank 0."""
+        t0 = time.perf_counter()
         res = scanner.scan_device(data.data_ptr(), n, emit_lo, n)
+        t1 = time.perf_counter()
         if world > 1:
             counts = sharded.exchange_counts(res.n_matches, tdev)
+            t2 = time.perf_counter()
             keys = sharded._as_tensor(scanner.keys_ptr(), max(1, int(res.n_matches)), tdev)
             keys = keys[:int(res.n_matches)] + (read_lo << sharded.KEY_PAT_BITS)
             out = sharded.gather_keys(keys, counts, 0)
             total_matches = sum(counts)
+            if prof is not None:
+                torch.cuda.synchronize()
+            t3 = time.perf_counter()
             if rank == 0:
-                out.cpu()
+                pinned_out[:total_matches].copy_(out, non_blocking=True)
+                stream.synchronize()
+            t4 = time.perf_counter()
+            if prof is not None:
+                prof["scan"] += t1 - t0
+                prof["counts"] += t2 - t1
+                prof["gather"] += t3 - t2
+                prof["d2h"] += t4 - t3
         else:
             total_matches = int(res.n_matches)
         return res, total_matches
 
     for _ in range(args.warmup):
         step()
+    if prof is not None:
+        prof = {k: 0.0 for k in prof}
 
     sampler = ClockSampler(local_rank)
     if rank == 0:
@@ -260,6 +278,9 @@ def main():
         k1_avg = float(k.item())
     else:
         k1_avg = sum(k1_ms) / len(k1_ms)
+    if prof is not None and rank == 0:
+        print("profile (ms/step):", {k: round(v * 1e3 / args.steps, 4)
+                                                    for k, v in prof.items()}, file=sys.stderr)
     ms_per_step = ms / args.steps
     value = total / (ms_per_step * 1e-3) / 1e9
 

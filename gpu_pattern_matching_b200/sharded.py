@@ -38,7 +38,11 @@ def exchange_counts(n_local, device):
     """All-gather of the per-rank match counts -> python list (one small collective)."""
     world = dist.get_world_size()
     mine = torch.tensor([int(n_local)], dtype=torch.int64, device=device)
-    outs = [torch.empty(1, dtype=torch.int64, device=device) for _ in range(world)]
+    if device.type == "cuda":
+        allc = torch.empty(world, dtype=torch.int64, device=device)
+        dist.all_gather_into_tensor(allc, mine)
+        return allc.tolist()                   # one synchronisation
+    outs = [torch.empty(1, dtype=torch.int64) for _ in range(world)]
     dist.all_gather(outs, mine)
     return [int(x.item()) for x in outs]
 
@@ -49,18 +53,22 @@ def gather_keys(keys, counts, dst=0):
     rank, world = dist.get_rank(), dist.get_world_size()
     if rank != dst:
         if counts[rank]:
-            dist.send(keys[:counts[rank]].contiguous(), dst=dst)
+            for w in dist.batch_isend_irecv([dist.P2POp(dist.isend, keys[:counts[rank]].contiguous(), dst)]):
+                w.wait()
         return None
     out = torch.empty(sum(counts), dtype=torch.int64, device=keys.device)
-    pos = 0
+    ops, pos = [], 0
     for r in range(world):
         n = counts[r]
         if n:
             if r == dst:
                 out[pos:pos + n] = keys[:n]
             else:
-                dist.recv(out[pos:pos + n], src=r)
+                ops.append(dist.P2POp(dist.irecv, out[pos:pos + n], r))
         pos += n
+    if ops:
+        for w in dist.batch_isend_irecv(ops):      # one grouped NCCL launch
+            w.wait()
     return out
 
 
