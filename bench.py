@@ -213,15 +213,24 @@ def main():
     scanner = g.Scanner(dev, acsm.automaton, hi - lo, timing=True)
     emit_lo = lo - read_lo
 
+    use_peer = world > 1 and os.environ.get("BENCH_GATHER", "peer") == "peer"
+    peer = sharded.PeerGather(dev, 1 << 22) if use_peer else None
     pinned_out = torch.empty(1 << 22, dtype=torch.int64).pin_memory() if (world > 1 and rank == 0) else None
     prof = {"scan": 0.0, "counts": 0.0, "gather": 0.0, "d2h": 0.0} if os.environ.get("BENCH_PROFILE") else None
 
     def step():
-        """scan + (N > 1) count exchange and gather to rank 0 + D2H of the list on rank 0."""
+        """scan + (N > 1) gather of the sorted lists into rank 0's HBM + D2H on rank 0."""
         t0 = time.perf_counter()
         res = scanner.scan_device(data.data_ptr(), n, emit_lo, n)
         t1 = time.perf_counter()
-        if world > 1:
+        if peer is not None:
+            # counts through shared memory, keys stored into rank 0's buffer over NVLink (IPC)
+            _, total_matches = peer.gather(scanner, int(res.n_matches), read_lo << sharded.KEY_PAT_BITS)
+            if prof is not None:
+                prof["scan"] += t1 - t0
+                prof["gather"] += time.perf_counter() - t1
+        elif world > 1:
+            # portable path: NCCL all-gather of the counts + grouped send/recv of the keys
             counts = sharded.exchange_counts(res.n_matches, tdev)
             t2 = time.perf_counter()
             keys = sharded._as_tensor(scanner.keys_ptr(), max(1, int(res.n_matches)), tdev)
@@ -329,6 +338,8 @@ def main():
         hs.close()
         del owner
 
+    if peer is not None:
+        peer.close()
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -350,7 +361,9 @@ def main():
                    "bytes_per_gpu": per, "matches": matches, "fallback": int(fallback),
                    "l2_policy": "input (1 GiB per GPU) is larger than L2 (126 MB); no flush needed",
                    "step": "scan + prefix sum + compaction/sort + count readback"
-                           + (" + count all-gather + key gather to rank 0 + D2H" if world > 1 else "")},
+                           + ((" + peer gather (counts via shared memory, keys pushed into rank 0's HBM over"
+                               " NVLink IPC) + D2H" if use_peer else
+                               " + NCCL count all-gather + key send/recv to rank 0 + D2H") if world > 1 else "")},
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                      "frac": achieved / peak, "traffic": traffic, "kernel": "k_scan_" + g.MODE_NAMES[res.mode],
                      "kernel_ms": k1_avg, "algorithmic_bytes_per_launch": per, "peak_source": peak_src},

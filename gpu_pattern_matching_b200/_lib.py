@@ -128,6 +128,10 @@ SIGNATURES = {
     "acm_scan_fetch": (C.c_int64, [vp, C.c_uint64, u64p, u32p, C.c_uint64]),
     "acm_scan_histogram": (C.c_int, [vp, vp]),
     "acm_scan_trace": (C.c_int, [vp, u64p, C.c_uint32]),
+    "acm_ipc_export": (C.c_int, [vp, vp, vp]),
+    "acm_ipc_open": (C.c_int, [vp, vp, C.POINTER(vp)]),
+    "acm_ipc_close": (C.c_int, [vp, vp]),
+    "acm_scan_push_keys": (C.c_int, [vp, vp, C.c_uint64, C.c_uint64]),
     "acm_scan_host": (C.c_int64, [vp, vp, C.c_uint64, C.c_uint64, u64p, u32p, C.c_uint64,
                                   C.POINTER(ScanResult)]),
     "acm_exclusive_scan_u32": (C.c_int, [vp, vp, vp, C.c_uint32, vp]),

@@ -976,6 +976,53 @@ acm_scan_fetch(struct acm_scanner *s, uint64_t base, uint64_t *h_off, uint32_t *
 	return fetch_on_stream(s, s->dev->stream, base, 0, h_off, h_pat, cap);
 }
 
+/* ---- peer gather (single node): CUDA IPC mapping + a store kernel ---- */
+
+extern "C" int
+acm_ipc_export(struct acm_device *d, void *d_ptr, void *handle64)
+{
+	cudaIpcMemHandle_t h;
+
+	CUDA_TRY(cudaSetDevice(d->ordinal));
+	CUDA_TRY(cudaIpcGetMemHandle(&h, d_ptr));
+	memcpy(handle64, &h, sizeof(h));
+	return ACM_OK;
+}
+
+extern "C" int
+acm_ipc_open(struct acm_device *d, const void *handle64, void **d_ptr)
+{
+	cudaIpcMemHandle_t h;
+
+	memcpy(&h, handle64, sizeof(h));
+	CUDA_TRY(cudaSetDevice(d->ordinal));
+	CUDA_TRY(cudaIpcOpenMemHandle(d_ptr, h, cudaIpcMemLazyEnablePeerAccess));
+	return ACM_OK;
+}
+
+extern "C" int
+acm_ipc_close(struct acm_device *d, void *d_ptr)
+{
+	CUDA_TRY(cudaSetDevice(d->ordinal));
+	CUDA_TRY(cudaIpcCloseMemHandle(d_ptr));
+	return ACM_OK;
+}
+
+extern "C" int
+acm_scan_push_keys(struct acm_scanner *s, uint64_t *d_dst, uint64_t dst_index, uint64_t key_add)
+{
+	CUDA_TRY(cudaSetDevice(s->dev->ordinal));
+	if (s->last_n == 0)
+		return ACM_OK;
+	uint64_t blocks = (s->last_n + 255) / 256;
+	if (blocks > 592)
+		blocks = 592;
+	k_push_keys<<<(unsigned)blocks, 256, 0, s->dev->stream>>>(s->out, s->last_n, d_dst + dst_index,
+	    key_add);
+	CUDA_TRY(cudaGetLastError());
+	return ACM_OK;
+}
+
 extern "C" int
 acm_scan_histogram(struct acm_scanner *s, uint64_t *d_counts)
 {

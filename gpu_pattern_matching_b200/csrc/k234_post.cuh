@@ -357,6 +357,19 @@ __global__ void k_unpack_pairs(const uint64_t *__restrict__ in, uint32_t *__rest
 	}
 }
 
+/*
+ * Gather step of the multi-GPU path: copy this GPU's sorted keys into the gather buffer of
+ * the collecting GPU (a peer mapping over NVLink, or local memory on that GPU itself),
+ * shifting the offsets to stream positions on the way.
+ */
+__global__ void k_push_keys(const uint64_t *__restrict__ keys, uint64_t n, uint64_t *__restrict__ dst,
+    uint64_t key_add)
+{
+	for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n;
+	     i += (uint64_t)gridDim.x * blockDim.x)
+		dst[i] = keys[i] + key_add;
+}
+
 /* per-pattern counts of a key list */
 __global__ void k_histogram(const uint64_t *__restrict__ keys, uint64_t n, unsigned long long *counts)
 {

@@ -68,6 +68,8 @@ class Device:
         """plants: synth.Plants (positions are absolute stream offsets)."""
         if plants.count == 0:
             return
+        if not plants.disjoint:
+            raise ValueError("overlapping plants are order dependent; apply them on the host")
         check(self.L.acm_plant_device(
             self._h, C.c_void_p(d_ptr), n, buf_offset,
             plants.pos.ctypes.data_as(_lib.u64p), plants.blob_off.ctypes.data_as(_lib.u32p),

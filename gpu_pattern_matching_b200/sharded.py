@@ -125,6 +125,108 @@ class ShardedScan:
         return unpack_keys(out)
 
 
+class PeerGather:
+    """Single-node gather of the per-rank sorted key lists into rank 0's HBM without a
+    collective on the critical path: counts travel through a few words of POSIX shared
+    memory, keys are stored by each rank's own kernel straight into rank 0's buffer through
+    a CUDA IPC mapping (NVLink peer stores), rank 0 copies the result to pinned host memory.
+
+    Step protocol (step ids 1, 2, ...; counts double-buffered by step parity):
+      every rank   counts[step & 1][r] = n_r ; gen_counts[r] = step
+      rank r       waits for all gen_counts >= step and consumed >= step - 1, pushes its keys at
+                   offset sum(counts[:r]), synchronises its stream, done[r] = step
+      rank 0       waits for all done >= step, D2H of sum(counts) keys, consumed = step
+    """
+
+    def __init__(self, device, cap_keys, timeout_s=60.0):
+        import ctypes as C
+        import os
+        import tempfile
+        from ._lib import check, lib
+        self.C, self.L, self.check = C, lib(), check
+        self.device = device
+        self.rank, self.world = dist.get_rank(), dist.get_world_size()
+        self.cap = int(cap_keys)
+        self.timeout = timeout_s
+        self.step = 0
+        box = [None, None]
+        if self.rank == 0:
+            fd, path = tempfile.mkstemp(prefix="acm_gather_", dir="/dev/shm" if os.path.isdir("/dev/shm") else None)
+            os.ftruncate(fd, 8 * 5 * self.world + 64)
+            os.close(fd)
+            self.buf = device.alloc(self.cap * 8)
+            h = (C.c_ubyte * 64)()
+            check(self.L.acm_ipc_export(device.handle, C.c_void_p(self.buf), h), "acm_ipc_export")
+            box = [path, bytes(h)]
+        dist.broadcast_object_list(box, src=0)
+        self.path = box[0]
+        self.shm = np.memmap(self.path, dtype=np.int64, mode="r+", shape=(5, self.world))
+        if self.rank == 0:
+            self.shm[:] = 0
+            self.shm.flush()
+            self.dst = self.buf
+            from .matcher import pinned_empty
+            self.host_bytes, self._owner = pinned_empty(self.cap * 8)
+            self.host = self.host_bytes.view(np.uint64)
+        else:
+            p = C.c_void_p()
+            h = (C.c_ubyte * 64).from_buffer_copy(box[1])
+            check(self.L.acm_ipc_open(device.handle, h, C.byref(p)), "acm_ipc_open")
+            self.dst = p.value
+        dist.barrier()
+
+    def _wait(self, row, value, ranks):
+        import time
+        t0 = time.perf_counter()
+        while True:
+            if all(int(self.shm[row, r]) >= value for r in ranks):
+                return
+            if time.perf_counter() - t0 > self.timeout:
+                raise RuntimeError(f"PeerGather: rank {self.rank} timed out waiting on row {row} >= {value}")
+
+    def gather(self, scanner, n_local, key_add):
+        """Returns (offsets, patterns) numpy arrays on rank 0 (views of pinned memory are copied
+        by unpack_keys), None on the other ranks; raises if the list exceeds the buffer."""
+        C = self.C
+        self.step += 1
+        st, par = self.step, self.step & 1
+        everyone = range(self.world)
+        self.shm[par, self.rank] = int(n_local)
+        self.shm[2, self.rank] = st
+        self._wait(2, st, everyone)
+        counts = [int(self.shm[par, r]) for r in everyone]
+        total = sum(counts)
+        if total > self.cap:
+            raise RuntimeError(f"PeerGather: {total} keys exceed the gather buffer ({self.cap})")
+        self._wait(4, st - 1, [0])
+        if n_local:
+            self.check(self.L.acm_scan_push_keys(scanner._h, C.c_void_p(self.dst), sum(counts[:self.rank]),
+                                                 key_add), "acm_scan_push_keys")
+        self.device.sync()
+        self.shm[3, self.rank] = st
+        if self.rank != 0:
+            return None, total
+        self._wait(3, st, everyone)
+        if total:
+            self.check(self.L.acm_memcpy_d2h(self.device.handle, C.c_void_p(self.host.ctypes.data),
+                                             C.c_void_p(self.buf), total * 8), "acm_memcpy_d2h")
+            self.device.sync()
+        self.shm[4, 0] = st
+        return self.host[:total], total
+
+    def close(self):
+        import os
+        try:
+            dist.barrier()
+            if self.rank == 0:
+                self.device.free(self.buf)
+                os.unlink(self.path)
+            else:
+                self.L.acm_ipc_close(self.device.handle, self.C.c_void_p(self.dst))
+        except Exception:
+            pass
+
+
 class _CudaArrayView:
     def __init__(self, ptr, n):
         self.__cuda_array_interface__ = {"shape": (n,), "typestr": "<i8", "data": (ptr, False),

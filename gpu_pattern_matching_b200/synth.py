@@ -55,6 +55,12 @@ class Plants:
             pos.append(int(p))
             pid.append(int(i))
         self.count = len(pos)
+        # overlapping plants depend on the order they are applied in: fine on the host
+        # (apply_host is sequential), a race in the device kernel (one warp per plant)
+        order = np.argsort(np.array(pos, dtype=np.int64), kind="stable") if pos else np.array([], dtype=np.int64)
+        ends = np.array([pos[i] + len(patterns[pid[i]]) for i in order], dtype=np.int64)
+        starts = np.array([pos[i] for i in order], dtype=np.int64)
+        self.disjoint = bool(np.all(ends[:-1] <= starts[1:])) if len(order) > 1 else True
         self.pos = np.array(pos, dtype=np.uint64)
         self.pid = np.array(pid, dtype=np.uint32)
         self.length = np.array([len(patterns[i]) for i in pid], dtype=np.uint32)

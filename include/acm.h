@@ -142,6 +142,18 @@ int64_t acm_scan_fetch(struct acm_scanner *, uint64_t base, uint64_t *h_off,
  * {t_entry, t_ready, t_exit, chunks} (globaltimer ns); this copies n_ctas x 4 u64 to h_out */
 int  acm_scan_trace(struct acm_scanner *, uint64_t *h_out, uint32_t n_ctas);
 
+/*
+ * Single-node gather without a collective: the collecting rank exports its gather buffer
+ * (cudaMalloc'd through acm_dev_alloc) as a 64-byte CUDA IPC handle, the other ranks map it
+ * and push their sorted keys straight into it over NVLink.  acm_scan_push_keys copies the last
+ * scan's keys to d_dst[dst_index ...], adding key_add to each (shifts end offsets, which sit
+ * above bit 24, to stream positions).  Asynchronous on the device's stream.
+ */
+int  acm_ipc_export(struct acm_device *, void *d_ptr, void *handle64);
+int  acm_ipc_open(struct acm_device *, const void *handle64, void **d_ptr);
+int  acm_ipc_close(struct acm_device *, void *d_ptr);
+int  acm_scan_push_keys(struct acm_scanner *, uint64_t *d_dst, uint64_t dst_index, uint64_t key_add);
+
 /* add the last scan's per-pattern match counts into d_counts[num_patterns] (u64, device) */
 int  acm_scan_histogram(struct acm_scanner *, uint64_t *d_counts);
 
