@@ -272,6 +272,8 @@ def main():
         k1_ms.append(res.ms_scan)
         launches += res.launches
         fallback |= res.fallback
+    if peer is not None:
+        peer.flush()                      # the last step's list must be on the host too
     ev1.record(stream)
     torch.cuda.synchronize()
     if world > 1:
@@ -362,7 +364,7 @@ def main():
                    "l2_policy": "input (1 GiB per GPU) is larger than L2 (126 MB); no flush needed",
                    "step": "scan + prefix sum + compaction/sort + count readback"
                            + ((" + peer gather (counts via shared memory, keys pushed into rank 0's HBM over"
-                               " NVLink IPC) + D2H" if use_peer else
+                               " NVLink IPC) + D2H on a side stream, overlapped with the next step's scan" if use_peer else
                                " + NCCL count all-gather + key send/recv to rank 0 + D2H") if world > 1 else "")},
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                      "frac": achieved / peak, "traffic": traffic, "kernel": "k_scan_" + g.MODE_NAMES[res.mode],

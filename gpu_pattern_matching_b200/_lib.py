@@ -109,6 +109,8 @@ SIGNATURES = {
     "acm_host_free_pinned": (None, [vp]),
     "acm_memcpy_h2d": (C.c_int, [vp, vp, vp, C.c_size_t]),
     "acm_memcpy_d2h": (C.c_int, [vp, vp, vp, C.c_size_t]),
+    "acm_memcpy_d2h_side": (C.c_int, [vp, vp, vp, C.c_size_t]),
+    "acm_side_sync": (C.c_int, [vp]),
     "acm_automaton_upload": (C.c_int, [vp, vp, C.POINTER(vp)]),
     "acm_automaton_free": (None, [vp]),
     "acm_automaton_states": (C.c_uint32, [vp]),

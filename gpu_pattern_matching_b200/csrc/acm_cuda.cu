@@ -33,7 +33,8 @@ struct acm_device {
 	int          sm_count;
 	cudaStream_t own_stream;
 	cudaStream_t stream;        /* own_stream or an adopted one */
-	cudaStream_t copy_stream;   /* H2D staging for acm_scan_host */
+	cudaStream_t copy_stream;   /* H2D staging for acm_scan_host, side D2H */
+	cudaEvent_t  side_ev;
 	/* scratch for the stand-alone scan / sort entry points */
 	uint64_t    *tile_state;
 	uint32_t    *tile_counter;
@@ -166,6 +167,8 @@ acm_device_close(struct acm_device *d)
 	cudaFree(d->tile_state);
 	cudaFree(d->tile_counter);
 	cudaFree(d->hist);
+	if (d->side_ev)
+		cudaEventDestroy(d->side_ev);
 	cudaStreamDestroy(d->own_stream);
 	cudaStreamDestroy(d->copy_stream);
 	free(d);
@@ -249,6 +252,27 @@ acm_memcpy_d2h(struct acm_device *d, void *dst, const void *src, size_t bytes)
 {
 	CUDA_TRY(cudaSetDevice(d->ordinal));
 	CUDA_TRY(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, d->stream));
+	return ACM_OK;
+}
+
+/* D2H on the side (copy) stream, ordered after everything queued so far on the main stream */
+extern "C" int
+acm_memcpy_d2h_side(struct acm_device *d, void *dst, const void *src, size_t bytes)
+{
+	CUDA_TRY(cudaSetDevice(d->ordinal));
+	if (!d->side_ev)
+		CUDA_TRY(cudaEventCreateWithFlags(&d->side_ev, cudaEventDisableTiming));
+	CUDA_TRY(cudaEventRecord(d->side_ev, d->stream));
+	CUDA_TRY(cudaStreamWaitEvent(d->copy_stream, d->side_ev, 0));
+	CUDA_TRY(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, d->copy_stream));
+	return ACM_OK;
+}
+
+extern "C" int
+acm_side_sync(struct acm_device *d)
+{
+	CUDA_TRY(cudaSetDevice(d->ordinal));
+	CUDA_TRY(cudaStreamSynchronize(d->copy_stream));
 	return ACM_OK;
 }
 

@@ -129,14 +129,19 @@ class PeerGather:
     """Single-node gather of the per-rank sorted key lists into rank 0's HBM without a
     collective on the critical path: counts travel through a few words of POSIX shared
     memory, keys are stored by each rank's own kernel straight into rank 0's buffer through
-    a CUDA IPC mapping (NVLink peer stores), rank 0 copies the result to pinned host memory.
+    a CUDA IPC mapping (NVLink peer stores), rank 0 copies the result to pinned host memory
+    on a side stream so the copy overlaps the next scan.
 
-    Step protocol (step ids 1, 2, ...; counts double-buffered by step parity):
+    Step protocol (step ids 1, 2, ...; counts and gather buffers double-buffered by parity):
       every rank   counts[step & 1][r] = n_r ; gen_counts[r] = step
-      rank r       waits for all gen_counts >= step and consumed >= step - 1, pushes its keys at
-                   offset sum(counts[:r]), synchronises its stream, done[r] = step
-      rank 0       waits for all done >= step, D2H of sum(counts) keys, consumed = step
+      rank r       waits for all gen_counts >= step and consumed >= step - 2, pushes its keys
+                   into buffer step & 1 at offset sum(counts[:r]), synchronises, done[r] = step
+      rank 0       waits for all done >= step; waits for the D2H of step - 1, consumed = step - 1;
+                   starts the D2H of this step on the side stream
+    gather() on rank 0 returns the PREVIOUS step's list (None for the first); flush() returns
+    the last one.
     """
+    ROW_CNT0, ROW_CNT1, ROW_GEN, ROW_DONE, ROW_CONSUMED = range(5)
 
     def __init__(self, device, cap_keys, timeout_s=60.0):
         import ctypes as C
@@ -149,12 +154,13 @@ class PeerGather:
         self.cap = int(cap_keys)
         self.timeout = timeout_s
         self.step = 0
+        self.pending = None          # (buffer parity, total) whose D2H is in flight
         box = [None, None]
         if self.rank == 0:
             fd, path = tempfile.mkstemp(prefix="acm_gather_", dir="/dev/shm" if os.path.isdir("/dev/shm") else None)
             os.ftruncate(fd, 8 * 5 * self.world + 64)
             os.close(fd)
-            self.buf = device.alloc(self.cap * 8)
+            self.buf = device.alloc(2 * self.cap * 8)
             h = (C.c_ubyte * 64)()
             check(self.L.acm_ipc_export(device.handle, C.c_void_p(self.buf), h), "acm_ipc_export")
             box = [path, bytes(h)]
@@ -166,7 +172,7 @@ class PeerGather:
             self.shm.flush()
             self.dst = self.buf
             from .matcher import pinned_empty
-            self.host_bytes, self._owner = pinned_empty(self.cap * 8)
+            self.host_bytes, self._owner = pinned_empty(2 * self.cap * 8)
             self.host = self.host_bytes.view(np.uint64)
         else:
             p = C.c_void_p()
@@ -184,39 +190,56 @@ class PeerGather:
             if time.perf_counter() - t0 > self.timeout:
                 raise RuntimeError(f"PeerGather: rank {self.rank} timed out waiting on row {row} >= {value}")
 
+    def _collect(self):
+        """rank 0: finish the D2H in flight, release its buffer, return its keys (a view)."""
+        if self.pending is None:
+            return None
+        par, total, st = self.pending
+        self.check(self.L.acm_side_sync(self.device.handle), "acm_side_sync")
+        self.shm[self.ROW_CONSUMED, 0] = st
+        self.pending = None
+        return self.host[par * self.cap: par * self.cap + total]
+
     def gather(self, scanner, n_local, key_add):
-        """Returns (offsets, patterns) numpy arrays on rank 0 (views of pinned memory are copied
-        by unpack_keys), None on the other ranks; raises if the list exceeds the buffer."""
+        """One step.  Returns (keys of the previous step or None, total of THIS step) on rank 0,
+        (None, total) elsewhere; raises if the list exceeds the buffer."""
         C = self.C
         self.step += 1
         st, par = self.step, self.step & 1
         everyone = range(self.world)
         self.shm[par, self.rank] = int(n_local)
-        self.shm[2, self.rank] = st
-        self._wait(2, st, everyone)
+        self.shm[self.ROW_GEN, self.rank] = st
+        self._wait(self.ROW_GEN, st, everyone)
         counts = [int(self.shm[par, r]) for r in everyone]
         total = sum(counts)
         if total > self.cap:
             raise RuntimeError(f"PeerGather: {total} keys exceed the gather buffer ({self.cap})")
-        self._wait(4, st - 1, [0])
+        self._wait(self.ROW_CONSUMED, st - 2, [0])
         if n_local:
-            self.check(self.L.acm_scan_push_keys(scanner._h, C.c_void_p(self.dst), sum(counts[:self.rank]),
-                                                 key_add), "acm_scan_push_keys")
+            self.check(self.L.acm_scan_push_keys(scanner._h, C.c_void_p(self.dst),
+                                                 par * self.cap + sum(counts[:self.rank]), key_add),
+                       "acm_scan_push_keys")
         self.device.sync()
-        self.shm[3, self.rank] = st
+        self.shm[self.ROW_DONE, self.rank] = st
         if self.rank != 0:
             return None, total
-        self._wait(3, st, everyone)
+        self._wait(self.ROW_DONE, st, everyone)
+        prev = self._collect()
         if total:
-            self.check(self.L.acm_memcpy_d2h(self.device.handle, C.c_void_p(self.host.ctypes.data),
-                                             C.c_void_p(self.buf), total * 8), "acm_memcpy_d2h")
-            self.device.sync()
-        self.shm[4, 0] = st
-        return self.host[:total], total
+            self.check(self.L.acm_memcpy_d2h_side(
+                self.device.handle, C.c_void_p(self.host.ctypes.data + par * self.cap * 8),
+                C.c_void_p(self.buf + par * self.cap * 8), total * 8), "acm_memcpy_d2h_side")
+        self.pending = (par, total, st)
+        return prev, total
+
+    def flush(self):
+        """rank 0: the last step's keys (waits for its D2H); None elsewhere."""
+        return self._collect() if self.rank == 0 else None
 
     def close(self):
         import os
         try:
+            self.flush()
             dist.barrier()
             if self.rank == 0:
                 self.device.free(self.buf)

@@ -62,6 +62,9 @@ int   acm_host_alloc_pinned(size_t bytes, void **h_ptr);
 void  acm_host_free_pinned(void *h_ptr);
 int   acm_memcpy_h2d(struct acm_device *, void *d_dst, const void *h_src, size_t bytes);  /* async on the stream */
 int   acm_memcpy_d2h(struct acm_device *, void *h_dst, const void *d_src, size_t bytes);  /* async on the stream */
+/* D2H on a side stream (ordered after the work queued so far), so it overlaps later kernels; acm_side_sync waits for it */
+int   acm_memcpy_d2h_side(struct acm_device *, void *h_dst, const void *d_src, size_t bytes);
+int   acm_side_sync(struct acm_device *);
 
 /* ---- automaton ---- */
 int   acm_automaton_upload(struct acm_device *, const struct acm_tables *, struct acm_automaton **out);

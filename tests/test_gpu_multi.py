@@ -55,16 +55,21 @@ def _worker(rank, world, port, total, outdir):
     sc = g.Scanner(dev, a.automaton, hi - lo)
     peer = sharded.PeerGather(dev, 1 << 16, timeout_s=30)
     ok = True
-    for it in range(3):                       # several steps: generation counters, buffer reuse
+    if rank == 0:
+        o = build_oracle(pats)
+        whole = synth.stream(total, 5)
+        plants.apply_host(whole)
+        eo, ep, _, _ = o.search(whole)
+    for it in range(5):                       # several steps: generation counters, buffer reuse
         res = sc.scan_device(d, n, lo - read_lo, n)
         keys, tot = peer.gather(sc, int(res.n_matches), read_lo << sharded.KEY_PAT_BITS)
+        if it == 4:
+            keys = peer.flush()               # the list of the last step
+        elif it == 0:
+            assert keys is None               # gather() hands back the previous step's list
+            continue
         if rank == 0:
             goff, gpat = sharded.unpack_keys(np.array(keys, copy=True))
-            if it == 0:
-                o = build_oracle(pats)
-                whole = synth.stream(total, 5)
-                plants.apply_host(whole)
-                eo, ep, _, _ = o.search(whole)
             good = tot == eo.size and np.array_equal(goff, eo) and np.array_equal(gpat, ep)
             if not good:
                 bad = np.nonzero(goff[:min(tot, eo.size)] != eo[:min(tot, eo.size)])[0]
