@@ -63,7 +63,10 @@ struct acm_scanner {
 	uint32_t  shift, cap, max_buckets;
 	uint64_t *buckets;
 	uint32_t *counts, *offsets;
-	uint32_t *flags;            /* [0] overflow, [1] total, [2] final state, [3] tile counter */
+	uint8_t  *scratch;          /* one allocation, one memset per scan: flags | bucket_tiles | counts */
+	uint64_t *bucket_tiles;     /* look-back tile states of the bucket-count scan */
+	uint32_t  n_bucket_tiles;
+	uint32_t *flags;            /* [0] overflow, [1] total, [2] final state, [3] scan tile counter, [5] output too small, [6,7] K1 work counters */
 	uint64_t *tile_state;
 	uint32_t  max_tiles;
 	uint64_t *out;              /* sorted keys of the last scan */
@@ -419,7 +422,7 @@ acm_automaton_default_mode(const struct acm_automaton *a)
 
 static int
 launch_exclusive_scan(cudaStream_t st, const uint32_t *in, uint32_t *out, uint32_t n,
-    uint64_t *tile_state, uint32_t *tile_counter, uint32_t *total)
+    uint64_t *tile_state, uint32_t *tile_counter, uint32_t *total, int pre_zeroed = 0)
 {
 	const uint32_t tiles = (n + SCAN_TILE - 1) / SCAN_TILE;
 
@@ -428,8 +431,10 @@ launch_exclusive_scan(cudaStream_t st, const uint32_t *in, uint32_t *out, uint32
 			CUDA_TRY(cudaMemsetAsync(total, 0, 4, st));
 		return ACM_OK;
 	}
-	CUDA_TRY(cudaMemsetAsync(tile_state, 0, (size_t)tiles * 8, st));
-	CUDA_TRY(cudaMemsetAsync(tile_counter, 0, 4, st));
+	if (!pre_zeroed) {
+		CUDA_TRY(cudaMemsetAsync(tile_state, 0, (size_t)tiles * 8, st));
+		CUDA_TRY(cudaMemsetAsync(tile_counter, 0, 4, st));
+	}
 	k_scan_lookback<<<tiles, SCAN_THREADS, 0, st>>>(in, out, n, tile_state, tile_counter, total);
 	CUDA_TRY(cudaGetLastError());
 	return ACM_OK;
@@ -586,7 +591,7 @@ acm_scanner_free(struct acm_scanner *s)
 	cudaSetDevice(s->dev->ordinal);
 	cudaStreamSynchronize(s->dev->stream);
 	cudaStreamSynchronize(s->dev->copy_stream);
-	cudaFree(s->buckets); cudaFree(s->counts); cudaFree(s->offsets); cudaFree(s->flags);
+	cudaFree(s->buckets); cudaFree(s->scratch); cudaFree(s->offsets);
 	cudaFree(s->tile_state); cudaFree(s->out); cudaFree(s->tmp); cudaFree(s->hist);
 	cudaFree(s->stage[0]); cudaFree(s->stage[1]); cudaFree(s->trace);
 	if (s->h_flags)
@@ -670,9 +675,12 @@ acm_scanner_create(struct acm_device *dev, struct acm_automaton *aut, uint64_t m
 		}                                                                           \
 	} while (0)
 	SALLOC(s->buckets, (size_t)s->max_buckets * s->cap * 8);
-	SALLOC(s->counts, (size_t)s->max_buckets * 4);
+	s->n_bucket_tiles = (s->max_buckets + SCAN_TILE - 1) / SCAN_TILE + 1;
+	SALLOC(s->scratch, 64 + (size_t)s->n_bucket_tiles * 8 + (size_t)s->max_buckets * 4);
+	s->flags = (uint32_t *)s->scratch;
+	s->bucket_tiles = (uint64_t *)(s->scratch + 64);
+	s->counts = (uint32_t *)(s->scratch + 64 + (size_t)s->n_bucket_tiles * 8);
 	SALLOC(s->offsets, (size_t)s->max_buckets * 4);
-	SALLOC(s->flags, 64);
 	SALLOC(s->tile_state, (size_t)s->max_tiles * 8);
 	s->out_cap = 1u << 16;
 	SALLOC(s->out, s->out_cap * 8);
@@ -715,7 +723,8 @@ grow(uint64_t **buf, uint64_t *cap, uint64_t need, const char *what)
 }
 
 static int
-launch_k1(struct acm_scanner *s, cudaStream_t st, const void *d_data, uint64_t n, const EmitCtx &E)
+launch_k1(struct acm_scanner *s, cudaStream_t st, const void *d_data, uint64_t n, const EmitCtx &E,
+    int zero_work_counter)
 {
 	const struct acm_automaton *a = s->aut;
 	const uint64_t limit = E.emit_hi < n ? E.emit_hi : n;
@@ -733,10 +742,11 @@ launch_k1(struct acm_scanner *s, cudaStream_t st, const void *d_data, uint64_t n
 		uint64_t blocks = (vec_hi - vec_lo + unit - 1) / unit;
 		if (blocks > (uint64_t)s->dev->sm_count)
 			blocks = s->dev->sm_count;
-		CUDA_TRY(cudaMemsetAsync(s->flags + 4, 0, 8, st));
+		if (zero_work_counter)
+			CUDA_TRY(cudaMemsetAsync(s->flags + 6, 0, 8, st));
 		/* the last two chunks per resident warp are handed out singly */
 		k_scan_sampled4<<<(unsigned)blocks, S4_THREADS, S4_SMEM_BYTES, st>>>(a->d, E,
-		    (const uint8_t *)d_data, n, vec_lo, vec_hi, limit, s->flags + 4,
+		    (const uint8_t *)d_data, n, vec_lo, vec_hi, limit, s->flags + 6,
 		    (uint32_t)(blocks * (S4_THREADS / 32) * 2));
 	} else if (s->p.mode == ACM_MODE_START2) {
 		const uint64_t tile = (uint64_t)S2_THREADS * S2_UNROLL;
@@ -805,17 +815,17 @@ scan_on_stream(struct acm_scanner *s, cudaStream_t st, const void *d_data, uint6
 	E.cap = s->cap;
 	E.shift = s->shift;
 
-	CUDA_TRY(cudaMemsetAsync(s->counts, 0, (size_t)nb * 4, st));
-	CUDA_TRY(cudaMemsetAsync(s->flags, 0, 64, st));
+	/* flags (incl. the K1 work counters and the scan's tile counter), tile states, counts */
+	CUDA_TRY(cudaMemsetAsync(s->scratch, 0, 64 + (size_t)s->n_bucket_tiles * 8 + (size_t)nb * 4, st));
 	if (timing)
 		CUDA_TRY(cudaEventRecord(s->ev[0], st));
-	if ((rc = launch_k1(s, st, d_data, n, E)) != ACM_OK)
+	if ((rc = launch_k1(s, st, d_data, n, E, 0)) != ACM_OK)
 		return rc;
 	launches++;
 	if (timing)
 		CUDA_TRY(cudaEventRecord(s->ev[1], st));
-	if ((rc = launch_exclusive_scan(st, s->counts, s->offsets, nb, s->tile_state, s->flags + 3,
-	    s->flags + 1)) != ACM_OK)
+	if ((rc = launch_exclusive_scan(st, s->counts, s->offsets, nb, s->bucket_tiles, s->flags + 3,
+	    s->flags + 1, 1)) != ACM_OK)
 		return rc;
 	launches++;
 	if (timing)
@@ -880,7 +890,7 @@ scan_on_stream(struct acm_scanner *s, cudaStream_t st, const void *d_data, uint6
 		E.offsets = s->offsets;
 		E.out = s->out;
 		CUDA_TRY(cudaMemsetAsync(s->counts, 0, (size_t)nb * 4, st));
-		if ((rc = launch_k1(s, st, d_data, n, E)) != ACM_OK)
+		if ((rc = launch_k1(s, st, d_data, n, E, 1)) != ACM_OK)
 			return rc;
 		launches++;
 		if ((rc = radix_sort_impl(st, s->out, s->tmp, total, 0, bits, 0, s->hist, s->tile_state,
