@@ -40,8 +40,11 @@ def test_cli_plain_patterns_verbose(tmp_path):
     o = build_oracle(pats)
     eo, ep, _, _ = o.search(text)
     got = [LINE.match(l).groups() for l in out.split(b"\n") if l.startswith(b"Pattern ")]
+    # like the reference, the printed offset is relative to the current BUFFER (here 8 x 256 B),
+    # and is the end offset + 1 (reference databuf.c:771, ocl_aho_grep.c:295)
     assert [(int(g[0]), g[1], int(g[3])) for g in got] == \
-        [(pats[p][1], pats[p][0], int(e) + 1) for e, p in zip(eo, ep)]          # offset = end + 1
+        [(pats[p][1], pats[p][0], int(e) % 2048 + 1) for e, p in zip(eo, ep)]
+    assert all(int(g[4]) == (int(g[3]) - 1) % 256 + 1 for g in got)            # relative to the chunk
     assert all(g[2] == tf.encode() for g in got)
     st = stats(out)
     assert st["Matches"] == eo.size == 24 and st["Matches reported"] == 24
