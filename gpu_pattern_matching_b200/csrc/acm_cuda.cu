@@ -77,6 +77,8 @@ struct acm_scanner {
 	uint64_t  hist_cap;
 	uint32_t *h_flags;          /* pinned, 4 words */
 	uint64_t  last_n;           /* matches of the last scan */
+	int       densify;          /* a bucket overflowed: use smaller, deeper buckets from the next scan on */
+	int       user_shape;       /* bucket shape was given by the caller: never change it */
 	cudaEvent_t ev[4];
 	/* acm_scan_host staging */
 	uint8_t  *stage[2];
@@ -610,12 +612,38 @@ acm_scanner_free(struct acm_scanner *s)
 	free(s);
 }
 
+/* (re)allocates buckets, scratch (flags | tile states | counts) and offsets for s->shift / s->cap */
+static int
+scanner_alloc_buckets(struct acm_scanner *s)
+{
+	cudaFree(s->buckets);
+	cudaFree(s->scratch);
+	cudaFree(s->offsets);
+	s->buckets = NULL;
+	s->scratch = NULL;
+	s->offsets = NULL;
+	s->max_buckets = (uint32_t)((s->max_bytes + (1ull << s->shift) - 1) >> s->shift) + 1;
+	s->n_bucket_tiles = (s->max_buckets + SCAN_TILE - 1) / SCAN_TILE + 1;
+	if (cudaMalloc((void **)&s->buckets, (size_t)s->max_buckets * s->cap * 8) != cudaSuccess ||
+	    cudaMalloc((void **)&s->scratch, 64 + (size_t)s->n_bucket_tiles * 8 + (size_t)s->max_buckets * 4) !=
+	    cudaSuccess ||
+	    cudaMalloc((void **)&s->offsets, (size_t)s->max_buckets * 4) != cudaSuccess) {
+		acm_set_error("scanner: cannot allocate %zu bytes of result buckets: %s",
+		    (size_t)s->max_buckets * s->cap * 8, cudaGetErrorString(cudaGetLastError()));
+		return ACM_ERR_CUDA;
+	}
+	s->flags = (uint32_t *)s->scratch;
+	s->bucket_tiles = (uint64_t *)(s->scratch + 64);
+	s->counts = (uint32_t *)(s->scratch + 64 + (size_t)s->n_bucket_tiles * 8);
+	return ACM_OK;
+}
+
 extern "C" int
 acm_scanner_create(struct acm_device *dev, struct acm_automaton *aut, uint64_t max_bytes,
     const struct acm_scan_params *params, struct acm_scanner **out)
 {
 	struct acm_scanner *s;
-	int mode;
+	int mode, rc;
 
 	*out = NULL;
 	if (!dev || !aut) {
@@ -648,6 +676,7 @@ acm_scanner_create(struct acm_device *dev, struct acm_automaton *aut, uint64_t m
 	}
 	s->p.mode = mode;
 	s->max_bytes = max_bytes;
+	s->user_shape = s->p.bucket_shift || s->p.bucket_cap;
 	s->shift = s->p.bucket_shift ? (uint32_t)s->p.bucket_shift : 15u;
 	if (s->shift < 8 || s->shift > 30) {
 		acm_set_error("scanner_create: bucket_shift must be in 8..30");
@@ -661,7 +690,10 @@ acm_scanner_create(struct acm_device *dev, struct acm_automaton *aut, uint64_t m
 	if (s->cap > 8192)
 		s->cap = 8192;
 	s->cap = next_pow2(s->cap);
-	s->max_buckets = (uint32_t)((max_bytes + (1ull << s->shift) - 1) >> s->shift) + 1;
+	if ((rc = scanner_alloc_buckets(s)) != ACM_OK) {
+		acm_scanner_free(s);
+		return rc;
+	}
 	s->max_tiles = (s->max_buckets + SCAN_TILE - 1) / SCAN_TILE + 1;
 
 #define SALLOC(ptr, bytes)                                                          \
@@ -674,13 +706,6 @@ acm_scanner_create(struct acm_device *dev, struct acm_automaton *aut, uint64_t m
 			return ACM_ERR_CUDA;                                                    \
 		}                                                                           \
 	} while (0)
-	SALLOC(s->buckets, (size_t)s->max_buckets * s->cap * 8);
-	s->n_bucket_tiles = (s->max_buckets + SCAN_TILE - 1) / SCAN_TILE + 1;
-	SALLOC(s->scratch, 64 + (size_t)s->n_bucket_tiles * 8 + (size_t)s->max_buckets * 4);
-	s->flags = (uint32_t *)s->scratch;
-	s->bucket_tiles = (uint64_t *)(s->scratch + 64);
-	s->counts = (uint32_t *)(s->scratch + 64 + (size_t)s->n_bucket_tiles * 8);
-	SALLOC(s->offsets, (size_t)s->max_buckets * 4);
 	SALLOC(s->tile_state, (size_t)s->max_tiles * 8);
 	s->out_cap = 1u << 16;
 	SALLOC(s->out, s->out_cap * 8);
@@ -800,6 +825,28 @@ scan_on_stream(struct acm_scanner *s, cudaStream_t st, const void *d_data, uint6
 		return ACM_ERR_LIMIT;
 	}
 	CUDA_TRY(cudaSetDevice(s->dev->ordinal));
+	if (s->densify) {
+		/*
+		 * The previous scan overflowed its buckets and paid for the exact two-pass path.
+		 * Dense output (a lexicon over text: one match per ~9 bytes) wants 4 KiB buckets of
+		 * 1024 records -- 2 bytes of bucket per input byte, so only when that fits easily.
+		 */
+		size_t free_b = 0, total_b = 0;
+		const size_t want = (size_t)((s->max_bytes >> 12) + 2) * 1024 * 8;
+		s->densify = 0;
+		if (cudaMemGetInfo(&free_b, &total_b) == cudaSuccess &&
+		    want < free_b / 2 + (size_t)s->max_buckets * s->cap * 8) {
+			const uint32_t old_shift = s->shift, old_cap = s->cap;
+			s->shift = 12;
+			s->cap = 1024;
+			if (scanner_alloc_buckets(s) != ACM_OK) {
+				s->shift = old_shift;
+				s->cap = old_cap;
+				if ((rc = scanner_alloc_buckets(s)) != ACM_OK)
+					return rc;
+			}
+		}
+	}
 	nb = (uint32_t)((emit_hi - emit_lo + (1ull << s->shift) - 1) >> s->shift);
 
 	memset(&E, 0, sizeof(E));
@@ -902,6 +949,8 @@ scan_on_stream(struct acm_scanner *s, cudaStream_t st, const void *d_data, uint6
 	if (timing)
 		CUDA_TRY(cudaStreamSynchronize(st));
 	s->last_n = total;
+	if (overflow && !s->user_shape && s->shift > 12)
+		s->densify = 1;
 	if (res) {
 		res->n_matches = total;
 		res->n_bytes = emit_hi - emit_lo;
