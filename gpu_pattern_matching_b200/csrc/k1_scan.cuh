@@ -173,11 +173,54 @@ __device__ __forceinline__ void emit_own(const AutDev &A, const EmitCtx &E, uint
 }
 
 /*
- * Enter the automaton at position s: follow trie edges while they exist, report
- * the patterns ending at every node passed.  `limit` is exclusive.
+ * Per-warp staging of match records in shared memory.  A walk emits from one lane at a
+ * time, and a global atomicAdd per record is a ~500-cycle round trip on the emitting lane's
+ * critical path; staged, a record costs one shared-memory atomic, and the whole warp later
+ * flushes up to WQ_CAP records with one global atomic per (bucket, 32 records).
  */
-__device__ __noinline__ void walk_from(const AutDev A, const EmitCtx E, const uint8_t *__restrict__ data,
-    uint64_t s, uint64_t limit)
+#define WQ_CAP   128
+#define WQ_FLUSH 64
+
+struct WarpQueue {
+	uint64_t *rec;          /* [WQ_CAP] in shared memory */
+	uint32_t *count;        /* records appended since the last flush (may exceed WQ_CAP) */
+};
+
+__device__ __forceinline__ void stage_record(const WarpQueue &Q, const EmitCtx &E, uint64_t end, uint32_t pat)
+{
+	if (end < E.emit_lo || end >= E.emit_hi)
+		return;
+	const uint32_t slot = atomicAdd(Q.count, 1u);
+	if (slot < WQ_CAP)
+		Q.rec[slot] = (end << ACM_KEY_PAT_BITS) | pat;
+	else
+		emit_record(E, end, pat);           /* queue full: straight to the bucket */
+}
+
+/* whole warp, converged */
+__device__ __forceinline__ void flush_queue(const WarpQueue &Q, const EmitCtx &E, int lane)
+{
+	__syncwarp();
+	uint32_t n = *Q.count;
+	if (n > WQ_CAP)
+		n = WQ_CAP;
+	for (uint32_t i = lane; i < n; i += 32) {
+		const uint64_t key = Q.rec[i];
+		emit_record(E, key >> ACM_KEY_PAT_BITS, (uint32_t)(key & ACM_KEY_PAT_MASK));
+	}
+	__syncwarp();
+	if (lane == 0)
+		*Q.count = 0;
+	__syncwarp();
+}
+
+/*
+ * Enter the automaton at position s: follow trie edges while they exist, report the
+ * patterns ending at every node passed.  `limit` is exclusive.
+ */
+template <bool STAGED>
+__device__ __forceinline__ void walk_from_t(const AutDev &A, const EmitCtx &E, const WarpQueue &Q,
+    const uint8_t *__restrict__ data, uint64_t s, uint64_t limit)
 {
 	uint32_t state = 0;
 	uint32_t d = 0;
@@ -188,9 +231,24 @@ __device__ __noinline__ void walk_from(const AutDev A, const EmitCtx E, const ui
 			break;
 		state = nx;
 		++d;
-		if (e & ACM_T_OWN)
-			emit_own(A, E, state, pos);
+		if (e & ACM_T_OWN) {
+			const uint32_t lo = __ldg(&A.own_begin[state]);
+			const uint32_t hi = __ldg(&A.own_begin[state + 1]);
+			for (uint32_t k = lo; k < hi; ++k) {
+				if (STAGED)
+					stage_record(Q, E, pos, __ldg(&A.own_pat[k]));
+				else
+					emit_record(E, pos, __ldg(&A.own_pat[k]));
+			}
+		}
 	}
+}
+
+__device__ __noinline__ void walk_from(const AutDev A, const EmitCtx E, const uint8_t *__restrict__ data,
+    uint64_t s, uint64_t limit)
+{
+	WarpQueue none = {nullptr, nullptr};
+	walk_from_t<false>(A, E, none, data, s, limit);
 }
 
 /*
@@ -509,7 +567,7 @@ k_scan_sampled4(const __grid_constant__ AutDev A, const __grid_constant__ EmitCt
 
 #define S2_THREADS 512
 #define S2_UNROLL  2
-#define S2_SMEM_BYTES (65536 / 8 + 16)
+#define S2_SMEM_BYTES (65536 / 8 + 16 + (S2_THREADS / 32) * (WQ_CAP * 8 + 16))
 
 __global__ void __launch_bounds__(S2_THREADS, 2)
 k_scan_start2(const AutDev A, const EmitCtx E, const uint8_t *__restrict__ data, uint64_t n,
@@ -518,6 +576,15 @@ k_scan_start2(const AutDev A, const EmitCtx E, const uint8_t *__restrict__ data,
 	extern __shared__ __align__(128) uint32_t s2_smem[];
 	uint32_t *b2 = s2_smem;
 	uint64_t *bar = reinterpret_cast<uint64_t *>(s2_smem + 2048);
+	WarpQueue Q;
+	{
+		uint8_t *qbase = reinterpret_cast<uint8_t *>(s2_smem) + 65536 / 8 + 16 +
+		    (threadIdx.x >> 5) * (WQ_CAP * 8 + 16);
+		Q.rec = reinterpret_cast<uint64_t *>(qbase + 16);
+		Q.count = reinterpret_cast<uint32_t *>(qbase);
+		if ((threadIdx.x & 31) == 0)
+			*Q.count = 0;
+	}
 
 	if (threadIdx.x == 0) {
 		mbar_init(bar, 1);
@@ -564,15 +631,23 @@ k_scan_start2(const AutDev A, const EmitCtx E, const uint8_t *__restrict__ data,
 			}
 			if (!live)
 				hits = 0;
-			while (hits) {
-				const int p = 31 - __clz(hits);
-				hits &= ~(1u << p);
-				const uint64_t s = idx * 16 + (uint64_t)(15 - p);
-				if (s >= E.valid_lo && s < limit)
-					walk_from(A, E, data, s, limit);
+			/* warp-uniform loop: every lane pops one of its hits per round and walks the
+			 * automaton from there; records are staged per warp and flushed together */
+			while (__any_sync(FULL_MASK, hits != 0)) {
+				if (hits) {
+					const int p = 31 - __clz(hits);
+					hits &= ~(1u << p);
+					const uint64_t s = idx * 16 + (uint64_t)(15 - p);
+					if (s >= E.valid_lo && s < limit)
+						walk_from_t<true>(A, E, Q, data, s, limit);
+				}
+				__syncwarp();
+				if (*Q.count >= WQ_FLUSH)
+					flush_queue(Q, E, lane);
 			}
 		}
 	}
+	flush_queue(Q, E, lane);
 }
 
 /* ------------------------------------------------------------------------- */
