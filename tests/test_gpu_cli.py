@@ -84,3 +84,44 @@ def test_cli_text_mode_categorical(tmp_path):
     assert st["Matches"] == 40 and st["Processed lines"] == read_fixture("kat_text_readme.txt.gz").count(b"\n")
     ids = [int(LINE.match(l).group(1)) for l in out.split(b"\n") if l.startswith(b"Pattern ")]
     assert len(ids) == 40 and all(i != 0 for i in ids)          # categorical ids (+/- scores), not line numbers
+
+
+def test_flow_grep_ushort_application(tmp_path):
+    """AC_ushorts application layer: signature file `tokens;len;details`, flow files named
+    src_sport_dst_dport_proto, one alert per (flow, signature) occurrence, flows independent."""
+    from oracle_lib import Oracle, fixture_path
+    sig_path = fixture_path("ushort_signatures.txt")
+    sig_lines = [l for l in read_fixture("ushort_signatures.txt").decode().splitlines() if l]
+    o = Oracle(2048)
+    for k, line in enumerate(sig_lines):
+        o.add_csv(line.split(";")[0], k)
+    o.compile()
+    d = tmp_path / "flows"
+    d.mkdir()
+    flows = {"10.19.1.5_333_152.29.9.15_443_tcp": read_fixture("ushort_flow_333.txt"),
+             "10.19.1.5_666_152.29.9.115_443_tcp": read_fixture("ushort_flow_666.txt"),
+             # a signature split over the end of one flow and the start of the next must NOT match
+             "10.0.0.1_1_10.0.0.2_2_udp": b"5,5,5,666\n",
+             "10.0.0.1_1_10.0.0.3_2_udp": b"676,1,2\n3,9\n"}
+    expect = {}
+    for name, data in flows.items():
+        (d / name).write_bytes(data)
+        toks = np.array([int(x) for x in re.split(rb"[,\s]+", data) if x], dtype=np.uint16)
+        off, pat, _, _ = o.search(toks)
+        expect[name] = sorted(pat.tolist())
+    out = subprocess.run([os.path.join(ROOT, "cli", "b200_flow_grep"), "-p", sig_path, "-f", str(d), "-v"],
+                         capture_output=True, timeout=120)
+    assert out.returncode == 0, out.stderr.decode()
+    got = {n: [] for n in flows}
+    for line in out.stdout.decode().splitlines():
+        m = re.match(r"^date: \d{4}-\d\d-\d\d, time: \d\d:\d\d:\d\d, signature id: (\d+), signature pattern: "
+                     r"'([\d,]+)', signature length: (\d+), signature details: '(.*)', source ip: (\S+), "
+                     r"source port: (\S+), destination ip: (\S+), destination port: (\S+), protocol: (\S+) $", line)
+        if m:
+            sid = int(m.group(1))
+            assert m.group(2) == sig_lines[sid].split(";")[0] and int(m.group(3)) == int(sig_lines[sid].split(";")[1])
+            got["_".join(m.group(i) for i in range(5, 10))].append(sid)
+    assert {k: sorted(v) for k, v in got.items()} == expect
+    assert expect["10.0.0.1_1_10.0.0.2_2_udp"] == [] and expect["10.0.0.1_1_10.0.0.3_2_udp"] == [2]
+    assert sum(len(v) for v in expect.values()) >= 3
+    assert f"Alerts:              {sum(len(v) for v in expect.values())}".encode() in out.stdout
