@@ -125,8 +125,9 @@ def test_error_codes_instead_of_exit():
     a.add_pattern(b"ok", 2)
     a.compile()
     assert a.num_patterns == 2 and a.get_states() == 2
-    with pytest.raises(g.AcmError):
-        a.gen_state_table()                           # no GPU here: must fail loudly, not fall back
+    if L.acm_device_count() == 0:
+        with pytest.raises(g.AcmError):
+            a.gen_state_table()                       # no GPU here: must fail loudly, not fall back
     h = L.printable_hex_to_bytes(b"4D5a90")
     assert h and bytes((C.c_ubyte * 3).from_address(h)) == b"\x4d\x5a\x90"
     assert not L.printable_hex_to_bytes(b"4d5")
