@@ -352,7 +352,7 @@ def main():
     traffic = None
     tp = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.exists(tp):
-        traffic = json.load(open(tp)).get("k_scan_sampled4_dram_bytes_per_launch")
+        traffic = json.load(open(tp)).get("k_scan_sampled_dram_bytes_per_launch")
     line = {
         "metric": METRIC, "value": value, "unit": "GB/s", "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
@@ -367,7 +367,9 @@ def main():
                                " NVLink IPC) + D2H on a side stream, overlapped with the next step's scan" if use_peer else
                                " + NCCL count all-gather + key send/recv to rank 0 + D2H") if world > 1 else "")},
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                     "frac": achieved / peak, "traffic": traffic, "kernel": "k_scan_" + g.MODE_NAMES[res.mode],
+                     "frac": achieved / peak, "traffic": traffic,
+                     "kernel": "k_scan_" + g.MODE_NAMES[res.mode] + (
+                         f"<{g.lib().acm_automaton_sample_stride(acsm.automaton)}>" if res.mode == 1 else ""),
                      "kernel_ms": k1_avg, "algorithmic_bytes_per_launch": per, "peak_source": peak_src},
         "gpu_launches": int(launches),
         "clocks": clocks,

@@ -245,23 +245,41 @@ build_filters(struct acm_core *c)
 	if (t->min_pattern_len < 7)
 		return ACM_OK;
 
-	/* hashed 4-gram filters over pattern offsets 0..3, exact gram table, candidate lists */
+	/*
+	 * Sampled entry filter.  stride 4: every occurrence of a pattern >= 7 bytes contains a
+	 * 4-byte window at a multiple of 4; stride 8: every occurrence of a pattern >= 10 bytes
+	 * contains a 3-byte window at a multiple of 8 (half the bitmap lookups per input byte).
+	 * f1 / f2 hash the window bytes (G = 4 or 3); the exact table is keyed by the 4 bytes at
+	 * the window position in both cases -- when the pattern ends after the third byte (length
+	 * 10, offset 7) the fourth is a wildcard and all 256 keys are entered.
+	 */
 	t->f1 = calloc((1u << ACM_F1_BITS_LOG2) / 32, 4);
 	t->f2 = calloc((1u << ACM_F2_BITS_LOG2) / 32, 4);
 	if (!t->f1 || !t->f2)
 		return ACM_ERR_NOMEM;
 	{
 		struct gtrip { uint32_t gram, cand; } *tr;
-		uint64_t want = (uint64_t)c->npats * 4 * 2;
+		const char *force = getenv("ACM_SAMPLE_STRIDE");
+		const uint32_t S = (t->min_pattern_len >= 10 && !(force && atoi(force) == 4)) ? 8 : 4;
+		const uint32_t G = S == 8 ? 3 : 4;
+		uint64_t want, ntr_max = 0;
 		uint32_t slots = 1024, lg = 10, ntr = 0, blob = 0;
 
+		t->sample_stride = (int)S;
+		for (k = 0; k < (uint32_t)c->npats; k++) {
+			if (c->pats[k].n == 0)
+				continue;
+			for (uint32_t j = 0; j < S; j++)
+				ntr_max += (j + 4 <= (uint32_t)c->pats[k].n) ? 1 : 256;
+		}
+		want = ntr_max * 2;
 		while (slots < want) {
 			slots <<= 1;
 			lg++;
 		}
 		t->gram_slots = slots;
 		t->grams = calloc(slots, sizeof(*t->grams));
-		tr = malloc(((size_t)c->npats * 4 + 1) * sizeof(*tr));
+		tr = malloc((ntr_max + 1) * sizeof(*tr));
 		t->pat_off = calloc((size_t)c->npats + 1, 4);
 		if (!t->grams || !tr || !t->pat_off) {
 			free(tr);
@@ -279,21 +297,30 @@ build_filters(struct acm_core *c)
 		}
 		for (k = 0; k < (uint32_t)c->npats; k++) {
 			const unsigned char *p = c->pats[k].syms;
-			if (c->pats[k].n == 0)
+			const uint32_t n = (uint32_t)c->pats[k].n;
+			if (n == 0)
 				continue;
-			memcpy(t->pat_blob + t->pat_off[k], p, (size_t)c->pats[k].n);
-			for (uint32_t j = 0; j < 4; j++) {
-				uint32_t g = (uint32_t)p[j] | ((uint32_t)p[j + 1] << 8) |
-				    ((uint32_t)p[j + 2] << 16) | ((uint32_t)p[j + 3] << 24);
-				uint32_t h1 = g * ACM_HASH1_MUL;
-				uint32_t h2 = g * ACM_HASH2_MUL;
-				t->f1[h1 >> (32 - (ACM_F1_BITS_LOG2 - 5))] |=
-				    0x80000000u >> (h1 & 31);
-				t->f2[h2 >> (32 - (ACM_F2_BITS_LOG2 - 5))] |=
-				    0x80000000u >> (h2 & 31);
-				tr[ntr].gram = g;
-				tr[ntr].cand = k | (j << ACM_CAND_J_SHIFT);
-				ntr++;
+			memcpy(t->pat_blob + t->pat_off[k], p, n);
+			for (uint32_t j = 0; j < S; j++) {
+				uint32_t g = 0;
+				for (uint32_t b = 0; b < G; b++)
+					g |= (uint32_t)p[j + b] << (8 * b);
+				const uint32_t h1 = g * ACM_HASH1_MUL;
+				const uint32_t h2 = g * ACM_HASH2_MUL;
+				t->f1[h1 >> (32 - (ACM_F1_BITS_LOG2 - 5))] |= 0x80000000u >> (h1 & 31);
+				t->f2[h2 >> (32 - (ACM_F2_BITS_LOG2 - 5))] |= 0x80000000u >> (h2 & 31);
+				if (j + 4 <= n) {
+					tr[ntr].gram = (uint32_t)p[j] | ((uint32_t)p[j + 1] << 8) |
+					    ((uint32_t)p[j + 2] << 16) | ((uint32_t)p[j + 3] << 24);
+					tr[ntr].cand = k | (j << ACM_CAND_J_SHIFT);
+					ntr++;
+				} else {
+					for (uint32_t b3 = 0; b3 < 256; b3++) {
+						tr[ntr].gram = g | (b3 << 24);
+						tr[ntr].cand = k | (j << ACM_CAND_J_SHIFT);
+						ntr++;
+					}
+				}
 			}
 		}
 		/* group by gram (stable order inside a gram is irrelevant: results get sorted) */

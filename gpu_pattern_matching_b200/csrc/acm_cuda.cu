@@ -111,7 +111,9 @@ set_kernel_attrs(int ordinal)
 {
 	if (ordinal < 64 && g_attr_done[ordinal])
 		return ACM_OK;
-	CUDA_TRY(cudaFuncSetAttribute(k_scan_sampled4, cudaFuncAttributeMaxDynamicSharedMemorySize,
+	CUDA_TRY(cudaFuncSetAttribute(k_scan_sampled<4>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+	    S4_SMEM_BYTES));
+	CUDA_TRY(cudaFuncSetAttribute(k_scan_sampled<8>, cudaFuncAttributeMaxDynamicSharedMemorySize,
 	    S4_SMEM_BYTES));
 	CUDA_TRY(cudaFuncSetAttribute(k_scan_start2, cudaFuncAttributeMaxDynamicSharedMemorySize,
 	    S2_SMEM_BYTES));
@@ -388,6 +390,7 @@ acm_automaton_upload(struct acm_device *dev, const struct acm_tables *t, struct 
 	a->d.num_states = t->num_states;
 	a->d.alpha = t->alpha;
 	a->d.max_len = t->max_pattern_len;
+	a->d.sample_stride = t->sample_stride;
 	if (rc == ACM_OK && cudaStreamSynchronize(dev->stream) != cudaSuccess) {
 		acm_set_error("automaton_upload: %s", cudaGetErrorString(cudaGetLastError()));
 		rc = ACM_ERR_CUDA;
@@ -407,6 +410,7 @@ extern "C" int acm_automaton_min_pattern_len(const struct acm_automaton *a) { re
 extern "C" int acm_automaton_alphabet(const struct acm_automaton *a) { return a->alpha; }
 extern "C" size_t acm_automaton_device_bytes(const struct acm_automaton *a) { return a->bytes; }
 extern "C" uint32_t acm_automaton_gram_count(const struct acm_automaton *a) { return a->gram_count; }
+extern "C" int acm_automaton_sample_stride(const struct acm_automaton *a) { return a->d.sample_stride; }
 
 extern "C" int
 acm_automaton_default_mode(const struct acm_automaton *a)
@@ -770,9 +774,14 @@ launch_k1(struct acm_scanner *s, cudaStream_t st, const void *d_data, uint64_t n
 		if (zero_work_counter)
 			CUDA_TRY(cudaMemsetAsync(s->flags + 6, 0, 8, st));
 		/* the last two chunks per resident warp are handed out singly */
-		k_scan_sampled4<<<(unsigned)blocks, S4_THREADS, S4_SMEM_BYTES, st>>>(a->d, E,
-		    (const uint8_t *)d_data, n, vec_lo, vec_hi, limit, s->flags + 6,
-		    (uint32_t)(blocks * (S4_THREADS / 32) * 2));
+		if (a->d.sample_stride == 8)
+			k_scan_sampled<8><<<(unsigned)blocks, S4_THREADS, S4_SMEM_BYTES, st>>>(a->d, E,
+			    (const uint8_t *)d_data, n, vec_lo, vec_hi, limit, s->flags + 6,
+			    (uint32_t)(blocks * (S4_THREADS / 32) * 2));
+		else
+			k_scan_sampled<4><<<(unsigned)blocks, S4_THREADS, S4_SMEM_BYTES, st>>>(a->d, E,
+			    (const uint8_t *)d_data, n, vec_lo, vec_hi, limit, s->flags + 6,
+			    (uint32_t)(blocks * (S4_THREADS / 32) * 2));
 	} else if (s->p.mode == ACM_MODE_START2) {
 		const uint64_t tile = (uint64_t)S2_THREADS * S2_UNROLL;
 		uint64_t blocks = (vec_hi - vec_lo + tile - 1) / tile;

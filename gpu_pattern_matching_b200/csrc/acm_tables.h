@@ -45,7 +45,7 @@ struct acm_gram_slot {     /* exact 4-gram table, open addressing in HBM/L2 */
 };
 
 /*
- * candidate: pattern `id` has the gram at byte offset j; LAST marks the end of a gram's
+ * candidate: pattern `id` has the gram at byte offset j (3 bits); LAST marks the end of a gram's
  * list.  pre0/pre1 (first 8 bytes, zero padded) and tail (last 4 bytes) give a quick reject
  * before the full compare; 32 bytes per record = two 16-byte loads.
  */
@@ -82,6 +82,7 @@ struct acm_tables {
 	uint32_t *bfs_to_ref;        /* [num_states] id in the reference's numbering  */
 
 	/* --- byte alphabet only: scan filters --- */
+	int       sample_stride;     /* 0 none, 4: 4-byte grams at offsets 0..3 (min len >= 7), 8: 3-byte grams at offsets 0..7 (min len >= 10) */
 	uint32_t *f1;                /* 2^20-bit bitmap of hashed pattern 4-grams at offsets 0..3 (bit-reversed words) */
 	uint32_t *f2;                /* 2^19-bit second hash of the same grams        */
 	struct acm_gram_slot *grams; /* exact gram table                              */

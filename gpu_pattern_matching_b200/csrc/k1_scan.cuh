@@ -62,6 +62,7 @@ struct AutDev {
 	uint32_t num_states;
 	int      alpha;
 	int      max_len;
+	int      sample_stride;
 };
 
 struct EmitCtx {
@@ -315,18 +316,19 @@ __device__ __forceinline__ void s4_verify(const AutDev &A, const EmitCtx &E, con
  * s in [lo - 3, lo + 60], walks the DFA cold from the first of them until no match that
  * started there can still be open, and keeps a match iff its start is one of its own.
  */
-#define S4_DENSE_HITS 128      /* of 512 windows per chunk; random data sees ~4..6 % */
+/* a quarter of the chunk's windows hit: random data sees 3..6 % */
 
 __device__ __noinline__ void s4_chunk_dfa(const AutDev *__restrict__ Ap, const EmitCtx *__restrict__ Ep,
-    const uint8_t *__restrict__ data, uint64_t chunk_lo, uint64_t limit, int lane)
+    const uint8_t *__restrict__ data, uint64_t chunk_lo, uint64_t limit, int lane, uint32_t stride)
 {
 	const AutDev &A = *Ap;
 	const EmitCtx &E = *Ep;
 	const uint64_t lo = chunk_lo + 64ull * (uint64_t)lane;
-	uint64_t s_min = lo >= 3 ? lo - 3 : 0;
+	/* starts whose first stride-aligned window lies in [lo, lo + 64) */
+	uint64_t s_min = lo >= stride - 1 ? lo - (stride - 1) : 0;
 	if (s_min < E.valid_lo)
 		s_min = E.valid_lo;
-	const uint64_t s_max = lo + 60;
+	const uint64_t s_max = lo + 64 - stride;
 	uint64_t end = s_max + (uint64_t)A.max_len;
 	if (end > limit)
 		end = limit;
@@ -354,8 +356,14 @@ __device__ __noinline__ void s4_chunk_dfa(const AutDev *__restrict__ Ap, const E
 	}
 }
 
+/*
+ * STRIDE 4: 4-byte windows at multiples of 4 (every pattern >= 7 bytes).
+ * STRIDE 8: 3-byte windows at multiples of 8 (every pattern >= 10 bytes): half the bitmap
+ *           lookups per input byte; the exact stage still keys on the 4 bytes at the window.
+ */
+template <int STRIDE>
 __global__ void __launch_bounds__(S4_THREADS, 1)
-k_scan_sampled4(const __grid_constant__ AutDev A, const __grid_constant__ EmitCtx E,
+k_scan_sampled(const __grid_constant__ AutDev A, const __grid_constant__ EmitCtx E,
     const uint8_t *__restrict__ data, uint64_t n,
     uint64_t vec_lo, uint64_t vec_hi, uint64_t limit, uint32_t *work_counter, uint32_t tail_chunks)
 {
@@ -365,6 +373,9 @@ k_scan_sampled4(const __grid_constant__ AutDev A, const __grid_constant__ EmitCt
 	uint64_t *bar = reinterpret_cast<uint64_t *>(s4_smem + F1_WORDS + F2_WORDS);
 	const int lane = threadIdx.x & 31;
 	uint32_t trace_chunks = 0;
+	constexpr int WPV = 16 / STRIDE;                 /* windows per 16-byte vector */
+	constexpr int NW = S4_UNROLL * WPV;              /* windows per lane per chunk */
+	constexpr uint32_t GMASK = STRIDE == 4 ? 0xffffffffu : 0x00ffffffu;
 
 	if (E.trace && threadIdx.x == 0)
 		E.trace[blockIdx.x * 4 + 0] = globaltimer_ns();
@@ -455,8 +466,8 @@ k_scan_sampled4(const __grid_constant__ AutDev A, const __grid_constant__ EmitCt
 		for (int u = 0; u < S4_UNROLL; ++u) {
 			const uint32_t w[4] = {v[u].x, v[u].y, v[u].z, v[u].w};
 #pragma unroll
-			for (int k = 0; k < 4; ++k) {
-				const uint32_t h = w[k] * ACM_HASH1_MUL;
+			for (int k = 0; k < WPV; ++k) {
+				const uint32_t h = (w[k * (4 / WPV)] & GMASK) * ACM_HASH1_MUL;
 				const uint32_t word = f1[h >> (32 - (ACM_F1_BITS_LOG2 - 5))];
 				/* bitmap words are bit-reversed: the tested bit lands in the MSB */
 				const uint32_t t = __funnelshift_l(0u, word, h);
@@ -469,13 +480,13 @@ k_scan_sampled4(const __grid_constant__ AutDev A, const __grid_constant__ EmitCt
 #pragma unroll
 			for (int u = 0; u < S4_UNROLL; ++u)
 				if (cur_first + (uint64_t)u * 32 + lane >= vec_hi)
-					hits &= ~(0xF000u >> (4 * u));
+					hits &= ~((((1u << WPV) - 1u) << (NW - WPV)) >> (WPV * u));
 		}
-		if (__reduce_add_sync(FULL_MASK, (uint32_t)__popc(hits)) >= S4_DENSE_HITS) {
-			s4_chunk_dfa(&A, &E, data, cur_first * 16, limit, lane);
+		if (__reduce_add_sync(FULL_MASK, (uint32_t)__popc(hits)) >= NW * 32 / 4) {
+			s4_chunk_dfa(&A, &E, data, cur_first * 16, limit, lane, STRIDE);
 			continue;
 		}
-		/* bit (15 - q) of hits belongs to window q = u * 4 + k.  Survivors are rare: from
+		/* bit (NW - 1 - q) of hits belongs to window q = u * WPV + k.  Survivors are rare: from
 		 * here on control flow is warp-uniform and verification is done by the whole warp. */
 		while (__any_sync(FULL_MASK, hits != 0)) {
 			uint32_t cbegin = 0;
@@ -483,25 +494,30 @@ k_scan_sampled4(const __grid_constant__ AutDev A, const __grid_constant__ EmitCt
 			if (hits) {
 				const int p = 31 - __clz(hits);
 				hits &= ~(1u << p);
-				const int q = 15 - p;
-				const uint4 x = (q & 8) ? ((q & 4) ? v[3] : v[2]) : ((q & 4) ? v[1] : v[0]);
-				const uint32_t g = (q & 2) ? ((q & 1) ? x.w : x.z) : ((q & 1) ? x.y : x.x);
-				const uint32_t h2 = g * ACM_HASH2_MUL;
+				const int q = NW - 1 - p;
+				const int u = q / WPV, k = q % WPV;
+				const uint4 x = (u & 2) ? ((u & 1) ? v[3] : v[2]) : ((u & 1) ? v[1] : v[0]);
+				uint32_t word4;                          /* the 4 bytes at the window */
+				if (STRIDE == 4)
+					word4 = (k & 2) ? ((k & 1) ? x.w : x.z) : ((k & 1) ? x.y : x.x);
+				else
+					word4 = k ? x.z : x.x;
+				const uint32_t h2 = (word4 & GMASK) * ACM_HASH2_MUL;
 				const uint32_t word2 = f2[h2 >> (32 - (ACM_F2_BITS_LOG2 - 5))];
 				if (__funnelshift_l(0u, word2, h2) & 0x80000000u) {
-					/* exact gram table (L2 resident) */
-					uint32_t sl = (g * ACM_HASH3_MUL) >> A.gram_shift;
+					/* exact table keyed by the 4 bytes at the window (L2 resident) */
+					uint32_t sl = (word4 * ACM_HASH3_MUL) >> A.gram_shift;
 					for (;;) {
 						const uint2 slot = __ldg(reinterpret_cast<const uint2 *>(A.grams) + sl);
 						if (slot.y == 0)
 							break;
-						if (slot.x == g) {
+						if (slot.x == word4) {
 							cbegin = slot.y;
 							break;
 						}
 						sl = (sl + 1) & A.gram_mask;
 					}
-					e = (cur_first + (uint64_t)(q >> 2) * 32 + lane) * 16 + (uint64_t)(q & 3) * 4;
+					e = (cur_first + (uint64_t)u * 32 + lane) * 16 + (uint64_t)k * STRIDE;
 				}
 			}
 			uint32_t pend = __ballot_sync(FULL_MASK, cbegin != 0);
@@ -510,21 +526,23 @@ k_scan_sampled4(const __grid_constant__ AutDev A, const __grid_constant__ EmitCt
 				pend &= pend - 1;
 				uint32_t ci = __shfl_sync(FULL_MASK, cbegin, src) - 1;
 				const uint64_t ew = __shfl_sync(FULL_MASK, e, src);
-				/* the aligned words around the window: enough for any candidate's first 8 bytes */
+				/* 16 bytes of text around the window, [ew - 8, ew + 8): enough for the first
+				 * 8 bytes of any candidate (it starts at ew - j, j < 8) */
 				const uint32_t *wp = reinterpret_cast<const uint32_t *>(data + ew);
-				const uint64_t wm = ew >= 4 ? __ldg(wp - 1) : 0u;
-				const uint64_t w0 = __ldg(wp);
-				const uint64_t w1 = (ew + 4 < n) ? __ldg(wp + 1) : 0u;
+				const uint64_t lo64 = ((uint64_t)(ew >= 4 ? __ldg(wp - 1) : 0u) << 32) |
+				    (STRIDE > 4 && ew >= 8 ? __ldg(wp - 2) : 0u);
+				const uint64_t hi64 = ((uint64_t)((ew + 4 < n) ? __ldg(wp + 1) : 0u) << 32) | __ldg(wp);
 				for (;;) {
 					/* one candidate per lane (lists are padded, lanes past LAST are ignored) */
 					const uint4 *cp = reinterpret_cast<const uint4 *>(A.cand) + 2 * (size_t)(ci + lane);
 					const uint4 c = __ldg(cp);
 					const uint32_t lastm = __ballot_sync(FULL_MASK, (c.x & ACM_CAND_LAST) != 0);
 					const int nvalid = lastm ? __ffs(lastm) : 32;
-					const uint32_t j = (c.x >> ACM_CAND_J_SHIFT) & 3u;
+					const uint32_t j = (c.x >> ACM_CAND_J_SHIFT) & 7u;
 					const uint32_t len = c.w;
-					const uint32_t t0 = (uint32_t)(((w0 << 32) | wm) >> (32 - 8 * j));
-					const uint32_t t1 = (uint32_t)(((w1 << 32) | w0) >> (32 - 8 * j));
+					const uint32_t o = 8u - j;                    /* byte offset of s in the block, 1..8 */
+					const uint64_t first8 = (o == 8u) ? hi64 : ((lo64 >> (8u * o)) | (hi64 << (64u - 8u * o)));
+					const uint32_t t0 = (uint32_t)first8, t1 = (uint32_t)(first8 >> 32);
 					const uint32_t m1 = len >= 8 ? 0xffffffffu : ((1u << (8 * (len - 4))) - 1u);
 					const uint64_t s = ew - j;
 					bool ok = lane < nvalid && ew >= j && s >= E.valid_lo && s + len <= limit &&

@@ -12,7 +12,7 @@ from . import _lib
 from ._lib import AcmError, ScanParams, ScanResult, check, lib
 
 MODE_AUTO, MODE_SAMPLED4, MODE_START2, MODE_DFA = 0, 1, 2, 3
-MODE_NAMES = {1: "sampled4", 2: "start2", 3: "dfa"}
+MODE_NAMES = {1: "sampled", 2: "start2", 3: "dfa"}
 KEY_PAT_BITS = 24
 
 

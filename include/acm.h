@@ -78,6 +78,9 @@ size_t   acm_automaton_device_bytes(const struct acm_automaton *);
 /* which kernel ACM_MODE_AUTO picks: 1 = sampled 4-gram, 2 = 2-byte start filter, 3 = DFA */
 int      acm_automaton_default_mode(const struct acm_automaton *);
 uint32_t acm_automaton_gram_count(const struct acm_automaton *);
+/* window stride of the sampled kernel for this automaton: 8 (every pattern >= 10 bytes), 4 (>= 7), 0 (not available).
+ * ACM_SAMPLE_STRIDE=4 in the environment at compile (acsm_compile) time forces 4. */
+int      acm_automaton_sample_stride(const struct acm_automaton *);
 
 /* ---- scan ---- */
 struct acm_scan_params {

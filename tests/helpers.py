@@ -32,14 +32,31 @@ def build_oracle(pats, alphabet=256):
     return o
 
 
-def build_product(pats, upload=True):
+def build_product(pats, upload=True, stride=None):
+    """stride=4 forces the 4-byte / stride-4 sampled filter even when every pattern is >= 10
+    bytes (the builder then would pick 3-byte windows at stride 8)."""
+    import os
     a = g.Acsm()
     for p, iid in pats:
         a.add_pattern(p, iid)
-    a.compile()
+    old = os.environ.get("ACM_SAMPLE_STRIDE")
+    if stride is not None:
+        os.environ["ACM_SAMPLE_STRIDE"] = str(stride)
+    try:
+        a.compile()
+    finally:
+        if stride is not None:
+            if old is None:
+                del os.environ["ACM_SAMPLE_STRIDE"]
+            else:
+                os.environ["ACM_SAMPLE_STRIDE"] = old
     if upload:
         a.gen_state_table()
     return a
+
+
+def sample_stride(acsm):
+    return g.lib().acm_automaton_sample_stride(acsm.automaton)
 
 
 def clamav_pats(n):

@@ -6,7 +6,7 @@ import pytest
 import gpu_pattern_matching_b200 as g
 from gpu_pattern_matching_b200 import synth
 from helpers import (HAND_PATTERNS, HAND_TEXT, KAT_CASES, assert_same, build_oracle, build_product,
-                     clamav_pats, gpu_scan, load_patterns, modes_for, planted_stream)
+                     clamav_pats, gpu_scan, load_patterns, modes_for, planted_stream, sample_stride)
 from oracle_lib import read_fixture
 
 pytestmark = pytest.mark.gpu
@@ -51,11 +51,17 @@ def test_clamav_planted(device, nsig, nbytes, plants):
         off, pat, res = gpu_scan(device, a, buf, mode)
         assert_same(off, pat, eo, ep, f"clamav{nsig} mode {mode}")
         assert not res.fallback
+    # both sampled variants: 3-byte windows at stride 8 (default, min length 10) and 4-byte at stride 4
+    a4 = build_product(pats, stride=4)
+    assert (sample_stride(a), sample_stride(a4)) == (8, 4)
+    off, pat, res = gpu_scan(device, a4, buf, g.MODE_SAMPLED4)
+    assert_same(off, pat, eo, ep, f"clamav{nsig} sampled stride 4")
 
 
 def test_unaligned_lengths_and_tails(device):
     pats = clamav_pats(2000)
     o, a = build_oracle(pats), build_product(pats)
+    a4 = build_product(pats, stride=4)
     for n in (1, 3, 15, 16, 17, 31, 33, 64, 4095, 65537):
         buf = synth.stream(max(n, 256), 11)[:n].copy()
         # a signature that ends exactly at the last byte whenever it fits
@@ -66,6 +72,8 @@ def test_unaligned_lengths_and_tails(device):
         for mode in modes_for(a):
             off, pat, _ = gpu_scan(device, a, buf, mode)
             assert_same(off, pat, eo, ep, f"n={n} mode {mode}")
+        off, pat, _ = gpu_scan(device, a4, buf, g.MODE_SAMPLED4)
+        assert_same(off, pat, eo, ep, f"n={n} sampled stride 4")
 
 
 def test_emit_window_sharding(device):
@@ -78,11 +86,12 @@ def test_emit_window_sharding(device):
     buf, _ = planted_stream(pats, n, seed=3, plants=128, forced=forced)
     eo, ep, _, _ = o.search(buf)
     halo = a.get_max_pattern_size() - 1
-    for mode in modes_for(a):
+    a4 = build_product(pats, stride=4)
+    for aut, mode in [(a, m) for m in modes_for(a)] + [(a4, g.MODE_SAMPLED4)]:
         offs, pts = [], []
         for lo, hi in zip(cuts[:-1], cuts[1:]):
             start = max(0, lo - halo) & ~15       # device buffers are 16-byte aligned
-            off, pat, _ = gpu_scan(device, a, buf[start:hi], mode, emit_lo=lo - start, emit_hi=hi - start)
+            off, pat, _ = gpu_scan(device, aut, buf[start:hi], mode, emit_lo=lo - start, emit_hi=hi - start)
             offs.append(off + np.uint64(start))
             pts.append(pat)
         assert_same(np.concatenate(offs), np.concatenate(pts), eo, ep, f"sharded mode {mode}")
@@ -196,3 +205,5 @@ def test_repetitive_input_dense_hit_fallback(device):
     for mode in modes_for(a):
         off, pat, res = gpu_scan(device, a, buf, mode)
         assert_same(off, pat, eo, ep, f"repetitive mode {mode}")
+    off, pat, res = gpu_scan(device, build_product(pats, stride=4), buf, g.MODE_SAMPLED4)
+    assert_same(off, pat, eo, ep, "repetitive sampled stride 4")
