@@ -307,7 +307,10 @@ build_filters(struct acm_core *c)
 					g |= (uint32_t)p[j + b] << (8 * b);
 				const uint32_t h1 = g * ACM_HASH1_MUL;
 				const uint32_t h2 = g * ACM_HASH2_MUL;
-				t->f1[h1 >> (32 - (ACM_F1_BITS_LOG2 - 5))] |= 0x80000000u >> (h1 & 31);
+				/* level 1 is a blocked Bloom filter, k = 2: both bits live in the one 32-bit
+				 * word the kernel fetches (bit indices from hash bits 0..4 and 12..16) */
+				t->f1[h1 >> (32 - (ACM_F1_BITS_LOG2 - 5))] |=
+				    (0x80000000u >> (h1 & 31)) | (0x80000000u >> ((h1 >> 12) & 31));
 				t->f2[h2 >> (32 - (ACM_F2_BITS_LOG2 - 5))] |= 0x80000000u >> (h2 & 31);
 				if (j + 4 <= n) {
 					tr[ntr].gram = (uint32_t)p[j] | ((uint32_t)p[j + 1] << 8) |
