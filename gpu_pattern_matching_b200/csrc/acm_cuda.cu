@@ -681,14 +681,15 @@ acm_scanner_create(struct acm_device *dev, struct acm_automaton *aut, uint64_t m
 	s->p.mode = mode;
 	s->max_bytes = max_bytes;
 	s->user_shape = s->p.bucket_shift || s->p.bucket_cap;
-	s->shift = s->p.bucket_shift ? (uint32_t)s->p.bucket_shift : 15u;
+	/* sparse matches (signature sets): 128 KiB buckets of up to 1024 records keep the
+	 * post-passes at ~8k buckets per GiB; dense output is handled by the adaptive re-shape */
+	s->shift = s->p.bucket_shift ? (uint32_t)s->p.bucket_shift : (mode == ACM_MODE_SAMPLED4 ? 17u : 15u);
 	if (s->shift < 8 || s->shift > 30) {
 		acm_set_error("scanner_create: bucket_shift must be in 8..30");
 		free(s);
 		return ACM_ERR_ARG;
 	}
-	s->cap = s->p.bucket_cap ? (uint32_t)s->p.bucket_cap
-	                         : (mode == ACM_MODE_SAMPLED4 ? 256u : 1024u);
+	s->cap = s->p.bucket_cap ? (uint32_t)s->p.bucket_cap : 1024u;
 	if (s->cap < 32)
 		s->cap = 32;
 	if (s->cap > 8192)

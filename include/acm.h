@@ -85,7 +85,7 @@ int      acm_automaton_sample_stride(const struct acm_automaton *);
 /* ---- scan ---- */
 struct acm_scan_params {
 	int      mode;          /* 0 auto, 1 sampled4, 2 start2, 3 dfa                        */
-	int      bucket_shift;  /* log2 bytes of input per result bucket; 0 = default (15)   */
+	int      bucket_shift;  /* log2 bytes of input per result bucket; 0 = default (17 sampled, 15 otherwise) */
 	int      bucket_cap;    /* records per bucket before the exact 2-pass fallback; 0 = default */
 	int      timing;        /* record CUDA events around each kernel                      */
 	int      dfa_chunk;     /* bytes per thread in DFA mode; 0 = default (4096)          */
