@@ -210,53 +210,59 @@ def main():
     dev.plant(data.data_ptr(), n, read_lo, plants)
     dev.sync()
 
-    scanner = g.Scanner(dev, acsm.automaton, hi - lo, timing=True)
     emit_lo = lo - read_lo
+    key_add = read_lo << sharded.KEY_PAT_BITS
+    use_nccl = world > 1 and os.environ.get("BENCH_GATHER", "peer") == "nccl"
+    k1_ms, stats = [], {"launches": 0, "fallback": 0, "matches": 0, "mode": 0, "list_bytes": 0}
 
-    use_peer = world > 1 and os.environ.get("BENCH_GATHER", "peer") == "peer"
-    peer = sharded.PeerGather(dev, 1 << 22) if use_peer else None
-    pinned_out = torch.empty(1 << 22, dtype=torch.int64).pin_memory() if (world > 1 and rank == 0) else None
-    prof = {"scan": 0.0, "counts": 0.0, "gather": 0.0, "d2h": 0.0} if os.environ.get("BENCH_PROFILE") else None
+    if not use_nccl:
+        # default: pipelined steps, keys pushed into rank 0's HBM by the step itself (NVLink IPC
+        # stores at N > 1), D2H of the gathered list on rank 0's side stream, every step
+        pipe = sharded.StepPipeline(dev, acsm.automaton, hi - lo, 1 << 21, rank, world,
+                                    scanner_kwargs={"timing": True})
 
-    def step():
-        """scan + (N > 1) gather of the sorted lists into rank 0's HBM + D2H on rank 0."""
-        t0 = time.perf_counter()
-        res = scanner.scan_device(data.data_ptr(), n, emit_lo, n)
-        t1 = time.perf_counter()
-        if peer is not None:
-            # counts through shared memory, keys stored into rank 0's buffer over NVLink (IPC)
-            _, total_matches = peer.gather(scanner, int(res.n_matches), read_lo << sharded.KEY_PAT_BITS)
-            if prof is not None:
-                prof["scan"] += t1 - t0
-                prof["gather"] += time.perf_counter() - t1
-        elif world > 1:
-            # portable path: NCCL all-gather of the counts + grouped send/recv of the keys
-            counts = sharded.exchange_counts(res.n_matches, tdev)
-            t2 = time.perf_counter()
-            keys = sharded._as_tensor(scanner.keys_ptr(), max(1, int(res.n_matches)), tdev)
-            keys = keys[:int(res.n_matches)] + (read_lo << sharded.KEY_PAT_BITS)
-            out = sharded.gather_keys(keys, counts, 0)
-            total_matches = sum(counts)
-            if prof is not None:
-                torch.cuda.synchronize()
-            t3 = time.perf_counter()
-            if rank == 0:
-                pinned_out[:total_matches].copy_(out, non_blocking=True)
-                stream.synchronize()
-            t4 = time.perf_counter()
-            if prof is not None:
-                prof["scan"] += t1 - t0
-                prof["counts"] += t2 - t1
-                prof["gather"] += t3 - t2
-                prof["d2h"] += t4 - t3
-        else:
-            total_matches = int(res.n_matches)
-        return res, total_matches
+        def note(out):
+            res, total, keys = out
+            k1_ms.append(res.ms_scan)
+            stats["launches"] += res.launches
+            stats["fallback"] |= res.fallback
+            stats["mode"] = res.mode
+            if total is not None:
+                stats["matches"] = total
+                stats["list_bytes"] = int(keys.nbytes)
 
-    for _ in range(args.warmup):
-        step()
-    if prof is not None:
-        prof = {k: 0.0 for k in prof}
+        def run_steps(k):
+            for i in range(k):
+                pipe.submit(data.data_ptr(), n, emit_lo, n, key_add)
+                if i > 0:
+                    note(pipe.complete())
+            if k > 0:
+                note(pipe.complete())
+    else:
+        # portable path: NCCL all-gather of the counts + grouped send/recv of the keys, synchronous
+        scanner = g.Scanner(dev, acsm.automaton, hi - lo, timing=True)
+        pinned_out = torch.empty(1 << 22, dtype=torch.int64).pin_memory() if rank == 0 else None
+
+        def run_steps(k):
+            for _ in range(k):
+                res = scanner.scan_device(data.data_ptr(), n, emit_lo, n)
+                counts = sharded.exchange_counts(res.n_matches, tdev)
+                keys = sharded._as_tensor(scanner.keys_ptr(), max(1, int(res.n_matches)), tdev)
+                keys = keys[:int(res.n_matches)] + key_add
+                out = sharded.gather_keys(keys, counts, 0)
+                if rank == 0:
+                    pinned_out[:sum(counts)].copy_(out, non_blocking=True)
+                    stream.synchronize()
+                k1_ms.append(res.ms_scan)
+                stats["launches"] += res.launches
+                stats["fallback"] |= res.fallback
+                stats["mode"] = res.mode
+                stats["matches"] = sum(counts)
+                stats["list_bytes"] = sum(counts) * 8
+
+    run_steps(args.warmup)
+    k1_ms.clear()
+    stats["launches"] = 0
 
     sampler = ClockSampler(local_rank)
     if rank == 0:
@@ -266,32 +272,22 @@ def main():
     torch.cuda.synchronize()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     ev0.record(stream)
-    k1_ms, launches, matches, fallback = [], 0, 0, 0
-    for _ in range(args.steps):
-        res, matches = step()
-        k1_ms.append(res.ms_scan)
-        launches += res.launches
-        fallback |= res.fallback
-    if peer is not None:
-        peer.flush()                      # the last step's list must be on the host too
+    run_steps(args.steps)            # the last complete() has waited for the last step and its D2H
     ev1.record(stream)
     torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
     ms = ev0.elapsed_time(ev1)
     clocks = sampler.stop() if rank == 0 else None
+    k1_avg = sum(k1_ms) / len(k1_ms)
+    launches, matches, fallback, mode = stats["launches"], stats["matches"], stats["fallback"], stats["mode"]
     if world > 1:
-        t = torch.tensor([ms], dtype=torch.float64, device=tdev)
+        t = torch.tensor([ms, k1_avg], dtype=torch.float64, device=tdev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms = float(t.item())
-        k = torch.tensor([sum(k1_ms) / len(k1_ms)], dtype=torch.float64, device=tdev)
-        dist.all_reduce(k, op=dist.ReduceOp.MAX)
-        k1_avg = float(k.item())
-    else:
-        k1_avg = sum(k1_ms) / len(k1_ms)
-    if prof is not None and rank == 0:
-        print("profile (ms/step):", {k: round(v * 1e3 / args.steps, 4)
-                                                    for k, v in prof.items()}, file=sys.stderr)
+        ms, k1_avg = float(t[0].item()), float(t[1].item())
+        t = torch.tensor([launches], dtype=torch.int64, device=tdev)
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        launches = int(t.item())
     ms_per_step = ms / args.steps
     value = total / (ms_per_step * 1e-3) / 1e9
 
@@ -340,8 +336,8 @@ def main():
         hs.close()
         del owner
 
-    if peer is not None:
-        peer.close()
+    if not use_nccl:
+        pipe.close()
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -359,17 +355,20 @@ def main():
         "vs_baseline": None, "dtype": "u8", "data": "synthetic",
         "config": {"workload": f"clamav{SIGS} x {total >> 30} GiB seeded random stream "
                                f"({per >> 30} GiB per GPU, halo {lmax - 1} B), {PLANTS_PER_GIB} planted signatures/GiB",
-                   "signatures": SIGS, "states": acsm.get_states(), "kernel": g.MODE_NAMES[res.mode],
+                   "signatures": SIGS, "states": acsm.get_states(), "kernel": g.MODE_NAMES[mode],
                    "bytes_per_gpu": per, "matches": matches, "fallback": int(fallback),
                    "l2_policy": "input (1 GiB per GPU) is larger than L2 (126 MB); no flush needed",
-                   "step": "scan + prefix sum + compaction/sort + count readback"
-                           + ((" + peer gather (counts via shared memory, keys pushed into rank 0's HBM over"
-                               " NVLink IPC) + D2H on a side stream, overlapped with the next step's scan" if use_peer else
-                               " + NCCL count all-gather + key send/recv to rank 0 + D2H") if world > 1 else "")},
+                   "step": ("scan + prefix sum + compaction/sort + NCCL count all-gather + key send/recv to "
+                            "rank 0 + D2H of the list" if use_nccl else
+                            "scan + prefix sum + compaction/sort + push of the sorted keys into rank 0's gather "
+                            "buffer (NVLink IPC stores at N > 1) + D2H of the gathered list to pinned host "
+                            "memory, every step; steps are queued two deep (acm_scan_device_async / "
+                            "acm_scan_finish), so the host round trip overlaps the next step's scan"),
+                   "list_d2h_bytes_per_step": stats["list_bytes"]},
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                      "frac": achieved / peak, "traffic": traffic,
-                     "kernel": "k_scan_" + g.MODE_NAMES[res.mode] + (
-                         f"<{g.lib().acm_automaton_sample_stride(acsm.automaton)}>" if res.mode == 1 else ""),
+                     "kernel": "k_scan_" + g.MODE_NAMES[mode] + (
+                         f"<{g.lib().acm_automaton_sample_stride(acsm.automaton)}>" if mode == 1 else ""),
                      "kernel_ms": k1_avg, "algorithmic_bytes_per_launch": per, "peak_source": peak_src},
         "gpu_launches": int(launches),
         "clocks": clocks,

@@ -34,6 +34,10 @@ class ScanResult(C.Structure):
                 ("ms_total", C.c_float), ("launches", C.c_uint32), ("reserved", C.c_uint32)]
 
 
+class PushTarget(C.Structure):
+    _fields_ = [("d_dst", C.c_void_p), ("cap", C.c_uint64), ("key_add", C.c_uint64)]
+
+
 class AcsmPattern(C.Structure):
     pass
 
@@ -111,6 +115,7 @@ SIGNATURES = {
     "acm_memcpy_d2h": (C.c_int, [vp, vp, vp, C.c_size_t]),
     "acm_memcpy_d2h_side": (C.c_int, [vp, vp, vp, C.c_size_t]),
     "acm_side_sync": (C.c_int, [vp]),
+    "acm_memcpy_d2h_segments": (C.c_int, [vp, vp, C.POINTER(vp), u64p, C.c_uint32]),
     "acm_automaton_upload": (C.c_int, [vp, vp, C.POINTER(vp)]),
     "acm_automaton_free": (None, [vp]),
     "acm_automaton_states": (C.c_uint32, [vp]),
@@ -127,6 +132,9 @@ SIGNATURES = {
     "acm_scan_device": (C.c_int, [vp, vp, C.c_uint64, C.c_uint64, C.c_uint64, C.POINTER(ScanResult)]),
     "acm_scan_device_ex": (C.c_int, [vp, vp, C.c_uint64, C.c_uint64, C.c_uint64, C.c_uint64,
                                      C.POINTER(ScanResult)]),
+    "acm_scan_device_async": (C.c_int, [vp, vp, C.c_uint64, C.c_uint64, C.c_uint64, C.c_uint64,
+                                        C.POINTER(PushTarget)]),
+    "acm_scan_finish": (C.c_int, [vp, C.POINTER(ScanResult)]),
     "acm_scan_keys": (vp, [vp]),
     "acm_scan_fetch": (C.c_int64, [vp, C.c_uint64, u64p, u32p, C.c_uint64]),
     "acm_scan_histogram": (C.c_int, [vp, vp]),

@@ -87,6 +87,18 @@ struct acm_scanner {
 	uint64_t *trace;            /* ACM_TRACE=1: per-CTA timestamps of the last K1 launch */
 	uint64_t *h_keys;           /* pinned bounce buffer for results */
 	uint64_t  h_keys_cap;
+	/* a scan queued by acm_scan_device_async and not yet finished */
+	struct {
+		int          active;
+		cudaStream_t st;
+		const void  *d_data;
+		uint64_t     n, emit_lo, emit_hi, out_cap_at_launch;
+		EmitCtx      E;
+		uint32_t     nb, k3_blocks, launches;
+		uint64_t    *push_dst;      /* optional: keys pushed to a gather region by the step itself */
+		uint64_t     push_cap, push_add;
+	} pend;
+	cudaEvent_t ev_done;
 };
 
 /* ------------------------------------------------------------------------- */
@@ -272,6 +284,32 @@ acm_memcpy_d2h_side(struct acm_device *d, void *dst, const void *src, size_t byt
 	CUDA_TRY(cudaEventRecord(d->side_ev, d->stream));
 	CUDA_TRY(cudaStreamWaitEvent(d->copy_stream, d->side_ev, 0));
 	CUDA_TRY(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, d->copy_stream));
+	return ACM_OK;
+}
+
+/*
+ * D2H of nseg device segments, packed back to back into h_dst, on the side stream with NO
+ * ordering against the main stream: for data the caller already knows to be complete (gather
+ * regions whose writers have finished) while later steps are queued on the main stream.
+ * Waits for the copies.
+ */
+extern "C" int
+acm_memcpy_d2h_segments(struct acm_device *d, void *h_dst, const void *const *d_src, const uint64_t *bytes,
+    uint32_t nseg)
+{
+	uint8_t *dst = (uint8_t *)h_dst;
+	int queued = 0;
+
+	CUDA_TRY(cudaSetDevice(d->ordinal));
+	for (uint32_t i = 0; i < nseg; i++) {
+		if (!bytes[i])
+			continue;
+		CUDA_TRY(cudaMemcpyAsync(dst, d_src[i], bytes[i], cudaMemcpyDeviceToHost, d->copy_stream));
+		dst += bytes[i];
+		queued = 1;
+	}
+	if (queued)
+		CUDA_TRY(cudaStreamSynchronize(d->copy_stream));
 	return ACM_OK;
 }
 
@@ -607,6 +645,8 @@ acm_scanner_free(struct acm_scanner *s)
 	for (int i = 0; i < 4; i++)
 		if (s->ev[i])
 			cudaEventDestroy(s->ev[i]);
+	if (s->ev_done)
+		cudaEventDestroy(s->ev_done);
 	for (int i = 0; i < 2; i++) {
 		if (s->ev_copied[i])
 			cudaEventDestroy(s->ev_copied[i]);
@@ -724,6 +764,7 @@ acm_scanner_create(struct acm_device *dev, struct acm_automaton *aut, uint64_t m
 	}
 	for (int i = 0; i < 4; i++)
 		cudaEventCreate(&s->ev[i]);
+	cudaEventCreateWithFlags(&s->ev_done, cudaEventDisableTiming);
 	for (int i = 0; i < 2; i++) {
 		cudaEventCreateWithFlags(&s->ev_copied[i], cudaEventDisableTiming);
 		cudaEventCreateWithFlags(&s->ev_free[i], cudaEventDisableTiming);
@@ -805,22 +846,45 @@ launch_k1(struct acm_scanner *s, cudaStream_t st, const void *d_data, uint64_t n
 	return ACM_OK;
 }
 
-static int
-scan_on_stream(struct acm_scanner *s, cudaStream_t st, const void *d_data, uint64_t n, uint64_t valid_lo,
-    uint64_t emit_lo, uint64_t emit_hi, struct acm_scan_result *res)
+static void
+launch_k3(struct acm_scanner *s, cudaStream_t st, uint32_t nb, uint32_t k3_blocks)
 {
-	const struct acm_automaton *a = s->aut;
+	k_bucket_sort_compact<<<k3_blocks, K3_THREADS, (size_t)s->cap * 8, st>>>(s->buckets, s->counts,
+	    s->offsets, s->out, s->cap, nb, s->out_cap, s->flags);
+}
+
+/*
+ * First half of a scan: queue memset -> K1 -> K2 -> K3 (-> push) -> 32-byte flag readback on
+ * `st` and record ev_done.  Nothing is waited for.
+ */
+static int
+scan_launch(struct acm_scanner *s, cudaStream_t st, const void *d_data, uint64_t n, uint64_t valid_lo,
+    uint64_t emit_lo, uint64_t emit_hi, const struct acm_push_target *push)
+{
 	EmitCtx E;
 	uint32_t nb, launches = 0;
 	int rc, timing = s->p.timing;
 
+	if (s->pend.active) {
+		acm_set_error("scan: the previous asynchronous scan on this scanner was not finished");
+		return ACM_ERR_STATE;
+	}
 	if (emit_hi > n)
 		emit_hi = n;
-	if (res)
-		memset(res, 0, sizeof(*res));
 	s->last_n = 0;
-	if (emit_lo >= emit_hi)
+	memset(&s->pend, 0, sizeof(s->pend));
+	s->pend.st = st;
+	s->pend.emit_lo = emit_lo;
+	s->pend.emit_hi = emit_hi;
+	if (push) {
+		s->pend.push_dst = push->d_dst;
+		s->pend.push_cap = push->cap;
+		s->pend.push_add = push->key_add;
+	}
+	if (emit_lo >= emit_hi) {
+		s->pend.active = 2;         /* empty window: nothing queued */
 		return ACM_OK;
+	}
 	if (emit_hi - emit_lo > s->max_bytes) {
 		acm_set_error("scan: %llu bytes exceed the scanner's max_bytes %llu",
 		    (unsigned long long)(emit_hi - emit_lo), (unsigned long long)s->max_bytes);
@@ -896,23 +960,69 @@ scan_on_stream(struct acm_scanner *s, cudaStream_t st, const void *d_data, uint6
 	uint32_t k3_blocks = (nb + k3_warps - 1) / k3_warps;
 	if (k3_blocks > (uint32_t)s->dev->sm_count * 16)
 		k3_blocks = (uint32_t)s->dev->sm_count * 16;
-	k_bucket_sort_compact<<<k3_blocks, K3_THREADS, (size_t)s->cap * 8, st>>>(s->buckets, s->counts,
-	    s->offsets, s->out, s->cap, nb, s->out_cap, s->flags);
+	launch_k3(s, st, nb, k3_blocks);
 	CUDA_TRY(cudaGetLastError());
 	launches++;
 	if (timing)
 		CUDA_TRY(cudaEventRecord(s->ev[3], st));
+	if (s->pend.push_dst) {
+		/* the gather push reads the total on the device; it skips itself in the cases the
+		 * host repairs in scan_complete (overflow, output or region too small) */
+		k_push_keys_dev<<<s->dev->sm_count, 256, 0, st>>>(s->out, s->flags, s->out_cap, s->pend.push_dst,
+		    s->pend.push_cap, s->pend.push_add);
+		CUDA_TRY(cudaGetLastError());
+		launches++;
+	}
 	CUDA_TRY(cudaMemcpyAsync(s->h_flags, s->flags, 32, cudaMemcpyDeviceToHost, st));
-	CUDA_TRY(cudaStreamSynchronize(st));
+	CUDA_TRY(cudaEventRecord(s->ev_done, st));
+	s->pend.active = 1;
+	s->pend.d_data = d_data;
+	s->pend.n = n;
+	s->pend.E = E;
+	s->pend.nb = nb;
+	s->pend.k3_blocks = k3_blocks;
+	s->pend.launches = launches;
+	s->pend.out_cap_at_launch = s->out_cap;
+	return ACM_OK;
+}
+
+/*
+ * Second half: wait for the flag readback, repair the rare cases (output buffer too small,
+ * bucket overflow -> exact two-pass path) and fill the result.
+ */
+static int
+scan_complete(struct acm_scanner *s, struct acm_scan_result *res)
+{
+	int rc, timing = s->p.timing, repaired = 0;
+
+	if (res)
+		memset(res, 0, sizeof(*res));
+	if (!s->pend.active) {
+		acm_set_error("scan_finish: no scan is pending on this scanner");
+		return ACM_ERR_STATE;
+	}
+	if (s->pend.active == 2) {
+		s->pend.active = 0;
+		return ACM_OK;
+	}
+	s->pend.active = 0;
+	cudaStream_t st = s->pend.st;
+	EmitCtx E = s->pend.E;
+	const uint32_t nb = s->pend.nb, k3_blocks = s->pend.k3_blocks;
+	uint32_t launches = s->pend.launches;
+	const uint64_t emit_lo = s->pend.emit_lo, emit_hi = s->pend.emit_hi;
+
+	CUDA_TRY(cudaSetDevice(s->dev->ordinal));
+	CUDA_TRY(cudaEventSynchronize(s->ev_done));
 
 	const uint32_t overflow = s->h_flags[0];
 	const uint64_t total = s->h_flags[1];
 	if (total > s->out_cap) {
 		if ((rc = grow(&s->out, &s->out_cap, total, "the match list")) != ACM_OK)
 			return rc;
+		repaired = 1;
 		if (!overflow) {
-			k_bucket_sort_compact<<<k3_blocks, K3_THREADS, (size_t)s->cap * 8, st>>>(s->buckets,
-			    s->counts, s->offsets, s->out, s->cap, nb, s->out_cap, s->flags);
+			launch_k3(s, st, nb, k3_blocks);
 			CUDA_TRY(cudaGetLastError());
 			launches++;
 			if (timing)
@@ -928,6 +1038,7 @@ scan_on_stream(struct acm_scanner *s, cudaStream_t st, const void *d_data, uint6
 		const uint64_t nblocks = (total + RS_TILE - 1) / RS_TILE;
 		uint64_t hist_need = (256 * nblocks + 256 + 1) / 2;   /* in u64 units for grow() */
 
+		repaired = 1;
 		while (span) {
 			bits++;
 			span >>= 1;
@@ -947,7 +1058,7 @@ scan_on_stream(struct acm_scanner *s, cudaStream_t st, const void *d_data, uint6
 		E.offsets = s->offsets;
 		E.out = s->out;
 		CUDA_TRY(cudaMemsetAsync(s->counts, 0, (size_t)nb * 4, st));
-		if ((rc = launch_k1(s, st, d_data, n, E, 1)) != ACM_OK)
+		if ((rc = launch_k1(s, st, s->pend.d_data, s->pend.n, E, 1)) != ACM_OK)
 			return rc;
 		launches++;
 		if ((rc = radix_sort_impl(st, s->out, s->tmp, total, 0, bits, 0, s->hist, s->tile_state,
@@ -956,9 +1067,25 @@ scan_on_stream(struct acm_scanner *s, cudaStream_t st, const void *d_data, uint6
 		if (timing)
 			CUDA_TRY(cudaEventRecord(s->ev[3], st));
 	}
-	if (timing)
-		CUDA_TRY(cudaStreamSynchronize(st));
 	s->last_n = total;
+	if (s->pend.push_dst && total) {
+		if (total > s->pend.push_cap) {
+			acm_set_error("scan: %llu keys exceed the gather region (%llu)", (unsigned long long)total,
+			    (unsigned long long)s->pend.push_cap);
+			return ACM_ERR_LIMIT;
+		}
+		if (repaired) {             /* the step's own push skipped itself */
+			uint64_t blocks = (total + 255) / 256;
+			if (blocks > 592)
+				blocks = 592;
+			k_push_keys<<<(unsigned)blocks, 256, 0, st>>>(s->out, total, s->pend.push_dst,
+			    s->pend.push_add);
+			CUDA_TRY(cudaGetLastError());
+			launches++;
+		}
+	}
+	if (repaired)
+		CUDA_TRY(cudaStreamSynchronize(st));
 	if (overflow && !s->user_shape && s->shift > 12)
 		s->densify = 1;
 	if (res) {
@@ -976,8 +1103,21 @@ scan_on_stream(struct acm_scanner *s, cudaStream_t st, const void *d_data, uint6
 			cudaEventElapsedTime(&res->ms_total, s->ev[0], s->ev[3]);
 		}
 	}
-	(void)a;
 	return ACM_OK;
+}
+
+static int
+scan_on_stream(struct acm_scanner *s, cudaStream_t st, const void *d_data, uint64_t n, uint64_t valid_lo,
+    uint64_t emit_lo, uint64_t emit_hi, struct acm_scan_result *res)
+{
+	int rc = scan_launch(s, st, d_data, n, valid_lo, emit_lo, emit_hi, NULL);
+
+	if (rc != ACM_OK) {
+		if (res)
+			memset(res, 0, sizeof(*res));
+		return rc;
+	}
+	return scan_complete(s, res);
 }
 
 extern "C" int
@@ -996,6 +1136,23 @@ acm_scan_device_ex(struct acm_scanner *s, const void *d_data, uint64_t n, uint64
 		return ACM_ERR_ARG;
 	}
 	return scan_on_stream(s, s->dev->stream, d_data, n, valid_lo, emit_lo, emit_hi, res);
+}
+
+extern "C" int
+acm_scan_device_async(struct acm_scanner *s, const void *d_data, uint64_t n, uint64_t valid_lo,
+    uint64_t emit_lo, uint64_t emit_hi, const struct acm_push_target *push)
+{
+	if (valid_lo > emit_lo) {
+		acm_set_error("scan: valid_lo must not exceed emit_lo");
+		return ACM_ERR_ARG;
+	}
+	return scan_launch(s, s->dev->stream, d_data, n, valid_lo, emit_lo, emit_hi, push);
+}
+
+extern "C" int
+acm_scan_finish(struct acm_scanner *s, struct acm_scan_result *res)
+{
+	return scan_complete(s, res);
 }
 
 /* ACM_TRACE=1: copies {t_entry, t_ready, t_exit, chunks} x n_ctas (ns, globaltimer) of the last scan kernel */

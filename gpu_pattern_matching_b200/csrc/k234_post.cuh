@@ -370,6 +370,22 @@ __global__ void k_push_keys(const uint64_t *__restrict__ keys, uint64_t n, uint6
 		dst[i] = keys[i] + key_add;
 }
 
+/*
+ * Same, launched inside the step before the host knows the count: flags[1] is the total,
+ * flags[0] / "does not fit" are the cases the host repairs afterwards (acm_scan_finish pushes
+ * then), so this kernel simply does nothing for them.
+ */
+__global__ void k_push_keys_dev(const uint64_t *__restrict__ keys, const uint32_t *__restrict__ flags,
+    uint64_t out_cap, uint64_t *__restrict__ dst, uint64_t dst_cap, uint64_t key_add)
+{
+	const uint64_t n = flags[1];
+	if (flags[0] || n > out_cap || n > dst_cap)
+		return;
+	for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n;
+	     i += (uint64_t)gridDim.x * blockDim.x)
+		dst[i] = keys[i] + key_add;
+}
+
 /* per-pattern counts of a key list */
 __global__ void k_histogram(const uint64_t *__restrict__ keys, uint64_t n, unsigned long long *counts)
 {

@@ -9,7 +9,7 @@ import ctypes as C
 import numpy as np
 
 from . import _lib
-from ._lib import AcmError, ScanParams, ScanResult, check, lib
+from ._lib import AcmError, PushTarget, ScanParams, ScanResult, check, lib
 
 MODE_AUTO, MODE_SAMPLED4, MODE_START2, MODE_DFA = 0, 1, 2, 3
 MODE_NAMES = {1: "sampled", 2: "start2", 3: "dfa"}
@@ -106,6 +106,25 @@ class Scanner:
             emit_hi = n
         check(self.L.acm_scan_device_ex(self._h, C.c_void_p(d_ptr), n, valid_lo, emit_lo, emit_hi,
                                         C.byref(res)), "acm_scan_device")
+        self.last = res
+        return res
+
+    def scan_async(self, d_ptr, n, emit_lo=0, emit_hi=None, valid_lo=0, push=None):
+        """Queue a scan and return at once (acm_scan_device_async); finish() completes it.
+        push = (device pointer of a gather region, capacity in keys, key_add) makes the step
+        copy its sorted keys there itself."""
+        if emit_hi is None:
+            emit_hi = n
+        pt = None
+        if push is not None:
+            pt = C.byref(PushTarget(C.c_void_p(push[0]), push[1], push[2]))
+        check(self.L.acm_scan_device_async(self._h, C.c_void_p(d_ptr), n, valid_lo, emit_lo, emit_hi, pt),
+              "acm_scan_device_async")
+
+    def finish(self):
+        """Wait for the queued scan (acm_scan_finish); returns its ScanResult."""
+        res = ScanResult()
+        check(self.L.acm_scan_finish(self._h, C.byref(res)), "acm_scan_finish")
         self.last = res
         return res
 

@@ -250,6 +250,147 @@ class PeerGather:
             pass
 
 
+class StepPipeline:
+    """The multi-GPU step with no host round trip on the critical path.
+
+    Each rank owns two scanners and queues whole steps on its stream: scan -> prefix sum ->
+    compaction + sort -> push of the sorted keys (shifted to stream positions) into THIS rank's
+    fixed region of rank 0's gather buffer (CUDA IPC mapping: NVLink peer stores; local memory on
+    rank 0 itself).  No rank needs another rank's count before it pushes, so nothing waits on a
+    peer; the host finishes step i-1 (32-byte status readback, already complete or nearly) while
+    the GPU runs step i.  Counts and progress travel through a few words of POSIX shared memory:
+
+        cnt[s % DEPTH][r]   match count of rank r in step s
+        done[r]             last step whose keys are complete in rank 0's HBM
+        consumed            last step rank 0 has copied to the host (regions of step s are
+                            reused by step s + DEPTH, so submit(s + DEPTH) waits for it)
+
+    Rank 0 collects step s as soon as every done[r] >= s: one D2H per rank region on the side
+    stream, packed in rank order into pinned host memory -- the global sorted list (ranges are
+    disjoint and ordered).  world == 1 needs no torch.distributed.
+
+    Usage per rank:  submit(step 1); submit(2); complete() -> step 1; submit(3); complete() -> 2 ...
+    """
+    DEPTH = 4
+
+    def __init__(self, device, automaton, max_bytes, cap_keys, rank=0, world=1, scanner_kwargs=None,
+                 timeout_s=60.0):
+        import ctypes as C
+        import os
+        import tempfile
+        from ._lib import check, lib
+        from .matcher import Scanner, pinned_empty
+        self.C, self.L, self.check = C, lib(), check
+        self.device, self.rank, self.world = device, rank, world
+        self.cap = int(cap_keys)
+        self.timeout = timeout_s
+        self.scanners = [Scanner(device, automaton, max_bytes, **(scanner_kwargs or {})) for _ in range(2)]
+        self.launched = self.finished = 0
+        self.results = {}
+        rows = self.DEPTH + 2
+        box = [None, None]
+        if rank == 0:
+            fd, path = tempfile.mkstemp(prefix="acm_steps_", dir="/dev/shm" if os.path.isdir("/dev/shm") else None)
+            os.ftruncate(fd, 8 * rows * world)
+            os.close(fd)
+            self.buf = device.alloc(self.DEPTH * world * self.cap * 8)
+            h = (C.c_ubyte * 64)()
+            if world > 1:
+                check(self.L.acm_ipc_export(device.handle, C.c_void_p(self.buf), h), "acm_ipc_export")
+            box = [path, bytes(h)]
+        if world > 1:
+            dist.broadcast_object_list(box, src=0)
+        self.path = box[0]
+        self.shm = np.memmap(self.path, dtype=np.int64, mode="r+", shape=(rows, world))
+        self.ROW_DONE, self.ROW_CONSUMED = self.DEPTH, self.DEPTH + 1
+        if rank == 0:
+            self.shm[:] = 0
+            self.dst = self.buf
+            self.host_bytes, self._owner = pinned_empty(2 * world * self.cap * 8)
+            self.host = self.host_bytes.view(np.uint64)
+            self._srcs = (C.c_void_p * world)()
+            self._lens = (C.c_uint64 * world)()
+        else:
+            p = C.c_void_p()
+            h = (C.c_ubyte * 64).from_buffer_copy(box[1])
+            check(self.L.acm_ipc_open(device.handle, h, C.byref(p)), "acm_ipc_open")
+            self.dst = p.value
+        if world > 1:
+            dist.barrier()
+
+    def _region(self, step, r):
+        return self.dst + ((step % self.DEPTH) * self.world + r) * self.cap * 8
+
+    def _wait(self, row, value, ranks):
+        import time
+        shm = self.shm
+        t0 = None
+        while True:
+            if all(shm[row, r] >= value for r in ranks):
+                return
+            if t0 is None:
+                t0 = time.perf_counter()
+            elif time.perf_counter() - t0 > self.timeout:
+                raise RuntimeError(f"StepPipeline: rank {self.rank} timed out waiting on row {row} >= {value}")
+
+    def submit(self, d_ptr, n, emit_lo, emit_hi, key_add):
+        """Queue the next step on this rank's shard; returns its step id."""
+        if self.launched - self.finished >= 2:
+            raise RuntimeError("StepPipeline: complete() a step before submitting a third")
+        s = self.launched + 1
+        if s > self.DEPTH:
+            self._wait(self.ROW_CONSUMED, s - self.DEPTH, [0])
+        self.scanners[s & 1].scan_async(d_ptr, n, emit_lo, emit_hi, push=(self._region(s, self.rank), self.cap, key_add))
+        self.launched = s
+        return s
+
+    def complete(self):
+        """Finish the oldest queued step.  Returns (ScanResult of this rank, total matches of the
+        step over all ranks or None, keys) -- total and keys (a uint64 view of pinned memory,
+        valid until the step after next completes) on rank 0 only."""
+        if self.finished >= self.launched:
+            raise RuntimeError("StepPipeline: nothing to complete")
+        s = self.finished + 1
+        res = self.scanners[s & 1].finish()
+        self.finished = s
+        self.shm[s % self.DEPTH, self.rank] = int(res.n_matches)
+        self.shm[self.ROW_DONE, self.rank] = s
+        if self.rank != 0:
+            return res, None, None
+        everyone = range(self.world)
+        self._wait(self.ROW_DONE, s, everyone)
+        total = 0
+        for r in everyone:
+            c = int(self.shm[s % self.DEPTH, r])
+            self._srcs[r] = self._region(s, r)
+            self._lens[r] = c * 8
+            total += c
+        hbase = (s & 1) * self.world * self.cap
+        self.check(self.L.acm_memcpy_d2h_segments(
+            self.device.handle, self.C.c_void_p(self.host.ctypes.data + hbase * 8), self._srcs, self._lens,
+            self.world), "acm_memcpy_d2h_segments")
+        self.shm[self.ROW_CONSUMED, 0] = s
+        return res, total, self.host[hbase:hbase + total]
+
+    def close(self):
+        import os
+        try:
+            while self.finished < self.launched:
+                self.complete()
+            if self.world > 1:
+                dist.barrier()
+            for sc in self.scanners:
+                sc.close()
+            if self.rank == 0:
+                self.device.free(self.buf)
+                os.unlink(self.path)
+            elif self.dst:
+                self.L.acm_ipc_close(self.device.handle, self.C.c_void_p(self.dst))
+                self.dst = None
+        except Exception:
+            pass
+
+
 class _CudaArrayView:
     def __init__(self, ptr, n):
         self.__cuda_array_interface__ = {"shape": (n,), "typestr": "<i8", "data": (ptr, False),

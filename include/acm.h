@@ -65,6 +65,10 @@ int   acm_memcpy_d2h(struct acm_device *, void *h_dst, const void *d_src, size_t
 /* D2H on a side stream (ordered after the work queued so far), so it overlaps later kernels; acm_side_sync waits for it */
 int   acm_memcpy_d2h_side(struct acm_device *, void *h_dst, const void *d_src, size_t bytes);
 int   acm_side_sync(struct acm_device *);
+/* D2H of nseg device segments packed back to back into h_dst, on the side stream and NOT ordered
+ * against the main stream (for data already known to be complete); waits for the copies */
+int   acm_memcpy_d2h_segments(struct acm_device *, void *h_dst, const void *const *d_src,
+          const uint64_t *bytes, uint32_t nseg);
 
 /* ---- automaton ---- */
 int   acm_automaton_upload(struct acm_device *, const struct acm_tables *, struct acm_automaton **out);
@@ -131,6 +135,27 @@ int  acm_scan_device(struct acm_scanner *, const void *d_data, uint64_t n,
  */
 int  acm_scan_device_ex(struct acm_scanner *, const void *d_data, uint64_t n, uint64_t valid_lo,
          uint64_t emit_lo, uint64_t emit_hi, struct acm_scan_result *res);
+
+/*
+ * The same scan in two halves, so that a caller can keep the GPU busy: _async queues the whole
+ * step (memset, scan, prefix sum, compaction + sort, a 32-byte status readback) on the device's
+ * stream and returns; acm_scan_finish waits for that readback only, runs the exact two-pass
+ * path if a bucket overflowed, and fills res.  With two scanners used alternately
+ * (launch i, finish i-1) there is no idle gap between steps.  One scan may be pending per scanner.
+ *
+ * push (may be NULL): the step also copies its sorted keys, each plus key_add, to d_dst[0 ..
+ * total) -- a gather region that may live in another GPU's memory (acm_ipc_open) -- without the
+ * host ever seeing the count first.  If the list does not fit (total > cap) acm_scan_finish
+ * returns ACM_ERR_LIMIT; the keys stay available through acm_scan_keys.
+ */
+struct acm_push_target {
+	uint64_t *d_dst;
+	uint64_t  cap;          /* keys */
+	uint64_t  key_add;
+};
+int  acm_scan_device_async(struct acm_scanner *, const void *d_data, uint64_t n, uint64_t valid_lo,
+         uint64_t emit_lo, uint64_t emit_hi, const struct acm_push_target *push);
+int  acm_scan_finish(struct acm_scanner *, struct acm_scan_result *res);
 
 /* device pointer to the sorted u64 keys of the last scan: (end offset relative to d_data) << 24 | pattern index */
 const uint64_t *acm_scan_keys(struct acm_scanner *);

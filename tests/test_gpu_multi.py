@@ -76,10 +76,57 @@ def _worker(rank, world, port, total, outdir):
                 print(f"step {it}: gathered {tot} expected {eo.size}; first offset mismatch at {bad[:3]}: "
                       f"{goff[bad[:3]]} vs {eo[bad[:3]]}", flush=True)
             ok = ok and good
+    peer.close()
+    # the pipelined form: steps queued two deep, keys pushed by the step itself into per-rank regions
+    pipe = sharded.StepPipeline(dev, a.automaton, hi - lo, 1 << 14, rank, world, timeout_s=30)
+    outs = []
+    for it in range(7):                       # > DEPTH steps: region reuse and the consumed counter
+        pipe.submit(d, n, lo - read_lo, n, read_lo << sharded.KEY_PAT_BITS)
+        if it > 0:
+            outs.append(pipe.complete())
+    outs.append(pipe.complete())
+    for it, (res, tot, keys) in enumerate(outs):
+        if rank == 0:
+            goff, gpat = sharded.unpack_keys(np.array(keys, copy=True))
+            good = tot == eo.size and np.array_equal(goff, eo) and np.array_equal(gpat, ep)
+            if not good:
+                print(f"pipeline step {it}: gathered {tot} expected {eo.size}", flush=True)
+            ok = ok and good
+        else:
+            assert tot is None and keys is None
+    pipe.close()
     if rank == 0:
         open(os.path.join(outdir, "result"), "w").write(f"{int(ok)} {eo.size}")
-    peer.close()
     dist.destroy_process_group()
+
+
+def test_step_pipeline_single_rank(tmp_path):
+    """world == 1: same pipeline, no torch.distributed, list checked against the oracle."""
+    if not torch.cuda.is_available():
+        pytest.fail("gpu test selected but no CUDA device is visible")
+    import gpu_pattern_matching_b200 as g
+    from gpu_pattern_matching_b200 import sharded
+    from helpers import build_oracle, build_product, clamav_pats, planted_stream
+    pats = clamav_pats(2000)
+    o, a = build_oracle(pats), build_product(pats)
+    buf, _ = planted_stream(pats, (2 << 20) + 77, seed=9, plants=500)
+    eo, ep, _, _ = o.search(buf)
+    dev = g.Device(0)
+    d = dev.alloc(buf.size + 64)
+    dev.h2d(d, buf)
+    pipe = sharded.StepPipeline(dev, a.automaton, buf.size, 1 << 14)
+    got = []
+    for it in range(6):
+        pipe.submit(d, buf.size, 0, buf.size, 0)
+        if it > 0:
+            got.append(pipe.complete())
+    got.append(pipe.complete())
+    for res, tot, keys in got:
+        goff, gpat = sharded.unpack_keys(np.array(keys, copy=True))
+        assert tot == eo.size and np.array_equal(goff, eo) and np.array_equal(gpat, ep)
+    pipe.close()
+    dev.free(d)
+    dev.close()
 
 
 @pytest.mark.parametrize("world", [2, 3])

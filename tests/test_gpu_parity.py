@@ -207,3 +207,48 @@ def test_repetitive_input_dense_hit_fallback(device):
         assert_same(off, pat, eo, ep, f"repetitive mode {mode}")
     off, pat, res = gpu_scan(device, build_product(pats, stride=4), buf, g.MODE_SAMPLED4)
     assert_same(off, pat, eo, ep, "repetitive sampled stride 4")
+
+
+def test_async_scan_two_scanners_and_push(device):
+    """acm_scan_device_async / acm_scan_finish with two scanners in flight and the in-step push:
+    same list as the synchronous call, including when the step has to be repaired on the host
+    (bucket overflow -> two-pass path, output buffer growth) and the push is redone there."""
+    pats = clamav_pats(2000)
+    o, a = build_oracle(pats), build_product(pats)
+    bufs = [planted_stream(pats, (1 << 20) + 123 * k, seed=20 + k, plants=2000 + 300 * k)[0] for k in range(3)]
+    exp = [o.search(b)[:2] for b in bufs]
+    cap = 1 << 14
+    d_bufs = []
+    for b in bufs:
+        d = device.alloc(b.size + 64)
+        device.h2d(d, b)
+        d_bufs.append(d)
+    region = device.alloc(2 * cap * 8)
+    for kw in ({}, {"bucket_shift": 16, "bucket_cap": 32}):       # second shape overflows: host repair
+        scs = [g.Scanner(device, a.automaton, 2 << 20, **kw) for _ in range(2)]
+        order = [0, 1, 2, 0, 1]
+        for i, k in enumerate(order):
+            scs[i & 1].scan_async(d_bufs[k], bufs[k].size, push=(region + (i & 1) * cap * 8, cap, 5 << 24))
+            if i > 0:
+                j = i - 1
+                res = scs[j & 1].finish()
+                keys = device.d2h(region + (j & 1) * cap * 8, int(res.n_matches) * 8, dtype=np.uint64)
+                eo, ep = exp[order[j]]
+                assert_same((keys >> np.uint64(24)) - np.uint64(5), (keys & np.uint64(0xFFFFFF)).astype(np.uint32),
+                            eo, ep, f"async step {j} {kw}")
+                off, pat = scs[j & 1].fetch()
+                assert_same(off, pat, eo, ep, f"async fetch {j} {kw}")
+                if kw:
+                    assert res.fallback == 1
+        res = scs[0].finish()
+        assert int(res.n_matches) == exp[1][0].size
+        with pytest.raises(g.AcmError):
+            scs[0].finish()                                   # nothing pending
+        # a region that is too small is reported, not overrun
+        scs[0].scan_async(d_bufs[0], bufs[0].size, push=(region, 16, 0))
+        with pytest.raises(g.AcmError):
+            scs[0].finish()
+        for sc in scs:
+            sc.close()
+    for d in d_bufs + [region]:
+        device.free(d)
