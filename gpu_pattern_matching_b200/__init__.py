@@ -12,5 +12,5 @@ kernels, C ABI in include/*.h).  These modules are thin ctypes mirrors of that A
 """
 from ._lib import AcmError, LIB_PATH, lib  # noqa: F401
 from .acsm import Acsm, Iacsm  # noqa: F401
-from .matcher import (Device, Scanner, MODE_AUTO, MODE_DFA, MODE_SAMPLED4,  # noqa: F401
+from .matcher import (Device, Scanner, MODE_AUTO, MODE_CDFA, MODE_DFA, MODE_SAMPLED4,  # noqa: F401
                       MODE_START2, MODE_NAMES)

@@ -126,6 +126,7 @@ SIGNATURES = {
     "acm_automaton_device_bytes": (C.c_size_t, [vp]),
     "acm_automaton_default_mode": (C.c_int, [vp]),
     "acm_automaton_gram_count": (C.c_uint32, [vp]),
+    "acm_automaton_cdfa_classes": (C.c_int, [vp]),
     "acm_automaton_sample_stride": (C.c_int, [vp]),
     "acm_scanner_create": (C.c_int, [vp, vp, C.c_uint64, C.POINTER(ScanParams), C.POINTER(vp)]),
     "acm_scanner_free": (None, [vp]),

@@ -144,6 +144,7 @@ acm_tables_free(struct acm_tables *t)
 	free(t->olink); free(t->fail); free(t->pat_len); free(t->pat_iid);
 	free(t->bfs_to_ref); free(t->f1); free(t->f2); free(t->grams); free(t->b2);
 	free(t->cand); free(t->pat_blob); free(t->pat_off);
+	free(t->cd_cls); free(t->cd_tab); free(t->cd_flat_begin); free(t->cd_flat_pat);
 	memset(t, 0, sizeof(*t));
 }
 
@@ -162,6 +163,9 @@ acm_tables_device_bytes(const struct acm_tables *t)
 		    t->pat_blob_bytes + (size_t)t->num_patterns * 4;
 	if (t->b2)
 		b += 65536 / 8;
+	if (t->cd_tab)
+		b += (size_t)t->num_states * t->cd_classes * 2 + 256 + (size_t)(t->num_states + 1) * 4 +
+		    (size_t)t->cd_flat_total * 4;
 	return b;
 }
 
@@ -205,6 +209,131 @@ cmp_gtrip(const void *a, const void *b)
 	if (x[0] != y[0])
 		return x[0] < y[0] ? -1 : 1;
 	return x[1] < y[1] ? -1 : (x[1] > y[1]);
+}
+
+static int
+cmp_u32(const void *a, const void *b)
+{
+	const uint32_t x = *(const uint32_t *)a, y = *(const uint32_t *)b;
+
+	return x < y ? -1 : (x > y);
+}
+
+/*
+ * Class-compressed DFA for small automata over few distinct bytes (word lists over text):
+ * bytes that occur in no pattern all behave alike (every state goes to the root on them), so
+ * the 256 columns of T collapse to C = (distinct pattern bytes) + 1, and with <= 2^14 states
+ * an entry fits 16 bits together with a 2-bit "how many patterns end here" code.  Rows in
+ * breadth-first order: a prefix of the table (the shallow, most visited states) is what the
+ * scan kernel keeps in shared memory.  Each state's FULL match list (own patterns plus those
+ * inherited along the output links -- reference acsmx.c:417-429 copies them) is flattened and
+ * sorted by pattern index, so a sequential walk emits records already in canonical order.
+ */
+static int
+build_cdfa(struct acm_core *c)
+{
+	struct acm_tables *t = &c->tab;
+	uint8_t used[256];
+	uint8_t col_byte[ACM_CD_MAX_CLASSES];
+	uint32_t s, k, C = 0;
+	int lo = -1, hi = -1, b, other = -1;
+	uint64_t total = 0;
+	uint32_t *cnt;
+
+	if (t->num_states > ACM_CD_MAX_STATES || t->num_states == 0)
+		return ACM_OK;
+	memset(used, 0, sizeof(used));
+	for (k = 0; k < (uint32_t)c->npats; k++)
+		for (b = 0; b < c->pats[k].n; b++)
+			used[((const unsigned char *)c->pats[k].syms)[b]] = 1;
+	for (b = 0; b < 256; b++) {
+		if (used[b]) {
+			if (lo < 0)
+				lo = b;
+			hi = b;
+			C++;
+		} else if (other < 0) {
+			other = b;
+		}
+	}
+	if (C == 0 || C + 1 > ACM_CD_MAX_CLASSES || other < 0)
+		return ACM_OK;
+
+	t->cd_cls = malloc(256);
+	if (!t->cd_cls)
+		return ACM_ERR_NOMEM;
+	if (hi - lo + 2 <= ACM_CD_MAX_CLASSES) {
+		/* contiguous range: column = byte - lo (unused bytes inside the range keep a real column) */
+		t->cd_range_lo = lo;
+		C = (uint32_t)(hi - lo + 2);
+		for (b = 0; b < 256; b++)
+			t->cd_cls[b] = (uint8_t)((b >= lo && b <= hi) ? b - lo : (int)C - 1);
+		for (k = 0; k + 1 < C; k++)
+			col_byte[k] = (uint8_t)(lo + (int)k);
+	} else {
+		t->cd_range_lo = -1;
+		C = C + 1;
+		k = 0;
+		for (b = 0; b < 256; b++) {
+			if (used[b]) {
+				col_byte[k] = (uint8_t)b;
+				t->cd_cls[b] = (uint8_t)k++;
+			} else {
+				t->cd_cls[b] = (uint8_t)(C - 1);
+			}
+		}
+	}
+	col_byte[C - 1] = (uint8_t)other;
+
+	/* full lists: count, then fill through the output links (olink[s] < s in BFS order) */
+	cnt = calloc(t->num_states + 1, 4);
+	t->cd_flat_begin = malloc((size_t)(t->num_states + 1) * 4);
+	if (!cnt || !t->cd_flat_begin) {
+		free(cnt);
+		return ACM_ERR_NOMEM;
+	}
+	for (s = 0; s < t->num_states; s++) {
+		cnt[s] = t->own_begin[s + 1] - t->own_begin[s] + (s ? cnt[t->olink[s]] : 0);
+		total += cnt[s];
+	}
+	if (total > (1u << 24)) {          /* pathological nesting: leave this form out */
+		free(cnt);
+		free(t->cd_cls); free(t->cd_flat_begin);
+		t->cd_cls = NULL;
+		t->cd_flat_begin = NULL;
+		return ACM_OK;
+	}
+	t->cd_flat_total = (uint32_t)total;
+	t->cd_flat_pat = malloc((size_t)(total + 1) * 4);
+	t->cd_tab = malloc((size_t)t->num_states * C * 2);
+	if (!t->cd_flat_pat || !t->cd_tab) {
+		free(cnt);
+		return ACM_ERR_NOMEM;
+	}
+	{
+		uint32_t w = 0;
+		for (s = 0; s < t->num_states; s++) {
+			uint32_t v, w0 = w;
+			t->cd_flat_begin[s] = w;
+			for (v = s; v; v = t->olink[v]) {
+				for (k = t->own_begin[v]; k < t->own_begin[v + 1]; k++)
+					t->cd_flat_pat[w++] = t->own_pat[k];
+			}
+			if (w - w0 > 1)
+				qsort(t->cd_flat_pat + w0, w - w0, 4, cmp_u32);
+		}
+		t->cd_flat_begin[t->num_states] = w;
+	}
+	for (s = 0; s < t->num_states; s++) {
+		for (k = 0; k < C; k++) {
+			const uint32_t nx = t->T[(size_t)s * 256 + col_byte[k]] & ACM_T_MASK;
+			const uint32_t code = cnt[nx] < 3 ? cnt[nx] : 3;
+			t->cd_tab[(size_t)s * C + k] = (uint16_t)(nx | (code << ACM_CD_STATE_BITS));
+		}
+	}
+	free(cnt);
+	t->cd_classes = C;
+	return ACM_OK;
 }
 
 static int
@@ -577,6 +706,8 @@ acm_core_compile(struct acm_core *c)
 
 	if (A == 256)
 		rc = build_filters(c);
+	if (A == 256 && rc == ACM_OK)
+		rc = build_cdfa(c);
 
 out:
 	trie_free(&tr);

@@ -51,7 +51,7 @@ struct acm_automaton {
 	size_t    bytes;
 	uint32_t *h_pat_len;        /* host copies that outlive acsm_cleanup() */
 	int32_t  *h_pat_iid;
-	void     *allocs[16];
+	void     *allocs[24];
 	int       n_allocs;
 };
 
@@ -61,6 +61,7 @@ struct acm_scanner {
 	struct acm_scan_params p;
 	uint64_t  max_bytes;
 	uint32_t  shift, cap, max_buckets;
+	uint32_t  cd_hot, cd_hot_bytes;   /* CDFA: rows of the table kept in shared memory */
 	uint64_t *buckets;
 	uint32_t *counts, *offsets;
 	uint8_t  *scratch;          /* one allocation, one memset per scan: flags | bucket_tiles | counts */
@@ -131,6 +132,10 @@ set_kernel_attrs(int ordinal)
 	    S2_SMEM_BYTES));
 	CUDA_TRY(cudaFuncSetAttribute(k_bucket_sort_compact, cudaFuncAttributeMaxDynamicSharedMemorySize,
 	    65536));
+	CUDA_TRY(cudaFuncSetAttribute(k_scan_cdfa<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+	    CD_SMEM_MAX));
+	CUDA_TRY(cudaFuncSetAttribute(k_scan_cdfa<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+	    CD_SMEM_MAX));
 	if (ordinal < 64)
 		g_attr_done[ordinal] = 1;
 	return ACM_OK;
@@ -340,7 +345,7 @@ upload(struct acm_automaton *a, const void *src, size_t bytes, const void **dst)
 	size_t padded = (bytes + 255) & ~(size_t)255;
 
 	*dst = NULL;
-	if (a->n_allocs >= 16)
+	if (a->n_allocs >= 24)
 		return ACM_ERR_LIMIT;
 	CUDA_TRY(cudaMalloc(&p, padded ? padded : 256));
 	a->allocs[a->n_allocs++] = p;
@@ -424,6 +429,14 @@ acm_automaton_upload(struct acm_device *dev, const struct acm_tables *t, struct 
 			lg++;
 		a->d.gram_shift = 32 - lg;
 	}
+	if (t->cd_tab) {
+		UP(cd_tab, t->cd_tab, (size_t)t->num_states * t->cd_classes * 2);
+		UP(cd_cls, t->cd_cls, 256);
+		UP(cd_flat_begin, t->cd_flat_begin, (size_t)(t->num_states + 1) * 4);
+		UP(cd_flat_pat, t->cd_flat_pat, (size_t)(t->cd_flat_total + 1) * 4);
+		a->d.cd_classes = t->cd_classes;
+		a->d.cd_range_lo = t->cd_range_lo;
+	}
 #undef UP
 	a->d.num_states = t->num_states;
 	a->d.alpha = t->alpha;
@@ -457,7 +470,16 @@ acm_automaton_default_mode(const struct acm_automaton *a)
 		return ACM_MODE_DFA;
 	if (a->d.f1 && a->min_len >= 7)
 		return ACM_MODE_SAMPLED4;
+	if (a->d.cd_tab)
+		return ACM_MODE_CDFA;
 	return ACM_MODE_START2;
+}
+
+/* columns of the class-compressed table (ACM_MODE_CDFA), 0 when the automaton has none */
+extern "C" int
+acm_automaton_cdfa_classes(const struct acm_automaton *a)
+{
+	return a->d.cd_tab ? (int)a->d.cd_classes : 0;
 }
 
 /* ------------------------------------------------------------------------- */
@@ -666,7 +688,8 @@ scanner_alloc_buckets(struct acm_scanner *s)
 	s->buckets = NULL;
 	s->scratch = NULL;
 	s->offsets = NULL;
-	s->max_buckets = (uint32_t)((s->max_bytes + (1ull << s->shift) - 1) >> s->shift) + 1;
+	/* CDFA cuts chunks on absolute multiples of 2^shift: one more partial bucket */
+	s->max_buckets = (uint32_t)((s->max_bytes + (1ull << s->shift) - 1) >> s->shift) + 2;
 	s->n_bucket_tiles = (s->max_buckets + SCAN_TILE - 1) / SCAN_TILE + 1;
 	if (cudaMalloc((void **)&s->buckets, (size_t)s->max_buckets * s->cap * 8) != cudaSuccess ||
 	    cudaMalloc((void **)&s->scratch, 64 + (size_t)s->n_bucket_tiles * 8 + (size_t)s->max_buckets * 4) !=
@@ -718,9 +741,42 @@ acm_scanner_create(struct acm_device *dev, struct acm_automaton *aut, uint64_t m
 		free(s);
 		return ACM_ERR_ARG;
 	}
+	if (mode == ACM_MODE_CDFA && !aut->d.cd_tab) {
+		acm_set_error("scanner_create: this automaton has no class-compressed table "
+		    "(needs <= %u states and <= %d distinct pattern bytes)", ACM_CD_MAX_STATES, ACM_CD_MAX_CLASSES - 1);
+		free(s);
+		return ACM_ERR_ARG;
+	}
 	s->p.mode = mode;
 	s->max_bytes = max_bytes;
 	s->user_shape = s->p.bucket_shift || s->p.bucket_cap;
+	if (mode == ACM_MODE_CDFA) {
+		/*
+		 * A bucket is one thread's chunk: 256 bytes unless the halo (Lmax - 1) asks for more
+		 * (chunk >= 4 x halo keeps the cold-start overhead <= 25 %), room for one record per
+		 * 4 bytes before the exact two-pass path takes over.
+		 */
+		const uint32_t halo = aut->max_len > 0 ? (uint32_t)aut->max_len - 1 : 0;
+		uint32_t sh = s->p.bucket_shift ? (uint32_t)s->p.bucket_shift : 8u;
+		while (sh < 30 && (1u << sh) < 4 * halo)
+			sh++;
+		s->p.bucket_shift = (int)sh;
+		if (!s->p.bucket_cap)
+			s->p.bucket_cap = (int)((1u << sh) / 4 > 8192 ? 8192 : (1u << sh) / 4);
+		const uint32_t row = aut->d.cd_classes * 2;
+		uint32_t budget = CD_SMEM_MAX - 16 - (aut->d.cd_range_lo >= 0 ? 0 : CD_LUT_WORDS * 4);
+		const char *kb = getenv("ACM_CD_HOT_KB");
+		if (kb && atoi(kb) > 0 && (uint32_t)atoi(kb) * 1024 < budget)
+			budget = (uint32_t)atoi(kb) * 1024;
+		s->cd_hot = budget / row;
+		if (s->cd_hot > aut->num_states)
+			s->cd_hot = aut->num_states;
+		s->cd_hot_bytes = (s->cd_hot * row + 15) & ~15u;
+		if (s->cd_hot_bytes > budget) {
+			s->cd_hot--;
+			s->cd_hot_bytes = (s->cd_hot * row + 15) & ~15u;
+		}
+	}
 	/* sparse matches (signature sets): 128 KiB buckets of up to 1024 records keep the
 	 * post-passes at ~8k buckets per GiB; dense output is handled by the adaptive re-shape */
 	s->shift = s->p.bucket_shift ? (uint32_t)s->p.bucket_shift : (mode == ACM_MODE_SAMPLED4 ? 17u : 15u);
@@ -824,6 +880,19 @@ launch_k1(struct acm_scanner *s, cudaStream_t st, const void *d_data, uint64_t n
 			k_scan_sampled<4><<<(unsigned)blocks, S4_THREADS, S4_SMEM_BYTES, st>>>(a->d, E,
 			    (const uint8_t *)d_data, n, vec_lo, vec_hi, limit, s->flags + 6,
 			    (uint32_t)(blocks * (S4_THREADS / 32) * 2));
+	} else if (s->p.mode == ACM_MODE_CDFA) {
+		/* persistent: one CTA per SM holding the hot rows, threads stride over chunk pairs */
+		const uint64_t pairs = (((limit - 1) >> E.shift) - (E.emit_lo >> E.shift) + 2) / 2;
+		uint64_t blocks = (pairs + CD_THREADS - 1) / CD_THREADS;
+		if (blocks > (uint64_t)s->dev->sm_count)
+			blocks = s->dev->sm_count;
+		const size_t smem = s->cd_hot_bytes + (a->d.cd_range_lo >= 0 ? 0 : CD_LUT_WORDS * 4) + 16;
+		if (a->d.cd_range_lo >= 0)
+			k_scan_cdfa<true><<<(unsigned)blocks, CD_THREADS, smem, st>>>(a->d, E, (const uint8_t *)d_data,
+			    limit, s->cd_hot, s->cd_hot_bytes);
+		else
+			k_scan_cdfa<false><<<(unsigned)blocks, CD_THREADS, smem, st>>>(a->d, E, (const uint8_t *)d_data,
+			    limit, s->cd_hot, s->cd_hot_bytes);
 	} else if (s->p.mode == ACM_MODE_START2) {
 		const uint64_t tile = (uint64_t)S2_THREADS * S2_UNROLL;
 		uint64_t blocks = (vec_hi - vec_lo + tile - 1) / tile;
@@ -849,6 +918,15 @@ launch_k1(struct acm_scanner *s, cudaStream_t st, const void *d_data, uint64_t n
 static void
 launch_k3(struct acm_scanner *s, cudaStream_t st, uint32_t nb, uint32_t k3_blocks)
 {
+	if (s->p.mode == ACM_MODE_CDFA) {
+		/* buckets are in order already: a copy, one warp per bucket */
+		uint32_t blocks = (nb + 7) / 8;
+		if (blocks > (uint32_t)s->dev->sm_count * 8)
+			blocks = (uint32_t)s->dev->sm_count * 8;
+		k_bucket_copy_compact<<<blocks, 256, 0, st>>>(s->buckets, s->counts, s->offsets, s->out, s->cap,
+		    nb, s->out_cap, s->flags);
+		return;
+	}
 	k_bucket_sort_compact<<<k3_blocks, K3_THREADS, (size_t)s->cap * 8, st>>>(s->buckets, s->counts,
 	    s->offsets, s->out, s->cap, nb, s->out_cap, s->flags);
 }
@@ -921,7 +999,10 @@ scan_launch(struct acm_scanner *s, cudaStream_t st, const void *d_data, uint64_t
 			}
 		}
 	}
-	nb = (uint32_t)((emit_hi - emit_lo + (1ull << s->shift) - 1) >> s->shift);
+	if (s->p.mode == ACM_MODE_CDFA)        /* chunks are cut on absolute multiples of 2^shift */
+		nb = (uint32_t)(((emit_hi - 1) >> s->shift) - (emit_lo >> s->shift) + 1);
+	else
+		nb = (uint32_t)((emit_hi - emit_lo + (1ull << s->shift) - 1) >> s->shift);
 
 	memset(&E, 0, sizeof(E));
 	E.buckets = s->buckets;
@@ -1061,7 +1142,9 @@ scan_complete(struct acm_scanner *s, struct acm_scan_result *res)
 		if ((rc = launch_k1(s, st, s->pend.d_data, s->pend.n, E, 1)) != ACM_OK)
 			return rc;
 		launches++;
-		if ((rc = radix_sort_impl(st, s->out, s->tmp, total, 0, bits, 0, s->hist, s->tile_state,
+		/* a CDFA walk writes every chunk's records in order at its scanned offset: sorted already */
+		if (s->p.mode != ACM_MODE_CDFA &&
+		    (rc = radix_sort_impl(st, s->out, s->tmp, total, 0, bits, 0, s->hist, s->tile_state,
 		    s->flags + 3, &launches)) != ACM_OK)
 			return rc;
 		if (timing)

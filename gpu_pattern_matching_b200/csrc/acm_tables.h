@@ -30,8 +30,15 @@ enum {
 	ACM_MODE_AUTO     = 0,
 	ACM_MODE_SAMPLED4 = 1,   /* aligned 4-gram entry filter, needs min len >= 7 */
 	ACM_MODE_START2   = 2,   /* 2-byte start filter, any pattern length        */
-	ACM_MODE_DFA      = 3    /* plain per-chunk DFA walk with leading halo     */
+	ACM_MODE_DFA      = 3,   /* plain per-chunk DFA walk with leading halo     */
+	ACM_MODE_CDFA     = 4    /* class-compressed 16-bit DFA, hot rows in shared memory */
 };
+
+/* class-compressed DFA entry (uint16): low 14 bits next state, top 2 bits min(|full match list|, 3) */
+#define ACM_CD_STATE_BITS 14
+#define ACM_CD_STATE_MASK 0x3FFFu
+#define ACM_CD_MAX_STATES (1u << ACM_CD_STATE_BITS)
+#define ACM_CD_MAX_CLASSES 64
 
 #define ACM_F1_BITS_LOG2   20              /* level-1 gram bitmap: 128 KiB smem */
 #define ACM_F2_BITS_LOG2   19              /* level-2 gram bitmap:  64 KiB smem */
@@ -94,6 +101,15 @@ struct acm_tables {
 	uint32_t  pat_blob_bytes;
 	uint32_t *pat_off;           /* [num_patterns] byte offset into pat_blob      */
 	uint32_t *b2;                /* 2^16-bit exact start bitmap: bit (b0 | b1<<8) */
+
+	/* --- byte alphabet, <= 2^14 states, <= 63 distinct pattern bytes: class-compressed DFA --- */
+	uint32_t  cd_classes;        /* C = columns per row; column C-1 = "a byte that occurs in no pattern"; 0 = not built */
+	int       cd_range_lo;       /* >= 0: class(b) = min((unsigned)(b - lo), C-1) (pattern bytes span < 64 values); -1: use cd_cls */
+	uint8_t  *cd_cls;            /* [256] byte -> column                          */
+	uint16_t *cd_tab;            /* [num_states][C]                               */
+	uint32_t *cd_flat_begin;     /* [num_states + 1] CSR into cd_flat_pat         */
+	uint32_t *cd_flat_pat;       /* FULL match list of each state, ascending pattern index */
+	uint32_t  cd_flat_total;
 };
 
 void acm_tables_free(struct acm_tables *t);

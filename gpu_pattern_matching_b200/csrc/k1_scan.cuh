@@ -57,6 +57,12 @@ struct AutDev {
 	const uint32_t *pat_off;
 	const uint32_t *pat_len;
 	const uint32_t *b2;
+	const uint16_t *cd_tab;        /* class-compressed DFA (k_scan_cdfa), NULL if not built */
+	const uint8_t  *cd_cls;
+	const uint32_t *cd_flat_begin;
+	const uint32_t *cd_flat_pat;
+	uint32_t cd_classes;
+	int      cd_range_lo;
 	uint32_t gram_mask;
 	uint32_t gram_shift;     /* 32 - log2(slots) */
 	uint32_t num_states;
@@ -732,5 +738,203 @@ k_scan_dfa(const AutDev A, const EmitCtx E, const SYM *__restrict__ data, uint64
 			for (uint32_t v = state; v; v = __ldg(&A.olink[v]))
 				emit_own(A, E, v, pos);
 		}
+	}
+}
+
+/* ------------------------------------------------------------------------- */
+/* class-compressed DFA: 16-bit entries, hot rows in shared memory           */
+/* ------------------------------------------------------------------------- */
+
+/*
+ * k_scan_cdfa -- the dense-output kernel (word lists over text: one match per ~9 bytes).
+ *
+ * With that many matches a filter buys nothing: every byte has to go through the automaton.
+ * So this is the plain DFA walk of reference ahomatch.cl:56-65 -- one transition per byte,
+ * one thread per chunk, cold start Lmax-1 bytes early -- made cheap:
+ *   - the table is class-compressed to uint16[states][C] (acm_core.c build_cdfa): 54 bytes a
+ *     row for a lower-case lexicon instead of the reference's 2 KiB, 848 KiB in all instead of
+ *     30.7 MiB, so it lives in L2 and its first n_hot rows (breadth-first order = the shallow,
+ *     most visited states: 82 % of all lookups on English-like text) in SHARED MEMORY;
+ *   - byte -> column is arithmetic when the pattern bytes span < 64 values, else one lookup in
+ *     a 32-way replicated (bank-conflict-free) table;
+ *   - every thread walks TWO adjacent chunks in lockstep, two independent dependency chains,
+ *     which is what hides the L2 latency of the cold rows;
+ *   - a chunk is its own result bucket: the thread owns the slot counter (no atomics), records
+ *     come out in (end offset, pattern index) order because the walk is sequential and every
+ *     state's full match list is stored sorted, so the post-pass is a copy, not a sort.
+ * Chunks are cut on absolute multiples of 2^shift in the buffer, so interior chunks are
+ * 16-byte aligned and read with 16-byte loads; the first and last chunk of a scan (cut by
+ * emit_lo / the end) take a byte-wise path.
+ */
+#define CD_THREADS   1024
+#define CD_LUT_WORDS 2048          /* 64 words x 32 banks */
+#define CD_SMEM_MAX  (227 * 1024)
+
+struct CdOut {
+	uint64_t *dst;
+	uint32_t  k, cap;
+};
+
+template <bool RANGE>
+__device__ __forceinline__ uint32_t cd_class(uint32_t b, const uint32_t *lut, uint32_t lane, uint32_t lo,
+    uint32_t cmax)
+{
+	if (RANGE)
+		return min(b - lo, cmax);                 /* below lo wraps to huge -> cmax */
+	const uint32_t w = lut[((b & 0xFCu) << 3) | lane];
+	return (w >> ((b & 3u) * 8u)) & 0xFFu;
+}
+
+__device__ __forceinline__ uint32_t cd_next(uint32_t state, uint32_t c, const uint16_t *hot,
+    const uint16_t *__restrict__ tab, uint32_t C, uint32_t n_hot)
+{
+	const uint32_t idx = state * C + c;
+	return state < n_hot ? (uint32_t)hot[idx] : (uint32_t)__ldg(tab + idx);
+}
+
+__device__ __forceinline__ void cd_emit(const AutDev &A, CdOut &o, uint32_t state, uint32_t code, uint64_t pos)
+{
+	const uint32_t fb = __ldg(&A.cd_flat_begin[state]);
+	const uint32_t cnt = code < 3 ? code : __ldg(&A.cd_flat_begin[state + 1]) - fb;
+	for (uint32_t j = 0; j < cnt; ++j) {
+		if (o.k < o.cap)
+			o.dst[o.k] = (pos << ACM_KEY_PAT_BITS) | __ldg(&A.cd_flat_pat[fb + j]);
+		++o.k;
+	}
+}
+
+__device__ __forceinline__ CdOut cd_open(const EmitCtx &E, uint64_t b)
+{
+	CdOut o;
+	o.k = 0;
+	if (E.direct) {
+		o.dst = E.out + E.offsets[b];
+		o.cap = 0xffffffffu;
+	} else {
+		o.dst = E.buckets + b * E.cap;
+		o.cap = E.cap;
+	}
+	return o;
+}
+
+__device__ __forceinline__ void cd_close(const EmitCtx &E, uint64_t b, const CdOut &o)
+{
+	E.counts[b] = o.k;
+	if (o.k > o.cap)
+		*E.overflow = 1u;
+}
+
+/* byte-wise walk of chunk k (absolute chunk index): the first / last chunk of a scan */
+template <bool RANGE>
+__device__ __noinline__ void cd_chunk_bytes(const AutDev *__restrict__ Ap, const EmitCtx *__restrict__ Ep,
+    const uint8_t *__restrict__ data, uint64_t k, uint64_t limit, const uint16_t *hot, const uint32_t *lut,
+    uint32_t n_hot)
+{
+	const AutDev &A = *Ap;
+	const EmitCtx &E = *Ep;
+	const uint32_t C = A.cd_classes, lane = threadIdx.x & 31;
+	uint64_t lo = k << E.shift, hi = (k + 1) << E.shift;
+	if (lo < E.emit_lo)
+		lo = E.emit_lo;
+	if (hi > limit)
+		hi = limit;
+	const uint64_t halo = A.max_len > 0 ? (uint64_t)(A.max_len - 1) : 0;
+	uint64_t pos = lo > halo ? lo - halo : 0;
+	if (pos < E.valid_lo)
+		pos = E.valid_lo;
+	const uint64_t b = k - (E.emit_lo >> E.shift);
+	CdOut o = cd_open(E, b);
+	uint32_t state = 0;
+	for (; pos < hi; ++pos) {
+		const uint32_t e = cd_next(state, cd_class<RANGE>(__ldg(data + pos), lut, lane, (uint32_t)A.cd_range_lo, C - 1),
+		    hot, A.cd_tab, C, n_hot);
+		state = e & ACM_CD_STATE_MASK;
+		if ((e >> ACM_CD_STATE_BITS) && pos >= lo)
+			cd_emit(A, o, state, e >> ACM_CD_STATE_BITS, pos);
+	}
+	cd_close(E, b, o);
+}
+
+template <bool RANGE>
+__global__ void __launch_bounds__(CD_THREADS, 1)
+k_scan_cdfa(const __grid_constant__ AutDev A, const __grid_constant__ EmitCtx E,
+    const uint8_t *__restrict__ data, uint64_t limit, uint32_t n_hot, uint32_t hot_bytes)
+{
+	extern __shared__ __align__(128) uint32_t cd_smem[];
+	uint16_t *hot = reinterpret_cast<uint16_t *>(cd_smem);
+	uint32_t *lut = cd_smem + hot_bytes / 4;
+	uint64_t *bar = reinterpret_cast<uint64_t *>(cd_smem + hot_bytes / 4 + (RANGE ? 0 : CD_LUT_WORDS));
+	const uint32_t lane = threadIdx.x & 31;
+	const uint32_t C = A.cd_classes, cmax = C - 1, rlo = (uint32_t)A.cd_range_lo;
+
+	/* hot rows: TMA bulk copies of up to 16 KiB on one mbarrier */
+	if (threadIdx.x == 0) {
+		mbar_init(bar, 1);
+		mbar_expect_tx(bar, hot_bytes);
+		for (uint32_t off = 0; off < hot_bytes; off += 16384) {
+			const uint32_t nb = hot_bytes - off < 16384 ? hot_bytes - off : 16384;
+			bulk_g2s(reinterpret_cast<uint8_t *>(hot) + off, reinterpret_cast<const uint8_t *>(A.cd_tab) + off, nb, bar);
+		}
+	}
+	if (!RANGE) {
+		/* word (b >> 2) of the class map, once per bank */
+		const uint32_t *cls32 = reinterpret_cast<const uint32_t *>(A.cd_cls);
+		for (uint32_t i = threadIdx.x; i < CD_LUT_WORDS; i += CD_THREADS)
+			lut[i] = __ldg(cls32 + (i >> 5));
+	}
+	__syncthreads();
+	mbar_wait(bar, 0);
+
+	const uint32_t shift = E.shift;
+	const uint64_t chunk = 1ull << shift;
+	const uint64_t halo = A.max_len > 0 ? (uint64_t)(A.max_len - 1) : 0;
+	const uint64_t k_first = E.emit_lo >> shift, k_last = (limit - 1) >> shift;
+	const uint64_t n_pairs = (k_last - k_first + 2) / 2;
+
+	for (uint64_t g = (uint64_t)blockIdx.x * CD_THREADS + threadIdx.x; g < n_pairs;
+	     g += (uint64_t)gridDim.x * CD_THREADS) {
+		const uint64_t ka = k_first + 2 * g, kb = ka + 1;
+		const uint64_t a0 = ka << shift;
+		/* both chunks whole, aligned, with their halo inside the valid range */
+		const bool fast = kb <= k_last && a0 >= E.emit_lo && a0 + 2 * chunk <= limit &&
+		    a0 >= halo && a0 - halo >= E.valid_lo;
+		if (!fast) {
+			cd_chunk_bytes<RANGE>(&A, &E, data, ka, limit, hot, lut, n_hot);
+			if (kb <= k_last)
+				cd_chunk_bytes<RANGE>(&A, &E, data, kb, limit, hot, lut, n_hot);
+			continue;
+		}
+		const uint64_t ba = ka - k_first;
+		CdOut oa = cd_open(E, ba), ob = cd_open(E, ba + 1);
+		uint32_t sa = 0, sb = 0;
+		/* cold start: the halo of chunk a lies before it, the halo of chunk b is the end of a */
+		for (uint64_t p = a0 - halo; p < a0; ++p) {
+			sa = cd_next(sa, cd_class<RANGE>(__ldg(data + p), lut, lane, rlo, cmax), hot, A.cd_tab, C, n_hot) &
+			    ACM_CD_STATE_MASK;
+			sb = cd_next(sb, cd_class<RANGE>(__ldg(data + p + chunk), lut, lane, rlo, cmax), hot, A.cd_tab, C,
+			    n_hot) & ACM_CD_STATE_MASK;
+		}
+		const uint4 *pa = reinterpret_cast<const uint4 *>(data + a0);
+		const uint4 *pb = reinterpret_cast<const uint4 *>(data + a0 + chunk);
+		for (uint32_t i = 0; i < (uint32_t)(chunk >> 4); ++i) {
+			const uint4 va = __ldcs(pa + i), vb = __ldcs(pb + i);
+			const uint32_t wa[4] = {va.x, va.y, va.z, va.w}, wb[4] = {vb.x, vb.y, vb.z, vb.w};
+			const uint64_t pos = a0 + 16ull * i;
+#pragma unroll
+			for (int q = 0; q < 16; ++q) {
+				const uint32_t ca = cd_class<RANGE>((wa[q >> 2] >> (8 * (q & 3))) & 0xFFu, lut, lane, rlo, cmax);
+				const uint32_t cb = cd_class<RANGE>((wb[q >> 2] >> (8 * (q & 3))) & 0xFFu, lut, lane, rlo, cmax);
+				const uint32_t ea = cd_next(sa, ca, hot, A.cd_tab, C, n_hot);
+				const uint32_t eb = cd_next(sb, cb, hot, A.cd_tab, C, n_hot);
+				sa = ea & ACM_CD_STATE_MASK;
+				sb = eb & ACM_CD_STATE_MASK;
+				if (ea >> ACM_CD_STATE_BITS)
+					cd_emit(A, oa, sa, ea >> ACM_CD_STATE_BITS, pos + q);
+				if (eb >> ACM_CD_STATE_BITS)
+					cd_emit(A, ob, sb, eb >> ACM_CD_STATE_BITS, pos + chunk + q);
+			}
+		}
+		cd_close(E, ba, oa);
+		cd_close(E, ba + 1, ob);
 	}
 }

@@ -246,6 +246,37 @@ k_bucket_sort_compact(const uint64_t *__restrict__ buckets, const uint32_t *__re
 	}
 }
 
+/*
+ * K3 for buckets whose records are already in order (k_scan_cdfa: one bucket per chunk, filled
+ * by one thread walking sequentially): compaction is a copy, one warp per bucket.  Same guards
+ * as k_bucket_sort_compact.
+ */
+__global__ void __launch_bounds__(256)
+k_bucket_copy_compact(const uint64_t *__restrict__ buckets, const uint32_t *__restrict__ counts,
+    const uint32_t *__restrict__ offsets, uint64_t *__restrict__ out, uint32_t cap, uint32_t n_buckets,
+    uint64_t out_cap, uint32_t *flags)
+{
+	const uint32_t lane = threadIdx.x & 31;
+	const uint32_t warps = (gridDim.x * blockDim.x) >> 5;
+
+	if (*(volatile uint32_t *)flags)
+		return;
+	for (uint32_t b = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; b < n_buckets; b += warps) {
+		const uint32_t cnt = min(__ldg(&counts[b]), cap);
+		const uint64_t o = __ldg(&offsets[b]);
+		if (cnt == 0)
+			continue;
+		if (o + cnt > out_cap) {
+			if (lane == 0)
+				flags[5] = 1u;
+			continue;
+		}
+		const uint64_t *src = buckets + (uint64_t)b * cap;
+		for (uint32_t i = lane; i < cnt; i += 32)
+			out[o + i] = __ldcs(src + i);
+	}
+}
+
 /* reference bucket format -> [total, values..., tail]  (reference compactarray.cl:40-68) */
 __global__ void k_compact_columns(int32_t *__restrict__ dst, const int32_t *__restrict__ src,
     const int32_t *__restrict__ prefix, int32_t len, int32_t max_results)

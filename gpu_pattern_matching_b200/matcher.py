@@ -11,8 +11,8 @@ import numpy as np
 from . import _lib
 from ._lib import AcmError, PushTarget, ScanParams, ScanResult, check, lib
 
-MODE_AUTO, MODE_SAMPLED4, MODE_START2, MODE_DFA = 0, 1, 2, 3
-MODE_NAMES = {1: "sampled", 2: "start2", 3: "dfa"}
+MODE_AUTO, MODE_SAMPLED4, MODE_START2, MODE_DFA, MODE_CDFA = 0, 1, 2, 3, 4
+MODE_NAMES = {1: "sampled", 2: "start2", 3: "dfa", 4: "cdfa"}
 KEY_PAT_BITS = 24
 
 

@@ -79,16 +79,19 @@ int      acm_automaton_max_pattern_len(const struct acm_automaton *);
 int      acm_automaton_min_pattern_len(const struct acm_automaton *);
 int      acm_automaton_alphabet(const struct acm_automaton *);
 size_t   acm_automaton_device_bytes(const struct acm_automaton *);
-/* which kernel ACM_MODE_AUTO picks: 1 = sampled 4-gram, 2 = 2-byte start filter, 3 = DFA */
+/* which kernel ACM_MODE_AUTO picks: 1 = sampled gram filter, 2 = 2-byte start filter, 3 = DFA,
+ * 4 = class-compressed DFA with the hot rows in shared memory (small automata over few distinct bytes) */
 int      acm_automaton_default_mode(const struct acm_automaton *);
 uint32_t acm_automaton_gram_count(const struct acm_automaton *);
+/* columns of the class-compressed table (mode 4), 0 if the automaton has none */
+int      acm_automaton_cdfa_classes(const struct acm_automaton *);
 /* window stride of the sampled kernel for this automaton: 8 (every pattern >= 10 bytes), 4 (>= 7), 0 (not available).
  * ACM_SAMPLE_STRIDE=4 in the environment at compile (acsm_compile) time forces 4. */
 int      acm_automaton_sample_stride(const struct acm_automaton *);
 
 /* ---- scan ---- */
 struct acm_scan_params {
-	int      mode;          /* 0 auto, 1 sampled4, 2 start2, 3 dfa                        */
+	int      mode;          /* 0 auto, 1 sampled4, 2 start2, 3 dfa, 4 cdfa                */
 	int      bucket_shift;  /* log2 bytes of input per result bucket; 0 = default (17 sampled, 15 otherwise) */
 	int      bucket_cap;    /* records per bucket before the exact 2-pass fallback; 0 = default */
 	int      timing;        /* record CUDA events around each kernel                      */

@@ -74,6 +74,8 @@ def modes_for(acsm):
     m = [g.MODE_START2, g.MODE_DFA]
     if acsm.get_min_pattern_size() >= 7:
         m.insert(0, g.MODE_SAMPLED4)
+    if acsm.automaton and g.lib().acm_automaton_cdfa_classes(acsm.automaton) > 0:
+        m.append(g.MODE_CDFA)
     return m
 
 

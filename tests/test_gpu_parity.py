@@ -252,3 +252,71 @@ def test_async_scan_two_scanners_and_push(device):
             sc.close()
     for d in d_bufs + [region]:
         device.free(d)
+
+
+def _word_text(rng, pats, nbytes, seps=b" \n.,"):
+    parts, size = [], 0
+    while size < nbytes:
+        w = pats[int(rng.integers(0, len(pats)))][0]
+        if rng.random() < 0.3:                            # a non-word now and then
+            w = bytes(rng.integers(97, 123, size=int(rng.integers(1, 9))).tolist())
+        sep = seps[int(rng.integers(0, len(seps)))]
+        parts.append(w + bytes([sep]))
+        size += len(w) + 1
+    return np.frombuffer(b"".join(parts)[:nbytes], dtype=np.uint8).copy()
+
+
+def test_cdfa_windows_shapes_and_class_maps(device):
+    """The class-compressed DFA kernel (mode 4) on its own: both byte->column forms (arithmetic
+    range / replicated lookup table), hot-row budgets from "nothing in shared memory" upwards,
+    ragged lengths, unaligned emit windows with a hidden stale prefix, bucket overflow (exact
+    two-pass path) -- always the oracle's list."""
+    import os
+    rng = np.random.default_rng(77)
+    lex = load_patterns("sentiment_categorical.pat.gz")[:1500]
+    # wide byte span (> 63 values) but few distinct bytes -> lookup-table form
+    wide = [(bytes(rng.choice(np.array([0, 7, 65, 66, 200, 201, 255], dtype=np.uint8), size=int(rng.integers(1, 9))).tolist()), i)
+            for i in range(300)]
+    for pats, form in ((lex, "range"), (wide, "lut")):
+        o, a = build_oracle(pats), build_product(pats)
+        assert g.lib().acm_automaton_cdfa_classes(a.automaton) > 0
+        assert g.lib().acm_automaton_default_mode(a.automaton) == g.MODE_CDFA
+        if form == "range":
+            text = _word_text(rng, pats, 300000)
+        else:
+            text = rng.choice(np.array([0, 7, 65, 66, 200, 201, 255, 33], dtype=np.uint8), size=300000)
+        for n in (1, 15, 16, 255, 256, 257, 511, 513, 4096 + 17, 300000):
+            t = text[:n]
+            eo, ep, _, _ = o.search(t)
+            for hot_kb in ("1", "64", None):
+                if hot_kb is None:
+                    os.environ.pop("ACM_CD_HOT_KB", None)
+                else:
+                    os.environ["ACM_CD_HOT_KB"] = hot_kb
+                off, pat, res = gpu_scan(device, a, t, g.MODE_CDFA)
+                assert_same(off, pat, eo, ep, f"cdfa {form} n={n} hot={hot_kb}")
+        os.environ.pop("ACM_CD_HOT_KB", None)
+        # emit windows: any cut, with the bytes before valid_lo replaced by junk that would match
+        eo, ep, _, _ = o.search(text)
+        lmax = a.get_max_pattern_size()
+        for lo, hi in ((0, 100), (1, 257), (255, 256), (256, 512), (300, 300000), (70001, 140003), (299990, 300000)):
+            keep = (eo >= lo) & (eo < hi)
+            off, pat, _ = gpu_scan(device, a, text, g.MODE_CDFA, emit_lo=lo, emit_hi=hi)
+            assert_same(off, pat, eo[keep], ep[keep], f"cdfa {form} window [{lo},{hi})")
+            vlo = max(0, lo - (lmax - 1))
+            junk = text.copy()
+            if vlo:
+                # a pattern planted across valid_lo: matches only if the stale bytes are used
+                p0 = np.frombuffer(max((p for p, _ in pats), key=len), dtype=np.uint8)
+                cut = p0.size // 2
+                if cut and vlo >= cut and vlo + p0.size - cut <= junk.size:
+                    junk[vlo - cut:vlo] = p0[:cut]
+                    junk[vlo:vlo + p0.size - cut] = p0[cut:]
+            eo2, ep2, _, _ = o.search(junk[vlo:])
+            keep2 = (eo2 + vlo >= lo) & (eo2 + vlo < hi)
+            off, pat, _ = gpu_scan(device, a, junk, g.MODE_CDFA, emit_lo=lo, emit_hi=hi, valid_lo=vlo)
+            assert_same(off, pat, eo2[keep2] + np.uint64(vlo), ep2[keep2], f"cdfa {form} valid_lo {vlo} window [{lo},{hi})")
+        # overflow -> exact two-pass path (direct writes, no sort needed)
+        off, pat, res = gpu_scan(device, a, text, g.MODE_CDFA, bucket_shift=10, bucket_cap=32)
+        assert res.fallback == 1
+        assert_same(off, pat, eo, ep, f"cdfa {form} overflow")

@@ -14,8 +14,8 @@ text = synth.english_like(words, 32 << 20, seed=4)
 n = int(sys.argv[1]) << 20 if len(sys.argv) > 1 else 256 << 20
 d = dev.alloc(n + 64)
 dev.h2d(d, np.tile(text, n // text.size + 1)[:n])
-for mode in (2, 3):
-    for shift, cap in ((0, 0), (15, 1024), (12, 1024)):
+for mode in (4, 2, 3):
+    for shift, cap in (((0, 0),) if mode == 4 else ((0, 0), (12, 1024))):
         try:
             sc = g.Scanner(dev, a.automaton, n, mode=mode, timing=True, bucket_shift=shift, bucket_cap=cap)
         except Exception as e:
