@@ -919,12 +919,12 @@ static void
 launch_k3(struct acm_scanner *s, cudaStream_t st, uint32_t nb, uint32_t k3_blocks)
 {
 	if (s->p.mode == ACM_MODE_CDFA) {
-		/* buckets are in order already: a copy, one warp per bucket */
+		/* hits are in order already: an expanding copy, one warp per bucket */
 		uint32_t blocks = (nb + 7) / 8;
 		if (blocks > (uint32_t)s->dev->sm_count * 8)
 			blocks = (uint32_t)s->dev->sm_count * 8;
-		k_bucket_copy_compact<<<blocks, 256, 0, st>>>(s->buckets, s->counts, s->offsets, s->out, s->cap,
-		    nb, s->out_cap, s->flags);
+		k_bucket_expand_compact<<<blocks, 256, 0, st>>>(s->buckets, s->counts, s->offsets, s->out, s->cap,
+		    nb, s->out_cap, s->flags, s->aut->d.cd_flat_begin, s->aut->d.cd_flat_pat);
 		return;
 	}
 	k_bucket_sort_compact<<<k3_blocks, K3_THREADS, (size_t)s->cap * 8, st>>>(s->buckets, s->counts,

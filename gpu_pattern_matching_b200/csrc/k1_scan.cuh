@@ -759,9 +759,10 @@ k_scan_dfa(const AutDev A, const EmitCtx E, const SYM *__restrict__ data, uint64
  *     a 32-way replicated (bank-conflict-free) table;
  *   - every thread walks TWO adjacent chunks in lockstep, two independent dependency chains,
  *     which is what hides the L2 latency of the cold rows;
- *   - a chunk is its own result bucket: the thread owns the slot counter (no atomics), records
- *     come out in (end offset, pattern index) order because the walk is sequential and every
- *     state's full match list is stored sorted, so the post-pass is a copy, not a sort.
+ *   - a chunk is its own result bucket: the thread owns the slot counter (no atomics), hits
+ *     come out in end-offset order because the walk is sequential, and every state's full
+ *     match list is stored sorted by pattern index, so the post-pass is an expanding copy,
+ *     not a sort.
  * Chunks are cut on absolute multiples of 2^shift in the buffer, so interior chunks are
  * 16-byte aligned and read with 16-byte loads; the first and last chunk of a scan (cut by
  * emit_lo / the end) take a byte-wise path.
@@ -769,11 +770,6 @@ k_scan_dfa(const AutDev A, const EmitCtx E, const SYM *__restrict__ data, uint64
 #define CD_THREADS   1024
 #define CD_LUT_WORDS 2048          /* 64 words x 32 banks */
 #define CD_SMEM_MAX  (227 * 1024)
-
-struct CdOut {
-	uint64_t *dst;
-	uint32_t  k, cap;
-};
 
 template <bool RANGE>
 __device__ __forceinline__ uint32_t cd_class(uint32_t b, const uint32_t *lut, uint32_t lane, uint32_t lo,
@@ -792,24 +788,49 @@ __device__ __forceinline__ uint32_t cd_next(uint32_t state, uint32_t c, const ui
 	return state < n_hot ? (uint32_t)hot[idx] : (uint32_t)__ldg(tab + idx);
 }
 
+/*
+ * Emission.  Looking up a state's pattern list inside the walk would put two dependent L2
+ * round trips on the warp's critical path at almost every step (with one match per ~9 bytes
+ * nearly every warp step has a lane that matched): measured 60 % of all stall samples.  So the
+ * walk stores only the HIT, (end offset << 24) | state, a fire-and-forget 8-byte store, and adds
+ * the 2-bit list length carried by the transition entry to its record count; the expansion
+ * state -> pattern indices happens in the compaction kernel (k_bucket_expand_compact), which is
+ * a bandwidth-bound copy anyway.  Bucket row: slot 0 = number of hits, slots 1.. = hits.
+ * Direct mode (second pass after a bucket overflow) expands in place instead.
+ */
+struct CdOut {
+	uint64_t *dst;
+	uint32_t  k;        /* hits (bucket mode) or records (direct mode) written so far */
+	uint32_t  nrec;     /* records this chunk produces                                 */
+	uint32_t  cap;      /* 0 = direct mode                                             */
+};
+
 __device__ __forceinline__ void cd_emit(const AutDev &A, CdOut &o, uint32_t state, uint32_t code, uint64_t pos)
 {
-	const uint32_t fb = __ldg(&A.cd_flat_begin[state]);
-	const uint32_t cnt = code < 3 ? code : __ldg(&A.cd_flat_begin[state + 1]) - fb;
-	for (uint32_t j = 0; j < cnt; ++j) {
-		if (o.k < o.cap)
-			o.dst[o.k] = (pos << ACM_KEY_PAT_BITS) | __ldg(&A.cd_flat_pat[fb + j]);
-		++o.k;
+	uint32_t cnt = code;
+	if (code == 3 || o.cap == 0) {
+		const uint32_t fb = __ldg(&A.cd_flat_begin[state]);
+		cnt = __ldg(&A.cd_flat_begin[state + 1]) - fb;
+		if (o.cap == 0)
+			for (uint32_t j = 0; j < cnt; ++j)
+				o.dst[o.nrec + j] = (pos << ACM_KEY_PAT_BITS) | __ldg(&A.cd_flat_pat[fb + j]);
 	}
+	if (o.cap) {
+		++o.k;
+		if (o.k < o.cap)
+			o.dst[o.k] = (pos << ACM_KEY_PAT_BITS) | state;
+	}
+	o.nrec += cnt;
 }
 
 __device__ __forceinline__ CdOut cd_open(const EmitCtx &E, uint64_t b)
 {
 	CdOut o;
 	o.k = 0;
+	o.nrec = 0;
 	if (E.direct) {
 		o.dst = E.out + E.offsets[b];
-		o.cap = 0xffffffffu;
+		o.cap = 0;
 	} else {
 		o.dst = E.buckets + b * E.cap;
 		o.cap = E.cap;
@@ -819,9 +840,12 @@ __device__ __forceinline__ CdOut cd_open(const EmitCtx &E, uint64_t b)
 
 __device__ __forceinline__ void cd_close(const EmitCtx &E, uint64_t b, const CdOut &o)
 {
-	E.counts[b] = o.k;
-	if (o.k > o.cap)
-		*E.overflow = 1u;
+	E.counts[b] = o.nrec;
+	if (o.cap) {
+		o.dst[0] = o.k;
+		if (o.k >= o.cap)
+			*E.overflow = 1u;
+	}
 }
 
 /* byte-wise walk of chunk k (absolute chunk index): the first / last chunk of a scan */
@@ -916,12 +940,15 @@ k_scan_cdfa(const __grid_constant__ AutDev A, const __grid_constant__ EmitCtx E,
 		}
 		const uint4 *pa = reinterpret_cast<const uint4 *>(data + a0);
 		const uint4 *pb = reinterpret_cast<const uint4 *>(data + a0 + chunk);
-		for (uint32_t i = 0; i < (uint32_t)(chunk >> 4); ++i) {
-			const uint4 va = __ldcs(pa + i), vb = __ldcs(pb + i);
-			const uint32_t wa[4] = {va.x, va.y, va.z, va.w}, wb[4] = {vb.x, vb.y, vb.z, vb.w};
+		/* 32 bytes (one sector) per chain per round: both halves are requested together */
+		for (uint32_t i = 0; i < (uint32_t)(chunk >> 4); i += 2) {
+			const uint4 va0 = __ldg(pa + i), va1 = __ldg(pa + i + 1);
+			const uint4 vb0 = __ldg(pb + i), vb1 = __ldg(pb + i + 1);
+			const uint32_t wa[8] = {va0.x, va0.y, va0.z, va0.w, va1.x, va1.y, va1.z, va1.w};
+			const uint32_t wb[8] = {vb0.x, vb0.y, vb0.z, vb0.w, vb1.x, vb1.y, vb1.z, vb1.w};
 			const uint64_t pos = a0 + 16ull * i;
 #pragma unroll
-			for (int q = 0; q < 16; ++q) {
+			for (int q = 0; q < 32; ++q) {
 				const uint32_t ca = cd_class<RANGE>((wa[q >> 2] >> (8 * (q & 3))) & 0xFFu, lut, lane, rlo, cmax);
 				const uint32_t cb = cd_class<RANGE>((wb[q >> 2] >> (8 * (q & 3))) & 0xFFu, lut, lane, rlo, cmax);
 				const uint32_t ea = cd_next(sa, ca, hot, A.cd_tab, C, n_hot);

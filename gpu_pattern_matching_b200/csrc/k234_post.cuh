@@ -247,14 +247,18 @@ k_bucket_sort_compact(const uint64_t *__restrict__ buckets, const uint32_t *__re
 }
 
 /*
- * K3 for buckets whose records are already in order (k_scan_cdfa: one bucket per chunk, filled
- * by one thread walking sequentially): compaction is a copy, one warp per bucket.  Same guards
- * as k_bucket_sort_compact.
+ * K3 for k_scan_cdfa.  A bucket row holds one chunk's HITS in end-offset order,
+ * row[0] = number of hits, row[1 + i] = (end offset << 24) | state; counts[] / offsets[] are
+ * in RECORDS.  One warp per bucket: lane i expands hit i into the state's full match list
+ * (flat_begin / flat_pat, ascending pattern index), placed by a warp prefix sum -- the output
+ * is the canonical (end offset, pattern index) order with no sort.  Same guards as
+ * k_bucket_sort_compact.
  */
 __global__ void __launch_bounds__(256)
-k_bucket_copy_compact(const uint64_t *__restrict__ buckets, const uint32_t *__restrict__ counts,
+k_bucket_expand_compact(const uint64_t *__restrict__ buckets, const uint32_t *__restrict__ counts,
     const uint32_t *__restrict__ offsets, uint64_t *__restrict__ out, uint32_t cap, uint32_t n_buckets,
-    uint64_t out_cap, uint32_t *flags)
+    uint64_t out_cap, uint32_t *flags, const uint32_t *__restrict__ flat_begin,
+    const uint32_t *__restrict__ flat_pat)
 {
 	const uint32_t lane = threadIdx.x & 31;
 	const uint32_t warps = (gridDim.x * blockDim.x) >> 5;
@@ -262,18 +266,39 @@ k_bucket_copy_compact(const uint64_t *__restrict__ buckets, const uint32_t *__re
 	if (*(volatile uint32_t *)flags)
 		return;
 	for (uint32_t b = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; b < n_buckets; b += warps) {
-		const uint32_t cnt = min(__ldg(&counts[b]), cap);
-		const uint64_t o = __ldg(&offsets[b]);
-		if (cnt == 0)
+		const uint32_t nrec = __ldg(&counts[b]);
+		if (nrec == 0)
 			continue;
-		if (o + cnt > out_cap) {
+		uint64_t o = __ldg(&offsets[b]);
+		if (o + nrec > out_cap) {
 			if (lane == 0)
 				flags[5] = 1u;
 			continue;
 		}
-		const uint64_t *src = buckets + (uint64_t)b * cap;
-		for (uint32_t i = lane; i < cnt; i += 32)
-			out[o + i] = __ldcs(src + i);
+		const uint64_t *row = buckets + (uint64_t)b * cap;
+		const uint32_t nh = (uint32_t)__ldcs(row);
+		for (uint32_t base = 0; base < nh; base += 32) {
+			const uint32_t i = base + lane;
+			uint64_t key = 0;
+			uint32_t fb = 0, cnt = 0;
+			if (i < nh) {
+				key = __ldcs(row + 1 + i);
+				const uint32_t st = (uint32_t)(key & ACM_KEY_PAT_MASK);
+				fb = __ldg(&flat_begin[st]);
+				cnt = __ldg(&flat_begin[st + 1]) - fb;
+			}
+			uint32_t inc = cnt;
+#pragma unroll
+			for (int d = 1; d < 32; d <<= 1) {
+				const uint32_t y = __shfl_up_sync(0xffffffffu, inc, d);
+				if (lane >= (uint32_t)d)
+					inc += y;
+			}
+			const uint64_t hi = key & ~(uint64_t)ACM_KEY_PAT_MASK;
+			for (uint32_t j = 0; j < cnt; ++j)
+				out[o + (inc - cnt) + j] = hi | __ldg(&flat_pat[fb + j]);
+			o += __shfl_sync(0xffffffffu, inc, 31);
+		}
 	}
 }
 
