@@ -771,6 +771,17 @@ k_scan_dfa(const AutDev A, const EmitCtx E, const SYM *__restrict__ data, uint64
 #define CD_LUT_WORDS 2048          /* 64 words x 32 banks */
 #define CD_SMEM_MAX  (227 * 1024)
 
+/* predicated 8-byte store: no branch, nothing happens when p is false */
+__device__ __forceinline__ void st_pred_v2(uint64_t *addr, uint32_t lo, uint32_t hi, bool p)
+{
+	asm volatile(
+	    "{\n"
+	    ".reg .pred p;\n"
+	    "setp.ne.b32 p, %3, 0;\n"
+	    "@p st.global.v2.u32 [%0], {%1, %2};\n"
+	    "}\n" ::"l"(addr), "r"(lo), "r"(hi), "r"((uint32_t)p) : "memory");
+}
+
 template <bool RANGE>
 __device__ __forceinline__ uint32_t cd_class(uint32_t b, const uint32_t *lut, uint32_t lane, uint32_t lo,
     uint32_t cmax)
@@ -920,7 +931,7 @@ k_scan_cdfa(const __grid_constant__ AutDev A, const __grid_constant__ EmitCtx E,
 		const uint64_t ka = k_first + 2 * g, kb = ka + 1;
 		const uint64_t a0 = ka << shift;
 		/* both chunks whole, aligned, with their halo inside the valid range */
-		const bool fast = kb <= k_last && a0 >= E.emit_lo && a0 + 2 * chunk <= limit &&
+		const bool fast = !E.direct && kb <= k_last && a0 >= E.emit_lo && a0 + 2 * chunk <= limit &&
 		    a0 >= halo && a0 - halo >= E.valid_lo;
 		if (!fast) {
 			cd_chunk_bytes<RANGE>(&A, &E, data, ka, limit, hot, lut, n_hot);
@@ -928,8 +939,15 @@ k_scan_cdfa(const __grid_constant__ AutDev A, const __grid_constant__ EmitCtx E,
 				cd_chunk_bytes<RANGE>(&A, &E, data, kb, limit, hot, lut, n_hot);
 			continue;
 		}
+		/*
+		 * Bucket mode, branch-free: with one match per ~9 bytes nearly every warp step has a
+		 * lane that matched, so an `if (hit)` body would run (divergently) at every step.
+		 * Instead every lane executes a predicated 8-byte store of its hit and two adds.
+		 */
 		const uint64_t ba = ka - k_first;
-		CdOut oa = cd_open(E, ba), ob = cd_open(E, ba + 1);
+		uint64_t *rowa = E.buckets + ba * E.cap, *rowb = rowa + E.cap;
+		const uint32_t capm1 = E.cap - 1;
+		uint32_t hka = 0, hkb = 0, nra = 0, nrb = 0;       /* hits, records */
 		uint32_t sa = 0, sb = 0;
 		/* cold start: the halo of chunk a lies before it, the halo of chunk b is the end of a */
 		for (uint64_t p = a0 - halo; p < a0; ++p) {
@@ -946,7 +964,12 @@ k_scan_cdfa(const __grid_constant__ AutDev A, const __grid_constant__ EmitCtx E,
 			const uint4 vb0 = __ldg(pb + i), vb1 = __ldg(pb + i + 1);
 			const uint32_t wa[8] = {va0.x, va0.y, va0.z, va0.w, va1.x, va1.y, va1.z, va1.w};
 			const uint32_t wb[8] = {vb0.x, vb0.y, vb0.z, vb0.w, vb1.x, vb1.y, vb1.z, vb1.w};
-			const uint64_t pos = a0 + 16ull * i;
+			/* key = pos << 24 | state; pos = base + q with base a multiple of 32, so the low
+			 * word is (base << 24) | (q << 24) | state with no carries */
+			const uint64_t keya = (a0 + 16ull * i) << ACM_KEY_PAT_BITS;
+			const uint64_t keyb = (a0 + chunk + 16ull * i) << ACM_KEY_PAT_BITS;
+			const uint32_t kalo = (uint32_t)keya, kahi = (uint32_t)(keya >> 32);
+			const uint32_t kblo = (uint32_t)keyb, kbhi = (uint32_t)(keyb >> 32);
 #pragma unroll
 			for (int q = 0; q < 32; ++q) {
 				const uint32_t ca = cd_class<RANGE>((wa[q >> 2] >> (8 * (q & 3))) & 0xFFu, lut, lane, rlo, cmax);
@@ -955,13 +978,24 @@ k_scan_cdfa(const __grid_constant__ AutDev A, const __grid_constant__ EmitCtx E,
 				const uint32_t eb = cd_next(sb, cb, hot, A.cd_tab, C, n_hot);
 				sa = ea & ACM_CD_STATE_MASK;
 				sb = eb & ACM_CD_STATE_MASK;
-				if (ea >> ACM_CD_STATE_BITS)
-					cd_emit(A, oa, sa, ea >> ACM_CD_STATE_BITS, pos + q);
-				if (eb >> ACM_CD_STATE_BITS)
-					cd_emit(A, ob, sb, eb >> ACM_CD_STATE_BITS, pos + chunk + q);
+				const uint32_t da = ea >> ACM_CD_STATE_BITS, db = eb >> ACM_CD_STATE_BITS;
+				st_pred_v2(rowa + hka + 1, kalo | ((uint32_t)q << ACM_KEY_PAT_BITS) | sa, kahi, da && hka < capm1);
+				st_pred_v2(rowb + hkb + 1, kblo | ((uint32_t)q << ACM_KEY_PAT_BITS) | sb, kbhi, db && hkb < capm1);
+				hka += da ? 1u : 0u;
+				hkb += db ? 1u : 0u;
+				nra += da;
+				nrb += db;
+				if (da == 3)            /* three or more patterns end here: exact length (rare) */
+					nra += __ldg(&A.cd_flat_begin[sa + 1]) - __ldg(&A.cd_flat_begin[sa]) - 3;
+				if (db == 3)
+					nrb += __ldg(&A.cd_flat_begin[sb + 1]) - __ldg(&A.cd_flat_begin[sb]) - 3;
 			}
 		}
-		cd_close(E, ba, oa);
-		cd_close(E, ba + 1, ob);
+		E.counts[ba] = nra;
+		E.counts[ba + 1] = nrb;
+		rowa[0] = hka;
+		rowb[0] = hkb;
+		if (hka > capm1 || hkb > capm1)
+			*E.overflow = 1u;
 	}
 }
