@@ -145,6 +145,7 @@ acm_tables_free(struct acm_tables *t)
 	free(t->bfs_to_ref); free(t->f1); free(t->f2); free(t->grams); free(t->b2);
 	free(t->cand); free(t->pat_blob); free(t->pat_off);
 	free(t->cd_cls); free(t->cd_tab); free(t->cd_flat_begin); free(t->cd_flat_pat);
+	free(t->cd_rec); free(t->cd_t16);
 	memset(t, 0, sizeof(*t));
 }
 
@@ -166,6 +167,8 @@ acm_tables_device_bytes(const struct acm_tables *t)
 	if (t->cd_tab)
 		b += (size_t)t->num_states * t->cd_classes * 2 + 256 + (size_t)(t->num_states + 1) * 4 +
 		    (size_t)t->cd_flat_total * 4;
+	if (t->cd_rec)
+		b += (size_t)t->num_states * 8 + (size_t)t->cd_t16_count * 2;
 	return b;
 }
 
@@ -220,27 +223,119 @@ cmp_u32(const void *a, const void *b)
 }
 
 /*
+ * Delta encoding of cd_tab against the rows of shallow states (see acm_tables.h).  A state's row
+ * differs from the row of a state on its failure chain only in the columns where some state in
+ * between has a trie child, so deep states keep one or two explicit entries instead of C.
+ * fail[] / depth[] are in cd ids.  Picks the dense depth that makes the whole thing smallest;
+ * leaves cd_rec NULL when even that does not fit the shared-memory budget or a 16-bit index.
+ */
+static int
+build_cdfa_delta(struct acm_tables *t, const uint32_t *fail, const uint8_t *depth, int max_depth)
+{
+	const uint32_t C = t->cd_classes, n = t->num_states;
+	uint32_t *dflt = malloc((size_t)n * 4);
+	uint32_t s, k;
+	int d, best_d = -1;
+	size_t best = (size_t)-1;
+
+	if (!dflt)
+		return ACM_ERR_NOMEM;
+	/* cd ids keep breadth-first order except that a few deep states sit at the very end:
+	 * "depth <= d" is a prefix of the ids for every d that matters, checked here */
+	for (d = 0; d <= max_depth && d < 255; d++) {
+		uint32_t nd = 0;
+		size_t entries;
+		int prefix = 1;
+		while (nd < n && depth[nd] <= d)
+			nd++;
+		for (s = nd; s < n && prefix; s++)
+			prefix = depth[s] > d;
+		if (!prefix)
+			continue;
+		entries = (size_t)nd * C;
+		for (s = nd; s < n; s++) {
+			const uint16_t *a, *b;
+			dflt[s] = depth[fail[s]] <= d ? fail[s] : dflt[fail[s]];
+			a = t->cd_tab + (size_t)s * C;
+			b = t->cd_tab + (size_t)dflt[s] * C;
+			for (k = 0; k < C; k++)
+				entries += a[k] != b[k];
+		}
+		if (entries <= 65536 && (size_t)nd * C <= 65536 && entries * 2 < best) {
+			best = entries * 2;
+			best_d = d;
+		}
+	}
+	if (best_d < 0 || best + (size_t)n * 8 + 64 > ACM_CD_COMP_BUDGET) {
+		free(dflt);
+		return ACM_OK;
+	}
+	d = best_d;
+	t->cd_rec = malloc((size_t)n * 8);
+	t->cd_t16 = malloc(best + 64);
+	if (!t->cd_rec || !t->cd_t16) {
+		free(dflt);
+		return ACM_ERR_NOMEM;
+	}
+	{
+		uint32_t nd = 0, w;
+		while (nd < n && depth[nd] <= d)
+			nd++;
+		w = nd * C;
+		memcpy(t->cd_t16, t->cd_tab, (size_t)nd * C * 2);
+		for (s = 0; s < n; s++) {
+			uint32_t bitmap = 0, base = 0, D = s;
+			if (s >= nd) {
+				const uint16_t *a = t->cd_tab + (size_t)s * C, *b;
+				D = dflt[s] = depth[fail[s]] <= d ? fail[s] : dflt[fail[s]];
+				b = t->cd_tab + (size_t)D * C;
+				base = w;
+				for (k = 0; k < C; k++) {
+					if (a[k] != b[k]) {
+						bitmap |= 1u << k;
+						t->cd_t16[w++] = a[k];
+					}
+				}
+				if (!bitmap)
+					base = 0;
+			}
+			t->cd_rec[2 * s] = bitmap;
+			t->cd_rec[2 * s + 1] = (base & 0xFFFFu) | ((D * C) << 16);
+		}
+		t->cd_t16_count = w;
+	}
+	t->cd_dense_depth = d;
+	free(dflt);
+	return ACM_OK;
+}
+
+/*
  * Class-compressed DFA for small automata over few distinct bytes (word lists over text):
  * bytes that occur in no pattern all behave alike (every state goes to the root on them), so
  * the 256 columns of T collapse to C = (distinct pattern bytes) + 1, and with <= 2^14 states
- * an entry fits 16 bits together with a 2-bit "how many patterns end here" code.  Rows in
- * breadth-first order: a prefix of the table (the shallow, most visited states) is what the
- * scan kernel keeps in shared memory.  Each state's FULL match list (own patterns plus those
- * inherited along the output links -- reference acsmx.c:417-429 copies them) is flattened and
- * sorted by pattern index, so a sequential walk emits records already in canonical order.
+ * an entry fits 16 bits together with a 2-bit "how many patterns end here" code (0, 1, 2,
+ * 3 = three or four).  States keep their breadth-first ids (a prefix of the table = the shallow,
+ * most visited states) except that the states where FOUR patterns end are moved to the very
+ * end, so that "entry >= cd_thr4" tells three from four without a lookup; automata with a
+ * state where more than four patterns end do not get this form.  Each state's FULL match list
+ * (own patterns plus those inherited along the output links -- reference acsmx.c:417-429
+ * copies them) is flattened and sorted by pattern index, so a sequential walk emits records
+ * already in canonical order.
  */
 static int
 build_cdfa(struct acm_core *c)
 {
 	struct acm_tables *t = &c->tab;
+	const uint32_t n = t->num_states;
 	uint8_t used[256];
 	uint8_t col_byte[ACM_CD_MAX_CLASSES];
-	uint32_t s, k, C = 0;
-	int lo = -1, hi = -1, b, other = -1;
+	uint32_t s, k, C = 0, n4 = 0, next_lo, next_hi;
+	int lo = -1, hi = -1, b, other = -1, d, rc = ACM_OK;
 	uint64_t total = 0;
-	uint32_t *cnt;
+	uint32_t *cnt = NULL, *perm = NULL, *fail = NULL;
+	uint8_t *depth = NULL;
 
-	if (t->num_states > ACM_CD_MAX_STATES || t->num_states == 0)
+	if (n > ACM_CD_MAX_STATES || n == 0)
 		return ACM_OK;
 	memset(used, 0, sizeof(used));
 	for (k = 0; k < (uint32_t)c->npats; k++)
@@ -259,9 +354,40 @@ build_cdfa(struct acm_core *c)
 	if (C == 0 || C + 1 > ACM_CD_MAX_CLASSES || other < 0)
 		return ACM_OK;
 
+	/* full-list lengths (olink[s] < s in BFS order); more than four anywhere: no cdfa */
+	cnt = calloc(n + 1, 4);
+	perm = malloc((size_t)n * 4);
+	fail = malloc((size_t)n * 4);
+	depth = malloc(n);
+	if (!cnt || !perm || !fail || !depth) {
+		rc = ACM_ERR_NOMEM;
+		goto out;
+	}
+	for (s = 0; s < n; s++) {
+		cnt[s] = t->own_begin[s + 1] - t->own_begin[s] + (s ? cnt[t->olink[s]] : 0);
+		total += cnt[s];
+		if (cnt[s] > 4)
+			goto out;
+		n4 += cnt[s] == 4;
+	}
+	/* cd id: BFS order, four-pattern states last */
+	next_lo = 0;
+	next_hi = n - n4;
+	for (s = 0; s < n; s++)
+		perm[s] = cnt[s] == 4 ? next_hi++ : next_lo++;
+	for (d = 0; d <= t->max_depth; d++)
+		for (s = t->level_start[d]; s < t->level_start[d + 1]; s++)
+			depth[perm[s]] = (uint8_t)(d > 255 ? 255 : d);
+	for (s = 0; s < n; s++)
+		fail[perm[s]] = perm[t->fail[s]];
+
 	t->cd_cls = malloc(256);
-	if (!t->cd_cls)
-		return ACM_ERR_NOMEM;
+	t->cd_flat_begin = malloc((size_t)(n + 1) * 4);
+	t->cd_flat_pat = malloc((size_t)(total + 1) * 4);
+	if (!t->cd_cls || !t->cd_flat_begin || !t->cd_flat_pat) {
+		rc = ACM_ERR_NOMEM;
+		goto out;
+	}
 	if (hi - lo + 2 <= ACM_CD_MAX_CLASSES) {
 		/* contiguous range: column = byte - lo (unused bytes inside the range keep a real column) */
 		t->cd_range_lo = lo;
@@ -284,56 +410,57 @@ build_cdfa(struct acm_core *c)
 		}
 	}
 	col_byte[C - 1] = (uint8_t)other;
+	t->cd_tab = malloc((size_t)n * C * 2);
+	if (!t->cd_tab) {
+		rc = ACM_ERR_NOMEM;
+		goto out;
+	}
 
-	/* full lists: count, then fill through the output links (olink[s] < s in BFS order) */
-	cnt = calloc(t->num_states + 1, 4);
-	t->cd_flat_begin = malloc((size_t)(t->num_states + 1) * 4);
-	if (!cnt || !t->cd_flat_begin) {
-		free(cnt);
-		return ACM_ERR_NOMEM;
-	}
-	for (s = 0; s < t->num_states; s++) {
-		cnt[s] = t->own_begin[s + 1] - t->own_begin[s] + (s ? cnt[t->olink[s]] : 0);
-		total += cnt[s];
-	}
-	if (total > (1u << 24)) {          /* pathological nesting: leave this form out */
-		free(cnt);
-		free(t->cd_cls); free(t->cd_flat_begin);
-		t->cd_cls = NULL;
-		t->cd_flat_begin = NULL;
-		return ACM_OK;
-	}
-	t->cd_flat_total = (uint32_t)total;
-	t->cd_flat_pat = malloc((size_t)(total + 1) * 4);
-	t->cd_tab = malloc((size_t)t->num_states * C * 2);
-	if (!t->cd_flat_pat || !t->cd_tab) {
-		free(cnt);
-		return ACM_ERR_NOMEM;
-	}
+	/* flat lists in cd-id order: inv[] walks the cd ids */
 	{
-		uint32_t w = 0;
-		for (s = 0; s < t->num_states; s++) {
+		uint32_t *inv = malloc((size_t)n * 4);
+		uint32_t w = 0, id;
+		if (!inv) {
+			rc = ACM_ERR_NOMEM;
+			goto out;
+		}
+		for (s = 0; s < n; s++)
+			inv[perm[s]] = s;
+		for (id = 0; id < n; id++) {
 			uint32_t v, w0 = w;
-			t->cd_flat_begin[s] = w;
-			for (v = s; v; v = t->olink[v]) {
+			t->cd_flat_begin[id] = w;
+			for (v = inv[id]; v; v = t->olink[v])
 				for (k = t->own_begin[v]; k < t->own_begin[v + 1]; k++)
 					t->cd_flat_pat[w++] = t->own_pat[k];
-			}
 			if (w - w0 > 1)
 				qsort(t->cd_flat_pat + w0, w - w0, 4, cmp_u32);
 		}
-		t->cd_flat_begin[t->num_states] = w;
+		t->cd_flat_begin[n] = w;
+		t->cd_flat_total = w;
+		free(inv);
 	}
-	for (s = 0; s < t->num_states; s++) {
+	for (s = 0; s < n; s++) {
 		for (k = 0; k < C; k++) {
 			const uint32_t nx = t->T[(size_t)s * 256 + col_byte[k]] & ACM_T_MASK;
 			const uint32_t code = cnt[nx] < 3 ? cnt[nx] : 3;
-			t->cd_tab[(size_t)s * C + k] = (uint16_t)(nx | (code << ACM_CD_STATE_BITS));
+			t->cd_tab[(size_t)perm[s] * C + k] = (uint16_t)(perm[nx] | (code << ACM_CD_STATE_BITS));
 		}
 	}
-	free(cnt);
 	t->cd_classes = C;
-	return ACM_OK;
+	t->cd_thr4 = n4 ? ((3u << ACM_CD_STATE_BITS) | (n - n4)) : 0xFFFFFFFFu;
+	if (C <= 32)
+		rc = build_cdfa_delta(t, fail, depth, t->max_depth);
+out:
+	free(cnt); free(perm); free(fail); free(depth);
+	if (rc == ACM_OK && !t->cd_classes) {
+		/* not eligible: leave nothing half built */
+		free(t->cd_cls); free(t->cd_tab); free(t->cd_flat_begin); free(t->cd_flat_pat);
+		t->cd_cls = NULL;
+		t->cd_tab = NULL;
+		t->cd_flat_begin = NULL;
+		t->cd_flat_pat = NULL;
+	}
+	return rc;
 }
 
 static int

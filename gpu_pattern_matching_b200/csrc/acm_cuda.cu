@@ -61,7 +61,8 @@ struct acm_scanner {
 	struct acm_scan_params p;
 	uint64_t  max_bytes;
 	uint32_t  shift, cap, max_buckets;
-	uint32_t  cd_hot, cd_hot_bytes;   /* CDFA: rows of the table kept in shared memory */
+	uint32_t  cd_hot, cd_tab_bytes, cd_rec_bytes;   /* CDFA: shared-memory layout (see k_scan_cdfa) */
+	int       cd_comp;
 	uint64_t *buckets;
 	uint32_t *counts, *offsets;
 	uint8_t  *scratch;          /* one allocation, one memset per scan: flags | bucket_tiles | counts */
@@ -132,9 +133,13 @@ set_kernel_attrs(int ordinal)
 	    S2_SMEM_BYTES));
 	CUDA_TRY(cudaFuncSetAttribute(k_bucket_sort_compact, cudaFuncAttributeMaxDynamicSharedMemorySize,
 	    65536));
-	CUDA_TRY(cudaFuncSetAttribute(k_scan_cdfa<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+	CUDA_TRY(cudaFuncSetAttribute(k_scan_cdfa<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
 	    CD_SMEM_MAX));
-	CUDA_TRY(cudaFuncSetAttribute(k_scan_cdfa<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+	CUDA_TRY(cudaFuncSetAttribute(k_scan_cdfa<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+	    CD_SMEM_MAX));
+	CUDA_TRY(cudaFuncSetAttribute(k_scan_cdfa<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+	    CD_SMEM_MAX));
+	CUDA_TRY(cudaFuncSetAttribute(k_scan_cdfa<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
 	    CD_SMEM_MAX));
 	if (ordinal < 64)
 		g_attr_done[ordinal] = 1;
@@ -436,6 +441,12 @@ acm_automaton_upload(struct acm_device *dev, const struct acm_tables *t, struct 
 		UP(cd_flat_pat, t->cd_flat_pat, (size_t)(t->cd_flat_total + 1) * 4);
 		a->d.cd_classes = t->cd_classes;
 		a->d.cd_range_lo = t->cd_range_lo;
+		a->d.cd_thr4 = t->cd_thr4;
+		if (t->cd_rec) {
+			UP(cd_rec, t->cd_rec, (size_t)t->num_states * 8);
+			UP(cd_t16, t->cd_t16, (size_t)t->cd_t16_count * 2);
+			a->d.cd_t16_count = t->cd_t16_count;
+		}
 	}
 #undef UP
 	a->d.num_states = t->num_states;
@@ -743,7 +754,8 @@ acm_scanner_create(struct acm_device *dev, struct acm_automaton *aut, uint64_t m
 	}
 	if (mode == ACM_MODE_CDFA && !aut->d.cd_tab) {
 		acm_set_error("scanner_create: this automaton has no class-compressed table "
-		    "(needs <= %u states and <= %d distinct pattern bytes)", ACM_CD_MAX_STATES, ACM_CD_MAX_CLASSES - 1);
+		    "(needs <= %u states, <= %d distinct pattern bytes, <= 4 patterns ending in one state)",
+		    ACM_CD_MAX_STATES, ACM_CD_MAX_CLASSES - 1);
 		free(s);
 		return ACM_ERR_ARG;
 	}
@@ -763,18 +775,31 @@ acm_scanner_create(struct acm_device *dev, struct acm_automaton *aut, uint64_t m
 		s->p.bucket_shift = (int)sh;
 		if (!s->p.bucket_cap)
 			s->p.bucket_cap = (int)((1u << sh) / 4 > 8192 ? 8192 : (1u << sh) / 4);
-		const uint32_t row = aut->d.cd_classes * 2;
-		uint32_t budget = CD_SMEM_MAX - 16 - (aut->d.cd_range_lo >= 0 ? 0 : CD_LUT_WORDS * 4);
-		const char *kb = getenv("ACM_CD_HOT_KB");
-		if (kb && atoi(kb) > 0 && (uint32_t)atoi(kb) * 1024 < budget)
-			budget = (uint32_t)atoi(kb) * 1024;
-		s->cd_hot = budget / row;
-		if (s->cd_hot > aut->num_states)
+		const uint32_t lut_bytes = aut->d.cd_range_lo >= 0 ? 0 : CD_LUT_WORDS * 4;
+		const char *plain = getenv("ACM_CD_PLAIN");
+		if (aut->d.cd_rec && !(plain && atoi(plain))) {
+			/* delta-encoded table: all of it in shared memory */
+			s->cd_comp = 1;
+			s->cd_tab_bytes = (aut->d.cd_t16_count * 2 + 15) & ~15u;
+			s->cd_rec_bytes = (aut->num_states * 8 + 15) & ~15u;
 			s->cd_hot = aut->num_states;
-		s->cd_hot_bytes = (s->cd_hot * row + 15) & ~15u;
-		if (s->cd_hot_bytes > budget) {
-			s->cd_hot--;
-			s->cd_hot_bytes = (s->cd_hot * row + 15) & ~15u;
+		} else {
+			const uint32_t row = aut->d.cd_classes * 2;
+			uint32_t budget = CD_SMEM_MAX - 16 - lut_bytes;
+			const char *kb = getenv("ACM_CD_HOT_KB");
+			if (kb && atoi(kb) >= 0 && (uint32_t)atoi(kb) * 1024 < budget)
+				budget = (uint32_t)atoi(kb) * 1024;
+			else if (!kb && budget > 96 * 1024)
+				budget = 96 * 1024;     /* measured: the rest is worth more as L1 for the cold rows */
+			s->cd_hot = budget / row;
+			if (s->cd_hot > aut->num_states)
+				s->cd_hot = aut->num_states;
+			s->cd_tab_bytes = (s->cd_hot * row + 15) & ~15u;
+			if (s->cd_tab_bytes > budget) {
+				s->cd_hot = s->cd_hot ? s->cd_hot - 1 : 0;
+				s->cd_tab_bytes = (s->cd_hot * row + 15) & ~15u;
+			}
+			s->cd_rec_bytes = 0;
 		}
 	}
 	/* sparse matches (signature sets): 128 KiB buckets of up to 1024 records keep the
@@ -886,13 +911,21 @@ launch_k1(struct acm_scanner *s, cudaStream_t st, const void *d_data, uint64_t n
 		uint64_t blocks = (pairs + CD_THREADS - 1) / CD_THREADS;
 		if (blocks > (uint64_t)s->dev->sm_count)
 			blocks = s->dev->sm_count;
-		const size_t smem = s->cd_hot_bytes + (a->d.cd_range_lo >= 0 ? 0 : CD_LUT_WORDS * 4) + 16;
-		if (a->d.cd_range_lo >= 0)
-			k_scan_cdfa<true><<<(unsigned)blocks, CD_THREADS, smem, st>>>(a->d, E, (const uint8_t *)d_data,
-			    limit, s->cd_hot, s->cd_hot_bytes);
-		else
-			k_scan_cdfa<false><<<(unsigned)blocks, CD_THREADS, smem, st>>>(a->d, E, (const uint8_t *)d_data,
-			    limit, s->cd_hot, s->cd_hot_bytes);
+		const size_t smem = s->cd_tab_bytes + s->cd_rec_bytes + (a->d.cd_range_lo >= 0 ? 0 : CD_LUT_WORDS * 4) + 16;
+#define CD_LAUNCH(R, Cm) k_scan_cdfa<R, Cm><<<(unsigned)blocks, CD_THREADS, smem, st>>>(a->d, E, \
+	    (const uint8_t *)d_data, limit, s->cd_hot, s->cd_tab_bytes, s->cd_rec_bytes)
+		if (a->d.cd_range_lo >= 0) {
+			if (s->cd_comp)
+				CD_LAUNCH(true, true);
+			else
+				CD_LAUNCH(true, false);
+		} else {
+			if (s->cd_comp)
+				CD_LAUNCH(false, true);
+			else
+				CD_LAUNCH(false, false);
+		}
+#undef CD_LAUNCH
 	} else if (s->p.mode == ACM_MODE_START2) {
 		const uint64_t tile = (uint64_t)S2_THREADS * S2_UNROLL;
 		uint64_t blocks = (vec_hi - vec_lo + tile - 1) / tile;

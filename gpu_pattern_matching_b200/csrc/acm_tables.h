@@ -34,11 +34,12 @@ enum {
 	ACM_MODE_CDFA     = 4    /* class-compressed 16-bit DFA, hot rows in shared memory */
 };
 
-/* class-compressed DFA entry (uint16): low 14 bits next state, top 2 bits min(|full match list|, 3) */
+/* class-compressed DFA entry (uint16): low 14 bits next state (cd id), top 2 bits min(|full match list|, 3) */
 #define ACM_CD_STATE_BITS 14
 #define ACM_CD_STATE_MASK 0x3FFFu
 #define ACM_CD_MAX_STATES (1u << ACM_CD_STATE_BITS)
 #define ACM_CD_MAX_CLASSES 64
+#define ACM_CD_COMP_BUDGET (216 * 1024)   /* bytes of shared memory for cd_rec + cd_t16 */
 
 #define ACM_F1_BITS_LOG2   20              /* level-1 gram bitmap: 128 KiB smem */
 #define ACM_F2_BITS_LOG2   19              /* level-2 gram bitmap:  64 KiB smem */
@@ -110,6 +111,16 @@ struct acm_tables {
 	uint32_t *cd_flat_begin;     /* [num_states + 1] CSR into cd_flat_pat         */
 	uint32_t *cd_flat_pat;       /* FULL match list of each state, ascending pattern index */
 	uint32_t  cd_flat_total;
+	uint32_t  cd_thr4;           /* an entry >= this has FOUR patterns ending (code 3 = three or four) */
+	/* the same table delta-encoded so that ALL of it fits in shared memory (C <= 32 only):
+	 * rows of states up to depth cd_dense_depth are stored whole; a deeper state s keeps only
+	 * the columns where its row differs from the row of D(s), the first state of depth <=
+	 * cd_dense_depth on its failure chain.  cd_rec[s] = { bitmap of explicit columns,
+	 * first explicit entry | (row of D(s)) << 16 }, both indices into cd_t16.  NULL = not built. */
+	uint32_t *cd_rec;            /* [num_states][2]                               */
+	uint16_t *cd_t16;            /* dense rows, then the explicit entries of every state */
+	uint32_t  cd_t16_count;
+	int       cd_dense_depth;
 };
 
 void acm_tables_free(struct acm_tables *t);

@@ -61,6 +61,10 @@ struct AutDev {
 	const uint8_t  *cd_cls;
 	const uint32_t *cd_flat_begin;
 	const uint32_t *cd_flat_pat;
+	const uint32_t *cd_rec;        /* delta-encoded form (all of it fits in shared memory), NULL if not built */
+	const uint16_t *cd_t16;
+	uint32_t cd_t16_count;
+	uint32_t cd_thr4;              /* entry >= this: four patterns end there (code 3 = three or four) */
 	uint32_t cd_classes;
 	int      cd_range_lo;
 	uint32_t gram_mask;
@@ -742,7 +746,7 @@ k_scan_dfa(const AutDev A, const EmitCtx E, const SYM *__restrict__ data, uint64
 }
 
 /* ------------------------------------------------------------------------- */
-/* class-compressed DFA: 16-bit entries, hot rows in shared memory           */
+/* class-compressed DFA: 16-bit entries, table in shared memory              */
 /* ------------------------------------------------------------------------- */
 
 /*
@@ -753,12 +757,18 @@ k_scan_dfa(const AutDev A, const EmitCtx E, const SYM *__restrict__ data, uint64
  * one thread per chunk, cold start Lmax-1 bytes early -- made cheap:
  *   - the table is class-compressed to uint16[states][C] (acm_core.c build_cdfa): 54 bytes a
  *     row for a lower-case lexicon instead of the reference's 2 KiB, 848 KiB in all instead of
- *     30.7 MiB, so it lives in L2 and its first n_hot rows (breadth-first order = the shallow,
- *     most visited states: 82 % of all lookups on English-like text) in SHARED MEMORY;
+ *     30.7 MiB;
+ *   - COMP: that table is delta-encoded against the rows of the shallow states
+ *     (build_cdfa_delta: 188 KiB for the sentiment lexicon) and lives ENTIRELY in shared
+ *     memory; a transition is two dependent shared-memory loads (the state's 8-byte record,
+ *     then the entry) and no branch.  With the plain table a warp step waits for its slowest
+ *     lane, and some lane always missed the hot rows: 63 % of all stall samples were the L2
+ *     round trip of cold rows (profiles/).
+ *     !COMP (the encoding does not fit): first n_hot rows in shared memory, the rest through
+ *     L1/L2;
  *   - byte -> column is arithmetic when the pattern bytes span < 64 values, else one lookup in
  *     a 32-way replicated (bank-conflict-free) table;
- *   - every thread walks TWO adjacent chunks in lockstep, two independent dependency chains,
- *     which is what hides the L2 latency of the cold rows;
+ *   - every thread walks TWO adjacent chunks in lockstep, two independent dependency chains;
  *   - a chunk is its own result bucket: the thread owns the slot counter (no atomics), hits
  *     come out in end-offset order because the walk is sequential, and every state's full
  *     match list is stored sorted by pattern index, so the post-pass is an expanding copy,
@@ -782,21 +792,50 @@ __device__ __forceinline__ void st_pred_v2(uint64_t *addr, uint32_t lo, uint32_t
 	    "}\n" ::"l"(addr), "r"(lo), "r"(hi), "r"((uint32_t)p) : "memory");
 }
 
+/* the tables are read-only once staged: plain (non-volatile) asm so loads can be scheduled freely */
+__device__ __forceinline__ uint32_t lds_u16(uint32_t saddr)
+{
+	uint16_t v;
+	asm("ld.shared.u16 %0, [%1];" : "=h"(v) : "r"(saddr));
+	return v;
+}
+
+__device__ __forceinline__ uint2 lds_v2(uint32_t saddr)
+{
+	uint2 v;
+	asm("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(saddr));
+	return v;
+}
+
+struct CdLook {
+	uint32_t tab_sa;          /* shared address: t16 (COMP) or the hot rows               */
+	uint32_t rec_sa;          /* shared address: state records (COMP)                     */
+	uint32_t lut_sa;          /* shared address: replicated class map (!RANGE)            */
+	const uint16_t *tab;      /* !COMP: the whole table in global memory                  */
+	uint32_t C, n_hot, rlo, cmax, lane4;
+};
+
 template <bool RANGE>
-__device__ __forceinline__ uint32_t cd_class(uint32_t b, const uint32_t *lut, uint32_t lane, uint32_t lo,
-    uint32_t cmax)
+__device__ __forceinline__ uint32_t cd_class(const CdLook &L, uint32_t b)
 {
 	if (RANGE)
-		return min(b - lo, cmax);                 /* below lo wraps to huge -> cmax */
-	const uint32_t w = lut[((b & 0xFCu) << 3) | lane];
+		return min(b - L.rlo, L.cmax);            /* below lo wraps to huge -> cmax */
+	uint32_t w;
+	asm("ld.shared.u32 %0, [%1];" : "=r"(w) : "r"(L.lut_sa + ((b & 0xFCu) << 5) + L.lane4));
 	return (w >> ((b & 3u) * 8u)) & 0xFFu;
 }
 
-__device__ __forceinline__ uint32_t cd_next(uint32_t state, uint32_t c, const uint16_t *hot,
-    const uint16_t *__restrict__ tab, uint32_t C, uint32_t n_hot)
+template <bool COMP>
+__device__ __forceinline__ uint32_t cd_next(const CdLook &L, uint32_t state, uint32_t c)
 {
-	const uint32_t idx = state * C + c;
-	return state < n_hot ? (uint32_t)hot[idx] : (uint32_t)__ldg(tab + idx);
+	if (COMP) {
+		const uint2 r = lds_v2(L.rec_sa + state * 8);
+		const uint32_t onehot = 1u << c;
+		const uint32_t idx = (r.x & onehot) ? (r.y & 0xFFFFu) + __popc(r.x & (onehot - 1u)) : (r.y >> 16) + c;
+		return lds_u16(L.tab_sa + idx * 2);
+	}
+	const uint32_t idx = state * L.C + c;
+	return state < L.n_hot ? lds_u16(L.tab_sa + idx * 2) : (uint32_t)__ldg(L.tab + idx);
 }
 
 /*
@@ -811,7 +850,7 @@ __device__ __forceinline__ uint32_t cd_next(uint32_t state, uint32_t c, const ui
  */
 struct CdOut {
 	uint64_t *dst;
-	uint32_t  k;        /* hits (bucket mode) or records (direct mode) written so far */
+	uint32_t  k;        /* hits (bucket mode) written so far                            */
 	uint32_t  nrec;     /* records this chunk produces                                 */
 	uint32_t  cap;      /* 0 = direct mode                                             */
 };
@@ -859,15 +898,14 @@ __device__ __forceinline__ void cd_close(const EmitCtx &E, uint64_t b, const CdO
 	}
 }
 
-/* byte-wise walk of chunk k (absolute chunk index): the first / last chunk of a scan */
-template <bool RANGE>
+/* byte-wise walk of chunk k (absolute chunk index): the first / last chunk of a scan, direct mode */
+template <bool RANGE, bool COMP>
 __device__ __noinline__ void cd_chunk_bytes(const AutDev *__restrict__ Ap, const EmitCtx *__restrict__ Ep,
-    const uint8_t *__restrict__ data, uint64_t k, uint64_t limit, const uint16_t *hot, const uint32_t *lut,
-    uint32_t n_hot)
+    const CdLook *__restrict__ Lp, const uint8_t *__restrict__ data, uint64_t k, uint64_t limit)
 {
 	const AutDev &A = *Ap;
 	const EmitCtx &E = *Ep;
-	const uint32_t C = A.cd_classes, lane = threadIdx.x & 31;
+	const CdLook L = *Lp;
 	uint64_t lo = k << E.shift, hi = (k + 1) << E.shift;
 	if (lo < E.emit_lo)
 		lo = E.emit_lo;
@@ -881,8 +919,7 @@ __device__ __noinline__ void cd_chunk_bytes(const AutDev *__restrict__ Ap, const
 	CdOut o = cd_open(E, b);
 	uint32_t state = 0;
 	for (; pos < hi; ++pos) {
-		const uint32_t e = cd_next(state, cd_class<RANGE>(__ldg(data + pos), lut, lane, (uint32_t)A.cd_range_lo, C - 1),
-		    hot, A.cd_tab, C, n_hot);
+		const uint32_t e = cd_next<COMP>(L, state, cd_class<RANGE>(L, __ldg(data + pos)));
 		state = e & ACM_CD_STATE_MASK;
 		if ((e >> ACM_CD_STATE_BITS) && pos >= lo)
 			cd_emit(A, o, state, e >> ACM_CD_STATE_BITS, pos);
@@ -890,26 +927,30 @@ __device__ __noinline__ void cd_chunk_bytes(const AutDev *__restrict__ Ap, const
 	cd_close(E, b, o);
 }
 
-template <bool RANGE>
+/*
+ * Shared memory: [tab_bytes: t16 or hot rows][rec_bytes: state records (COMP)][class map
+ * (!RANGE)][mbarrier]; all sizes multiples of 16.
+ */
+template <bool RANGE, bool COMP>
 __global__ void __launch_bounds__(CD_THREADS, 1)
 k_scan_cdfa(const __grid_constant__ AutDev A, const __grid_constant__ EmitCtx E,
-    const uint8_t *__restrict__ data, uint64_t limit, uint32_t n_hot, uint32_t hot_bytes)
+    const uint8_t *__restrict__ data, uint64_t limit, uint32_t n_hot, uint32_t tab_bytes, uint32_t rec_bytes)
 {
 	extern __shared__ __align__(128) uint32_t cd_smem[];
-	uint16_t *hot = reinterpret_cast<uint16_t *>(cd_smem);
-	uint32_t *lut = cd_smem + hot_bytes / 4;
-	uint64_t *bar = reinterpret_cast<uint64_t *>(cd_smem + hot_bytes / 4 + (RANGE ? 0 : CD_LUT_WORDS));
-	const uint32_t lane = threadIdx.x & 31;
-	const uint32_t C = A.cd_classes, cmax = C - 1, rlo = (uint32_t)A.cd_range_lo;
+	uint8_t *sm = reinterpret_cast<uint8_t *>(cd_smem);
+	uint32_t *lut = reinterpret_cast<uint32_t *>(sm + tab_bytes + rec_bytes);
+	uint64_t *bar = reinterpret_cast<uint64_t *>(sm + tab_bytes + rec_bytes + (RANGE ? 0 : CD_LUT_WORDS * 4));
 
-	/* hot rows: TMA bulk copies of up to 16 KiB on one mbarrier */
+	/* stage the tables: TMA bulk copies of up to 16 KiB on one mbarrier */
 	if (threadIdx.x == 0) {
+		const uint8_t *src_tab = reinterpret_cast<const uint8_t *>(COMP ? A.cd_t16 : A.cd_tab);
 		mbar_init(bar, 1);
-		mbar_expect_tx(bar, hot_bytes);
-		for (uint32_t off = 0; off < hot_bytes; off += 16384) {
-			const uint32_t nb = hot_bytes - off < 16384 ? hot_bytes - off : 16384;
-			bulk_g2s(reinterpret_cast<uint8_t *>(hot) + off, reinterpret_cast<const uint8_t *>(A.cd_tab) + off, nb, bar);
-		}
+		mbar_expect_tx(bar, tab_bytes + rec_bytes);
+		for (uint32_t off = 0; off < tab_bytes; off += 16384)
+			bulk_g2s(sm + off, src_tab + off, min(tab_bytes - off, 16384u), bar);
+		for (uint32_t off = 0; off < rec_bytes; off += 16384)
+			bulk_g2s(sm + tab_bytes + off, reinterpret_cast<const uint8_t *>(A.cd_rec) + off,
+			    min(rec_bytes - off, 16384u), bar);
 	}
 	if (!RANGE) {
 		/* word (b >> 2) of the class map, once per bank */
@@ -919,6 +960,17 @@ k_scan_cdfa(const __grid_constant__ AutDev A, const __grid_constant__ EmitCtx E,
 	}
 	__syncthreads();
 	mbar_wait(bar, 0);
+
+	CdLook L;
+	L.tab_sa = smem_u32(sm);
+	L.rec_sa = smem_u32(sm + tab_bytes);
+	L.lut_sa = smem_u32(lut);
+	L.tab = A.cd_tab;
+	L.C = A.cd_classes;
+	L.n_hot = n_hot;
+	L.rlo = (uint32_t)A.cd_range_lo;
+	L.cmax = A.cd_classes - 1;
+	L.lane4 = (threadIdx.x & 31) * 4;
 
 	const uint32_t shift = E.shift;
 	const uint64_t chunk = 1ull << shift;
@@ -934,9 +986,9 @@ k_scan_cdfa(const __grid_constant__ AutDev A, const __grid_constant__ EmitCtx E,
 		const bool fast = !E.direct && kb <= k_last && a0 >= E.emit_lo && a0 + 2 * chunk <= limit &&
 		    a0 >= halo && a0 - halo >= E.valid_lo;
 		if (!fast) {
-			cd_chunk_bytes<RANGE>(&A, &E, data, ka, limit, hot, lut, n_hot);
+			cd_chunk_bytes<RANGE, COMP>(&A, &E, &L, data, ka, limit);
 			if (kb <= k_last)
-				cd_chunk_bytes<RANGE>(&A, &E, data, kb, limit, hot, lut, n_hot);
+				cd_chunk_bytes<RANGE, COMP>(&A, &E, &L, data, kb, limit);
 			continue;
 		}
 		/*
@@ -945,23 +997,45 @@ k_scan_cdfa(const __grid_constant__ AutDev A, const __grid_constant__ EmitCtx E,
 		 * Instead every lane executes a predicated 8-byte store of its hit and two adds.
 		 */
 		const uint64_t ba = ka - k_first;
-		uint64_t *rowa = E.buckets + ba * E.cap, *rowb = rowa + E.cap;
-		const uint32_t capm1 = E.cap - 1;
+		uint64_t *rowa = E.buckets + ba * E.cap + 1, *rowb = rowa + E.cap;   /* slot 0 = hit count */
+		/* keep the row pointers as pointers: the store address is then one IMAD.WIDE of the hit count */
+		asm volatile("" : "+l"(rowa), "+l"(rowb));
+		const uint32_t capm1 = E.cap - 1, thr4 = A.cd_thr4;
 		uint32_t hka = 0, hkb = 0, nra = 0, nrb = 0;       /* hits, records */
 		uint32_t sa = 0, sb = 0;
-		/* cold start: the halo of chunk a lies before it, the halo of chunk b is the end of a */
-		for (uint64_t p = a0 - halo; p < a0; ++p) {
-			sa = cd_next(sa, cd_class<RANGE>(__ldg(data + p), lut, lane, rlo, cmax), hot, A.cd_tab, C, n_hot) &
-			    ACM_CD_STATE_MASK;
-			sb = cd_next(sb, cd_class<RANGE>(__ldg(data + p + chunk), lut, lane, rlo, cmax), hot, A.cd_tab, C,
-			    n_hot) & ACM_CD_STATE_MASK;
-		}
 		const uint4 *pa = reinterpret_cast<const uint4 *>(data + a0);
 		const uint4 *pb = reinterpret_cast<const uint4 *>(data + a0 + chunk);
-		/* 32 bytes (one sector) per chain per round: both halves are requested together */
-		for (uint32_t i = 0; i < (uint32_t)(chunk >> 4); i += 2) {
+		/*
+		 * Cold start over the halo: the 16-byte vectors that cover [a0 - halo, a0) (for chunk b:
+		 * the end of chunk a).  Bytes in front of a0 - halo are walked too and then forgotten
+		 * (state reset at the first halo byte), which is the same as starting there.
+		 */
+		{
+			const uint32_t hv = (uint32_t)((halo + 15) >> 4), skip = hv * 16 - (uint32_t)halo;
+			for (uint32_t v = 0; v < hv; ++v) {
+				const uint4 xa = __ldg(pa - hv + v), xb = __ldg(pb - hv + v);
+				const uint32_t wa[4] = {xa.x, xa.y, xa.z, xa.w}, wb[4] = {xb.x, xb.y, xb.z, xb.w};
+#pragma unroll
+				for (int q = 0; q < 16; ++q) {
+					if (v == 0 && (uint32_t)q == skip)
+						sa = sb = 0;
+					sa = cd_next<COMP>(L, sa, cd_class<RANGE>(L, (wa[q >> 2] >> (8 * (q & 3))) & 0xFFu)) &
+					    ACM_CD_STATE_MASK;
+					sb = cd_next<COMP>(L, sb, cd_class<RANGE>(L, (wb[q >> 2] >> (8 * (q & 3))) & 0xFFu)) &
+					    ACM_CD_STATE_MASK;
+				}
+			}
+		}
+		/* 32 bytes (one sector) per chain per round: both halves are requested together; the
+		 * sectors of the round after next are pulled into L2 meanwhile */
+		const uint32_t rounds16 = (uint32_t)(chunk >> 4);
+		for (uint32_t i = 0; i < rounds16; i += 2) {
 			const uint4 va0 = __ldg(pa + i), va1 = __ldg(pa + i + 1);
 			const uint4 vb0 = __ldg(pb + i), vb1 = __ldg(pb + i + 1);
+			if (i + 4 < rounds16) {
+				asm volatile("prefetch.global.L2 [%0];" ::"l"(pa + i + 4));
+				asm volatile("prefetch.global.L2 [%0];" ::"l"(pb + i + 4));
+			}
 			const uint32_t wa[8] = {va0.x, va0.y, va0.z, va0.w, va1.x, va1.y, va1.z, va1.w};
 			const uint32_t wb[8] = {vb0.x, vb0.y, vb0.z, vb0.w, vb1.x, vb1.y, vb1.z, vb1.w};
 			/* key = pos << 24 | state; pos = base + q with base a multiple of 32, so the low
@@ -972,29 +1046,29 @@ k_scan_cdfa(const __grid_constant__ AutDev A, const __grid_constant__ EmitCtx E,
 			const uint32_t kblo = (uint32_t)keyb, kbhi = (uint32_t)(keyb >> 32);
 #pragma unroll
 			for (int q = 0; q < 32; ++q) {
-				const uint32_t ca = cd_class<RANGE>((wa[q >> 2] >> (8 * (q & 3))) & 0xFFu, lut, lane, rlo, cmax);
-				const uint32_t cb = cd_class<RANGE>((wb[q >> 2] >> (8 * (q & 3))) & 0xFFu, lut, lane, rlo, cmax);
-				const uint32_t ea = cd_next(sa, ca, hot, A.cd_tab, C, n_hot);
-				const uint32_t eb = cd_next(sb, cb, hot, A.cd_tab, C, n_hot);
+				const uint32_t ca = cd_class<RANGE>(L, (wa[q >> 2] >> (8 * (q & 3))) & 0xFFu);
+				const uint32_t cb = cd_class<RANGE>(L, (wb[q >> 2] >> (8 * (q & 3))) & 0xFFu);
+				const uint32_t ea = cd_next<COMP>(L, sa, ca);
+				const uint32_t eb = cd_next<COMP>(L, sb, cb);
 				sa = ea & ACM_CD_STATE_MASK;
 				sb = eb & ACM_CD_STATE_MASK;
 				const uint32_t da = ea >> ACM_CD_STATE_BITS, db = eb >> ACM_CD_STATE_BITS;
-				st_pred_v2(rowa + hka + 1, kalo | ((uint32_t)q << ACM_KEY_PAT_BITS) | sa, kahi, da && hka < capm1);
-				st_pred_v2(rowb + hkb + 1, kblo | ((uint32_t)q << ACM_KEY_PAT_BITS) | sb, kbhi, db && hkb < capm1);
-				hka += da ? 1u : 0u;
-				hkb += db ? 1u : 0u;
-				nra += da;
-				nrb += db;
-				if (da == 3)            /* three or more patterns end here: exact length (rare) */
-					nra += __ldg(&A.cd_flat_begin[sa + 1]) - __ldg(&A.cd_flat_begin[sa]) - 3;
-				if (db == 3)
-					nrb += __ldg(&A.cd_flat_begin[sb + 1]) - __ldg(&A.cd_flat_begin[sb]) - 3;
+				st_pred_v2(rowa + hka, kalo | ((uint32_t)q << ACM_KEY_PAT_BITS) | sa, kahi, da && hka < capm1);
+				st_pred_v2(rowb + hkb, kblo | ((uint32_t)q << ACM_KEY_PAT_BITS) | sb, kbhi, db && hkb < capm1);
+				if (da)
+					++hka;
+				if (db)
+					++hkb;
+				/* records: the 2-bit code, plus one where four patterns end (those states have the
+				 * highest ids, so the raw entry says it) */
+				nra += da + (ea >= thr4 ? 1u : 0u);
+				nrb += db + (eb >= thr4 ? 1u : 0u);
 			}
 		}
 		E.counts[ba] = nra;
 		E.counts[ba + 1] = nrb;
-		rowa[0] = hka;
-		rowb[0] = hkb;
+		rowa[-1] = hka;
+		rowb[-1] = hkb;
 		if (hka > capm1 || hkb > capm1)
 			*E.overflow = 1u;
 	}

@@ -275,8 +275,11 @@ def test_cdfa_windows_shapes_and_class_maps(device):
     rng = np.random.default_rng(77)
     lex = load_patterns("sentiment_categorical.pat.gz")[:1500]
     # wide byte span (> 63 values) but few distinct bytes -> lookup-table form
-    wide = [(bytes(rng.choice(np.array([0, 7, 65, 66, 200, 201, 255], dtype=np.uint8), size=int(rng.integers(1, 9))).tolist()), i)
-            for i in range(300)]
+    sym = np.array([0, 7, 65, 66, 200, 201, 255], dtype=np.uint8)
+    wide = [(bytes(rng.choice(sym, size=int(rng.integers(4, 10))).tolist()), i) for i in range(300)]
+    # four patterns ending in one state (the most this form takes), one of them twice over
+    wide += [(bytes([7, 0, 255, 200, 65]), 900), (bytes([0, 255, 200, 65]), 901), (bytes([255, 200, 65]), 902),
+             (bytes([200, 65]), 903), (bytes([66, 66]), 904), (bytes([66, 66]), 905)]
     for pats, form in ((lex, "range"), (wide, "lut")):
         o, a = build_oracle(pats), build_product(pats)
         assert g.lib().acm_automaton_cdfa_classes(a.automaton) > 0
@@ -288,13 +291,16 @@ def test_cdfa_windows_shapes_and_class_maps(device):
         for n in (1, 15, 16, 255, 256, 257, 511, 513, 4096 + 17, 300000):
             t = text[:n]
             eo, ep, _, _ = o.search(t)
-            for hot_kb in ("1", "64", None):
-                if hot_kb is None:
-                    os.environ.pop("ACM_CD_HOT_KB", None)
-                else:
-                    os.environ["ACM_CD_HOT_KB"] = hot_kb
+            # delta-encoded table wholly in shared memory (default), then the plain table with
+            # 1 KiB / 64 KiB / the default amount of hot rows in shared memory
+            for env in ({}, {"ACM_CD_PLAIN": "1", "ACM_CD_HOT_KB": "1"},
+                        {"ACM_CD_PLAIN": "1", "ACM_CD_HOT_KB": "64"}, {"ACM_CD_PLAIN": "1"}):
+                for k in ("ACM_CD_PLAIN", "ACM_CD_HOT_KB"):
+                    os.environ.pop(k, None)
+                os.environ.update(env)
                 off, pat, res = gpu_scan(device, a, t, g.MODE_CDFA)
-                assert_same(off, pat, eo, ep, f"cdfa {form} n={n} hot={hot_kb}")
+                assert_same(off, pat, eo, ep, f"cdfa {form} n={n} {env}")
+        os.environ.pop("ACM_CD_PLAIN", None)
         os.environ.pop("ACM_CD_HOT_KB", None)
         # emit windows: any cut, with the bytes before valid_lo replaced by junk that would match
         eo, ep, _, _ = o.search(text)
