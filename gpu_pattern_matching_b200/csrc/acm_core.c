@@ -145,7 +145,7 @@ acm_tables_free(struct acm_tables *t)
 	free(t->bfs_to_ref); free(t->f1); free(t->f2); free(t->grams); free(t->b2);
 	free(t->cand); free(t->pat_blob); free(t->pat_off);
 	free(t->cd_cls); free(t->cd_tab); free(t->cd_flat_begin); free(t->cd_flat_pat);
-	free(t->cd_rec); free(t->cd_t16);
+	free(t->cd_rec); free(t->cd_t16); free(t->cd_flat4);
 	memset(t, 0, sizeof(*t));
 }
 
@@ -166,7 +166,7 @@ acm_tables_device_bytes(const struct acm_tables *t)
 		b += 65536 / 8;
 	if (t->cd_tab)
 		b += (size_t)t->num_states * t->cd_classes * 2 + 256 + (size_t)(t->num_states + 1) * 4 +
-		    (size_t)t->cd_flat_total * 4;
+		    (size_t)t->cd_flat_total * 4 + (size_t)t->num_states * 16;
 	if (t->cd_rec)
 		b += (size_t)t->num_states * 8 + (size_t)t->cd_t16_count * 2;
 	return b;
@@ -438,6 +438,18 @@ build_cdfa(struct acm_core *c)
 		t->cd_flat_begin[n] = w;
 		t->cd_flat_total = w;
 		free(inv);
+		/* the same lists inline, one 16-byte load per hit in the expansion kernel */
+		t->cd_flat4 = calloc((size_t)n * 4, 4);
+		if (!t->cd_flat4) {
+			rc = ACM_ERR_NOMEM;
+			goto out;
+		}
+		for (id = 0; id < n; id++) {
+			const uint32_t fb = t->cd_flat_begin[id], m = t->cd_flat_begin[id + 1] - fb;
+			for (k = 0; k < m; k++)
+				t->cd_flat4[(size_t)id * 4 + k] = t->cd_flat_pat[fb + k];
+			t->cd_flat4[(size_t)id * 4] |= m << 24;
+		}
 	}
 	for (s = 0; s < n; s++) {
 		for (k = 0; k < C; k++) {
@@ -454,7 +466,8 @@ out:
 	free(cnt); free(perm); free(fail); free(depth);
 	if (rc == ACM_OK && !t->cd_classes) {
 		/* not eligible: leave nothing half built */
-		free(t->cd_cls); free(t->cd_tab); free(t->cd_flat_begin); free(t->cd_flat_pat);
+		free(t->cd_cls); free(t->cd_tab); free(t->cd_flat_begin); free(t->cd_flat_pat); free(t->cd_flat4);
+		t->cd_flat4 = NULL;
 		t->cd_cls = NULL;
 		t->cd_tab = NULL;
 		t->cd_flat_begin = NULL;

@@ -439,6 +439,7 @@ acm_automaton_upload(struct acm_device *dev, const struct acm_tables *t, struct 
 		UP(cd_cls, t->cd_cls, 256);
 		UP(cd_flat_begin, t->cd_flat_begin, (size_t)(t->num_states + 1) * 4);
 		UP(cd_flat_pat, t->cd_flat_pat, (size_t)(t->cd_flat_total + 1) * 4);
+		UP(cd_flat4, t->cd_flat4, (size_t)t->num_states * 16);
 		a->d.cd_classes = t->cd_classes;
 		a->d.cd_range_lo = t->cd_range_lo;
 		a->d.cd_thr4 = t->cd_thr4;
@@ -481,7 +482,8 @@ acm_automaton_default_mode(const struct acm_automaton *a)
 		return ACM_MODE_DFA;
 	if (a->d.f1 && a->min_len >= 7)
 		return ACM_MODE_SAMPLED4;
-	if (a->d.cd_tab)
+	/* cdfa chunks (>= 4 x (Lmax - 1) bytes) must fit the 18-bit offset of a hit */
+	if (a->d.cd_tab && a->max_len <= (1 << (32 - ACM_CD_STATE_BITS - 2)))
 		return ACM_MODE_CDFA;
 	return ACM_MODE_START2;
 }
@@ -702,12 +704,14 @@ scanner_alloc_buckets(struct acm_scanner *s)
 	/* CDFA cuts chunks on absolute multiples of 2^shift: one more partial bucket */
 	s->max_buckets = (uint32_t)((s->max_bytes + (1ull << s->shift) - 1) >> s->shift) + 2;
 	s->n_bucket_tiles = (s->max_buckets + SCAN_TILE - 1) / SCAN_TILE + 1;
-	if (cudaMalloc((void **)&s->buckets, (size_t)s->max_buckets * s->cap * 8) != cudaSuccess ||
+	/* CDFA rows hold 4-byte hits (offset in chunk, state); everything else 8-byte record keys */
+	const size_t slot = s->p.mode == ACM_MODE_CDFA ? 4 : 8;
+	if (cudaMalloc((void **)&s->buckets, (size_t)s->max_buckets * s->cap * slot) != cudaSuccess ||
 	    cudaMalloc((void **)&s->scratch, 64 + (size_t)s->n_bucket_tiles * 8 + (size_t)s->max_buckets * 4) !=
 	    cudaSuccess ||
 	    cudaMalloc((void **)&s->offsets, (size_t)s->max_buckets * 4) != cudaSuccess) {
 		acm_set_error("scanner: cannot allocate %zu bytes of result buckets: %s",
-		    (size_t)s->max_buckets * s->cap * 8, cudaGetErrorString(cudaGetLastError()));
+		    (size_t)s->max_buckets * s->cap * slot, cudaGetErrorString(cudaGetLastError()));
 		return ACM_ERR_CUDA;
 	}
 	s->flags = (uint32_t *)s->scratch;
@@ -772,6 +776,12 @@ acm_scanner_create(struct acm_device *dev, struct acm_automaton *aut, uint64_t m
 		uint32_t sh = s->p.bucket_shift ? (uint32_t)s->p.bucket_shift : 8u;
 		while (sh < 30 && (1u << sh) < 4 * halo)
 			sh++;
+		if (sh > 32 - ACM_CD_STATE_BITS) {
+			acm_set_error("scanner_create: cdfa chunks are at most 2^%d bytes (a hit is offset-in-chunk | state in "
+			    "32 bits); patterns of %d bytes need more", 32 - ACM_CD_STATE_BITS, aut->max_len);
+			free(s);
+			return ACM_ERR_ARG;
+		}
 		s->p.bucket_shift = (int)sh;
 		if (!s->p.bucket_cap)
 			s->p.bucket_cap = (int)((1u << sh) / 4 > 8192 ? 8192 : (1u << sh) / 4);
@@ -953,11 +963,11 @@ launch_k3(struct acm_scanner *s, cudaStream_t st, uint32_t nb, uint32_t k3_block
 {
 	if (s->p.mode == ACM_MODE_CDFA) {
 		/* hits are in order already: an expanding copy, one warp per bucket */
-		uint32_t blocks = (nb + 7) / 8;
+		uint32_t blocks = (nb + 8 * K3X_NB - 1) / (8 * K3X_NB);
 		if (blocks > (uint32_t)s->dev->sm_count * 8)
 			blocks = (uint32_t)s->dev->sm_count * 8;
-		k_bucket_expand_compact<<<blocks, 256, 0, st>>>(s->buckets, s->counts, s->offsets, s->out, s->cap,
-		    nb, s->out_cap, s->flags, s->aut->d.cd_flat_begin, s->aut->d.cd_flat_pat);
+		k_bucket_expand_compact<<<blocks, 256, 0, st>>>((const uint32_t *)s->buckets, s->counts, s->offsets,
+		    s->out, s->cap, nb, s->out_cap, s->flags, s->aut->d.cd_flat4, s->pend.emit_lo >> s->shift, s->shift);
 		return;
 	}
 	k_bucket_sort_compact<<<k3_blocks, K3_THREADS, (size_t)s->cap * 8, st>>>(s->buckets, s->counts,

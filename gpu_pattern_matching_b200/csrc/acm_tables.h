@@ -111,6 +111,7 @@ struct acm_tables {
 	uint32_t *cd_flat_begin;     /* [num_states + 1] CSR into cd_flat_pat         */
 	uint32_t *cd_flat_pat;       /* FULL match list of each state, ascending pattern index */
 	uint32_t  cd_flat_total;
+	uint32_t *cd_flat4;          /* [num_states][4]: the same lists inline (<= 4 entries): word 0 = first | count << 24 */
 	uint32_t  cd_thr4;           /* an entry >= this has FOUR patterns ending (code 3 = three or four) */
 	/* the same table delta-encoded so that ALL of it fits in shared memory (C <= 32 only):
 	 * rows of states up to depth cd_dense_depth are stored whole; a deeper state s keeps only

@@ -61,6 +61,7 @@ struct AutDev {
 	const uint8_t  *cd_cls;
 	const uint32_t *cd_flat_begin;
 	const uint32_t *cd_flat_pat;
+	const uint4    *cd_flat4;      /* [states]: list inline, .x = first | count << 24 */
 	const uint32_t *cd_rec;        /* delta-encoded form (all of it fits in shared memory), NULL if not built */
 	const uint16_t *cd_t16;
 	uint32_t cd_t16_count;
@@ -781,15 +782,15 @@ k_scan_dfa(const AutDev A, const EmitCtx E, const SYM *__restrict__ data, uint64
 #define CD_LUT_WORDS 2048          /* 64 words x 32 banks */
 #define CD_SMEM_MAX  (227 * 1024)
 
-/* predicated 8-byte store: no branch, nothing happens when p is false */
-__device__ __forceinline__ void st_pred_v2(uint64_t *addr, uint32_t lo, uint32_t hi, bool p)
+/* predicated 4-byte store: no branch, nothing happens when p is false */
+__device__ __forceinline__ void st_pred_u32(uint32_t *addr, uint32_t v, bool p)
 {
 	asm volatile(
 	    "{\n"
 	    ".reg .pred p;\n"
-	    "setp.ne.b32 p, %3, 0;\n"
-	    "@p st.global.v2.u32 [%0], {%1, %2};\n"
-	    "}\n" ::"l"(addr), "r"(lo), "r"(hi), "r"((uint32_t)p) : "memory");
+	    "setp.ne.b32 p, %2, 0;\n"
+	    "@p st.global.u32 [%0], %1;\n"
+	    "}\n" ::"l"(addr), "r"(v), "r"((uint32_t)p) : "memory");
 }
 
 /* the tables are read-only once staged: plain (non-volatile) asm so loads can be scheduled freely */
@@ -842,20 +843,25 @@ __device__ __forceinline__ uint32_t cd_next(const CdLook &L, uint32_t state, uin
  * Emission.  Looking up a state's pattern list inside the walk would put two dependent L2
  * round trips on the warp's critical path at almost every step (with one match per ~9 bytes
  * nearly every warp step has a lane that matched): measured 60 % of all stall samples.  So the
- * walk stores only the HIT, (end offset << 24) | state, a fire-and-forget 8-byte store, and adds
- * the 2-bit list length carried by the transition entry to its record count; the expansion
- * state -> pattern indices happens in the compaction kernel (k_bucket_expand_compact), which is
- * a bandwidth-bound copy anyway.  Bucket row: slot 0 = number of hits, slots 1.. = hits.
- * Direct mode (second pass after a bucket overflow) expands in place instead.
+ * walk stores only the HIT, (offset in chunk << 14) | state, a fire-and-forget 4-byte store (an
+ * 8-byte key needs a register pair per store, and the pair cannot be rewritten until the store
+ * has left the LSU queue: those write-after-read waits were 30 % of all stall samples), and
+ * adds the 2-bit list length carried by the transition entry to its record count; the
+ * expansion state -> pattern indices happens in the compaction kernel
+ * (k_bucket_expand_compact), which is a bandwidth-bound copy anyway.  Bucket row (32-bit
+ * words): slot 0 = number of hits, slots 1.. = hits.  Direct mode (second pass after a bucket
+ * overflow) expands in place instead.
  */
 struct CdOut {
-	uint64_t *dst;
+	uint64_t *dst;      /* direct mode: records                                        */
+	uint32_t *row;      /* bucket mode: hits                                           */
 	uint32_t  k;        /* hits (bucket mode) written so far                            */
 	uint32_t  nrec;     /* records this chunk produces                                 */
 	uint32_t  cap;      /* 0 = direct mode                                             */
 };
 
-__device__ __forceinline__ void cd_emit(const AutDev &A, CdOut &o, uint32_t state, uint32_t code, uint64_t pos)
+__device__ __forceinline__ void cd_emit(const AutDev &A, CdOut &o, uint32_t state, uint32_t code, uint64_t pos,
+    uint32_t off_in_chunk)
 {
 	uint32_t cnt = code;
 	if (code == 3 || o.cap == 0) {
@@ -868,7 +874,7 @@ __device__ __forceinline__ void cd_emit(const AutDev &A, CdOut &o, uint32_t stat
 	if (o.cap) {
 		++o.k;
 		if (o.k < o.cap)
-			o.dst[o.k] = (pos << ACM_KEY_PAT_BITS) | state;
+			o.row[o.k] = (off_in_chunk << ACM_CD_STATE_BITS) | state;
 	}
 	o.nrec += cnt;
 }
@@ -878,11 +884,13 @@ __device__ __forceinline__ CdOut cd_open(const EmitCtx &E, uint64_t b)
 	CdOut o;
 	o.k = 0;
 	o.nrec = 0;
+	o.dst = nullptr;
+	o.row = nullptr;
 	if (E.direct) {
 		o.dst = E.out + E.offsets[b];
 		o.cap = 0;
 	} else {
-		o.dst = E.buckets + b * E.cap;
+		o.row = reinterpret_cast<uint32_t *>(E.buckets) + b * E.cap;
 		o.cap = E.cap;
 	}
 	return o;
@@ -892,7 +900,7 @@ __device__ __forceinline__ void cd_close(const EmitCtx &E, uint64_t b, const CdO
 {
 	E.counts[b] = o.nrec;
 	if (o.cap) {
-		o.dst[0] = o.k;
+		o.row[0] = o.k;
 		if (o.k >= o.cap)
 			*E.overflow = 1u;
 	}
@@ -922,7 +930,7 @@ __device__ __noinline__ void cd_chunk_bytes(const AutDev *__restrict__ Ap, const
 		const uint32_t e = cd_next<COMP>(L, state, cd_class<RANGE>(L, __ldg(data + pos)));
 		state = e & ACM_CD_STATE_MASK;
 		if ((e >> ACM_CD_STATE_BITS) && pos >= lo)
-			cd_emit(A, o, state, e >> ACM_CD_STATE_BITS, pos);
+			cd_emit(A, o, state, e >> ACM_CD_STATE_BITS, pos, (uint32_t)(pos - (k << E.shift)));
 	}
 	cd_close(E, b, o);
 }
@@ -997,7 +1005,7 @@ k_scan_cdfa(const __grid_constant__ AutDev A, const __grid_constant__ EmitCtx E,
 		 * Instead every lane executes a predicated 8-byte store of its hit and two adds.
 		 */
 		const uint64_t ba = ka - k_first;
-		uint64_t *rowa = E.buckets + ba * E.cap + 1, *rowb = rowa + E.cap;   /* slot 0 = hit count */
+		uint32_t *rowa = reinterpret_cast<uint32_t *>(E.buckets) + ba * E.cap + 1, *rowb = rowa + E.cap;   /* slot 0 = hit count */
 		/* keep the row pointers as pointers: the store address is then one IMAD.WIDE of the hit count */
 		asm volatile("" : "+l"(rowa), "+l"(rowb));
 		const uint32_t capm1 = E.cap - 1, thr4 = A.cd_thr4;
@@ -1038,12 +1046,8 @@ k_scan_cdfa(const __grid_constant__ AutDev A, const __grid_constant__ EmitCtx E,
 			}
 			const uint32_t wa[8] = {va0.x, va0.y, va0.z, va0.w, va1.x, va1.y, va1.z, va1.w};
 			const uint32_t wb[8] = {vb0.x, vb0.y, vb0.z, vb0.w, vb1.x, vb1.y, vb1.z, vb1.w};
-			/* key = pos << 24 | state; pos = base + q with base a multiple of 32, so the low
-			 * word is (base << 24) | (q << 24) | state with no carries */
-			const uint64_t keya = (a0 + 16ull * i) << ACM_KEY_PAT_BITS;
-			const uint64_t keyb = (a0 + chunk + 16ull * i) << ACM_KEY_PAT_BITS;
-			const uint32_t kalo = (uint32_t)keya, kahi = (uint32_t)(keya >> 32);
-			const uint32_t kblo = (uint32_t)keyb, kbhi = (uint32_t)(keyb >> 32);
+			/* hit = (offset in chunk) << 14 | state; the offset is 16 i + q */
+			const uint32_t hbase = (16u * i) << ACM_CD_STATE_BITS;
 #pragma unroll
 			for (int q = 0; q < 32; ++q) {
 				const uint32_t ca = cd_class<RANGE>(L, (wa[q >> 2] >> (8 * (q & 3))) & 0xFFu);
@@ -1053,8 +1057,8 @@ k_scan_cdfa(const __grid_constant__ AutDev A, const __grid_constant__ EmitCtx E,
 				sa = ea & ACM_CD_STATE_MASK;
 				sb = eb & ACM_CD_STATE_MASK;
 				const uint32_t da = ea >> ACM_CD_STATE_BITS, db = eb >> ACM_CD_STATE_BITS;
-				st_pred_v2(rowa + hka, kalo | ((uint32_t)q << ACM_KEY_PAT_BITS) | sa, kahi, da && hka < capm1);
-				st_pred_v2(rowb + hkb, kblo | ((uint32_t)q << ACM_KEY_PAT_BITS) | sb, kbhi, db && hkb < capm1);
+				st_pred_u32(rowa + hka, hbase | ((uint32_t)q << ACM_CD_STATE_BITS) | sa, da && hka < capm1);
+				st_pred_u32(rowb + hkb, hbase | ((uint32_t)q << ACM_CD_STATE_BITS) | sb, db && hkb < capm1);
 				if (da)
 					++hka;
 				if (db)

@@ -247,57 +247,94 @@ k_bucket_sort_compact(const uint64_t *__restrict__ buckets, const uint32_t *__re
 }
 
 /*
- * K3 for k_scan_cdfa.  A bucket row holds one chunk's HITS in end-offset order,
- * row[0] = number of hits, row[1 + i] = (end offset << 24) | state; counts[] / offsets[] are
- * in RECORDS.  One warp per bucket: lane i expands hit i into the state's full match list
- * (flat_begin / flat_pat, ascending pattern index), placed by a warp prefix sum -- the output
- * is the canonical (end offset, pattern index) order with no sort.  Same guards as
- * k_bucket_sort_compact.
+ * K3 for k_scan_cdfa.  A bucket row holds one chunk's HITS in end-offset order as 32-bit words:
+ * row[0] = number of hits, row[1 + i] = (offset in chunk << 14) | state; counts[] / offsets[]
+ * are in RECORDS.  Lane i expands hit i into the state's full match list (flat4: up to four
+ * pattern indices inline, ascending, one 16-byte load), placed by a warp prefix sum -- the
+ * output is the canonical (end offset, pattern index) order with no sort.  Bucket b is chunk
+ * (chunk0 + b) of the buffer.  A warp works on K3X_NB buckets at a time, all loads of one stage
+ * issued before any is used: one bucket per warp was bound by four dependent round trips per
+ * 30 records.  Same guards as k_bucket_sort_compact.
  */
+#define K3X_NB 4
+
+__device__ __forceinline__ void k3x_expand(uint64_t *__restrict__ out, uint64_t &o, uint64_t base, uint32_t hit,
+    uint4 f, bool live, uint32_t lane)
+{
+	const uint32_t cnt = live ? (f.x >> 24) : 0u;
+	uint32_t inc = cnt;
+#pragma unroll
+	for (int d = 1; d < 32; d <<= 1) {
+		const uint32_t y = __shfl_up_sync(0xffffffffu, inc, d);
+		if (lane >= (uint32_t)d)
+			inc += y;
+	}
+	const uint64_t hi = (base + (hit >> ACM_CD_STATE_BITS)) << ACM_KEY_PAT_BITS;
+	uint64_t *dst = out + o + (inc - cnt);
+	if (cnt > 0)
+		dst[0] = hi | (f.x & ACM_KEY_PAT_MASK);
+	if (cnt > 1)
+		dst[1] = hi | f.y;
+	if (cnt > 2)
+		dst[2] = hi | f.z;
+	if (cnt > 3)
+		dst[3] = hi | f.w;
+	o += __shfl_sync(0xffffffffu, inc, 31);
+}
+
 __global__ void __launch_bounds__(256)
-k_bucket_expand_compact(const uint64_t *__restrict__ buckets, const uint32_t *__restrict__ counts,
+k_bucket_expand_compact(const uint32_t *__restrict__ buckets, const uint32_t *__restrict__ counts,
     const uint32_t *__restrict__ offsets, uint64_t *__restrict__ out, uint32_t cap, uint32_t n_buckets,
-    uint64_t out_cap, uint32_t *flags, const uint32_t *__restrict__ flat_begin,
-    const uint32_t *__restrict__ flat_pat)
+    uint64_t out_cap, uint32_t *flags, const uint4 *__restrict__ flat4, uint64_t chunk0, uint32_t shift)
 {
 	const uint32_t lane = threadIdx.x & 31;
 	const uint32_t warps = (gridDim.x * blockDim.x) >> 5;
 
 	if (*(volatile uint32_t *)flags)
 		return;
-	for (uint32_t b = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; b < n_buckets; b += warps) {
-		const uint32_t nrec = __ldg(&counts[b]);
-		if (nrec == 0)
-			continue;
-		uint64_t o = __ldg(&offsets[b]);
-		if (o + nrec > out_cap) {
-			if (lane == 0)
-				flags[5] = 1u;
-			continue;
+	for (uint32_t g = ((blockIdx.x * blockDim.x + threadIdx.x) >> 5) * K3X_NB; g < n_buckets;
+	     g += warps * K3X_NB) {
+		/* stage 1: lane k < K3X_NB reads the header of bucket g + k */
+		uint32_t nh_l = 0;
+		uint64_t o_l = 0;
+		if (lane < K3X_NB && g + lane < n_buckets) {
+			const uint32_t nrec = __ldg(&counts[g + lane]);
+			o_l = __ldg(&offsets[g + lane]);
+			if (nrec) {
+				if (o_l + nrec > out_cap)
+					flags[5] = 1u;
+				else
+					nh_l = __ldcs(buckets + (uint64_t)(g + lane) * cap);
+			}
 		}
-		const uint64_t *row = buckets + (uint64_t)b * cap;
-		const uint32_t nh = (uint32_t)__ldcs(row);
-		for (uint32_t base = 0; base < nh; base += 32) {
-			const uint32_t i = base + lane;
-			uint64_t key = 0;
-			uint32_t fb = 0, cnt = 0;
-			if (i < nh) {
-				key = __ldcs(row + 1 + i);
-				const uint32_t st = (uint32_t)(key & ACM_KEY_PAT_MASK);
-				fb = __ldg(&flat_begin[st]);
-				cnt = __ldg(&flat_begin[st + 1]) - fb;
-			}
-			uint32_t inc = cnt;
+		uint32_t nh[K3X_NB], hit[K3X_NB];
+		uint64_t o[K3X_NB];
+		uint4 f[K3X_NB];
+		/* stage 2: the first 32 hits of every bucket */
 #pragma unroll
-			for (int d = 1; d < 32; d <<= 1) {
-				const uint32_t y = __shfl_up_sync(0xffffffffu, inc, d);
-				if (lane >= (uint32_t)d)
-					inc += y;
+		for (int k = 0; k < K3X_NB; ++k) {
+			nh[k] = __shfl_sync(0xffffffffu, nh_l, k);
+			o[k] = __shfl_sync(0xffffffffu, o_l, k);
+			hit[k] = lane < nh[k] ? __ldcs(buckets + (uint64_t)(g + k) * cap + 1 + lane) : 0u;
+		}
+		/* stage 3: their match lists */
+#pragma unroll
+		for (int k = 0; k < K3X_NB; ++k)
+			f[k] = lane < nh[k] ? __ldg(flat4 + (hit[k] & ACM_CD_STATE_MASK)) : make_uint4(0, 0, 0, 0);
+		/* stage 4: place and store */
+#pragma unroll
+		for (int k = 0; k < K3X_NB; ++k) {
+			if (nh[k] == 0)
+				continue;
+			const uint64_t base = (chunk0 + g + k) << shift;
+			k3x_expand(out, o[k], base, hit[k], f[k], lane < nh[k], lane);
+			for (uint32_t i0 = 32; i0 < nh[k]; i0 += 32) {       /* more than 32 hits in the chunk */
+				const uint32_t i = i0 + lane;
+				const bool live = i < nh[k];
+				const uint32_t h = live ? __ldcs(buckets + (uint64_t)(g + k) * cap + 1 + i) : 0u;
+				const uint4 ff = live ? __ldg(flat4 + (h & ACM_CD_STATE_MASK)) : make_uint4(0, 0, 0, 0);
+				k3x_expand(out, o[k], base, h, ff, live, lane);
 			}
-			const uint64_t hi = key & ~(uint64_t)ACM_KEY_PAT_MASK;
-			for (uint32_t j = 0; j < cnt; ++j)
-				out[o + (inc - cnt) + j] = hi | __ldg(&flat_pat[fb + j]);
-			o += __shfl_sync(0xffffffffu, inc, 31);
 		}
 	}
 }
