@@ -150,10 +150,31 @@ def run_reference(args, rank):
         "e2e": {"value": rate, "unit": "GB/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
+
+
+_REAL_STDOUT = None
+
+
+def guard_stdout():
+    """The contract is ONE JSON line on stdout.  Libraries (NCCL's version banner, ...) write to
+    fd 1 behind Python's back: point fd 1 at stderr for the whole run and keep the real stdout
+    for emit()."""
+    global _REAL_STDOUT
+    if _REAL_STDOUT is None:
+        sys.stdout.flush()
+        _REAL_STDOUT = os.fdopen(os.dup(1), "w")
+        os.dup2(2, 1)
+
+
+def emit(line):
+    out = _REAL_STDOUT or sys.stdout
+    out.write(json.dumps(line) + "\n")
+    out.flush()
 
 
 def main():
+    guard_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)
@@ -382,7 +403,7 @@ def main():
         line["cpu_baseline"] = {"value": rate, "unit": "GB/s", "cores": cores, "kind": kind,
                                 "sample": f"first {sample >> 20} MiB of rank 0's stream, "
                                           f"{found} matches, {sec:.2f} s"}
-    print(json.dumps(line), flush=True)
+    emit(line)
     if world > 1:
         dist.destroy_process_group()
 
