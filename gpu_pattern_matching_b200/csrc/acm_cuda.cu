@@ -959,7 +959,7 @@ launch_k1(struct acm_scanner *s, cudaStream_t st, const void *d_data, uint64_t n
 }
 
 static void
-launch_k3(struct acm_scanner *s, cudaStream_t st, uint32_t nb, uint32_t k3_blocks)
+launch_k3(struct acm_scanner *s, cudaStream_t st, uint32_t nb, uint32_t k3_blocks, int with_push)
 {
 	if (s->p.mode == ACM_MODE_CDFA) {
 		/* hits are in order already: an expanding copy, one warp per bucket */
@@ -970,8 +970,11 @@ launch_k3(struct acm_scanner *s, cudaStream_t st, uint32_t nb, uint32_t k3_block
 		    s->out, s->cap, nb, s->out_cap, s->flags, s->aut->d.cd_flat4, s->pend.emit_lo >> s->shift, s->shift);
 		return;
 	}
+	/* with_push: the step's own launch also stores the keys into the gather region; the relaunch
+	 * after the output buffer grew does not (the host pushes then, scan_complete) */
 	k_bucket_sort_compact<<<k3_blocks, K3_THREADS, (size_t)s->cap * 8, st>>>(s->buckets, s->counts,
-	    s->offsets, s->out, s->cap, nb, s->out_cap, s->flags);
+	    s->offsets, s->out, s->cap, nb, s->out_cap, s->flags, with_push ? s->pend.push_dst : NULL,
+	    s->pend.push_cap, s->pend.push_add);
 }
 
 /*
@@ -1069,27 +1072,29 @@ scan_launch(struct acm_scanner *s, cudaStream_t st, const void *d_data, uint64_t
 	launches++;
 	if (timing)
 		CUDA_TRY(cudaEventRecord(s->ev[1], st));
+	const int cdfa = s->p.mode == ACM_MODE_CDFA;
 	if ((rc = launch_exclusive_scan(st, s->counts, s->offsets, nb, s->bucket_tiles, s->flags + 3,
 	    s->flags + 1, 1)) != ACM_OK)
 		return rc;
 	launches++;
-	if (timing)
+	if (timing == 1)
 		CUDA_TRY(cudaEventRecord(s->ev[2], st));
 	/*
 	 * K3 goes out right behind K2, before the host knows the total: it guards itself against
 	 * an overflowed scan (flags[0]) and against an output buffer that is too small (flags[5]);
-	 * one synchronisation per step instead of two.
+	 * one synchronisation per step instead of two.  For the bucketed kernels it is the gather
+	 * push as well.
 	 */
 	const uint32_t k3_warps = K3_THREADS / 32;
 	uint32_t k3_blocks = (nb + k3_warps - 1) / k3_warps;
 	if (k3_blocks > (uint32_t)s->dev->sm_count * 16)
 		k3_blocks = (uint32_t)s->dev->sm_count * 16;
-	launch_k3(s, st, nb, k3_blocks);
+	launch_k3(s, st, nb, k3_blocks, 1);
 	CUDA_TRY(cudaGetLastError());
 	launches++;
-	if (timing)
+	if (timing == 1)
 		CUDA_TRY(cudaEventRecord(s->ev[3], st));
-	if (s->pend.push_dst) {
+	if (cdfa && s->pend.push_dst) {
 		/* the gather push reads the total on the device; it skips itself in the cases the
 		 * host repairs in scan_complete (overflow, output or region too small) */
 		k_push_keys_dev<<<s->dev->sm_count, 256, 0, st>>>(s->out, s->flags, s->out_cap, s->pend.push_dst,
@@ -1146,10 +1151,10 @@ scan_complete(struct acm_scanner *s, struct acm_scan_result *res)
 			return rc;
 		repaired = 1;
 		if (!overflow) {
-			launch_k3(s, st, nb, k3_blocks);
+			launch_k3(s, st, nb, k3_blocks, 0);
 			CUDA_TRY(cudaGetLastError());
 			launches++;
-			if (timing)
+			if (timing == 1)
 				CUDA_TRY(cudaEventRecord(s->ev[3], st));
 		}
 	}
@@ -1190,7 +1195,7 @@ scan_complete(struct acm_scanner *s, struct acm_scan_result *res)
 		    (rc = radix_sort_impl(st, s->out, s->tmp, total, 0, bits, 0, s->hist, s->tile_state,
 		    s->flags + 3, &launches)) != ACM_OK)
 			return rc;
-		if (timing)
+		if (timing == 1)
 			CUDA_TRY(cudaEventRecord(s->ev[3], st));
 	}
 	s->last_n = total;
@@ -1222,8 +1227,9 @@ scan_complete(struct acm_scanner *s, struct acm_scan_result *res)
 		res->final_state = s->h_flags[2];
 		res->n_buckets = nb;
 		res->launches = launches;
-		if (timing) {
+		if (timing)
 			cudaEventElapsedTime(&res->ms_scan, s->ev[0], s->ev[1]);
+		if (timing == 1) {
 			cudaEventElapsedTime(&res->ms_prefix, s->ev[1], s->ev[2]);
 			cudaEventElapsedTime(&res->ms_compact, s->ev[2], s->ev[3]);
 			cudaEventElapsedTime(&res->ms_total, s->ev[0], s->ev[3]);

@@ -160,11 +160,16 @@ k_scan_lookback(const uint32_t *__restrict__ in, uint32_t *__restrict__ out, uin
  * (a bucket overflowed -> the exact two-pass path will run instead) makes it a no-op, and a
  * bucket whose output would not fit `out_cap` is skipped and reported in flags[5] (the host
  * then grows the buffer and relaunches).  Persistent over buckets: 4 buckets per block-step.
+ * push_dst (may be NULL): every key is also stored, plus key_add, at the same index of a
+ * gather region (possibly another GPU's memory, NVLink peer stores) when it fits push_cap --
+ * the multi-GPU gather costs no launch of its own.
+ * (Folding K2 into this kernel as well -- look-back over tiles of 4 buckets -- was tried and
+ * was slower for the sparse case, 25 us against 8 + 10 us, so K2 stays a kernel.)
  */
 __global__ void __launch_bounds__(K3_THREADS)
 k_bucket_sort_compact(const uint64_t *__restrict__ buckets, const uint32_t *__restrict__ counts,
     const uint32_t *__restrict__ offsets, uint64_t *__restrict__ out, uint32_t cap, uint32_t n_buckets,
-    uint64_t out_cap, uint32_t *flags)
+    uint64_t out_cap, uint32_t *flags, uint64_t *__restrict__ push_dst, uint64_t push_cap, uint64_t key_add)
 {
 	extern __shared__ uint64_t k3_keys[];
 	const uint32_t lane = threadIdx.x & 31;
@@ -186,6 +191,7 @@ k_bucket_sort_compact(const uint64_t *__restrict__ buckets, const uint32_t *__re
 				cnt = 0;
 			}
 		}
+		const bool push0 = push_dst && o0 + cnt <= push_cap;
 		const uint32_t big = __syncthreads_or(cnt > 32);
 
 		if (cnt > 0 && cnt <= 32) {
@@ -202,8 +208,11 @@ k_bucket_sort_compact(const uint64_t *__restrict__ buckets, const uint32_t *__re
 					key = take_min ? (key < other ? key : other) : (key > other ? key : other);
 				}
 			}
-			if (lane < cnt)
+			if (lane < cnt) {
 				out[o0 + lane] = key;
+				if (push0)
+					push_dst[o0 + lane] = key + key_add;
+			}
 		}
 		if (!big)
 			continue;
@@ -217,6 +226,7 @@ k_bucket_sort_compact(const uint64_t *__restrict__ buckets, const uint32_t *__re
 			const uint64_t o = __ldg(&offsets[b]);
 			if (c <= 32 || o + c > out_cap)
 				continue;
+			const bool pushw = push_dst && o + c <= push_cap;
 			uint32_t P = 64;
 			while (P < c)
 				P <<= 1;
@@ -239,8 +249,11 @@ k_bucket_sort_compact(const uint64_t *__restrict__ buckets, const uint32_t *__re
 					__syncthreads();
 				}
 			}
-			for (uint32_t i = threadIdx.x; i < c; i += K3_THREADS)
+			for (uint32_t i = threadIdx.x; i < c; i += K3_THREADS) {
 				out[o + i] = k3_keys[i];
+				if (pushw)
+					push_dst[o + i] = k3_keys[i] + key_add;
+			}
 			__syncthreads();
 		}
 	}

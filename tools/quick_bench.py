@@ -77,5 +77,5 @@ if __name__ == "__main__":
     if "sent" in which:
         words = [l.split(b"\t")[0] for l in read_fixture("english_top5000.txt.gz").split(b"\n") if l]
         text = synth.english_like(words, 16 << 20, seed=4)
-        run(dev, "sentiment", load_patterns("sentiment_categorical.pat.gz"), n >> 2, [2, 3], text=text,
+        run(dev, "sentiment", load_patterns("sentiment_categorical.pat.gz"), n >> 2, [4, 2, 3], text=text,
             iters=iters)
