@@ -303,6 +303,7 @@ build_cdfa_delta(struct acm_tables *t, const uint32_t *fail, const uint8_t *dept
 			t->cd_rec[2 * s + 1] = (base & 0xFFFFu) | ((D * C) << 16);
 		}
 		t->cd_t16_count = w;
+		t->cd_dense_states = nd;
 	}
 	t->cd_dense_depth = d;
 	free(dflt);

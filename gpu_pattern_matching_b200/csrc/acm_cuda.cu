@@ -447,6 +447,7 @@ acm_automaton_upload(struct acm_device *dev, const struct acm_tables *t, struct 
 			UP(cd_rec, t->cd_rec, (size_t)t->num_states * 8);
 			UP(cd_t16, t->cd_t16, (size_t)t->cd_t16_count * 2);
 			a->d.cd_t16_count = t->cd_t16_count;
+			a->d.cd_dense_states = t->cd_dense_states;
 		}
 	}
 #undef UP
@@ -792,7 +793,7 @@ acm_scanner_create(struct acm_device *dev, struct acm_automaton *aut, uint64_t m
 			s->cd_comp = 1;
 			s->cd_tab_bytes = (aut->d.cd_t16_count * 2 + 15) & ~15u;
 			s->cd_rec_bytes = (aut->num_states * 8 + 15) & ~15u;
-			s->cd_hot = aut->num_states;
+			s->cd_hot = aut->d.cd_dense_states;
 		} else {
 			const uint32_t row = aut->d.cd_classes * 2;
 			uint32_t budget = CD_SMEM_MAX - 16 - lut_bytes;

@@ -122,6 +122,7 @@ struct acm_tables {
 	uint16_t *cd_t16;            /* dense rows, then the explicit entries of every state */
 	uint32_t  cd_t16_count;
 	int       cd_dense_depth;
+	uint32_t  cd_dense_states;   /* states of depth <= cd_dense_depth = the first ids */
 };
 
 void acm_tables_free(struct acm_tables *t);

@@ -65,6 +65,7 @@ struct AutDev {
 	const uint32_t *cd_rec;        /* delta-encoded form (all of it fits in shared memory), NULL if not built */
 	const uint16_t *cd_t16;
 	uint32_t cd_t16_count;
+	uint32_t cd_dense_states;
 	uint32_t cd_thr4;              /* entry >= this: four patterns end there (code 3 = three or four) */
 	uint32_t cd_classes;
 	int      cd_range_lo;
@@ -814,6 +815,7 @@ struct CdLook {
 	uint32_t lut_sa;          /* shared address: replicated class map (!RANGE)            */
 	const uint16_t *tab;      /* !COMP: the whole table in global memory                  */
 	uint32_t C, n_hot, rlo, cmax, lane4;
+	uint32_t crow;            /* COMP: C << 16 (record word 1 of a dense state = state * crow); n_hot = dense states */
 };
 
 template <bool RANGE>
@@ -830,7 +832,11 @@ template <bool COMP>
 __device__ __forceinline__ uint32_t cd_next(const CdLook &L, uint32_t state, uint32_t c)
 {
 	if (COMP) {
-		const uint2 r = lds_v2(L.rec_sa + state * 8);
+		/* a dense state's record is {no explicit columns, its own row}: computed, not loaded, so
+		 * only the lanes in deep states take part in the (bank-conflicting) 8-byte read */
+		uint2 r = make_uint2(0u, state * L.crow);
+		if (state >= L.n_hot)
+			r = lds_v2(L.rec_sa + state * 8);
 		const uint32_t onehot = 1u << c;
 		const uint32_t idx = (r.x & onehot) ? (r.y & 0xFFFFu) + __popc(r.x & (onehot - 1u)) : (r.y >> 16) + c;
 		return lds_u16(L.tab_sa + idx * 2);
@@ -979,6 +985,7 @@ k_scan_cdfa(const __grid_constant__ AutDev A, const __grid_constant__ EmitCtx E,
 	L.rlo = (uint32_t)A.cd_range_lo;
 	L.cmax = A.cd_classes - 1;
 	L.lane4 = (threadIdx.x & 31) * 4;
+	L.crow = A.cd_classes << 16;
 
 	const uint32_t shift = E.shift;
 	const uint64_t chunk = 1ull << shift;

@@ -51,6 +51,11 @@ def run(dev, name, pats, n, modes, text=None, plants=0, iters=5):
                 (tr[:, 0].min() - t0) / 1e3, (tr[:, 0].max() - t0) / 1e3, (tr[:, 1].min() - t0) / 1e3,
                 (tr[:, 1].max() - t0) / 1e3, (tr[:, 2].min() - t0) / 1e3, (tr[:, 2].max() - t0) / 1e3,
                 tr[:, 3].min(), tr[:, 3].max()), flush=True)
+            ex = np.sort((tr[:, 2] - t0) / 1e3)
+            print("  exit times (us), sorted: " + " ".join(f"{x:.0f}" for x in ex), flush=True)
+            order = np.argsort(tr[:, 2])
+            print("  CTA ids by exit time:     " + " ".join(str(i) for i in order), flush=True)
+            print("  chunks by exit time:      " + " ".join(str(int(tr[i, 3])) for i in order), flush=True)
         sc.close()
     dev.free(d)
     a.free()
