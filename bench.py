@@ -174,6 +174,7 @@ def emit(line):
 
 
 def main():
+    global SIGS
     guard_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -181,10 +182,14 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--bytes-per-gpu", type=int, default=GIB)
+    ap.add_argument("--sigs", type=int, default=SIGS, choices=[2000, 10000, 15000],
+                    help="ClamAV signature set (default 10000 = BASELINE configs[1]; 15000 with "
+                         "--bytes-per-gpu 4294967296 is configs[2])")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 0)
+    SIGS = args.sigs
 
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -374,11 +379,13 @@ def main():
         "metric": METRIC, "value": value, "unit": "GB/s", "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "u8", "data": "synthetic",
-        "config": {"workload": f"clamav{SIGS} x {total >> 30} GiB seeded random stream "
-                               f"({per >> 30} GiB per GPU, halo {lmax - 1} B), {PLANTS_PER_GIB} planted signatures/GiB",
+        "config": {"workload": f"clamav{SIGS} x {total / GIB:g} GiB seeded random stream "
+                               f"({per / GIB:g} GiB per GPU, halo {lmax - 1} B), {PLANTS_PER_GIB} planted signatures/GiB",
                    "signatures": SIGS, "states": acsm.get_states(), "kernel": g.MODE_NAMES[mode],
                    "bytes_per_gpu": per, "matches": matches, "fallback": int(fallback),
-                   "l2_policy": "input (1 GiB per GPU) is larger than L2 (126 MB); no flush needed",
+                   "l2_policy": (f"input ({per / GIB:g} GiB per GPU) is larger than L2 (126 MB); no flush needed"
+                                 if per > (256 << 20) else
+                                 f"WARNING: input ({per >> 20} MiB per GPU) is not much larger than L2 (126 MB)"),
                    "step": ("scan + prefix sum + compaction/sort + NCCL count all-gather + key send/recv to "
                             "rank 0 + D2H of the list" if use_nccl else
                             "scan + prefix sum + compaction/sort + push of the sorted keys into rank 0's gather "

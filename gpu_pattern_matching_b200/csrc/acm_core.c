@@ -565,6 +565,59 @@ build_filters(struct acm_core *c)
 			free(tr);
 			return ACM_ERR_NOMEM;
 		}
+		/*
+		 * Which window of a pattern serves alignment j?  Any offset o = j + m * S with the
+		 * window inside the pattern will do: an occurrence starting at s with (-s) mod S = j has
+		 * an aligned window at s + o, and the kernel tests every aligned window.  The first one
+		 * (o = j) is taken unless its 4-byte key is popular -- virus prologues such as e8 00 00
+		 * 5d 81 ed head hundreds of signatures, and a text that contains one made the kernel walk
+		 * candidate lists for ~35 us in one chunk (per-chunk trace: 44 list rounds), which is
+		 * what spread the CTA exit times -- in which case the rarest key among the later windows of
+		 * that alignment is used.  Popularity = how many (pattern, alignment) entries a key would
+		 * get with first-window indexing.
+		 */
+		uint32_t *pop_key = NULL, *pop_cnt = NULL, pop_slots = 1024;
+		{
+			uint64_t first_entries = 0;
+			for (k = 0; k < (uint32_t)c->npats; k++)
+				if (c->pats[k].n)
+					first_entries += S;
+			while (pop_slots < first_entries * 2)
+				pop_slots <<= 1;
+			pop_key = calloc(pop_slots, 4);
+			pop_cnt = calloc(pop_slots, 4);
+			if (!pop_key || !pop_cnt) {
+				free(tr); free(pop_key); free(pop_cnt);
+				return ACM_ERR_NOMEM;
+			}
+			for (k = 0; k < (uint32_t)c->npats; k++) {
+				const unsigned char *p = c->pats[k].syms;
+				const uint32_t n = (uint32_t)c->pats[k].n;
+				for (uint32_t j = 0; n && j < S && j + 4 <= n; j++) {
+					const uint32_t g = (uint32_t)p[j] | ((uint32_t)p[j + 1] << 8) | ((uint32_t)p[j + 2] << 16) |
+					    ((uint32_t)p[j + 3] << 24);
+					for (s = (g * ACM_HASH3_MUL) & (pop_slots - 1);; s = (s + 1) & (pop_slots - 1)) {
+						if (pop_cnt[s] == 0 || pop_key[s] == g) {
+							pop_key[s] = g;
+							pop_cnt[s]++;
+							break;
+						}
+					}
+				}
+			}
+		}
+#define POP_OF(g, out)                                                                  \
+	do {                                                                            \
+		uint32_t s_ = ((g) * ACM_HASH3_MUL) & (pop_slots - 1);                      \
+		(out) = 0;                                                                  \
+		while (pop_cnt[s_]) {                                                       \
+			if (pop_key[s_] == (g)) {                                               \
+				(out) = pop_cnt[s_];                                                \
+				break;                                                              \
+			}                                                                       \
+			s_ = (s_ + 1) & (pop_slots - 1);                                        \
+		}                                                                           \
+	} while (0)
 		for (k = 0; k < (uint32_t)c->npats; k++) {
 			const unsigned char *p = c->pats[k].syms;
 			const uint32_t n = (uint32_t)c->pats[k].n;
@@ -572,9 +625,27 @@ build_filters(struct acm_core *c)
 				continue;
 			memcpy(t->pat_blob + t->pat_off[k], p, n);
 			for (uint32_t j = 0; j < S; j++) {
-				uint32_t g = 0;
+				uint32_t o = j, g = 0;
+				if (j + 4 <= n) {
+					uint32_t best;
+					const uint32_t g0 = (uint32_t)p[j] | ((uint32_t)p[j + 1] << 8) | ((uint32_t)p[j + 2] << 16) |
+					    ((uint32_t)p[j + 3] << 24);
+					POP_OF(g0, best);
+					if (best > ACM_CAND_POPULAR) {
+						for (uint32_t o2 = j + S; o2 + 4 <= n && o2 <= ACM_CAND_O_MAX; o2 += S) {
+							uint32_t pc;
+							const uint32_t g2 = (uint32_t)p[o2] | ((uint32_t)p[o2 + 1] << 8) |
+							    ((uint32_t)p[o2 + 2] << 16) | ((uint32_t)p[o2 + 3] << 24);
+							POP_OF(g2, pc);
+							if (pc < best) {
+								best = pc;
+								o = o2;
+							}
+						}
+					}
+				}
 				for (uint32_t b = 0; b < G; b++)
-					g |= (uint32_t)p[j + b] << (8 * b);
+					g |= (uint32_t)p[o + b] << (8 * b);
 				const uint32_t h1 = g * ACM_HASH1_MUL;
 				const uint32_t h2 = g * ACM_HASH2_MUL;
 				/* level 1 is a blocked Bloom filter, k = 2: both bits live in the one 32-bit
@@ -582,20 +653,23 @@ build_filters(struct acm_core *c)
 				t->f1[h1 >> (32 - (ACM_F1_BITS_LOG2 - 5))] |=
 				    (0x80000000u >> (h1 & 31)) | (0x80000000u >> ((h1 >> 12) & 31));
 				t->f2[h2 >> (32 - (ACM_F2_BITS_LOG2 - 5))] |= 0x80000000u >> (h2 & 31);
-				if (j + 4 <= n) {
-					tr[ntr].gram = (uint32_t)p[j] | ((uint32_t)p[j + 1] << 8) |
-					    ((uint32_t)p[j + 2] << 16) | ((uint32_t)p[j + 3] << 24);
-					tr[ntr].cand = k | (j << ACM_CAND_J_SHIFT);
+				if (o + 4 <= n) {
+					tr[ntr].gram = (uint32_t)p[o] | ((uint32_t)p[o + 1] << 8) |
+					    ((uint32_t)p[o + 2] << 16) | ((uint32_t)p[o + 3] << 24);
+					tr[ntr].cand = k | (o << ACM_CAND_O_SHIFT);
 					ntr++;
 				} else {
 					for (uint32_t b3 = 0; b3 < 256; b3++) {
 						tr[ntr].gram = g | (b3 << 24);
-						tr[ntr].cand = k | (j << ACM_CAND_J_SHIFT);
+						tr[ntr].cand = k | (o << ACM_CAND_O_SHIFT);
 						ntr++;
 					}
 				}
 			}
 		}
+#undef POP_OF
+		free(pop_key);
+		free(pop_cnt);
 		/* group by gram (stable order inside a gram is irrelevant: results get sorted) */
 		qsort(tr, ntr, sizeof(*tr), cmp_gtrip);
 		t->cand = calloc((size_t)ntr + ACM_CAND_PAD, sizeof(*t->cand));
@@ -608,15 +682,18 @@ build_filters(struct acm_core *c)
 			const int first = (k == 0) || tr[k - 1].gram != tr[k].gram;
 			const int lastc = (k + 1 == ntr) || tr[k + 1].gram != tr[k].gram;
 			const uint32_t pid = tr[k].cand & ACM_CAND_ID_MASK;
-			const unsigned char *pb = t->pat_blob + t->pat_off[pid];   /* zero padded */
-			t->cand[k].info = tr[k].cand | (lastc ? ACM_CAND_LAST : 0);
-			t->cand[k].pre0 = (uint32_t)pb[0] | ((uint32_t)pb[1] << 8) | ((uint32_t)pb[2] << 16) |
-			    ((uint32_t)pb[3] << 24);
-			t->cand[k].pre1 = (uint32_t)pb[4] | ((uint32_t)pb[5] << 8) | ((uint32_t)pb[6] << 16) |
-			    ((uint32_t)pb[7] << 24);
-			t->cand[k].len = (uint32_t)c->pats[pid].n;
+			const uint32_t o = tr[k].cand >> ACM_CAND_O_SHIFT;
+			const unsigned char *pb = t->pat_blob + t->pat_off[pid] + o;   /* zero padded: >= 4 zero bytes + next pattern */
+			const uint32_t rem = (uint32_t)c->pats[pid].n - o;           /* pattern bytes from o on, >= 3 */
+			uint32_t w[2] = {0, 0};
+			for (uint32_t b = 0; b < 8 && b < rem; b++)
+				w[b >> 2] |= (uint32_t)pb[b] << (8 * (b & 3));
+			t->cand[k].info = tr[k].cand;
+			t->cand[k].at0 = w[0];
+			t->cand[k].at1 = w[1];
+			t->cand[k].len = (uint32_t)c->pats[pid].n | (lastc ? ACM_CAND_LAST : 0);
 			{
-				const unsigned char *pe = pb + c->pats[pid].n - 4;   /* n >= 7 here */
+				const unsigned char *pe = t->pat_blob + t->pat_off[pid] + c->pats[pid].n - 4;   /* n >= 7 here */
 				t->cand[k].tail = (uint32_t)pe[0] | ((uint32_t)pe[1] << 8) | ((uint32_t)pe[2] << 16) |
 				    ((uint32_t)pe[3] << 24);
 			}

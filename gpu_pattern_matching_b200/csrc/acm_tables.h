@@ -53,19 +53,23 @@ struct acm_gram_slot {     /* exact 4-gram table, open addressing in HBM/L2 */
 };
 
 /*
- * candidate: pattern `id` has the gram at byte offset j (3 bits); LAST marks the end of a gram's
- * list.  pre0/pre1 (first 8 bytes, zero padded) and tail (last 4 bytes) give a quick reject
- * before the full compare; 32 bytes per record = two 16-byte loads.
+ * candidate: pattern `id` is indexed under the 4 bytes at its byte offset o (8 bits, o mod stride
+ * = the alignment this entry serves; the builder moves o from the first aligned window to a later
+ * one of the same alignment when the first one's gram is popular); bit 31 of len marks the end of
+ * a gram's list.  at0/at1 (pattern bytes o .. o+7, zero padded past the end) and tail (last 4
+ * bytes) give a quick reject before the full compare; 32 bytes per record = two 16-byte loads.
  */
 #define ACM_CAND_ID_MASK 0x00FFFFFFu
-#define ACM_CAND_J_SHIFT 24
-#define ACM_CAND_LAST    0x80000000u
+#define ACM_CAND_O_SHIFT 24
+#define ACM_CAND_O_MAX   248u        /* largest indexed offset */
+#define ACM_CAND_LAST    0x80000000u /* in len */
 #define ACM_CAND_PAD     32          /* zeroed entries after the last list */
+#define ACM_CAND_POPULAR 8           /* lists longer than this make the builder look for a rarer window */
 
 struct acm_cand {
-	uint32_t info;         /* id | j << 24 | LAST */
-	uint32_t pre0, pre1;   /* pattern bytes 0..7 */
-	uint32_t len;
+	uint32_t info;         /* id | o << 24 */
+	uint32_t at0, at1;     /* pattern bytes o .. o+7 */
+	uint32_t len;          /* | ACM_CAND_LAST */
 	uint32_t tail;         /* pattern bytes len-4 .. len-1 */
 	uint32_t pad[3];
 };

@@ -547,30 +547,27 @@ k_scan_sampled(const __grid_constant__ AutDev A, const __grid_constant__ EmitCtx
 				pend &= pend - 1;
 				uint32_t ci = __shfl_sync(FULL_MASK, cbegin, src) - 1;
 				const uint64_t ew = __shfl_sync(FULL_MASK, e, src);
-				/* 16 bytes of text around the window, [ew - 8, ew + 8): enough for the first
-				 * 8 bytes of any candidate (it starts at ew - j, j < 8) */
+				/* the 8 bytes of text at the window: every candidate of this gram is compared on its
+				 * own bytes o .. o+7 (it starts at ew - o) */
 				const uint32_t *wp = reinterpret_cast<const uint32_t *>(data + ew);
-				const uint64_t lo64 = ((uint64_t)(ew >= 4 ? __ldg(wp - 1) : 0u) << 32) |
-				    (STRIDE > 4 && ew >= 8 ? __ldg(wp - 2) : 0u);
-				const uint64_t hi64 = ((uint64_t)((ew + 4 < n) ? __ldg(wp + 1) : 0u) << 32) | __ldg(wp);
+				const uint32_t t0 = __ldg(wp), t1 = (ew + 4 < n) ? __ldg(wp + 1) : 0u;
 				for (;;) {
 					/* one candidate per lane (lists are padded, lanes past LAST are ignored) */
 					const uint4 *cp = reinterpret_cast<const uint4 *>(A.cand) + 2 * (size_t)(ci + lane);
 					const uint4 c = __ldg(cp);
-					const uint32_t lastm = __ballot_sync(FULL_MASK, (c.x & ACM_CAND_LAST) != 0);
+					const uint32_t lastm = __ballot_sync(FULL_MASK, (c.w & ACM_CAND_LAST) != 0);
 					const int nvalid = lastm ? __ffs(lastm) : 32;
-					const uint32_t j = (c.x >> ACM_CAND_J_SHIFT) & 7u;
-					const uint32_t len = c.w;
-					const uint32_t o = 8u - j;                    /* byte offset of s in the block, 1..8 */
-					const uint64_t first8 = (o == 8u) ? hi64 : ((lo64 >> (8u * o)) | (hi64 << (64u - 8u * o)));
-					const uint32_t t0 = (uint32_t)first8, t1 = (uint32_t)(first8 >> 32);
-					const uint32_t m1 = len >= 8 ? 0xffffffffu : ((1u << (8 * (len - 4))) - 1u);
-					const uint64_t s = ew - j;
-					bool ok = lane < nvalid && ew >= j && s >= E.valid_lo && s + len <= limit &&
-					    t0 == c.y && ((t1 ^ c.z) & m1) == 0;
-					if (ok && len > 8) {
+					const uint32_t o = c.x >> ACM_CAND_O_SHIFT;
+					const uint32_t len = c.w & ~ACM_CAND_LAST;
+					const uint32_t rem = len - o;                  /* pattern bytes from the window on, >= 3 */
+					const uint32_t m0 = rem >= 4 ? 0xffffffffu : 0x00ffffffu;
+					const uint32_t m1 = rem >= 8 ? 0xffffffffu : (rem <= 4 ? 0u : ((1u << (8 * (rem - 4))) - 1u));
+					const uint64_t s = ew - o;
+					bool ok = lane < nvalid && ew >= o && s >= E.valid_lo && s + len <= limit &&
+					    ((t0 ^ c.y) & m0) == 0 && ((t1 ^ c.z) & m1) == 0;
+					if (ok) {
 						/* the pattern's last 4 bytes against the text: repetitive text makes many
-						 * candidates share their first 8 bytes, very few also share their end */
+						 * candidates share the bytes at the window, very few also share their end */
 						const uint64_t ta = s + len - 4;
 						const uint32_t *tp = reinterpret_cast<const uint32_t *>(data + (ta & ~3ull));
 						const uint32_t sh = (uint32_t)(ta & 3) * 8;
@@ -578,9 +575,7 @@ k_scan_sampled(const __grid_constant__ AutDev A, const __grid_constant__ EmitCtx
 						const uint32_t a1 = sh ? __ldg(tp + 1) : 0u;
 						ok = __funnelshift_r(a0, a1, sh) == __ldg(reinterpret_cast<const uint32_t *>(cp + 1));
 					}
-					if (ok && len <= 8)
-						emit_record(E, s + len - 1, c.x & ACM_CAND_ID_MASK);
-					uint32_t surv = __ballot_sync(FULL_MASK, ok && len > 8);
+					uint32_t surv = __ballot_sync(FULL_MASK, ok);
 					while (surv) {
 						const int l = __ffs(surv) - 1;
 						surv &= surv - 1;
