@@ -387,7 +387,6 @@ k_scan_sampled(const __grid_constant__ AutDev A, const __grid_constant__ EmitCtx
 	uint32_t trace_chunks = 0;
 	constexpr int WPV = 16 / STRIDE;                 /* windows per 16-byte vector */
 	constexpr int NW = S4_UNROLL * WPV;              /* windows per lane per chunk */
-	constexpr uint32_t GMASK = STRIDE == 4 ? 0xffffffffu : 0x00ffffffu;
 
 	if (E.trace && threadIdx.x == 0)
 		E.trace[blockIdx.x * 4 + 0] = globaltimer_ns();
@@ -454,8 +453,31 @@ k_scan_sampled(const __grid_constant__ AutDev A, const __grid_constant__ EmitCtx
 	if (E.trace && threadIdx.x == 0)
 		E.trace[blockIdx.x * 4 + 1] = globaltimer_ns();
 
+#ifdef S4_TRACE_DETAIL
+	/* per-chunk timestamps: the slowest chunk of every CTA with what it did (make EXTRA=-DS4_TRACE_DETAIL,
+	 * ACM_TRACE=1 ACM_TRACE_DETAIL=1 tools/quick_bench.py) */
+	uint64_t td_prev = globaltimer_ns(), td_max = 0, td_slow = 0, td_filter = 0;
+	uint32_t tdc_rounds = 0, tdc_pend = 0, tdc_cand = 0, tdc_verify = 0, td_info = 0;
+#endif
 	while (run_count) {
 		++trace_chunks;
+#ifdef S4_TRACE_DETAIL
+		{
+			const uint64_t now = globaltimer_ns();
+			const uint64_t d = now - td_prev;
+			td_prev = now;
+			if (trace_chunks > 1) {
+				if (d > td_max) {
+					td_max = d;
+					td_info = ((td_filter / 250) > 255 ? 255 : (uint32_t)(td_filter / 250)) | (min(tdc_rounds, 63u) << 8) |
+					    (min(tdc_pend, 63u) << 14) | (min(tdc_cand, 63u) << 20) | (min(tdc_verify, 63u) << 26);
+				}
+				td_slow += d > 8000;
+			}
+			tdc_rounds = tdc_pend = tdc_cand = tdc_verify = 0;
+			td_filter = 0;
+		}
+#endif
 		const uint64_t cur_first = first;
 		if (cur_first + chunk_vecs <= vec_hi) {          /* all but the last chunk */
 			const uint4 *p = reinterpret_cast<const uint4 *>(data) + cur_first + lane;
@@ -486,7 +508,7 @@ k_scan_sampled(const __grid_constant__ AutDev A, const __grid_constant__ EmitCtx
 			const uint32_t w[4] = {v[u].x, v[u].y, v[u].z, v[u].w};
 #pragma unroll
 			for (int k = 0; k < WPV; ++k) {
-				const uint32_t h = (w[k * (4 / WPV)] & GMASK) * ACM_HASH1_MUL;
+				const uint32_t h = w[k * (4 / WPV)] * ACM_HASH1_MUL;
 				const uint32_t word = f1[h >> (32 - (ACM_F1_BITS_LOG2 - 5))];
 				/* bitmap words are bit-reversed: a tested bit lands in the MSB.  Two bits per
 				 * gram (blocked Bloom filter in the one word fetched): 3 more ALU ops per
@@ -510,6 +532,10 @@ k_scan_sampled(const __grid_constant__ AutDev A, const __grid_constant__ EmitCtx
 		/* bit (NW - 1 - q) of hits belongs to window q = u * WPV + k.  Survivors are rare: from
 		 * here on control flow is warp-uniform and verification is done by the whole warp. */
 		while (__any_sync(FULL_MASK, hits != 0)) {
+#ifdef S4_TRACE_DETAIL
+			if (tdc_rounds++ == 0)
+				td_filter = globaltimer_ns() - td_prev;
+#endif
 			uint32_t cbegin = 0;
 			uint64_t e = 0;
 			if (hits) {
@@ -523,7 +549,7 @@ k_scan_sampled(const __grid_constant__ AutDev A, const __grid_constant__ EmitCtx
 					word4 = (k & 2) ? ((k & 1) ? x.w : x.z) : ((k & 1) ? x.y : x.x);
 				else
 					word4 = k ? x.z : x.x;
-				const uint32_t h2 = (word4 & GMASK) * ACM_HASH2_MUL;
+				const uint32_t h2 = word4 * ACM_HASH2_MUL;
 				const uint32_t word2 = f2[h2 >> (32 - (ACM_F2_BITS_LOG2 - 5))];
 				if (__funnelshift_l(0u, word2, h2) & 0x80000000u) {
 					/* exact table keyed by the 4 bytes at the window (L2 resident) */
@@ -542,6 +568,9 @@ k_scan_sampled(const __grid_constant__ AutDev A, const __grid_constant__ EmitCtx
 				}
 			}
 			uint32_t pend = __ballot_sync(FULL_MASK, cbegin != 0);
+#ifdef S4_TRACE_DETAIL
+			tdc_pend += __popc(pend);
+#endif
 			while (pend) {
 				const int src = __ffs(pend) - 1;
 				pend &= pend - 1;
@@ -555,6 +584,9 @@ k_scan_sampled(const __grid_constant__ AutDev A, const __grid_constant__ EmitCtx
 					/* one candidate per lane (lists are padded, lanes past LAST are ignored) */
 					const uint4 *cp = reinterpret_cast<const uint4 *>(A.cand) + 2 * (size_t)(ci + lane);
 					const uint4 c = __ldg(cp);
+#ifdef S4_TRACE_DETAIL
+					++tdc_cand;
+#endif
 					const uint32_t lastm = __ballot_sync(FULL_MASK, (c.w & ACM_CAND_LAST) != 0);
 					const int nvalid = lastm ? __ffs(lastm) : 32;
 					const uint32_t o = c.x >> ACM_CAND_O_SHIFT;
@@ -579,6 +611,9 @@ k_scan_sampled(const __grid_constant__ AutDev A, const __grid_constant__ EmitCtx
 					while (surv) {
 						const int l = __ffs(surv) - 1;
 						surv &= surv - 1;
+#ifdef S4_TRACE_DETAIL
+						++tdc_verify;
+#endif
 						s4_verify(A, E, data, __shfl_sync(FULL_MASK, c.x, l) & ACM_CAND_ID_MASK,
 						    __shfl_sync(FULL_MASK, len, l), __shfl_sync(FULL_MASK, s, l), lane);
 					}
@@ -592,6 +627,13 @@ k_scan_sampled(const __grid_constant__ AutDev A, const __grid_constant__ EmitCtx
 	if (E.trace && lane == 0) {
 		atomicMax((unsigned long long *)&E.trace[blockIdx.x * 4 + 2], (unsigned long long)globaltimer_ns());
 		atomicAdd((unsigned long long *)&E.trace[blockIdx.x * 4 + 3], (unsigned long long)trace_chunks);
+#ifdef S4_TRACE_DETAIL
+		{
+			uint64_t *x = E.trace + (512 + blockIdx.x) * 4;
+			atomicMax((unsigned long long *)&x[0], (unsigned long long)((td_max / 100) << 32 | td_info));
+			atomicAdd((unsigned long long *)&x[1], (unsigned long long)td_slow);
+		}
+#endif
 	}
 }
 
