@@ -657,11 +657,12 @@ build_filters(struct acm_core *c)
 					const uint32_t gg = fixed == 4 ? g : (g | (b3 << 24));
 					const uint32_t h1 = gg * ACM_HASH1_MUL;
 					const uint32_t h2 = gg * ACM_HASH2_MUL;
-					/* level 1 is a blocked Bloom filter, k = 2: both bits live in the one 32-bit
+					/* both levels are blocked Bloom filters, k = 2: both bits live in the one 32-bit
 					 * word the kernel fetches (bit indices from hash bits 0..4 and 12..16) */
 					t->f1[h1 >> (32 - (ACM_F1_BITS_LOG2 - 5))] |=
 					    (0x80000000u >> (h1 & 31)) | (0x80000000u >> ((h1 >> 12) & 31));
-					t->f2[h2 >> (32 - (ACM_F2_BITS_LOG2 - 5))] |= 0x80000000u >> (h2 & 31);
+					t->f2[h2 >> (32 - (ACM_F2_BITS_LOG2 - 5))] |=
+					    (0x80000000u >> (h2 & 31)) | (0x80000000u >> ((h2 >> 12) & 31));
 				}
 				if (o + 4 <= n) {
 					tr[ntr].gram = (uint32_t)p[o] | ((uint32_t)p[o + 1] << 8) |

@@ -529,20 +529,22 @@ k_scan_sampled(const __grid_constant__ AutDev A, const __grid_constant__ EmitCtx
 			s4_chunk_dfa(&A, &E, data, cur_first * 16, limit, lane, STRIDE);
 			continue;
 		}
-		/* bit (NW - 1 - q) of hits belongs to window q = u * WPV + k.  Survivors are rare: from
-		 * here on control flow is warp-uniform and verification is done by the whole warp. */
-		while (__any_sync(FULL_MASK, hits != 0)) {
-#ifdef S4_TRACE_DETAIL
-			if (tdc_rounds++ == 0)
-				td_filter = globaltimer_ns() - td_prev;
-#endif
-			uint32_t cbegin = 0;
-			uint64_t e = 0;
-			if (hits) {
-				const int p = 31 - __clz(hits);
-				hits &= ~(1u << p);
-				const int q = NW - 1 - p;
-				const int u = q / WPV, k = q % WPV;
+		/*
+		 * bit (NW - 1 - q) of hits belongs to window q = u * WPV + k.  Level 2 (second hash, own
+		 * bitmap, two bits per gram in the one word fetched) is tested lane-locally first: a
+		 * short divergent loop, one iteration per level-1 survivor of the lane (random data:
+		 * ~5 per chunk over the whole warp, 1.1 iterations).  It leaves ~0.15 windows per chunk,
+		 * so most chunks never enter the warp-uniform loop below and its L2 round trips.
+		 */
+		{
+			uint32_t hh = hits;
+			hits = 0;
+			while (hh) {
+				const uint32_t p = 31u - (uint32_t)__clz(hh);
+				const uint32_t bit = 1u << p;
+				hh ^= bit;
+				const uint32_t q = NW - 1 - p;
+				const uint32_t u = q / WPV, k = q % WPV;
 				const uint4 x = (u & 2) ? ((u & 1) ? v[3] : v[2]) : ((u & 1) ? v[1] : v[0]);
 				uint32_t word4;                          /* the 4 bytes at the window */
 				if (STRIDE == 4)
@@ -551,20 +553,42 @@ k_scan_sampled(const __grid_constant__ AutDev A, const __grid_constant__ EmitCtx
 					word4 = k ? x.z : x.x;
 				const uint32_t h2 = word4 * ACM_HASH2_MUL;
 				const uint32_t word2 = f2[h2 >> (32 - (ACM_F2_BITS_LOG2 - 5))];
-				if (__funnelshift_l(0u, word2, h2) & 0x80000000u) {
-					/* exact table keyed by the 4 bytes at the window (L2 resident) */
-					uint32_t sl = (word4 * ACM_HASH3_MUL) >> A.gram_shift;
-					for (;;) {
-						const uint2 slot = __ldg(reinterpret_cast<const uint2 *>(A.grams) + sl);
-						if (slot.y == 0)
-							break;
-						if (slot.x == word4) {
-							cbegin = slot.y;
-							break;
-						}
-						sl = (sl + 1) & A.gram_mask;
+				if ((int32_t)(__funnelshift_l(0u, word2, h2) & __funnelshift_l(0u, word2, h2 >> 12)) < 0)
+					hits |= bit;
+			}
+		}
+		/* Survivors are rare: from here on control flow is warp-uniform and verification is done
+		 * by the whole warp. */
+		while (__any_sync(FULL_MASK, hits != 0)) {
+#ifdef S4_TRACE_DETAIL
+			if (tdc_rounds++ == 0)
+				td_filter = globaltimer_ns() - td_prev;
+#endif
+			uint32_t cbegin = 0;
+			uint64_t e = 0;
+			if (hits) {
+				const uint32_t p = 31u - (uint32_t)__clz(hits);
+				hits ^= 1u << p;
+				const uint32_t q = NW - 1 - p;
+				const uint32_t u = q / WPV, k = q % WPV;
+				e = (cur_first + (uint64_t)u * 32 + lane) * 16 + (uint64_t)k * STRIDE;
+				const uint4 x = (u & 2) ? ((u & 1) ? v[3] : v[2]) : ((u & 1) ? v[1] : v[0]);
+				uint32_t word4;
+				if (STRIDE == 4)
+					word4 = (k & 2) ? ((k & 1) ? x.w : x.z) : ((k & 1) ? x.y : x.x);
+				else
+					word4 = k ? x.z : x.x;
+				/* exact table keyed by the 4 bytes at the window (L2 resident) */
+				uint32_t sl = (word4 * ACM_HASH3_MUL) >> A.gram_shift;
+				for (;;) {
+					const uint2 slot = __ldg(reinterpret_cast<const uint2 *>(A.grams) + sl);
+					if (slot.y == 0)
+						break;
+					if (slot.x == word4) {
+						cbegin = slot.y;
+						break;
 					}
-					e = (cur_first + (uint64_t)u * 32 + lane) * 16 + (uint64_t)k * STRIDE;
+					sl = (sl + 1) & A.gram_mask;
 				}
 			}
 			uint32_t pend = __ballot_sync(FULL_MASK, cbegin != 0);
