@@ -8,7 +8,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libacmatch_b200.so")
+LIB_PATH = os.environ.get("ACM_LIB_PATH") or os.path.join(_HERE, "libacmatch_b200.so")   # override: kernel experiments
 
 u8p = C.POINTER(C.c_ubyte)
 u16p = C.POINTER(C.c_ushort)

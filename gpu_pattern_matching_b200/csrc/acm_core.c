@@ -158,7 +158,7 @@ acm_tables_device_bytes(const struct acm_tables *t)
 	b += (size_t)t->num_states * 4 + (size_t)t->num_patterns * 4;
 	b += (size_t)(t->max_depth + 2) * 4;
 	if (t->f1)
-		b += (1u << ACM_F1_BITS_LOG2) / 8 + (1u << ACM_F2_BITS_LOG2) / 8 +
+		b += (1u << ACM_F1_BITS_LOG2) / 8 + ACM_F2_WORDS * 4 +
 		    (size_t)t->gram_slots * sizeof(struct acm_gram_slot) +
 		    ((size_t)t->cand_count + ACM_CAND_PAD) * sizeof(struct acm_cand) +
 		    t->pat_blob_bytes + (size_t)t->num_patterns * 4;
@@ -524,7 +524,7 @@ build_filters(struct acm_core *c)
 	 * 10, offset 7) the fourth is a wildcard and all 256 keys are entered.
 	 */
 	t->f1 = calloc((1u << ACM_F1_BITS_LOG2) / 32, 4);
-	t->f2 = calloc((1u << ACM_F2_BITS_LOG2) / 32, 4);
+	t->f2 = calloc(ACM_F2_WORDS, 4);
 	if (!t->f1 || !t->f2)
 		return ACM_ERR_NOMEM;
 	{
@@ -657,12 +657,13 @@ build_filters(struct acm_core *c)
 					const uint32_t gg = fixed == 4 ? g : (g | (b3 << 24));
 					const uint32_t h1 = gg * ACM_HASH1_MUL;
 					const uint32_t h2 = gg * ACM_HASH2_MUL;
-					/* both levels are blocked Bloom filters, k = 2: both bits live in the one 32-bit
-					 * word the kernel fetches (bit indices from hash bits 0..4 and 12..16) */
+					/* both levels are blocked Bloom filters: all bits of a gram live in the one 32-bit
+					 * word the kernel fetches.  Level 1: k = 2 (bit indices from hash bits 0..4 and
+					 * 12..16); level 2, tested only for level-1 survivors: k = 3 (+ bits 6..10) */
 					t->f1[h1 >> (32 - (ACM_F1_BITS_LOG2 - 5))] |=
 					    (0x80000000u >> (h1 & 31)) | (0x80000000u >> ((h1 >> 12) & 31));
-					t->f2[h2 >> (32 - (ACM_F2_BITS_LOG2 - 5))] |=
-					    (0x80000000u >> (h2 & 31)) | (0x80000000u >> ((h2 >> 12) & 31));
+					t->f2[(uint32_t)(((uint64_t)h2 * ACM_F2_WORDS) >> 32)] |= (0x80000000u >> (h2 & 31)) |
+					    (0x80000000u >> ((h2 >> 12) & 31)) | (0x80000000u >> ((h2 >> 6) & 31));
 				}
 				if (o + 4 <= n) {
 					tr[ntr].gram = (uint32_t)p[o] | ((uint32_t)p[o + 1] << 8) |

@@ -422,7 +422,7 @@ acm_automaton_upload(struct acm_device *dev, const struct acm_tables *t, struct 
 		UP(b2, t->b2, 65536 / 8);
 	if (t->f1) {
 		UP(f1, t->f1, (1u << ACM_F1_BITS_LOG2) / 8);
-		UP(f2, t->f2, (1u << ACM_F2_BITS_LOG2) / 8);
+		UP(f2, t->f2, ACM_F2_WORDS * 4);
 		UP(grams, t->grams, (size_t)t->gram_slots * sizeof(struct acm_gram_slot));
 		UP(cand, t->cand, ((size_t)t->cand_count + ACM_CAND_PAD) * sizeof(struct acm_cand));
 		UP(pat_blob, t->pat_blob, t->pat_blob_bytes);

@@ -42,7 +42,7 @@ enum {
 #define ACM_CD_COMP_BUDGET (216 * 1024)   /* bytes of shared memory for cd_rec + cd_t16 */
 
 #define ACM_F1_BITS_LOG2   20              /* level-1 gram bitmap: 128 KiB smem */
-#define ACM_F2_BITS_LOG2   19              /* level-2 gram bitmap:  64 KiB smem */
+#define ACM_F2_WORDS       24576u          /* level-2 gram bitmap:  96 KiB smem, word = mulhi(hash, words) */
 #define ACM_HASH1_MUL 0x9E3779B1u
 #define ACM_HASH2_MUL 0x85EBCA6Bu
 #define ACM_HASH3_MUL 0xC2B2AE35u

@@ -92,7 +92,7 @@ struct EmitCtx {
 };
 
 #define F1_WORDS (1u << (ACM_F1_BITS_LOG2 - 5))
-#define F2_WORDS (1u << (ACM_F2_BITS_LOG2 - 5))
+#define F2_WORDS ACM_F2_WORDS
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p)
 {
@@ -282,6 +282,9 @@ __device__ __forceinline__ uint4 load_vec(const uint8_t *__restrict__ data, uint
 #define S4_THREADS 1024
 #define S4_UNROLL  4
 #define S4_UNIT_CHUNKS 8
+#ifndef S4_PF_DIST
+#define S4_PF_DIST 1                     /* L2 prefetch distance in chunks (1 or 2) */
+#endif
 #define S4_SMEM_BYTES ((F1_WORDS + F2_WORDS) * 4 + 16)
 #define FULL_MASK 0xffffffffu
 
@@ -447,8 +450,20 @@ k_scan_sampled(const __grid_constant__ AutDev A, const __grid_constant__ EmitCtx
 	 */
 	uint4 v[S4_UNROLL];
 	uint64_t first = vec_lo + run_start * chunk_vecs;        /* first vector of the next chunk */
-	if (run_count && lane == 0)
+	/* lane 0: pull the chunk AFTER `first` into L2 (S4_PF_DIST == 2 keeps two chunks in flight
+	 * per warp, 128 KiB per SM instead of 64; measured 1-2 % SLOWER on all three ClamAV sets,
+	 * so prefetch depth is not what bounds the kernel; distance 1 is the default) */
+	auto prefetch_after_first = [&]() {
+		if (run_count >= 2)
+			prefetch_l2_bulk(data + (first + chunk_vecs) * 16, (uint32_t)chunk_vecs * 16);
+		else if (run_count == 1 && next_count)
+			prefetch_l2_bulk(data + (vec_lo + next_start * chunk_vecs) * 16, (uint32_t)chunk_vecs * 16);
+	};
+	if (run_count && lane == 0) {
 		prefetch_l2_bulk(data + first * 16, (uint32_t)chunk_vecs * 16);
+		if (S4_PF_DIST == 2)
+			prefetch_after_first();
+	}
 	mbar_wait(bar, 0);
 	if (E.trace && threadIdx.x == 0)
 		E.trace[blockIdx.x * 4 + 1] = globaltimer_ns();
@@ -500,8 +515,12 @@ k_scan_sampled(const __grid_constant__ AutDev A, const __grid_constant__ EmitCtx
 		} else {
 			first += chunk_vecs;
 		}
-		if (run_count && lane == 0)
-			prefetch_l2_bulk(data + first * 16, (uint32_t)chunk_vecs * 16);
+		if (run_count && lane == 0) {
+			if (S4_PF_DIST == 2)
+				prefetch_after_first();
+			else
+				prefetch_l2_bulk(data + first * 16, (uint32_t)chunk_vecs * 16);
+		}
 		uint32_t hits = 0;
 #pragma unroll
 		for (int u = 0; u < S4_UNROLL; ++u) {
@@ -531,9 +550,9 @@ k_scan_sampled(const __grid_constant__ AutDev A, const __grid_constant__ EmitCtx
 		}
 		/*
 		 * bit (NW - 1 - q) of hits belongs to window q = u * WPV + k.  Level 2 (second hash, own
-		 * bitmap, two bits per gram in the one word fetched) is tested lane-locally first: a
+		 * bitmap of 96 KiB, three bits per gram in the one word fetched) is tested lane-locally first: a
 		 * short divergent loop, one iteration per level-1 survivor of the lane (random data:
-		 * ~5 per chunk over the whole warp, 1.1 iterations).  It leaves ~0.15 windows per chunk,
+		 * ~5 per chunk over the whole warp, 1.1 iterations).  It leaves < 0.1 windows per chunk,
 		 * so most chunks never enter the warp-uniform loop below and its L2 round trips.
 		 */
 		{
@@ -552,8 +571,9 @@ k_scan_sampled(const __grid_constant__ AutDev A, const __grid_constant__ EmitCtx
 				else
 					word4 = k ? x.z : x.x;
 				const uint32_t h2 = word4 * ACM_HASH2_MUL;
-				const uint32_t word2 = f2[h2 >> (32 - (ACM_F2_BITS_LOG2 - 5))];
-				if ((int32_t)(__funnelshift_l(0u, word2, h2) & __funnelshift_l(0u, word2, h2 >> 12)) < 0)
+				const uint32_t word2 = f2[__umulhi(h2, F2_WORDS)];
+				if ((int32_t)(__funnelshift_l(0u, word2, h2) & __funnelshift_l(0u, word2, h2 >> 12) &
+				    __funnelshift_l(0u, word2, h2 >> 6)) < 0)
 					hits |= bit;
 			}
 		}
