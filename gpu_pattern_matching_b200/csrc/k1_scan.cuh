@@ -281,11 +281,18 @@ __device__ __forceinline__ uint4 load_vec(const uint8_t *__restrict__ data, uint
 
 #define S4_THREADS 1024
 #define S4_UNROLL  4
-#define S4_UNIT_CHUNKS 8
+#ifndef S4_UNIT_CHUNKS
+#define S4_UNIT_CHUNKS 8                 /* chunks per run (16 KiB) while plenty of work is left */
+#endif
+#ifndef S4_INTERLEAVE
+#define S4_INTERLEAVE 0                  /* 1: the 32 runs of a block are interleaved chunk by chunk */
+#endif
+#define S4_BLOCK_RUNS 32                 /* runs per block = warps per CTA */
+#define S4_SLOTS 4                       /* published blocks per CTA (ring) */
 #ifndef S4_PF_DIST
 #define S4_PF_DIST 1                     /* L2 prefetch distance in chunks (1 or 2) */
 #endif
-#define S4_SMEM_BYTES ((F1_WORDS + F2_WORDS) * 4 + 16)
+#define S4_SMEM_BYTES ((F1_WORDS + F2_WORDS) * 4 + 16 + 16 + S4_SLOTS * 16)
 #define FULL_MASK 0xffffffffu
 
 /*
@@ -407,35 +414,88 @@ k_scan_sampled(const __grid_constant__ AutDev A, const __grid_constant__ EmitCtx
 	/*
 	 * Work distribution.  The range is cut into chunks of 32 lanes x S4_UNROLL vectors
 	 * (2 KiB; a lane reads vectors chunk_base + u * 32 + lane, so each load instruction
-	 * covers 512 contiguous bytes).  Warps pull runs of S4_UNIT_CHUNKS chunks from
-	 * work_counter[0], one run ahead of use, so SMs that run slower (far-die L2,
-	 * verification-heavy regions) simply take fewer; the last tail_chunks chunks are handed
-	 * out one at a time from work_counter[1] so that no warp is left holding 32 KiB of
-	 * work when the others have run dry.
+	 * covers 512 contiguous bytes).  Two levels:
+	 *   - the CTA takes BLOCKS of 32 runs x L chunks from the one global counter (L = 8, i.e.
+	 *     512 KiB, while plenty is left; 4, 2, 1 towards the end so that all SMs -- they differ
+	 *     by +-5 % in speed -- finish together): ~2 300 global atomics per GiB;
+	 *   - its warps take RUNS from the block by tickets from a shared-memory counter, one run
+	 *     ahead of use.  Ticket t is run t % 32 of the CTA's block t / 32; the warp that draws
+	 *     run 0 of block k fetches block k + 2 and publishes it in slot (k + 2) % 4.
+	 * The whole grid sweeps the stream front to back, 148 x 512 KiB at a time.  (One global
+	 * atomic per 16 KiB run -- the first version -- cost 13 % of the kernel: 65 536
+	 * same-address atomics per GiB keep one L2 slice busy a third of the time and every
+	 * warp's loads pass through it; loads alone ran at 5.46 TB/s with 16 KiB runs and at
+	 * 6.32 TB/s with 64 KiB runs.  Static per-CTA ranges with stealing ran at 3.7 TB/s: 148
+	 * separate streams are much worse for DRAM than one front.)
 	 */
 	const uint64_t chunk_vecs = 32ull * S4_UNROLL;
-	const uint64_t n_chunks = (vec_hi - vec_lo + chunk_vecs - 1) / chunk_vecs;
-	const uint64_t n_big = (n_chunks > tail_chunks ? n_chunks - tail_chunks : 0) / S4_UNIT_CHUNKS;
-	const uint64_t tail0 = n_big * S4_UNIT_CHUNKS;            /* first chunk of the tail zone */
-	/* a run is (first chunk, number of chunks); count 0 = nothing left */
-	auto grab = [&](uint64_t &start, uint32_t &count) {
+	const uint32_t n_chunks = (uint32_t)((vec_hi - vec_lo + chunk_vecs - 1) / chunk_vecs);
+	uint32_t *s_ticket = reinterpret_cast<uint32_t *>(bar + 2);
+	/* slot: {seq = block number + 1 once published, first chunk, L, readers} */
+	volatile uint32_t *s_slot = reinterpret_cast<volatile uint32_t *>(bar + 4);
+	auto fetch_block = [&](uint32_t &first_chunk, uint32_t &len) {
+		const uint32_t seen = *reinterpret_cast<volatile uint32_t *>(work_counter);
+		const uint32_t left = seen < n_chunks ? n_chunks - seen : 0;
+		const uint32_t full = S4_BLOCK_RUNS * S4_UNIT_CHUNKS * gridDim.x;   /* one full block per CTA */
+		len = S4_UNIT_CHUNKS;
+		while (len > 1 && left < 2 * (full / S4_UNIT_CHUNKS) * len)
+			len >>= 1;
+		first_chunk = atomicAdd(work_counter, S4_BLOCK_RUNS * len);
+	};
+	if (threadIdx.x == 32) {
+		*s_ticket = 0;
+		for (uint32_t j = 0; j < S4_SLOTS; ++j) {
+			uint32_t fc = 0, len = 0;
+			if (j < 2)
+				fetch_block(fc, len);
+			s_slot[4 * j + 1] = fc;
+			s_slot[4 * j + 2] = len;
+			s_slot[4 * j + 3] = j < 2 ? 0 : S4_BLOCK_RUNS;       /* unused slots count as fully read */
+			s_slot[4 * j + 0] = j < 2 ? j + 1 : 0;
+		}
+	}
+	__syncthreads();
+	/* lane 0 only: a run is (first chunk, number of chunks); count 0 = nothing left */
+	auto grab = [&](uint32_t &start, uint32_t &count) {
 		start = 0;
 		count = 0;
 		if (lane == 0) {
-			const uint64_t u = atomicAdd(&work_counter[0], 1u);
-			if (u < n_big) {
-				start = u * S4_UNIT_CHUNKS;
-				count = S4_UNIT_CHUNKS;
-			} else {
-				const uint64_t t = tail0 + atomicAdd(&work_counter[1], 1u);
-				if (t < n_chunks) {
-					start = t;
-					count = 1;
+			const uint32_t t = atomicAdd(s_ticket, 1u);
+			const uint32_t k = t / S4_BLOCK_RUNS, r = t % S4_BLOCK_RUNS;
+			if (r == 0) {
+				/* block k + 2 goes where block k - 2 was: wait until its 32 runs have been read */
+				const uint32_t j = (k + 2) % S4_SLOTS;
+				while (s_slot[4 * j + 3] < S4_BLOCK_RUNS)
+					;
+				uint32_t fc, len;
+				fetch_block(fc, len);
+				s_slot[4 * j + 1] = fc;
+				s_slot[4 * j + 2] = len;
+				s_slot[4 * j + 3] = 0;
+				__threadfence_block();
+				s_slot[4 * j + 0] = k + 3;
+			}
+			const uint32_t j = k % S4_SLOTS;
+			while (s_slot[4 * j + 0] != k + 1)
+				;
+			__threadfence_block();
+			const uint32_t fc = s_slot[4 * j + 1], len = s_slot[4 * j + 2];
+			atomicAdd(const_cast<uint32_t *>(&s_slot[4 * j + 3]), 1u);
+			if (S4_INTERLEAVE) {
+				start = fc + r;
+				if (start < n_chunks) {
+					const uint32_t fit = (n_chunks - start + S4_BLOCK_RUNS - 1) / S4_BLOCK_RUNS;
+					count = fit < len ? fit : len;
 				}
+			} else {
+				start = fc + r * len;
+				if (start < n_chunks)
+					count = n_chunks - start < len ? n_chunks - start : len;
 			}
 		}
 	};
-	uint64_t run_start, next_start;
+	constexpr uint64_t run_step = (S4_INTERLEAVE ? S4_BLOCK_RUNS : 1) * 32ull * S4_UNROLL;   /* vectors between chunks of a run */
+	uint32_t run_start, next_start;
 	uint32_t run_count, next_count;
 	grab(run_start, run_count);
 	grab(next_start, next_count);
@@ -455,7 +515,7 @@ k_scan_sampled(const __grid_constant__ AutDev A, const __grid_constant__ EmitCtx
 	 * so prefetch depth is not what bounds the kernel; distance 1 is the default) */
 	auto prefetch_after_first = [&]() {
 		if (run_count >= 2)
-			prefetch_l2_bulk(data + (first + chunk_vecs) * 16, (uint32_t)chunk_vecs * 16);
+			prefetch_l2_bulk(data + (first + run_step) * 16, (uint32_t)chunk_vecs * 16);
 		else if (run_count == 1 && next_count)
 			prefetch_l2_bulk(data + (vec_lo + next_start * chunk_vecs) * 16, (uint32_t)chunk_vecs * 16);
 	};
@@ -513,7 +573,7 @@ k_scan_sampled(const __grid_constant__ AutDev A, const __grid_constant__ EmitCtx
 				grab(next_start, next_count);
 			first = vec_lo + run_start * chunk_vecs;
 		} else {
-			first += chunk_vecs;
+			first += run_step;
 		}
 		if (run_count && lane == 0) {
 			if (S4_PF_DIST == 2)
@@ -536,6 +596,13 @@ k_scan_sampled(const __grid_constant__ AutDev A, const __grid_constant__ EmitCtx
 				hits = __funnelshift_l(t, hits, 1);
 			}
 		}
+#ifdef S4_EXPERIMENT
+		/* roofline experiments (never shipped): 1 = loads only, 2 = loads + level-1 filter, no hit handling */
+		if (S4_EXPERIMENT == 1)
+			hits = ((v[0].x ^ v[1].x ^ v[2].x ^ v[3].x ^ v[0].z ^ v[1].z ^ v[2].z ^ v[3].z) == 0x12345678u) ? 1u : 0u;
+		else if (S4_EXPERIMENT == 2)
+			hits = (hits == 0x00a5a5a5u && v[0].x == 0x12345678u) ? 1u : 0u;
+#endif
 		/* the last chunk may stick out past vec_hi: those vectors were not loaded (zeros) and
 		 * must not be tested -- an all-zero window is a real, and popular, pattern gram */
 		if (cur_first + chunk_vecs > vec_hi) {
