@@ -704,6 +704,7 @@ build_filters(struct acm_core *c)
 			t->cand[k].at0 = w[0];
 			t->cand[k].at1 = w[1];
 			t->cand[k].len = (uint32_t)c->pats[pid].n | (lastc ? ACM_CAND_LAST : 0);
+			t->cand[k].pat_off = t->pat_off[pid];
 			{
 				const unsigned char *pe = t->pat_blob + t->pat_off[pid] + c->pats[pid].n - 4;   /* n >= 7 here */
 				t->cand[k].tail = (uint32_t)pe[0] | ((uint32_t)pe[1] << 8) | ((uint32_t)pe[2] << 16) |
@@ -714,7 +715,11 @@ build_filters(struct acm_core *c)
 				for (s = (g * ACM_HASH3_MUL) >> (32 - lg);; s = (s + 1) & (slots - 1))
 					if (t->grams[s].begin1 == 0) {
 						t->grams[s].gram = g;
+						uint32_t cnt = 1;
+						while (k + cnt < ntr && tr[k + cnt].gram == g)
+							cnt++;
 						t->grams[s].begin1 = k + 1;
+						t->grams[s].count = cnt;
 						t->gram_count++;
 						break;
 					}

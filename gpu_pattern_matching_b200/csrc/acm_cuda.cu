@@ -87,6 +87,9 @@ struct acm_scanner {
 	uint64_t  stage_bytes;
 	cudaEvent_t ev_copied[2], ev_free[2];
 	uint64_t *trace;            /* ACM_TRACE=1: per-CTA timestamps of the last K1 launch */
+	uint4    *vq;               /* sampled mode: verification queue, one region per scanning warp */
+	uint32_t *vq_count;
+	uint32_t  vq_cap;
 	uint64_t *h_keys;           /* pinned bounce buffer for results */
 	uint64_t  h_keys_cap;
 	/* a scan queued by acm_scan_device_async and not yet finished */
@@ -674,6 +677,7 @@ acm_scanner_free(struct acm_scanner *s)
 	cudaFree(s->buckets); cudaFree(s->scratch); cudaFree(s->offsets);
 	cudaFree(s->tile_state); cudaFree(s->out); cudaFree(s->tmp); cudaFree(s->hist);
 	cudaFree(s->stage[0]); cudaFree(s->stage[1]); cudaFree(s->trace);
+	cudaFree(s->vq); cudaFree(s->vq_count);
 	if (s->h_flags)
 		cudaFreeHost(s->h_flags);
 	if (s->h_keys)
@@ -848,6 +852,18 @@ acm_scanner_create(struct acm_device *dev, struct acm_automaton *aut, uint64_t m
 	SALLOC(s->out, s->out_cap * 8);
 	if (getenv("ACM_TRACE"))
 		SALLOC(s->trace, 1024 * 4 * 8);
+	if (s->p.mode == ACM_MODE_SAMPLED4) {
+		/* room for one filter survivor per KiB of input (random data with 15 000 signatures: one per
+		 * 5 KiB; the bench plants one signature per 10 KiB), at least 64 per scanning warp; beyond
+		 * that the scan kernel resolves inline */
+		const uint32_t regions = (uint32_t)dev->sm_count * (S4_THREADS / 32);
+		const uint64_t want = (max_bytes >> 10) / regions;
+		s->vq_cap = 64;
+		while (s->vq_cap < want && s->vq_cap < 4096)
+			s->vq_cap <<= 1;
+		SALLOC(s->vq, (size_t)regions * s->vq_cap * sizeof(uint4));
+		SALLOC(s->vq_count, (size_t)regions * 4);
+	}
 #undef SALLOC
 	if (cudaHostAlloc((void **)&s->h_flags, 64, cudaHostAllocDefault) != cudaSuccess) {
 		acm_set_error("scanner_create: cudaHostAlloc failed");
@@ -887,7 +903,7 @@ grow(uint64_t **buf, uint64_t *cap, uint64_t need, const char *what)
 
 static int
 launch_k1(struct acm_scanner *s, cudaStream_t st, const void *d_data, uint64_t n, const EmitCtx &E,
-    int zero_work_counter)
+    int zero_work_counter, uint32_t *launches)
 {
 	const struct acm_automaton *a = s->aut;
 	const uint64_t limit = E.emit_hi < n ? E.emit_hi : n;
@@ -900,22 +916,27 @@ launch_k1(struct acm_scanner *s, cudaStream_t st, const void *d_data, uint64_t n
 	if (limit <= E.emit_lo)
 		return ACM_OK;
 	if (s->p.mode == ACM_MODE_SAMPLED4) {
-		/* persistent: one CTA per SM, warps pull 16 KiB units from flags[4] */
+		/* persistent: one CTA per SM; CTAs pull 512 KiB blocks from flags[6], their warps 16 KiB runs
+		 * from the block; then the queued candidates are compared in full, one CTA per scanning warp */
 		const uint64_t unit = 32ull * S4_UNROLL * S4_UNIT_CHUNKS * (S4_THREADS / 32);
 		uint64_t blocks = (vec_hi - vec_lo + unit - 1) / unit;
 		if (blocks > (uint64_t)s->dev->sm_count)
 			blocks = s->dev->sm_count;
 		if (zero_work_counter)
 			CUDA_TRY(cudaMemsetAsync(s->flags + 6, 0, 8, st));
-		/* the last two chunks per resident warp are handed out singly */
+		EmitCtx Eq = E;
+		Eq.vq = s->vq;
+		Eq.vq_count = s->vq_count;
+		Eq.vq_cap = s->vq_cap;
 		if (a->d.sample_stride == 8)
-			k_scan_sampled<8><<<(unsigned)blocks, S4_THREADS, S4_SMEM_BYTES, st>>>(a->d, E,
-			    (const uint8_t *)d_data, n, vec_lo, vec_hi, limit, s->flags + 6,
-			    (uint32_t)(blocks * (S4_THREADS / 32) * 2));
+			k_scan_sampled<8><<<(unsigned)blocks, S4_THREADS, S4_SMEM_BYTES, st>>>(a->d, Eq,
+			    (const uint8_t *)d_data, n, vec_lo, vec_hi, limit, s->flags + 6);
 		else
-			k_scan_sampled<4><<<(unsigned)blocks, S4_THREADS, S4_SMEM_BYTES, st>>>(a->d, E,
-			    (const uint8_t *)d_data, n, vec_lo, vec_hi, limit, s->flags + 6,
-			    (uint32_t)(blocks * (S4_THREADS / 32) * 2));
+			k_scan_sampled<4><<<(unsigned)blocks, S4_THREADS, S4_SMEM_BYTES, st>>>(a->d, Eq,
+			    (const uint8_t *)d_data, n, vec_lo, vec_hi, limit, s->flags + 6);
+		k_resolve_queue<<<(unsigned)blocks * (S4_THREADS / 32), RQ_THREADS, 0, st>>>(a->d, Eq,
+		    (const uint8_t *)d_data, n, limit);
+		*launches += 1;
 	} else if (s->p.mode == ACM_MODE_CDFA) {
 		/* persistent: one CTA per SM holding the hot rows, threads stride over chunk pairs */
 		const uint64_t pairs = (((limit - 1) >> E.shift) - (E.emit_lo >> E.shift) + 2) / 2;
@@ -1068,7 +1089,7 @@ scan_launch(struct acm_scanner *s, cudaStream_t st, const void *d_data, uint64_t
 	CUDA_TRY(cudaMemsetAsync(s->scratch, 0, 64 + (size_t)s->n_bucket_tiles * 8 + (size_t)nb * 4, st));
 	if (timing)
 		CUDA_TRY(cudaEventRecord(s->ev[0], st));
-	if ((rc = launch_k1(s, st, d_data, n, E, 0)) != ACM_OK)
+	if ((rc = launch_k1(s, st, d_data, n, E, 0, &launches)) != ACM_OK)
 		return rc;
 	launches++;
 	if (timing)
@@ -1188,7 +1209,7 @@ scan_complete(struct acm_scanner *s, struct acm_scan_result *res)
 		E.offsets = s->offsets;
 		E.out = s->out;
 		CUDA_TRY(cudaMemsetAsync(s->counts, 0, (size_t)nb * 4, st));
-		if ((rc = launch_k1(s, st, s->pend.d_data, s->pend.n, E, 1)) != ACM_OK)
+		if ((rc = launch_k1(s, st, s->pend.d_data, s->pend.n, E, 1, &launches)) != ACM_OK)
 			return rc;
 		launches++;
 		/* a CDFA walk writes every chunk's records in order at its scanned offset: sorted already */

@@ -47,9 +47,11 @@ enum {
 #define ACM_HASH2_MUL 0x85EBCA6Bu
 #define ACM_HASH3_MUL 0xC2B2AE35u
 
-struct acm_gram_slot {     /* exact 4-gram table, open addressing in HBM/L2 */
+struct acm_gram_slot {     /* exact 4-gram table, open addressing in HBM/L2, 16 bytes */
 	uint32_t gram;         /* little-endian 4 bytes of the pattern          */
 	uint32_t begin1;       /* 1 + index of the gram's first candidate in cand[]; 0 = empty slot */
+	uint32_t count;        /* candidates of this gram (cand[begin1 - 1 ...])  */
+	uint32_t pad;
 };
 
 /*
@@ -71,7 +73,8 @@ struct acm_cand {
 	uint32_t at0, at1;     /* pattern bytes o .. o+7 */
 	uint32_t len;          /* | ACM_CAND_LAST */
 	uint32_t tail;         /* pattern bytes len-4 .. len-1 */
-	uint32_t pad[3];
+	uint32_t pat_off;      /* byte offset of the pattern in pat_blob (what the verification queue stores) */
+	uint32_t pad[2];
 };
 
 struct acm_tables {

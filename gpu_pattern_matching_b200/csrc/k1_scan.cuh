@@ -86,6 +86,9 @@ struct EmitCtx {
 	uint64_t  emit_lo, emit_hi;
 	uint64_t  valid_lo;      /* positions before this are never read nor used as walk starts */
 	uint64_t *trace;         /* optional: per CTA {t_entry, t_ready, t_exit, chunks} (globaltimer ns) */
+	uint4    *vq;            /* sampled kernel: per-warp regions of candidates awaiting the full compare */
+	uint32_t *vq_count;      /* [regions] entries written (<= vq_cap)                */
+	uint32_t  vq_cap;        /* entries per region                                   */
 	uint32_t  cap;
 	uint32_t  shift;
 	int       direct;
@@ -287,10 +290,13 @@ __device__ __forceinline__ uint4 load_vec(const uint8_t *__restrict__ data, uint
 #ifndef S4_INTERLEAVE
 #define S4_INTERLEAVE 0                  /* 1: the 32 runs of a block are interleaved chunk by chunk */
 #endif
+#ifndef S4_DBUF
+#define S4_DBUF 0                       /* 1: register double buffer for the stream loads */
+#endif
 #define S4_BLOCK_RUNS 32                 /* runs per block = warps per CTA */
 #define S4_SLOTS 4                       /* published blocks per CTA (ring) */
 #ifndef S4_PF_DIST
-#define S4_PF_DIST 1                     /* L2 prefetch distance in chunks (1 or 2) */
+#define S4_PF_DIST 1                     /* L2 prefetch distance in chunks (1 .. S4_UNIT_CHUNKS) */
 #endif
 #define S4_SMEM_BYTES ((F1_WORDS + F2_WORDS) * 4 + 16 + 16 + S4_SLOTS * 16)
 #define FULL_MASK 0xffffffffu
@@ -387,7 +393,7 @@ template <int STRIDE>
 __global__ void __launch_bounds__(S4_THREADS, 1)
 k_scan_sampled(const __grid_constant__ AutDev A, const __grid_constant__ EmitCtx E,
     const uint8_t *__restrict__ data, uint64_t n,
-    uint64_t vec_lo, uint64_t vec_hi, uint64_t limit, uint32_t *work_counter, uint32_t tail_chunks)
+    uint64_t vec_lo, uint64_t vec_hi, uint64_t limit, uint32_t *work_counter)
 {
 	extern __shared__ __align__(128) uint32_t s4_smem[];
 	uint32_t *f1 = s4_smem;
@@ -510,19 +516,18 @@ k_scan_sampled(const __grid_constant__ AutDev A, const __grid_constant__ EmitCtx
 	 */
 	uint4 v[S4_UNROLL];
 	uint64_t first = vec_lo + run_start * chunk_vecs;        /* first vector of the next chunk */
-	/* lane 0: pull the chunk AFTER `first` into L2 (S4_PF_DIST == 2 keeps two chunks in flight
-	 * per warp, 128 KiB per SM instead of 64; measured 1-2 % SLOWER on all three ClamAV sets,
-	 * so prefetch depth is not what bounds the kernel; distance 1 is the default) */
-	auto prefetch_after_first = [&]() {
-		if (run_count >= 2)
-			prefetch_l2_bulk(data + (first + run_step) * 16, (uint32_t)chunk_vecs * 16);
-		else if (run_count == 1 && next_count)
-			prefetch_l2_bulk(data + (vec_lo + next_start * chunk_vecs) * 16, (uint32_t)chunk_vecs * 16);
+	/* lane 0: pull the chunk d positions ahead in this warp's sequence into L2 (d = 1 is `first`;
+	 * run_count chunks are left in the current run, `first` included, then comes the next run) */
+	auto prefetch_ahead = [&](uint32_t d) {
+		if (d <= run_count)
+			prefetch_l2_bulk(data + (first + (d - 1) * run_step) * 16, (uint32_t)chunk_vecs * 16);
+		else if (d - 1 - run_count < next_count)
+			prefetch_l2_bulk(data + (vec_lo + next_start * chunk_vecs + (d - 1 - run_count) * run_step) * 16,
+			    (uint32_t)chunk_vecs * 16);
 	};
 	if (run_count && lane == 0) {
-		prefetch_l2_bulk(data + first * 16, (uint32_t)chunk_vecs * 16);
-		if (S4_PF_DIST == 2)
-			prefetch_after_first();
+		for (uint32_t d = 1; d <= S4_PF_DIST; ++d)
+			prefetch_ahead(d);
 	}
 	mbar_wait(bar, 0);
 	if (E.trace && threadIdx.x == 0)
@@ -534,6 +539,76 @@ k_scan_sampled(const __grid_constant__ AutDev A, const __grid_constant__ EmitCtx
 	uint64_t td_prev = globaltimer_ns(), td_max = 0, td_slow = 0, td_filter = 0;
 	uint32_t tdc_rounds = 0, tdc_pend = 0, tdc_cand = 0, tdc_verify = 0, td_info = 0;
 #endif
+	const uint32_t vq_region = blockIdx.x * (S4_THREADS / 32) + (threadIdx.x >> 5);
+	uint4 *const vq_mine = E.vq + (size_t)vq_region * E.vq_cap;
+	uint32_t vq_n = 0;
+	auto load_chunk = [&](uint4 (&d)[S4_UNROLL], uint64_t f) {
+		if (f + chunk_vecs <= vec_hi) {                  /* all but the last chunk */
+			const uint4 *p = reinterpret_cast<const uint4 *>(data) + f + lane;
+#pragma unroll
+			for (int u = 0; u < S4_UNROLL; ++u)
+				d[u] = __ldcs(p + u * 32);
+		} else {
+#pragma unroll
+			for (int u = 0; u < S4_UNROLL; ++u) {
+				const uint64_t idx = f + (uint64_t)u * 32 + lane;
+				d[u] = (idx < vec_hi) ? load_vec(data, idx) : make_uint4(0, 0, 0, 0);
+			}
+		}
+	};
+	/* `first` moves on to the chunk after the one just loaded; its successor is prefetched into L2 */
+	auto advance = [&]() {
+		if (--run_count == 0) {
+			run_start = __shfl_sync(FULL_MASK, next_start, 0);
+			run_count = __shfl_sync(FULL_MASK, next_count, 0);
+			if (run_count)
+				grab(next_start, next_count);
+			first = vec_lo + run_start * chunk_vecs;
+		} else {
+			first += run_step;
+		}
+		if (run_count && lane == 0)
+			prefetch_ahead(S4_PF_DIST);
+	};
+#if S4_DBUF
+	/* register double buffer: the loads of chunk i + 1 are in flight while chunk i is processed */
+	uint4 nv[S4_UNROLL];
+	uint64_t next_first = first;
+	bool have = run_count != 0;
+	if (have) {
+		load_chunk(nv, first);
+		advance();
+	}
+	while (have) {
+		++trace_chunks;
+#ifdef S4_TRACE_DETAIL
+		{
+			const uint64_t now = globaltimer_ns();
+			const uint64_t d = now - td_prev;
+			td_prev = now;
+			if (trace_chunks > 1) {
+				if (d > td_max) {
+					td_max = d;
+					td_info = ((td_filter / 250) > 255 ? 255 : (uint32_t)(td_filter / 250)) | (min(tdc_rounds, 63u) << 8) |
+					    (min(tdc_pend, 63u) << 14) | (min(tdc_cand, 63u) << 20) | (min(tdc_verify, 63u) << 26);
+				}
+				td_slow += d > 8000;
+			}
+			tdc_rounds = tdc_pend = tdc_cand = tdc_verify = 0;
+			td_filter = 0;
+		}
+#endif
+		const uint64_t cur_first = next_first;
+#pragma unroll
+		for (int u = 0; u < S4_UNROLL; ++u)
+			v[u] = nv[u];
+		have = run_count != 0;
+		if (have) {
+			next_first = first;
+			load_chunk(nv, first);
+			advance();
+		}
+#else
 	while (run_count) {
 		++trace_chunks;
 #ifdef S4_TRACE_DETAIL
@@ -554,33 +629,9 @@ k_scan_sampled(const __grid_constant__ AutDev A, const __grid_constant__ EmitCtx
 		}
 #endif
 		const uint64_t cur_first = first;
-		if (cur_first + chunk_vecs <= vec_hi) {          /* all but the last chunk */
-			const uint4 *p = reinterpret_cast<const uint4 *>(data) + cur_first + lane;
-#pragma unroll
-			for (int u = 0; u < S4_UNROLL; ++u)
-				v[u] = __ldcs(p + u * 32);
-		} else {
-#pragma unroll
-			for (int u = 0; u < S4_UNROLL; ++u) {
-				const uint64_t idx = cur_first + (uint64_t)u * 32 + lane;
-				v[u] = (idx < vec_hi) ? load_vec(data, idx) : make_uint4(0, 0, 0, 0);
-			}
-		}
-		if (--run_count == 0) {
-			run_start = __shfl_sync(FULL_MASK, next_start, 0);
-			run_count = __shfl_sync(FULL_MASK, next_count, 0);
-			if (run_count)
-				grab(next_start, next_count);
-			first = vec_lo + run_start * chunk_vecs;
-		} else {
-			first += run_step;
-		}
-		if (run_count && lane == 0) {
-			if (S4_PF_DIST == 2)
-				prefetch_after_first();
-			else
-				prefetch_l2_bulk(data + first * 16, (uint32_t)chunk_vecs * 16);
-		}
+		load_chunk(v, cur_first);
+		advance();
+#endif
 		uint32_t hits = 0;
 #pragma unroll
 		for (int u = 0; u < S4_UNROLL; ++u) {
@@ -651,24 +702,46 @@ k_scan_sampled(const __grid_constant__ AutDev A, const __grid_constant__ EmitCtx
 			if (tdc_rounds++ == 0)
 				td_filter = globaltimer_ns() - td_prev;
 #endif
-			uint32_t cbegin = 0;
+			uint32_t cbegin = 0, word4 = 0;
 			uint64_t e = 0;
-			if (hits) {
+			const bool has = hits != 0;
+			if (has) {
 				const uint32_t p = 31u - (uint32_t)__clz(hits);
 				hits ^= 1u << p;
 				const uint32_t q = NW - 1 - p;
 				const uint32_t u = q / WPV, k = q % WPV;
 				e = (cur_first + (uint64_t)u * 32 + lane) * 16 + (uint64_t)k * STRIDE;
 				const uint4 x = (u & 2) ? ((u & 1) ? v[3] : v[2]) : ((u & 1) ? v[1] : v[0]);
-				uint32_t word4;
 				if (STRIDE == 4)
 					word4 = (k & 2) ? ((k & 1) ? x.w : x.z) : ((k & 1) ? x.y : x.x);
 				else
 					word4 = k ? x.z : x.x;
+			}
+			/*
+			 * Deferred resolution.  What a surviving window still needs -- exact-table probe,
+			 * candidate list, bytes at the window, full compare, bucket counter -- is a chain of
+			 * five to six dependent L2 / DRAM round trips that this warp would sit through (2.3 us
+			 * of warp time per real match: 25 % of the whole kernel at one match per 10 KiB; the
+			 * stream loads of a stalled warp are not in flight).  So the window is only WRITTEN
+			 * here -- a plain store into this warp's own region, no atomic, nothing to wait for
+			 * -- and k_resolve_queue does the rest for all windows at once.  A full region falls
+			 * back to the inline path below.
+			 */
+			{
+				const uint32_t qm = __ballot_sync(FULL_MASK, has);
+				if (vq_n + (uint32_t)__popc(qm) <= E.vq_cap) {
+					if (has)
+						vq_mine[vq_n + (uint32_t)__popc(qm & lanemask_lt())] =
+						    make_uint4((uint32_t)e, (uint32_t)(e >> 32), word4, 0u);
+					vq_n += (uint32_t)__popc(qm);
+					continue;
+				}
+			}
+			if (has) {
 				/* exact table keyed by the 4 bytes at the window (L2 resident) */
 				uint32_t sl = (word4 * ACM_HASH3_MUL) >> A.gram_shift;
 				for (;;) {
-					const uint2 slot = __ldg(reinterpret_cast<const uint2 *>(A.grams) + sl);
+					const uint2 slot = __ldg(reinterpret_cast<const uint2 *>(A.grams) + 2 * (size_t)sl);
 					if (slot.y == 0)
 						break;
 					if (slot.x == word4) {
@@ -735,6 +808,8 @@ k_scan_sampled(const __grid_constant__ AutDev A, const __grid_constant__ EmitCtx
 			}
 		}
 	}
+	if (lane == 0)
+		E.vq_count[vq_region] = vq_n;
 	if (E.trace && lane == 0) {
 		atomicMax((unsigned long long *)&E.trace[blockIdx.x * 4 + 2], (unsigned long long)globaltimer_ns());
 		atomicAdd((unsigned long long *)&E.trace[blockIdx.x * 4 + 3], (unsigned long long)trace_chunks);
@@ -745,6 +820,173 @@ k_scan_sampled(const __grid_constant__ AutDev A, const __grid_constant__ EmitCtx
 			atomicAdd((unsigned long long *)&x[1], (unsigned long long)td_slow);
 		}
 #endif
+	}
+}
+
+/*
+ * Everything the filter survivors of k_scan_sampled still need, as a pipeline of CTA-wide
+ * phases so that every dependent L2 / DRAM round trip is taken once for all the windows of a
+ * region (and, over the grid, for all ~2 x 10^5 queued windows of a GiB) instead of stalling
+ * one streaming warp at a time:
+ *   1a  one lane per queued window: exact-table probe (L2) with the text bytes 4..7 after the
+ *       window fetched alongside (DRAM); a hit posts its candidates as work items;
+ *   1b  one lane per candidate: record load (L2), compare on the bytes at the window; the
+ *       survivors -- on anything but repetitive text, real occurrences -- go to a list;
+ *   2   four lanes per listed candidate: full compare (lane j takes bytes [16 j + 64 r,
+ *       16 j + 64 r + 16) in round r, all loads of a round issued together; 90 % of the ClamAV
+ *       signatures are one round, 187 bytes are three), then the record is emitted.
+ * One CTA per region (= per scanning warp).  Queue entry: {window offset lo, hi, the 4 bytes at
+ * the window, -}.
+ */
+#define RQ_THREADS 64
+#define RQ_WORK    256                      /* candidate work items per CTA round */
+#define RQ_LIST    128                      /* candidates awaiting the full compare, per CTA round */
+
+struct RqShared {
+	uint4    list[RQ_LIST];                 /* {start lo, start hi | pattern << 8, length, offset in pat_blob} */
+	uint2    work[RQ_WORK];                 /* {candidate index, source lane} */
+	uint64_t e[RQ_THREADS];                 /* per source lane: window offset */
+	uint2    t[RQ_THREADS];                 /*                  text bytes 0..3, 4..7 at the window */
+	uint32_t n_work, n_list;
+};
+
+/* one lane, whole pattern: only when the shared list is full */
+__device__ __noinline__ bool rq_compare_lane(const uint8_t *__restrict__ data, const uint8_t *__restrict__ pat,
+    uint64_t s, uint32_t len)
+{
+	for (uint32_t k = 0; k < len; ++k)
+		if (__ldg(data + s + k) != __ldg(pat + k))
+			return false;
+	return true;
+}
+
+/* phase 1b for one candidate: compare on the bytes at the window, then list it */
+__device__ __forceinline__ bool rq_candidate(const AutDev &A, const EmitCtx &E, RqShared &S,
+    const uint8_t *__restrict__ data, uint64_t limit, uint32_t ci, uint64_t e, uint32_t t0, uint32_t t1)
+{
+	const uint4 *cp = reinterpret_cast<const uint4 *>(A.cand) + 2 * (size_t)ci;
+	const uint4 c = __ldg(cp);
+	const uint4 c2 = __ldg(cp + 1);                      /* .y = offset of the pattern bytes */
+	const uint32_t o = c.x >> ACM_CAND_O_SHIFT;
+	const uint32_t len = c.w & ~ACM_CAND_LAST;
+	const uint32_t rem = len - o;                        /* pattern bytes from the window on, >= 3 */
+	const uint32_t m0 = rem >= 4 ? 0xffffffffu : 0x00ffffffu;
+	const uint32_t m1 = rem >= 8 ? 0xffffffffu : (rem <= 4 ? 0u : ((1u << (8 * (rem - 4))) - 1u));
+	const uint64_t s = e - o;
+	if (e >= o && s >= E.valid_lo && s + len <= limit && ((t0 ^ c.y) & m0) == 0 && ((t1 ^ c.z) & m1) == 0) {
+		const uint32_t pid = c.x & ACM_CAND_ID_MASK;
+		const uint32_t i = atomicAdd(&S.n_list, 1u);
+		if (i < RQ_LIST)
+			S.list[i] = make_uint4((uint32_t)s, (uint32_t)(s >> 32) | (pid << 8), len, c2.y);
+		else if (rq_compare_lane(data, A.pat_blob + c2.y, s, len))
+			emit_record(E, s + len - 1, pid);
+	}
+	return (c.w & ACM_CAND_LAST) != 0;
+}
+
+__global__ void __launch_bounds__(RQ_THREADS)
+k_resolve_queue(const __grid_constant__ AutDev A, const __grid_constant__ EmitCtx E,
+    const uint8_t *__restrict__ data, uint64_t n, uint64_t limit)
+{
+	__shared__ RqShared S;
+	const uint4 *q = E.vq + (size_t)blockIdx.x * E.vq_cap;
+	/* the first entry is fetched before the count is known (the region exists either way) */
+	uint4 ent = threadIdx.x < E.vq_cap ? q[threadIdx.x] : make_uint4(0, 0, 0, 0);
+	const uint32_t count = E.vq_count[blockIdx.x];
+
+	for (uint32_t base = 0; base < count; base += RQ_THREADS) {      /* CTA-uniform */
+		if (threadIdx.x == 0) {
+			S.n_work = 0;
+			S.n_list = 0;
+		}
+		__syncthreads();
+		/* ---- 1a: probe ---- */
+		const uint32_t slot = base + threadIdx.x;
+		if (slot < count) {
+			if (base)
+				ent = q[slot];
+			const uint64_t e = (uint64_t)ent.x | ((uint64_t)ent.y << 32);
+			const uint32_t word4 = ent.z;
+			const uint32_t t1 = (e + 4 < n) ? __ldg(reinterpret_cast<const uint32_t *>(data + e) + 1) : 0u;
+			uint32_t sl = (word4 * ACM_HASH3_MUL) >> A.gram_shift;
+			uint32_t cbegin = 0, cnt = 0;
+			for (;;) {
+				const uint4 g = __ldg(reinterpret_cast<const uint4 *>(A.grams) + sl);
+				if (g.y == 0)
+					break;
+				if (g.x == word4) {
+					cbegin = g.y;
+					cnt = g.z;
+					break;
+				}
+				sl = (sl + 1) & A.gram_mask;
+			}
+			if (cbegin) {
+				S.e[threadIdx.x] = e;
+				S.t[threadIdx.x] = make_uint2(word4, t1);
+				const uint32_t w0 = atomicAdd(&S.n_work, cnt);
+				for (uint32_t i = 0; i < cnt; ++i) {
+					if (w0 + i < RQ_WORK)
+						S.work[w0 + i] = make_uint2(cbegin - 1 + i, threadIdx.x);
+					else
+						rq_candidate(A, E, S, data, limit, cbegin - 1 + i, e, word4, t1);   /* work list full */
+				}
+			}
+		}
+		__syncthreads();
+		/* ---- 1b: candidates ---- */
+		const uint32_t nw = S.n_work < RQ_WORK ? S.n_work : RQ_WORK;
+		for (uint32_t w = threadIdx.x; w < nw; w += RQ_THREADS) {
+			const uint2 it = S.work[w];
+			const uint2 t = S.t[it.y];
+			rq_candidate(A, E, S, data, limit, it.x, S.e[it.y], t.x, t.y);
+		}
+		__syncthreads();
+		/* ---- 2: full compare, emission ---- */
+		const uint32_t m = S.n_list < RQ_LIST ? S.n_list : RQ_LIST;
+		const uint32_t j = threadIdx.x & 3;
+		for (uint32_t i0 = 0; i0 < m; i0 += RQ_THREADS / 4) {         /* CTA-uniform */
+			const uint32_t i = i0 + (threadIdx.x >> 2);
+			const bool live = i < m;
+			const uint4 c = live ? S.list[i] : make_uint4(0, 0, 0, 0);
+			const uint64_t s = (uint64_t)c.x | ((uint64_t)(c.y & 0xffu) << 32);
+			const uint32_t pid = c.y >> 8, len = c.z;
+			const uint32_t *pw = reinterpret_cast<const uint32_t *>(A.pat_blob + c.w);
+			const uint32_t *tw = reinterpret_cast<const uint32_t *>(data + (s & ~3ull));
+			const uint32_t sh = (uint32_t)(s & 3) * 8;
+			uint32_t diff = 0;
+			for (uint32_t r = 0; __any_sync(FULL_MASK, live && r < len && diff == 0); r += 64) {
+				uint32_t t0[4], t1[4], p[4];
+#pragma unroll
+				for (int w = 0; w < 4; ++w) {
+					const uint32_t k = r + 16 * j + 4 * (uint32_t)w;   /* byte offset inside the pattern */
+					t0[w] = t1[w] = p[w] = 0;
+					if (live && k < len) {
+						const uint32_t rem = len - k;
+						t0[w] = __ldg(tw + (k >> 2));
+						/* the next aligned word only when these bytes really reach into it */
+						if ((uint32_t)(s & 3) + (rem < 4 ? rem : 4u) > 4u)
+							t1[w] = __ldg(tw + (k >> 2) + 1);
+						p[w] = __ldg(pw + (k >> 2));
+					}
+				}
+#pragma unroll
+				for (int w = 0; w < 4; ++w) {
+					const uint32_t k = r + 16 * j + 4 * (uint32_t)w;
+					if (live && k < len) {
+						const uint32_t rem = len - k;
+						const uint32_t mask = rem >= 4 ? 0xffffffffu : ((1u << (8 * rem)) - 1u);
+						diff |= (__funnelshift_r(t0[w], t1[w], sh) ^ p[w]) & mask;
+					}
+				}
+				/* a mismatch anywhere in the quad ends the candidate */
+				diff |= __shfl_xor_sync(FULL_MASK, diff, 1);
+				diff |= __shfl_xor_sync(FULL_MASK, diff, 2);
+			}
+			if (live && j == 0 && diff == 0)
+				emit_record(E, s + len - 1, pid);
+		}
+		__syncthreads();
 	}
 }
 

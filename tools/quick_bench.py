@@ -85,6 +85,8 @@ if __name__ == "__main__":
         run(dev, "clamav10k", clamav_pats(10000), n, [1, 2], plants=int(100000 * per_gib), iters=iters)
     if "10k-s4" in which:
         run(dev, "clamav10k", clamav_pats(10000), n, [1], plants=int(100000 * per_gib), iters=iters)
+    if "10k-noplant" in which:
+        run(dev, "clamav10k-noplant", clamav_pats(10000), n, [1], plants=0, iters=iters)
     if "15k" in which:
         run(dev, "clamav15k", clamav_pats(15000), n, [1, 2], plants=int(100000 * per_gib), iters=iters)
     if "dfa" in which:
