@@ -290,9 +290,6 @@ __device__ __forceinline__ uint4 load_vec(const uint8_t *__restrict__ data, uint
 #ifndef S4_INTERLEAVE
 #define S4_INTERLEAVE 0                  /* 1: the 32 runs of a block are interleaved chunk by chunk */
 #endif
-#ifndef S4_DBUF
-#define S4_DBUF 0                       /* 1: register double buffer for the stream loads */
-#endif
 #define S4_BLOCK_RUNS 32                 /* runs per block = warps per CTA */
 #define S4_SLOTS 4                       /* published blocks per CTA (ring) */
 #ifndef S4_PF_DIST
@@ -570,45 +567,6 @@ k_scan_sampled(const __grid_constant__ AutDev A, const __grid_constant__ EmitCtx
 		if (run_count && lane == 0)
 			prefetch_ahead(S4_PF_DIST);
 	};
-#if S4_DBUF
-	/* register double buffer: the loads of chunk i + 1 are in flight while chunk i is processed */
-	uint4 nv[S4_UNROLL];
-	uint64_t next_first = first;
-	bool have = run_count != 0;
-	if (have) {
-		load_chunk(nv, first);
-		advance();
-	}
-	while (have) {
-		++trace_chunks;
-#ifdef S4_TRACE_DETAIL
-		{
-			const uint64_t now = globaltimer_ns();
-			const uint64_t d = now - td_prev;
-			td_prev = now;
-			if (trace_chunks > 1) {
-				if (d > td_max) {
-					td_max = d;
-					td_info = ((td_filter / 250) > 255 ? 255 : (uint32_t)(td_filter / 250)) | (min(tdc_rounds, 63u) << 8) |
-					    (min(tdc_pend, 63u) << 14) | (min(tdc_cand, 63u) << 20) | (min(tdc_verify, 63u) << 26);
-				}
-				td_slow += d > 8000;
-			}
-			tdc_rounds = tdc_pend = tdc_cand = tdc_verify = 0;
-			td_filter = 0;
-		}
-#endif
-		const uint64_t cur_first = next_first;
-#pragma unroll
-		for (int u = 0; u < S4_UNROLL; ++u)
-			v[u] = nv[u];
-		have = run_count != 0;
-		if (have) {
-			next_first = first;
-			load_chunk(nv, first);
-			advance();
-		}
-#else
 	while (run_count) {
 		++trace_chunks;
 #ifdef S4_TRACE_DETAIL
@@ -631,7 +589,6 @@ k_scan_sampled(const __grid_constant__ AutDev A, const __grid_constant__ EmitCtx
 		const uint64_t cur_first = first;
 		load_chunk(v, cur_first);
 		advance();
-#endif
 		uint32_t hits = 0;
 #pragma unroll
 		for (int u = 0; u < S4_UNROLL; ++u) {
@@ -838,9 +795,9 @@ k_scan_sampled(const __grid_constant__ AutDev A, const __grid_constant__ EmitCtx
  * One CTA per region (= per scanning warp).  Queue entry: {window offset lo, hi, the 4 bytes at
  * the window, -}.
  */
-#define RQ_THREADS 64
-#define RQ_WORK    256                      /* candidate work items per CTA round */
-#define RQ_LIST    128                      /* candidates awaiting the full compare, per CTA round */
+#define RQ_THREADS 128
+#define RQ_WORK    512                      /* candidate work items per CTA round */
+#define RQ_LIST    (2 * RQ_THREADS)         /* candidates awaiting the full compare: one batch of 1b + overflow of 1a */
 
 struct RqShared {
 	uint4    list[RQ_LIST];                 /* {start lo, start hi | pattern << 8, length, offset in pat_blob} */
@@ -850,13 +807,21 @@ struct RqShared {
 	uint32_t n_work, n_list;
 };
 
-/* one lane, whole pattern: only when the shared list is full */
+/* one lane, whole pattern: only when the shared list is full (the work list overflowed into it) */
 __device__ __noinline__ bool rq_compare_lane(const uint8_t *__restrict__ data, const uint8_t *__restrict__ pat,
     uint64_t s, uint32_t len)
 {
-	for (uint32_t k = 0; k < len; ++k)
-		if (__ldg(data + s + k) != __ldg(pat + k))
+	const uint32_t *pw = reinterpret_cast<const uint32_t *>(pat);
+	const uint32_t *tw = reinterpret_cast<const uint32_t *>(data + (s & ~3ull));
+	const uint32_t sh = (uint32_t)(s & 3) * 8;
+	for (uint32_t k = 0; k < len; k += 4) {
+		const uint32_t rem = len - k;
+		const uint32_t w0 = __ldg(tw + (k >> 2));
+		const uint32_t w1 = ((uint32_t)(s & 3) + (rem < 4 ? rem : 4u) > 4u) ? __ldg(tw + (k >> 2) + 1) : 0u;
+		const uint32_t mask = rem >= 4 ? 0xffffffffu : ((1u << (8 * rem)) - 1u);
+		if ((__funnelshift_r(w0, w1, sh) ^ __ldg(pw + (k >> 2))) & mask)
 			return false;
+	}
 	return true;
 }
 
@@ -934,57 +899,62 @@ k_resolve_queue(const __grid_constant__ AutDev A, const __grid_constant__ EmitCt
 			}
 		}
 		__syncthreads();
-		/* ---- 1b: candidates ---- */
+		/* ---- 1b + 2, one batch of RQ_THREADS candidates at a time (the list cannot overflow) ---- */
 		const uint32_t nw = S.n_work < RQ_WORK ? S.n_work : RQ_WORK;
-		for (uint32_t w = threadIdx.x; w < nw; w += RQ_THREADS) {
-			const uint2 it = S.work[w];
-			const uint2 t = S.t[it.y];
-			rq_candidate(A, E, S, data, limit, it.x, S.e[it.y], t.x, t.y);
-		}
-		__syncthreads();
-		/* ---- 2: full compare, emission ---- */
-		const uint32_t m = S.n_list < RQ_LIST ? S.n_list : RQ_LIST;
 		const uint32_t j = threadIdx.x & 3;
-		for (uint32_t i0 = 0; i0 < m; i0 += RQ_THREADS / 4) {         /* CTA-uniform */
-			const uint32_t i = i0 + (threadIdx.x >> 2);
-			const bool live = i < m;
-			const uint4 c = live ? S.list[i] : make_uint4(0, 0, 0, 0);
-			const uint64_t s = (uint64_t)c.x | ((uint64_t)(c.y & 0xffu) << 32);
-			const uint32_t pid = c.y >> 8, len = c.z;
-			const uint32_t *pw = reinterpret_cast<const uint32_t *>(A.pat_blob + c.w);
-			const uint32_t *tw = reinterpret_cast<const uint32_t *>(data + (s & ~3ull));
-			const uint32_t sh = (uint32_t)(s & 3) * 8;
-			uint32_t diff = 0;
-			for (uint32_t r = 0; __any_sync(FULL_MASK, live && r < len && diff == 0); r += 64) {
-				uint32_t t0[4], t1[4], p[4];
-#pragma unroll
-				for (int w = 0; w < 4; ++w) {
-					const uint32_t k = r + 16 * j + 4 * (uint32_t)w;   /* byte offset inside the pattern */
-					t0[w] = t1[w] = p[w] = 0;
-					if (live && k < len) {
-						const uint32_t rem = len - k;
-						t0[w] = __ldg(tw + (k >> 2));
-						/* the next aligned word only when these bytes really reach into it */
-						if ((uint32_t)(s & 3) + (rem < 4 ? rem : 4u) > 4u)
-							t1[w] = __ldg(tw + (k >> 2) + 1);
-						p[w] = __ldg(pw + (k >> 2));
-					}
-				}
-#pragma unroll
-				for (int w = 0; w < 4; ++w) {
-					const uint32_t k = r + 16 * j + 4 * (uint32_t)w;
-					if (live && k < len) {
-						const uint32_t rem = len - k;
-						const uint32_t mask = rem >= 4 ? 0xffffffffu : ((1u << (8 * rem)) - 1u);
-						diff |= (__funnelshift_r(t0[w], t1[w], sh) ^ p[w]) & mask;
-					}
-				}
-				/* a mismatch anywhere in the quad ends the candidate */
-				diff |= __shfl_xor_sync(FULL_MASK, diff, 1);
-				diff |= __shfl_xor_sync(FULL_MASK, diff, 2);
+		for (uint32_t wb = 0; wb == 0 || wb < nw; wb += RQ_THREADS) {  /* CTA-uniform */
+			if (wb + threadIdx.x < nw) {
+				const uint2 it = S.work[wb + threadIdx.x];
+				const uint2 t = S.t[it.y];
+				rq_candidate(A, E, S, data, limit, it.x, S.e[it.y], t.x, t.y);
 			}
-			if (live && j == 0 && diff == 0)
-				emit_record(E, s + len - 1, pid);
+			__syncthreads();
+			const uint32_t m = S.n_list < RQ_LIST ? S.n_list : RQ_LIST;
+			for (uint32_t i0 = 0; i0 < m; i0 += RQ_THREADS / 4) {     /* CTA-uniform */
+				const uint32_t i = i0 + (threadIdx.x >> 2);
+				const bool live = i < m;
+				const uint4 c = live ? S.list[i] : make_uint4(0, 0, 0, 0);
+				const uint64_t s = (uint64_t)c.x | ((uint64_t)(c.y & 0xffu) << 32);
+				const uint32_t pid = c.y >> 8, len = c.z;
+				const uint32_t *pw = reinterpret_cast<const uint32_t *>(A.pat_blob + c.w);
+				const uint32_t *tw = reinterpret_cast<const uint32_t *>(data + (s & ~3ull));
+				const uint32_t sh = (uint32_t)(s & 3) * 8;
+				uint32_t diff = 0;
+				for (uint32_t r = 0; __any_sync(FULL_MASK, live && r < len && diff == 0); r += 64) {
+					uint32_t t0[4], t1[4], p[4];
+#pragma unroll
+					for (int w = 0; w < 4; ++w) {
+						const uint32_t k = r + 16 * j + 4 * (uint32_t)w;   /* byte offset inside the pattern */
+						t0[w] = t1[w] = p[w] = 0;
+						if (live && k < len) {
+							const uint32_t rem = len - k;
+							t0[w] = __ldg(tw + (k >> 2));
+							/* the next aligned word only when these bytes really reach into it */
+							if ((uint32_t)(s & 3) + (rem < 4 ? rem : 4u) > 4u)
+								t1[w] = __ldg(tw + (k >> 2) + 1);
+							p[w] = __ldg(pw + (k >> 2));
+						}
+					}
+#pragma unroll
+					for (int w = 0; w < 4; ++w) {
+						const uint32_t k = r + 16 * j + 4 * (uint32_t)w;
+						if (live && k < len) {
+							const uint32_t rem = len - k;
+							const uint32_t mask = rem >= 4 ? 0xffffffffu : ((1u << (8 * rem)) - 1u);
+							diff |= (__funnelshift_r(t0[w], t1[w], sh) ^ p[w]) & mask;
+						}
+					}
+					/* a mismatch anywhere in the quad ends the candidate */
+					diff |= __shfl_xor_sync(FULL_MASK, diff, 1);
+					diff |= __shfl_xor_sync(FULL_MASK, diff, 2);
+				}
+				if (live && j == 0 && diff == 0)
+					emit_record(E, s + len - 1, pid);
+			}
+			__syncthreads();
+			if (threadIdx.x == 0)
+				S.n_list = 0;
+			__syncthreads();
 		}
 		__syncthreads();
 	}
