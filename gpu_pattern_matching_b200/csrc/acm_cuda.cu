@@ -861,6 +861,9 @@ acm_scanner_create(struct acm_device *dev, struct acm_automaton *aut, uint64_t m
 		s->vq_cap = 64;
 		while (s->vq_cap < want && s->vq_cap < 4096)
 			s->vq_cap <<= 1;
+		/* test hook: a tiny queue sends most survivors down the inline path of the scan kernel */
+		if (getenv("ACM_VQ_CAP") && atoi(getenv("ACM_VQ_CAP")) > 0)
+			s->vq_cap = (uint32_t)atoi(getenv("ACM_VQ_CAP"));
 		SALLOC(s->vq, (size_t)regions * s->vq_cap * sizeof(uint4));
 		SALLOC(s->vq_count, (size_t)regions * 4);
 	}

@@ -209,6 +209,27 @@ def test_repetitive_input_dense_hit_fallback(device):
     assert_same(off, pat, eo, ep, "repetitive sampled stride 4")
 
 
+@pytest.mark.parametrize("cap", [1, 3, 16])
+def test_resolve_queue_overflow_takes_inline_path(device, cap, monkeypatch):
+    """The sampled kernel queues its filter survivors for k_resolve_queue; when a warp's region is
+    full it resolves them inline.  A tiny queue (test hook ACM_VQ_CAP) forces that path; planted,
+    overlapping and repetitive input must give the oracle's list either way."""
+    monkeypatch.setenv("ACM_VQ_CAP", str(cap))
+    pats = clamav_pats(10000)
+    o, a = build_oracle(pats), build_product(pats)
+    n = 3 << 19
+    buf, _ = planted_stream(pats, n, seed=11, plants=3000, forced=[(0, 3), (n - len(pats[5][0]), 5)])
+    buf[300000:300000 + 20000] = np.tile(np.frombuffer(bytes.fromhex("e800005d81ed0000"), np.uint8), 2500)
+    s = np.frombuffer(pats[504][0], dtype=np.uint8)
+    for k in range(40):                                   # one signature over and over, 3 bytes apart from the next
+        buf[400000 + k * (s.size + 3):400000 + k * (s.size + 3) + s.size] = s
+    eo, ep, _, _ = o.search(buf)
+    assert eo.size >= 3000
+    for stride in (8, 4):
+        off, pat, res = gpu_scan(device, build_product(pats, stride=stride) if stride == 4 else a, buf, g.MODE_SAMPLED4)
+        assert_same(off, pat, eo, ep, f"queue cap {cap} stride {stride}")
+
+
 def test_async_scan_two_scanners_and_push(device):
     """acm_scan_device_async / acm_scan_finish with two scanners in flight and the in-step push:
     same list as the synchronous call, including when the step has to be repaired on the host
