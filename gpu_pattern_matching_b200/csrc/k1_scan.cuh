@@ -921,27 +921,25 @@ k_resolve_queue(const __grid_constant__ AutDev A, const __grid_constant__ EmitCt
 				const uint32_t sh = (uint32_t)(s & 3) * 8;
 				uint32_t diff = 0;
 				for (uint32_t r = 0; __any_sync(FULL_MASK, live && r < len && diff == 0); r += 64) {
-					uint32_t t0[4], t1[4], p[4];
+					const uint32_t k0 = r + 16 * j;                    /* this lane's 16 pattern bytes */
+					if (live && k0 < len) {
+						const uint32_t nv = len - k0 < 16u ? len - k0 : 16u;       /* valid bytes, 1..16 */
+						const uint32_t nwords = (nv + 3) >> 2;
+						/* aligned text words: one more than pattern words when the last bytes reach into it */
+						const uint32_t need = nwords + (((uint32_t)(s & 3) + (nv - 4 * (nwords - 1)) > 4u) ? 1u : 0u);
+						const uint32_t *tp = tw + (k0 >> 2), *pp = pw + (k0 >> 2);
+						uint32_t w[5], p[4];
 #pragma unroll
-					for (int w = 0; w < 4; ++w) {
-						const uint32_t k = r + 16 * j + 4 * (uint32_t)w;   /* byte offset inside the pattern */
-						t0[w] = t1[w] = p[w] = 0;
-						if (live && k < len) {
-							const uint32_t rem = len - k;
-							t0[w] = __ldg(tw + (k >> 2));
-							/* the next aligned word only when these bytes really reach into it */
-							if ((uint32_t)(s & 3) + (rem < 4 ? rem : 4u) > 4u)
-								t1[w] = __ldg(tw + (k >> 2) + 1);
-							p[w] = __ldg(pw + (k >> 2));
-						}
-					}
+						for (int i = 0; i < 5; ++i)
+							w[i] = (uint32_t)i < need ? __ldg(tp + i) : 0u;
 #pragma unroll
-					for (int w = 0; w < 4; ++w) {
-						const uint32_t k = r + 16 * j + 4 * (uint32_t)w;
-						if (live && k < len) {
-							const uint32_t rem = len - k;
-							const uint32_t mask = rem >= 4 ? 0xffffffffu : ((1u << (8 * rem)) - 1u);
-							diff |= (__funnelshift_r(t0[w], t1[w], sh) ^ p[w]) & mask;
+						for (int i = 0; i < 4; ++i)
+							p[i] = (uint32_t)i < nwords ? __ldg(pp + i) : 0u;
+#pragma unroll
+						for (int i = 0; i < 4; ++i) {
+							const uint32_t left = nv > 4u * i ? nv - 4u * i : 0u;      /* valid bytes from word i on */
+							const uint32_t mask = left >= 4 ? 0xffffffffu : ((1u << (8 * left)) - 1u);
+							diff |= (__funnelshift_r(w[i], w[i + 1], sh) ^ p[i]) & mask;
 						}
 					}
 					/* a mismatch anywhere in the quad ends the candidate */
