@@ -170,6 +170,7 @@ SIGNATURES = {
     "acsm_free": (None, [C.POINTER(AcsmStruct)]),
     "acsm_status": (C.c_int, [C.POINTER(AcsmStruct)]),
     "acsm_export_ref_table": (C.c_int, [C.POINTER(AcsmStruct)]),
+    "acsm_check_filters": (C.c_int, [C.POINTER(AcsmStruct)]),
     "acsm_device_automaton": (vp, [C.POINTER(AcsmStruct)]),
     # iacsmx.h
     "iacsm_new": (C.POINTER(IacsmStruct), []),

@@ -76,6 +76,10 @@ class Acsm:
     def num_patterns(self):
         return self._p.contents.num_patterns
 
+    def check_filters(self):
+        """Host-side self-check of the scan-filter tables: violations (0 = consistent), -1 = no filter."""
+        return self.L.acsm_check_filters(self._p)
+
     def export_ref_table(self):
         """The table in the reference's layout and numbering, int32[num_states][512]."""
         check(self.L.acsm_export_ref_table(self._p), "acsm_export_ref_table")

@@ -730,6 +730,92 @@ build_filters(struct acm_core *c)
 	return ACM_OK;
 }
 
+/*
+ * Consistency of the sampled-filter tables with the patterns (host side, no device): for every
+ * pattern and every alignment j < stride exactly one window o = j (mod stride) is indexed; its
+ * 4-byte key (all 256 completions when the pattern ends after the third byte) has its bits in
+ * both bitmaps and a slot in the exact table whose candidate list -- `count` records, the last
+ * one flagged -- holds (pattern, o) with the pattern's bytes at o, its length, its last four
+ * bytes and its offset in pat_blob.  Returns the number of violations, -1 if no filter was built.
+ */
+int
+acm_core_check_filters(const struct acm_core *c)
+{
+	const struct acm_tables *t = &c->tab;
+	const uint32_t S = (uint32_t)t->sample_stride;
+	int bad = 0;
+
+	if (!c->compiled || !t->f1 || !t->grams || S == 0)
+		return -1;
+	for (int k = 0; k < c->npats; k++) {
+		const unsigned char *p = c->pats[k].syms;
+		const uint32_t n = (uint32_t)c->pats[k].n;
+		if (n == 0)
+			continue;
+		if (memcmp(t->pat_blob + t->pat_off[k], p, n) != 0)
+			bad++;
+		for (uint32_t j = 0; j < S; j++) {
+			uint32_t found = 0;
+			for (uint32_t o = j; o + 3 <= n; o += S) {
+				const uint32_t fixed = o + 4 <= n ? 4 : 3;
+				uint32_t g = 0, hit_all = 1;
+				for (uint32_t b = 0; b < fixed; b++)
+					g |= (uint32_t)p[o + b] << (8 * b);
+				for (uint32_t b3 = 0; b3 < (fixed == 4 ? 1u : 256u) && hit_all; b3++) {
+					const uint32_t gg = fixed == 4 ? g : (g | (b3 << 24));
+					const uint32_t h1 = gg * ACM_HASH1_MUL, h2 = gg * ACM_HASH2_MUL;
+					const uint32_t w1 = t->f1[h1 >> (32 - (ACM_F1_BITS_LOG2 - 5))];
+					const uint32_t w2 = t->f2[(uint32_t)(((uint64_t)h2 * ACM_F2_WORDS) >> 32)];
+					const uint32_t m1 = (0x80000000u >> (h1 & 31)) | (0x80000000u >> ((h1 >> 12) & 31));
+					const uint32_t m2 = (0x80000000u >> (h2 & 31)) | (0x80000000u >> ((h2 >> 12) & 31)) |
+					    (0x80000000u >> ((h2 >> 6) & 31));
+					uint32_t s, in_list = 0;
+					if ((w1 & m1) != m1 || (w2 & m2) != m2) {
+						hit_all = 0;
+						break;
+					}
+					for (s = (gg * ACM_HASH3_MUL) >> (32 - __builtin_ctz(t->gram_slots));; s = (s + 1) & (t->gram_slots - 1)) {
+						if (t->grams[s].begin1 == 0 || t->grams[s].gram == gg)
+							break;
+					}
+					if (t->grams[s].begin1 == 0) {
+						hit_all = 0;
+						break;
+					}
+					for (uint32_t i = 0; i < t->grams[s].count; i++) {
+						const struct acm_cand *cd = &t->cand[t->grams[s].begin1 - 1 + i];
+						const int last = (cd->len & ACM_CAND_LAST) != 0;
+						if (last != (i + 1 == t->grams[s].count))
+							bad++;
+						if ((cd->info & ACM_CAND_ID_MASK) == (uint32_t)k && (cd->info >> ACM_CAND_O_SHIFT) == o) {
+							uint32_t w[2] = {0, 0}, tail;
+							for (uint32_t b = 0; b < 8 && o + b < n; b++)
+								w[b >> 2] |= (uint32_t)p[o + b] << (8 * (b & 3));
+							tail = (uint32_t)p[n - 4] | ((uint32_t)p[n - 3] << 8) | ((uint32_t)p[n - 2] << 16) |
+							    ((uint32_t)p[n - 1] << 24);
+							/* with a free fourth byte the record holds this completion's byte */
+							if (fixed == 3)
+								w[0] |= b3 << 24;
+							if ((cd->len & ~ACM_CAND_LAST) != n || cd->pat_off != t->pat_off[k] || cd->tail != tail ||
+							    cd->at1 != w[1] || (fixed == 4 && cd->at0 != w[0]) ||
+							    (fixed == 3 && (cd->at0 & 0x00ffffffu) != (w[0] & 0x00ffffffu)))
+								bad++;
+							in_list++;
+						}
+					}
+					if (in_list != 1)
+						hit_all = 0;
+				}
+				found += hit_all;
+			}
+			/* alignments past the end of a short pattern cannot occur (n >= stride + 2) */
+			if (found != 1)
+				bad++;
+		}
+	}
+	return bad;
+}
+
 int
 acm_core_compile(struct acm_core *c)
 {

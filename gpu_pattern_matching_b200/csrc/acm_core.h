@@ -40,6 +40,8 @@ int  acm_core_add(struct acm_core *, const void *syms, int n, int nocase,
 int  acm_core_compile(struct acm_core *);
 /* reference-layout table, reference numbering; *out is malloc'd (memalign 4096) */
 int  acm_core_export_ref(struct acm_core *, int **out);
+/* sampled-filter tables against the patterns: number of violations, -1 if no filter was built */
+int  acm_core_check_filters(const struct acm_core *);
 /* drop host tables and pattern bytes (device copy stays) */
 void acm_core_cleanup(struct acm_core *);
 void acm_core_free(struct acm_core *);

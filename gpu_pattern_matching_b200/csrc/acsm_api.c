@@ -182,6 +182,13 @@ acsm_status(acsm_t *a)
 }
 
 int
+acsm_check_filters(acsm_t *a)
+{
+	struct acm_core *c = core_of(a);
+	return c ? acm_core_check_filters(c) : ACM_ERR_ARG;
+}
+
+int
 acsm_export_ref_table(acsm_t *a)
 {
 	struct acm_core *c = core_of(a);

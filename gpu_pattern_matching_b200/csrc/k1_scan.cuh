@@ -796,6 +796,9 @@ k_scan_sampled(const __grid_constant__ AutDev A, const __grid_constant__ EmitCtx
  * the window, -}.
  */
 #define RQ_THREADS 128
+#ifndef RQ_MINB
+#define RQ_MINB 1
+#endif
 #define RQ_WORK    512                      /* candidate work items per CTA round */
 #define RQ_LIST    (2 * RQ_THREADS)         /* candidates awaiting the full compare: one batch of 1b + overflow of 1a */
 
@@ -849,7 +852,7 @@ __device__ __forceinline__ bool rq_candidate(const AutDev &A, const EmitCtx &E, 
 	return (c.w & ACM_CAND_LAST) != 0;
 }
 
-__global__ void __launch_bounds__(RQ_THREADS)
+__global__ void __launch_bounds__(RQ_THREADS, RQ_MINB)
 k_resolve_queue(const __grid_constant__ AutDev A, const __grid_constant__ EmitCtx E,
     const uint8_t *__restrict__ data, uint64_t n, uint64_t limit)
 {

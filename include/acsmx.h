@@ -125,6 +125,13 @@ int  acsm_get_min_pattern_size(acsm_t *);
  */
 int  acsm_export_ref_table(acsm_t *);
 
+/*
+ * Host-side self-check of the scan-filter tables built by acsm_compile() for byte patterns of
+ * length >= 7 (bitmaps, exact table, candidate records, pattern blob) against the patterns:
+ * number of violations (0 = consistent), -1 if this automaton has no filter.  Test support.
+ */
+int  acsm_check_filters(acsm_t *);
+
 /* device automaton handle for the native API in acm.h (NULL before upload) */
 struct acm_automaton *acsm_device_automaton(acsm_t *);
 

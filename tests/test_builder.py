@@ -134,6 +134,20 @@ def test_error_codes_instead_of_exit():
     assert not L.printable_hex_to_bytes(b"zz")
 
 
+@pytest.mark.parametrize("nsig,stride", [(2000, 8), (2000, 4), (10000, 8), (15000, 8)])
+def test_filter_tables_consistent_with_patterns(nsig, stride):
+    """For every pattern and every alignment exactly one window is indexed: its key is in both
+    bitmaps and in the exact table, whose candidate list (count field, LAST flag) holds the
+    pattern with its bytes at the window, length, tail and blob offset (acm_core_check_filters)."""
+    a = build_product(clamav_pats(nsig), upload=False, stride=stride)
+    assert a.check_filters() == 0
+
+
+def test_filter_check_reports_no_filter_for_short_patterns():
+    a = build_product(load_patterns("sentiment_categorical.pat.gz"), upload=False)
+    assert a.check_filters() == -1          # patterns shorter than 7 bytes: no sampled filter
+
+
 def test_filter_tables_cover_every_pattern():
     """Every pattern's four leading 4-grams must be present in both bitmaps: checked through the
     exported reference table indirectly by test_gpu_parity; here: builder statistics."""
