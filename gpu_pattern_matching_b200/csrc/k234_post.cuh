@@ -538,3 +538,16 @@ __global__ void k_plant(uint8_t *__restrict__ buf, uint64_t n, uint64_t buf_offs
 			buf[g - buf_offset] = src[k];
 	}
 }
+
+/* ------------------------------------------------------------------------- */
+/* status words -> mapped pinned host memory                                 */
+/* ------------------------------------------------------------------------- */
+
+__global__ void
+k_publish_flags(const uint32_t *__restrict__ flags, uint32_t *__restrict__ h_flags)
+{
+	if (threadIdx.x < 8) {
+		h_flags[threadIdx.x] = flags[threadIdx.x];
+		__threadfence_system();
+	}
+}
