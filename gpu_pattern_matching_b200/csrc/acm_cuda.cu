@@ -906,6 +906,29 @@ grow(uint64_t **buf, uint64_t *cap, uint64_t need, const char *what)
 	return ACM_OK;
 }
 
+
+/*
+ * Symbols per thread of k_scan_dfa.  The walk is latency bound, so a scan is cut into one chunk
+ * per thread the GPU can hold (6 CTAs of 256 per SM) -- but never below twice the halo (the
+ * cold-start walk every chunk repeats) or 128 symbols, and no more than 4096.
+ */
+static uint64_t
+scan_dfa_chunk(const struct acm_scanner *s, uint64_t span)
+{
+	if (s->p.dfa_chunk > 0)
+		return (uint64_t)s->p.dfa_chunk;
+	const uint64_t resident = (uint64_t)s->dev->sm_count * 1536;
+	const uint64_t halo = s->aut->max_len > 0 ? (uint64_t)(s->aut->max_len - 1) : 0;
+	uint64_t chunk = (span + resident - 1) / resident;
+	if (chunk < 2 * halo)
+		chunk = 2 * halo;
+	if (chunk < 128)
+		chunk = 128;
+	if (chunk > 4096)
+		chunk = 4096;
+	return (chunk + 15) & ~(uint64_t)15;
+}
+
 static int
 launch_k1(struct acm_scanner *s, cudaStream_t st, const void *d_data, uint64_t n, const EmitCtx &E,
     int zero_work_counter, uint32_t *launches)
@@ -971,7 +994,7 @@ launch_k1(struct acm_scanner *s, cudaStream_t st, const void *d_data, uint64_t n
 		k_scan_start2<<<(unsigned)blocks, S2_THREADS, S2_SMEM_BYTES, st>>>(a->d, E,
 		    (const uint8_t *)d_data, n, vec_lo, vec_hi, limit);
 	} else {
-		const uint64_t chunk = s->p.dfa_chunk > 0 ? (uint64_t)s->p.dfa_chunk : 4096;
+		const uint64_t chunk = scan_dfa_chunk(s, limit - E.emit_lo);
 		const uint64_t nthreads = (limit - E.emit_lo + chunk - 1) / chunk;
 		const uint64_t blocks = (nthreads + 1 + 255) / 256;
 		if (a->alpha == 256)

@@ -1054,11 +1054,42 @@ k_scan_start2(const AutDev A, const EmitCtx E, const uint8_t *__restrict__ data,
 /* plain DFA walk, one thread per chunk, leading halo                        */
 /* ------------------------------------------------------------------------- */
 
+/*
+ * One transition of reference ahomatch.cl:56-65 (AC_ushorts/ahomatch.cl:37-66 for ushort
+ * symbols): a symbol outside the alphabet sends the automaton back to the root; the full match
+ * list of the target = the own lists along the output links (acsmx.c:417-429).
+ */
+__device__ __forceinline__ void dfa_step(const AutDev &A, const EmitCtx &E, uint32_t alpha, uint32_t &state,
+    uint32_t c, uint64_t pos, uint64_t a)
+{
+	if (c >= alpha) {
+		state = 0;
+		return;
+	}
+	const uint32_t e = __ldg(&A.T[(size_t)state * alpha + c]);
+	state = e & ACM_T_MASK;
+	if ((e & ACM_T_ANY) && pos >= a) {
+		for (uint32_t v = state; v; v = __ldg(&A.olink[v]))
+			emit_own(A, E, v, pos);
+	}
+}
+
+/*
+ * One thread per chunk, cold start Lmax-1 symbols early.  The walk is a chain of
+ * dependent table reads (L1 for the root and depth-1 rows, L2 beyond), so what the kernel needs is
+ * many chains in flight: the host cuts the scan into as many chunks as the GPU holds threads
+ * (scan_dfa_chunk), and the symbols arrive 16 bytes at a time (one sector per lane per two loads)
+ * instead of one load per symbol.
+ */
 template <typename SYM>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 6)
 k_scan_dfa(const AutDev A, const EmitCtx E, const SYM *__restrict__ data, uint64_t n, uint64_t chunk,
     uint64_t nthreads, uint32_t *final_state)
 {
+	constexpr uint64_t VS = 16 / sizeof(SYM);          /* symbols per 16-byte vector */
+	constexpr uint32_t PER_WORD = 4 / sizeof(SYM);
+	constexpr uint32_t SYM_BITS = 8 * sizeof(SYM);
+	constexpr uint32_t SYM_MASK = (1u << SYM_BITS) - 1u;
 	const uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
 	const uint32_t alpha = (uint32_t)A.alpha;
 	const uint64_t limit = E.emit_hi < n ? E.emit_hi : n;
@@ -1089,23 +1120,28 @@ k_scan_dfa(const AutDev A, const EmitCtx E, const SYM *__restrict__ data, uint64
 		return;
 	const uint64_t halo = A.max_len > 0 ? (uint64_t)(A.max_len - 1) : 0;
 	uint32_t state = 0;
-	uint64_t pos0 = a > halo ? a - halo : 0;
-	if (pos0 < E.valid_lo)
-		pos0 = E.valid_lo;
-	for (uint64_t pos = pos0; pos < b; ++pos) {
-		const uint32_t c = data[pos];
-		if (c >= alpha) {
-			state = 0;
-			continue;
-		}
-		const uint32_t e = __ldg(&A.T[(size_t)state * alpha + c]);
-		state = e & ACM_T_MASK;
-		if ((e & ACM_T_ANY) && pos >= a) {
-			/* full match list = own lists along the output links */
-			for (uint32_t v = state; v; v = __ldg(&A.olink[v]))
-				emit_own(A, E, v, pos);
-		}
+	uint64_t pos = a > halo ? a - halo : 0;
+	if (pos < E.valid_lo)
+		pos = E.valid_lo;
+
+	/* head: symbol by symbol up to the next 16-byte boundary (all of it when the buffer itself
+	 * is not 16-byte aligned) */
+	uint64_t head_end = (pos + VS - 1) / VS * VS;
+	if (head_end > b || ((uintptr_t)data & 15) != 0)
+		head_end = b;
+	for (; pos < head_end; ++pos)
+		dfa_step(A, E, alpha, state, data[pos], pos, a);
+	/* body: whole vectors */
+	for (; pos + VS <= b; pos += VS) {
+		const uint4 v = __ldg(reinterpret_cast<const uint4 *>(data + pos));
+		const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+		for (uint32_t k = 0; k < (uint32_t)VS; ++k)
+			dfa_step(A, E, alpha, state, (w[k / PER_WORD] >> ((k % PER_WORD) * SYM_BITS)) & SYM_MASK,
+			    pos + k, a);
 	}
+	for (; pos < b; ++pos)
+		dfa_step(A, E, alpha, state, data[pos], pos, a);
 }
 
 /* ------------------------------------------------------------------------- */

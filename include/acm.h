@@ -95,7 +95,7 @@ struct acm_scan_params {
 	int      bucket_shift;  /* log2 bytes of input per result bucket; 0 = default (17 sampled, 15 otherwise) */
 	int      bucket_cap;    /* records per bucket before the exact 2-pass fallback; 0 = default */
 	int      timing;        /* 1: CUDA events around each kernel; 2: around the scan kernel only (ms_scan) */
-	int      dfa_chunk;     /* bytes per thread in DFA mode; 0 = default (4096)          */
+	int      dfa_chunk;     /* symbols per thread in DFA mode; 0 = sized to fill the GPU */
 	int      reserved[3];
 };
 

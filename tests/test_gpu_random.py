@@ -73,3 +73,63 @@ def test_long_patterns_and_all_byte_values(device):
     for mode in modes_for(a):
         off, pat, _ = gpu_scan(device, a, text, mode)
         assert_same(off, pat, eo, ep, f"long patterns mode {mode}")
+
+
+def _ushort_case(rng, npat, lo, hi, ntok, tokens):
+    pats = [(rng.choice(tokens, size=int(rng.integers(lo, hi + 1))).astype(np.uint16), int(rng.integers(0, 5000)))
+            for _ in range(npat)]
+    if npat >= 3:
+        pats[1] = (pats[0][0].copy(), 7)                        # duplicate
+        pats[2] = (pats[0][0][-max(1, pats[0][0].size // 2):].copy(), 8)   # proper suffix
+    text = rng.choice(np.concatenate([tokens, [2048, 0xFFFF]]).astype(np.uint16), size=ntok).astype(np.uint16)
+    for _ in range(min(60, ntok // 4)):
+        p = pats[int(rng.integers(0, npat))][0]
+        if p.size <= ntok:
+            pos = int(rng.integers(0, ntok - p.size + 1))
+            text[pos:pos + p.size] = p
+    p = pats[0][0]
+    if ntok >= p.size:
+        text[:p.size] = p
+        text[ntok - p.size:] = p
+    return pats, text
+
+
+@pytest.mark.parametrize("seed", range(6))
+def test_random_ushort_sets(device, seed):
+    """AC_ushorts path (iacsm_*, alphabet 2048): random symbol-sequence signatures over random
+    packet-size trains with out-of-alphabet separators, ragged lengths, every chunk size of the
+    walk kernel, chunk cuts on and off the 16-byte grid -- against the oracle."""
+    from oracle_lib import Oracle
+    rng = np.random.default_rng(2000 + seed)
+    tokens = [np.array([0, 1], dtype=np.uint16), np.array([0, 40, 52, 1448, 2047], dtype=np.uint16),
+              np.arange(2048, dtype=np.uint16)][seed % 3]
+    lo, hi = [(1, 5), (3, 30), (8, 64)][seed % 3]
+    for rep in range(4):
+        npat = int(rng.integers(1, 80))
+        ntok = int(rng.choice([1, 2, 7, 8, 9, 127, 128, 129, 1000, 4097, 30000]))
+        pats, text = _ushort_case(rng, npat, lo, hi, ntok, tokens)
+        m, o = g.Iacsm(), Oracle(2048)
+        for p, iid in pats:
+            m.add_pattern(p, iid)
+            o.add(p, iid)
+        m.compile()
+        o.compile()
+        m.gen_state_table(0, device.handle, None)
+        eo, ep, _, _ = o.search(text)
+        d = device.alloc(text.nbytes + 128)
+        try:
+            device.h2d(d, text)
+            for emit_lo in (0, 1, 5):                            # chunk cuts off the 16-byte grid
+                if emit_lo >= ntok and emit_lo:
+                    continue
+                keep = eo >= emit_lo
+                for chunk in (0, 16, 48, 1000):
+                    sc = g.Scanner(device, m.automaton, max(ntok, 1), dfa_chunk=chunk)
+                    res = sc.scan_device(d, ntok, emit_lo)
+                    off, pat = sc.fetch()
+                    sc.close()
+                    assert res.mode == g.MODE_DFA
+                    assert_same(off, pat, eo[keep], ep[keep], f"ushort seed {seed} rep {rep} n={ntok} "
+                                                              f"npat={npat} emit_lo={emit_lo} chunk={chunk}")
+        finally:
+            device.free(d)
