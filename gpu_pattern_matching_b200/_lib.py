@@ -128,6 +128,7 @@ SIGNATURES = {
     "acm_automaton_gram_count": (C.c_uint32, [vp]),
     "acm_automaton_cdfa_classes": (C.c_int, [vp]),
     "acm_automaton_sample_stride": (C.c_int, [vp]),
+    "acm_automaton_split_len": (C.c_int, [vp]),
     "acm_scanner_create": (C.c_int, [vp, vp, C.c_uint64, C.POINTER(ScanParams), C.POINTER(vp)]),
     "acm_scanner_free": (None, [vp]),
     "acm_scan_device": (C.c_int, [vp, vp, C.c_uint64, C.c_uint64, C.c_uint64, C.POINTER(ScanResult)]),

@@ -142,7 +142,7 @@ acm_tables_free(struct acm_tables *t)
 {
 	free(t->T); free(t->level_start); free(t->own_begin); free(t->own_pat);
 	free(t->olink); free(t->fail); free(t->pat_len); free(t->pat_iid);
-	free(t->bfs_to_ref); free(t->f1); free(t->f2); free(t->grams); free(t->b2);
+	free(t->bfs_to_ref); free(t->f1); free(t->f2); free(t->grams); free(t->b2); free(t->b2s);
 	free(t->cand); free(t->pat_blob); free(t->pat_off);
 	free(t->cd_cls); free(t->cd_tab); free(t->cd_flat_begin); free(t->cd_flat_pat);
 	free(t->cd_rec); free(t->cd_t16); free(t->cd_flat4);
@@ -512,8 +512,51 @@ build_filters(struct acm_core *c)
 		}
 	}
 
-	if (t->min_pattern_len < 7)
-		return ACM_OK;
+	/*
+	 * Mixed sets: a few patterns shorter than the sampled filter can index (7 bytes at stride
+	 * 4, 10 at stride 8) among many long ones.  Instead of giving the whole set to the 2-byte
+	 * start filter (15 x slower on signature sets), the patterns shorter than split_len are left
+	 * out of the sampled filter and found by a second pass: the start filter over b2s, the start
+	 * bitmap of the short patterns alone, walking the trie to depth split_len - 1 at most (a
+	 * node at depth d ends patterns of length d only, so that pass reports short patterns
+	 * and nothing else).  Taken when at most one pattern in eight is short; ACM_HYBRID=0 turns
+	 * it off, ACM_HYBRID=1 takes it whenever both kinds exist (tests).
+	 */
+	t->split_len = 0;
+	if (t->min_pattern_len < 7) {
+		const char *hy = getenv("ACM_HYBRID"), *force = getenv("ACM_SAMPLE_STRIDE");
+		const int forced = hy && atoi(hy) == 1;
+		uint32_t total = 0, n7 = 0, n10 = 0;
+
+		if (hy && atoi(hy) == 0)
+			return ACM_OK;
+		for (k = 0; k < (uint32_t)c->npats; k++) {
+			const uint32_t n = (uint32_t)c->pats[k].n;
+			total += n > 0;
+			n7 += n > 0 && n < 7;
+			n10 += n > 0 && n < 10;
+		}
+		if (!(force && atoi(force) == 4) && n10 < total && (forced || n10 * 8 <= total))
+			t->split_len = 10;
+		else if (n7 < total && (forced || n7 * 8 <= total))
+			t->split_len = 7;
+		else
+			return ACM_OK;
+		t->b2s = calloc(65536 / 32, 4);
+		if (!t->b2s)
+			return ACM_ERR_NOMEM;
+		for (k = 0; k < (uint32_t)c->npats; k++) {
+			const unsigned char *p = c->pats[k].syms;
+			const uint32_t n = (uint32_t)c->pats[k].n;
+			if (n == 0 || n >= (uint32_t)t->split_len)
+				continue;
+			for (unsigned b1 = (n == 1 ? 0 : p[1]); b1 < (n == 1 ? 256u : (unsigned)p[1] + 1u); b1++) {
+				const uint32_t idx = p[0] | (b1 << 8);
+				t->b2s[idx >> 5] |= 0x80000000u >> (idx & 31);
+			}
+		}
+	}
+#define IS_SHORT(n_) ((n_) == 0 || (n_) < (uint32_t)t->split_len)
 
 	/*
 	 * Sampled entry filter.  stride 4: every occurrence of a pattern >= 7 bytes contains a
@@ -530,13 +573,14 @@ build_filters(struct acm_core *c)
 	{
 		struct gtrip { uint32_t gram, cand; } *tr;
 		const char *force = getenv("ACM_SAMPLE_STRIDE");
-		const uint32_t S = (t->min_pattern_len >= 10 && !(force && atoi(force) == 4)) ? 8 : 4;
+		const uint32_t long_min = t->split_len ? (uint32_t)t->split_len : (uint32_t)t->min_pattern_len;
+		const uint32_t S = (long_min >= 10 && !(force && atoi(force) == 4)) ? 8 : 4;
 		uint64_t want, ntr_max = 0;
 		uint32_t slots = 1024, lg = 10, ntr = 0, blob = 0;
 
 		t->sample_stride = (int)S;
 		for (k = 0; k < (uint32_t)c->npats; k++) {
-			if (c->pats[k].n == 0)
+			if (IS_SHORT((uint32_t)c->pats[k].n))
 				continue;
 			for (uint32_t j = 0; j < S; j++)
 				ntr_max += (j + 4 <= (uint32_t)c->pats[k].n) ? 1 : 256;
@@ -579,7 +623,7 @@ build_filters(struct acm_core *c)
 		{
 			uint64_t first_entries = 0;
 			for (k = 0; k < (uint32_t)c->npats; k++)
-				if (c->pats[k].n)
+				if (!IS_SHORT((uint32_t)c->pats[k].n))
 					first_entries += S;
 			while (pop_slots < first_entries * 2)
 				pop_slots <<= 1;
@@ -592,7 +636,7 @@ build_filters(struct acm_core *c)
 			for (k = 0; k < (uint32_t)c->npats; k++) {
 				const unsigned char *p = c->pats[k].syms;
 				const uint32_t n = (uint32_t)c->pats[k].n;
-				for (uint32_t j = 0; n && j < S && j + 4 <= n; j++) {
+				for (uint32_t j = 0; !IS_SHORT(n) && j < S && j + 4 <= n; j++) {
 					const uint32_t g = (uint32_t)p[j] | ((uint32_t)p[j + 1] << 8) | ((uint32_t)p[j + 2] << 16) |
 					    ((uint32_t)p[j + 3] << 24);
 					for (s = (g * ACM_HASH3_MUL) & (pop_slots - 1);; s = (s + 1) & (pop_slots - 1)) {
@@ -623,6 +667,8 @@ build_filters(struct acm_core *c)
 			if (n == 0)
 				continue;
 			memcpy(t->pat_blob + t->pat_off[k], p, n);
+			if (IS_SHORT(n))
+				continue;
 			for (uint32_t j = 0; j < S; j++) {
 				uint32_t o = j, g = 0;
 				if (j + 4 <= n) {
@@ -727,6 +773,7 @@ build_filters(struct acm_core *c)
 		}
 		free(tr);
 	}
+#undef IS_SHORT
 	return ACM_OK;
 }
 
@@ -754,6 +801,15 @@ acm_core_check_filters(const struct acm_core *c)
 			continue;
 		if (memcmp(t->pat_blob + t->pat_off[k], p, n) != 0)
 			bad++;
+		if (n < (uint32_t)t->split_len) {
+			/* a short pattern: not in the sampled filter, its start is in b2s */
+			for (unsigned b1 = 0; b1 < 256; b1++) {
+				const uint32_t idx = p[0] | (b1 << 8);
+				if ((n == 1 || b1 == p[1]) && !(t->b2s[idx >> 5] & (0x80000000u >> (idx & 31))))
+					bad++;
+			}
+			continue;
+		}
 		for (uint32_t j = 0; j < S; j++) {
 			uint32_t found = 0;
 			for (uint32_t o = j; o + 3 <= n; o += S) {

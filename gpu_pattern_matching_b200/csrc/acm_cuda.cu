@@ -424,6 +424,8 @@ acm_automaton_upload(struct acm_device *dev, const struct acm_tables *t, struct 
 	UP(olink, t->olink, (size_t)t->num_states * 4);
 	if (t->b2)
 		UP(b2, t->b2, 65536 / 8);
+	if (t->b2s)
+		UP(b2s, t->b2s, 65536 / 8);
 	if (t->f1) {
 		UP(f1, t->f1, (1u << ACM_F1_BITS_LOG2) / 8);
 		UP(f2, t->f2, ACM_F2_WORDS * 4);
@@ -459,6 +461,7 @@ acm_automaton_upload(struct acm_device *dev, const struct acm_tables *t, struct 
 	a->d.alpha = t->alpha;
 	a->d.max_len = t->max_pattern_len;
 	a->d.sample_stride = t->sample_stride;
+	a->d.split_len = t->b2s ? (uint32_t)t->split_len : 0u;
 	if (rc == ACM_OK && cudaStreamSynchronize(dev->stream) != cudaSuccess) {
 		acm_set_error("automaton_upload: %s", cudaGetErrorString(cudaGetLastError()));
 		rc = ACM_ERR_CUDA;
@@ -479,6 +482,7 @@ extern "C" int acm_automaton_alphabet(const struct acm_automaton *a) { return a-
 extern "C" size_t acm_automaton_device_bytes(const struct acm_automaton *a) { return a->bytes; }
 extern "C" uint32_t acm_automaton_gram_count(const struct acm_automaton *a) { return a->gram_count; }
 extern "C" int acm_automaton_sample_stride(const struct acm_automaton *a) { return a->d.sample_stride; }
+extern "C" int acm_automaton_split_len(const struct acm_automaton *a) { return (int)a->d.split_len; }
 
 extern "C" int
 acm_automaton_default_mode(const struct acm_automaton *a)
@@ -490,6 +494,9 @@ acm_automaton_default_mode(const struct acm_automaton *a)
 	/* cdfa chunks (>= 4 x (Lmax - 1) bytes) must fit the 18-bit offset of a hit */
 	if (a->d.cd_tab && a->max_len <= (1 << (32 - ACM_CD_STATE_BITS - 2)))
 		return ACM_MODE_CDFA;
+	/* mixed set: sampled filter over the long patterns + start filter over the few short ones */
+	if (a->d.f1 && a->d.split_len)
+		return ACM_MODE_SAMPLED4;
 	return ACM_MODE_START2;
 }
 
@@ -756,7 +763,7 @@ acm_scanner_create(struct acm_device *dev, struct acm_automaton *aut, uint64_t m
 		free(s);
 		return ACM_ERR_ARG;
 	}
-	if (mode == ACM_MODE_SAMPLED4 && (!aut->d.f1 || aut->min_len < 7)) {
+	if (mode == ACM_MODE_SAMPLED4 && (!aut->d.f1 || (aut->min_len < 7 && !aut->d.split_len))) {
 		acm_set_error("scanner_create: sampled mode needs every pattern >= 7 bytes (shortest is %d)",
 		    aut->min_len);
 		free(s);
@@ -965,6 +972,20 @@ launch_k1(struct acm_scanner *s, cudaStream_t st, const void *d_data, uint64_t n
 		k_resolve_queue<<<(unsigned)blocks * (S4_THREADS / 32), RQ_THREADS, 0, st>>>(a->d, Eq,
 		    (const uint8_t *)d_data, n, limit);
 		*launches += 1;
+		if (a->d.split_len) {
+			/* mixed set: the patterns shorter than split_len, second pass into the same buckets */
+			const uint64_t lead = (uint64_t)a->d.split_len - 2;      /* longest short pattern - 1 */
+			uint64_t lo2 = E.emit_lo > lead ? E.emit_lo - lead : 0;
+			if (lo2 < E.valid_lo)
+				lo2 = E.valid_lo;
+			const uint64_t tile = (uint64_t)S2_THREADS * S2_UNROLL, v2 = lo2 >> 4;
+			uint64_t b2 = (vec_hi - v2 + tile - 1) / tile;
+			if (b2 > (uint64_t)s->dev->sm_count * 2)
+				b2 = (uint64_t)s->dev->sm_count * 2;
+			k_scan_start2<<<(unsigned)b2, S2_THREADS, S2_SMEM_BYTES, st>>>(a->d, E, (const uint8_t *)d_data,
+			    n, v2, vec_hi, limit, a->d.b2s, a->d.split_len - 1);
+			*launches += 1;
+		}
 	} else if (s->p.mode == ACM_MODE_CDFA) {
 		/* persistent: one CTA per SM holding the hot rows, threads stride over chunk pairs */
 		const uint64_t pairs = (((limit - 1) >> E.shift) - (E.emit_lo >> E.shift) + 2) / 2;
@@ -992,7 +1013,7 @@ launch_k1(struct acm_scanner *s, cudaStream_t st, const void *d_data, uint64_t n
 		if (blocks > (uint64_t)s->dev->sm_count * 2)
 			blocks = (uint64_t)s->dev->sm_count * 2;
 		k_scan_start2<<<(unsigned)blocks, S2_THREADS, S2_SMEM_BYTES, st>>>(a->d, E,
-		    (const uint8_t *)d_data, n, vec_lo, vec_hi, limit);
+		    (const uint8_t *)d_data, n, vec_lo, vec_hi, limit, a->d.b2, 0xFFFFFFFFu);
 	} else {
 		const uint64_t chunk = scan_dfa_chunk(s, limit - E.emit_lo);
 		const uint64_t nthreads = (limit - E.emit_lo + chunk - 1) / chunk;

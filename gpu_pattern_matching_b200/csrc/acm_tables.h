@@ -109,6 +109,8 @@ struct acm_tables {
 	uint32_t  pat_blob_bytes;
 	uint32_t *pat_off;           /* [num_patterns] byte offset into pat_blob      */
 	uint32_t *b2;                /* 2^16-bit exact start bitmap: bit (b0 | b1<<8) */
+	int       split_len;         /* > 0: patterns shorter than this are not in the sampled filter (mixed sets) */
+	uint32_t *b2s;               /* start bitmap of those short patterns alone; NULL when split_len == 0 */
 
 	/* --- byte alphabet, <= 2^14 states, <= 63 distinct pattern bytes: class-compressed DFA --- */
 	uint32_t  cd_classes;        /* C = columns per row; column C-1 = "a byte that occurs in no pattern"; 0 = not built */

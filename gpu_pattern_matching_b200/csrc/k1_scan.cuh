@@ -57,6 +57,8 @@ struct AutDev {
 	const uint32_t *pat_off;
 	const uint32_t *pat_len;
 	const uint32_t *b2;
+	const uint32_t *b2s;        /* start bitmap of the patterns shorter than split_len (mixed sets) */
+	uint32_t split_len;         /* 0: every pattern is in the sampled filter */
 	const uint16_t *cd_tab;        /* class-compressed DFA (k_scan_cdfa), NULL if not built */
 	const uint8_t  *cd_cls;
 	const uint32_t *cd_flat_begin;
@@ -236,11 +238,11 @@ __device__ __forceinline__ void flush_queue(const WarpQueue &Q, const EmitCtx &E
  */
 template <bool STAGED>
 __device__ __forceinline__ void walk_from_t(const AutDev &A, const EmitCtx &E, const WarpQueue &Q,
-    const uint8_t *__restrict__ data, uint64_t s, uint64_t limit)
+    const uint8_t *__restrict__ data, uint64_t s, uint64_t limit, uint32_t max_depth)
 {
 	uint32_t state = 0;
 	uint32_t d = 0;
-	for (uint64_t pos = s; pos < limit; ++pos) {
+	for (uint64_t pos = s; pos < limit && d < max_depth; ++pos) {
 		const uint32_t e = __ldg(&A.T[(size_t)state * 256 + __ldg(&data[pos])]);
 		const uint32_t nx = e & ACM_T_MASK;
 		if (nx < __ldg(&A.level_start[d + 1]))
@@ -264,7 +266,7 @@ __device__ __noinline__ void walk_from(const AutDev A, const EmitCtx E, const ui
     uint64_t s, uint64_t limit)
 {
 	WarpQueue none = {nullptr, nullptr};
-	walk_from_t<false>(A, E, none, data, s, limit);
+	walk_from_t<false>(A, E, none, data, s, limit, 0xFFFFFFFFu);
 }
 
 /*
@@ -367,7 +369,8 @@ __device__ __noinline__ void s4_chunk_dfa(const AutDev *__restrict__ Ap, const E
 				for (uint32_t k = b; k < t; ++k) {
 					const uint32_t pid = __ldg(&A.own_pat[k]);
 					const uint64_t len = __ldg(&A.pat_len[pid]);
-					if (pos + 1 >= len + s_min && pos + 1 - len <= s_max)
+					/* mixed sets: the short patterns belong to the start-filter pass */
+					if (pos + 1 >= len + s_min && pos + 1 - len <= s_max && len >= A.split_len)
 						emit_record(E, pos, pid);
 				}
 			}
@@ -971,7 +974,8 @@ k_resolve_queue(const __grid_constant__ AutDev A, const __grid_constant__ EmitCt
 
 __global__ void __launch_bounds__(S2_THREADS, 2)
 k_scan_start2(const AutDev A, const EmitCtx E, const uint8_t *__restrict__ data, uint64_t n,
-    uint64_t vec_lo, uint64_t vec_hi, uint64_t limit)
+    uint64_t vec_lo, uint64_t vec_hi, uint64_t limit, const uint32_t *__restrict__ start_bitmap,
+    uint32_t max_depth)
 {
 	extern __shared__ __align__(128) uint32_t s2_smem[];
 	uint32_t *b2 = s2_smem;
@@ -989,7 +993,7 @@ k_scan_start2(const AutDev A, const EmitCtx E, const uint8_t *__restrict__ data,
 	if (threadIdx.x == 0) {
 		mbar_init(bar, 1);
 		mbar_expect_tx(bar, 8192);
-		bulk_g2s(b2, A.b2, 8192, bar);
+		bulk_g2s(b2, start_bitmap, 8192, bar);
 	}
 	__syncthreads();
 	mbar_wait(bar, 0);
@@ -1039,7 +1043,7 @@ k_scan_start2(const AutDev A, const EmitCtx E, const uint8_t *__restrict__ data,
 					hits &= ~(1u << p);
 					const uint64_t s = idx * 16 + (uint64_t)(15 - p);
 					if (s >= E.valid_lo && s < limit)
-						walk_from_t<true>(A, E, Q, data, s, limit);
+						walk_from_t<true>(A, E, Q, data, s, limit, max_depth);
 				}
 				__syncwarp();
 				if (*Q.count >= WQ_FLUSH)

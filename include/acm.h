@@ -88,6 +88,11 @@ int      acm_automaton_cdfa_classes(const struct acm_automaton *);
 /* window stride of the sampled kernel for this automaton: 8 (every pattern >= 10 bytes), 4 (>= 7), 0 (not available).
  * ACM_SAMPLE_STRIDE=4 in the environment at compile (acsm_compile) time forces 4. */
 int      acm_automaton_sample_stride(const struct acm_automaton *);
+/* mixed sets (a few patterns shorter than 7 bytes among many long ones; at most one in eight, or
+ * ACM_HYBRID=1 at compile time): the patterns shorter than this many bytes are left out of the
+ * sampled filter and found by a second pass of the 2-byte start filter into the same result
+ * buckets; mode 1 then means both passes.  0 = not a split automaton.  ACM_HYBRID=0 disables. */
+int      acm_automaton_split_len(const struct acm_automaton *);
 
 /* ---- scan ---- */
 struct acm_scan_params {

@@ -72,8 +72,8 @@ def planted_stream(pats, nbytes, seed, plants, forced=()):
 
 def modes_for(acsm):
     m = [g.MODE_START2, g.MODE_DFA]
-    if acsm.get_min_pattern_size() >= 7:
-        m.insert(0, g.MODE_SAMPLED4)
+    if acsm.get_min_pattern_size() >= 7 or (acsm.automaton and g.lib().acm_automaton_split_len(acsm.automaton) > 0):
+        m.insert(0, g.MODE_SAMPLED4)             # mixed sets: sampled + start-filter pass
     if acsm.automaton and g.lib().acm_automaton_cdfa_classes(acsm.automaton) > 0:
         m.append(g.MODE_CDFA)
     return m

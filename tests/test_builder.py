@@ -148,6 +148,21 @@ def test_filter_check_reports_no_filter_for_short_patterns():
     assert a.check_filters() == -1          # patterns shorter than 7 bytes: no sampled filter
 
 
+def test_filter_tables_of_mixed_sets_leave_out_the_short_patterns(monkeypatch):
+    """A few patterns under 7 bytes among many long ones: the sampled filter is still built, over
+    the long patterns only (stride 8 when at most 1/8 of the set is under 10 bytes, else stride
+    4 with the split at 7); the short ones must be in the short-start bitmap."""
+    short = [(b"a", 9001), (b"MZ", 9002), (b"\x00\x01\x02", 9003), (b"virus!", 9004)]
+    a = build_product(clamav_pats(2000) + short, upload=False)
+    assert a.get_min_pattern_size() == 1 and a.check_filters() == 0
+    mid = [(bytes([200 + i, 7, 7, 7, 7, 7, 7, i]), 9100 + i) for i in range(40)]   # 8 bytes: under 10
+    a = build_product(clamav_pats(2000)[:200] + short + mid, upload=False)          # 44 of 244 under 10
+    assert a.check_filters() == 0
+    monkeypatch.setenv("ACM_HYBRID", "0")
+    a = build_product(clamav_pats(2000) + short, upload=False)
+    assert a.check_filters() == -1          # switched off: no sampled filter for this set
+
+
 def test_filter_tables_cover_every_pattern():
     """Every pattern's four leading 4-grams must be present in both bitmaps: checked through the
     exported reference table indirectly by test_gpu_parity; here: builder statistics."""

@@ -347,3 +347,64 @@ def test_cdfa_windows_shapes_and_class_maps(device):
         off, pat, res = gpu_scan(device, a, text, g.MODE_CDFA, bucket_shift=10, bucket_cap=32)
         assert res.fallback == 1
         assert_same(off, pat, eo, ep, f"cdfa {form} overflow")
+
+
+def _split_len(a):
+    return g.lib().acm_automaton_split_len(a.automaton)
+
+
+def test_mixed_set_sampled_plus_short_pass(device):
+    """ClamAV signatures plus a few patterns of 1..9 bytes: mode auto stays on the sampled filter
+    (long patterns) and adds the start-filter pass for the short ones; same list as the oracle,
+    and as the other kernels, also with tiny buckets (overflow -> exact two-pass path)."""
+    base = clamav_pats(2000)
+    short = [(b"\x00", 9000), (b"MZ", 9001), (b"\x90\x90\x90", 9002), (b"PE\x00\x00", 9003),
+             (b"virus", 9004), (b"abcdef", 9005), (b"\xe8\x00\x00\x00\x00\x5d\x81", 9006),
+             (base[5][0][:9], 9007), (base[5][0][-6:], 9008), (base[7][0][3:8], 9009)]
+    pats = base + short
+    o, a = build_oracle(pats), build_product(pats)
+    assert _split_len(a) == 10 and sample_stride(a) == 8
+    assert g.lib().acm_automaton_default_mode(a.automaton) == g.MODE_SAMPLED4
+    buf, _ = planted_stream(pats, 3 << 20, seed=21, plants=600)
+    buf[:2] = np.frombuffer(b"MZ", dtype=np.uint8)
+    buf[-5:] = np.frombuffer(b"virus", dtype=np.uint8)
+    eo, ep, _, _ = o.search(buf)
+    assert (ep >= 2000).sum() > 1000 and (ep < 2000).sum() > 300
+    for mode in [0] + modes_for(a):
+        off, pat, res = gpu_scan(device, a, buf, mode)
+        assert_same(off, pat, eo, ep, f"mixed set mode {mode}")
+    off, pat, res = gpu_scan(device, a, buf, 0, bucket_shift=10, bucket_cap=4)
+    assert res.mode == g.MODE_SAMPLED4 and res.fallback
+    assert_same(off, pat, eo, ep, "mixed set, overflow fallback")
+    # shard windows: the short pass has its own (shorter) lead-in
+    for lo, hi in ((1, 2), (4096, 70001), ((1 << 20) + 3, 3 << 20)):
+        keep = (eo >= lo) & (eo < hi)
+        off, pat, _ = gpu_scan(device, a, buf, 0, emit_lo=lo, emit_hi=hi)
+        assert_same(off, pat, eo[keep], ep[keep], f"mixed set window [{lo}, {hi})")
+    # split at 7 / stride 4 when many patterns are under 10 bytes
+    mid = [(bytes([200 + i, 7, 7, 7, 7, 7, 7, i]), 9100 + i) for i in range(40)]
+    pats2 = base[:200] + short[:6] + mid
+    o2, a2 = build_oracle(pats2), build_product(pats2)
+    assert _split_len(a2) == 7 and sample_stride(a2) == 4
+    buf2, _ = planted_stream(pats2, 1 << 20, seed=22, plants=500)
+    eo2, ep2, _, _ = o2.search(buf2)
+    for mode in [0] + modes_for(a2):
+        off, pat, _ = gpu_scan(device, a2, buf2, mode)
+        assert_same(off, pat, eo2, ep2, f"mixed set (split 7) mode {mode}")
+
+
+def test_mixed_set_on_repetitive_input(device):
+    """Dense chunks of a mixed set go through the in-kernel DFA fallback, which must leave the
+    short patterns to the start-filter pass (no duplicates)."""
+    base = clamav_pats(2000)
+    pats = base + [(b"\x00", 9000), (b"\x00\x00\x00", 9001), (b"ab", 9002), (bytes(12), 9003)]
+    o, a = build_oracle(pats), build_product(pats)
+    assert _split_len(a) == 10
+    buf = np.zeros(1 << 18, dtype=np.uint8)
+    buf[100000:100000 + 4000] = np.frombuffer(b"ab" * 2000, dtype=np.uint8)
+    sig = np.frombuffer(base[3][0], dtype=np.uint8)
+    buf[50000:50000 + sig.size] = sig
+    eo, ep, _, _ = o.search(buf)
+    off, pat, res = gpu_scan(device, a, buf, 0)
+    assert res.mode == g.MODE_SAMPLED4
+    assert_same(off, pat, eo, ep, "mixed set on zero pages")

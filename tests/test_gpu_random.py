@@ -95,6 +95,35 @@ def _ushort_case(rng, npat, lo, hi, ntok, tokens):
 
 
 @pytest.mark.parametrize("seed", range(6))
+def test_random_mixed_sets_forced_hybrid(device, seed, monkeypatch):
+    """ACM_HYBRID=1: every set that has both a pattern under the split and one at or above it is
+    scanned as sampled filter (long) + start filter (short), whatever the proportions."""
+    monkeypatch.setenv("ACM_HYBRID", "1")
+    rng = np.random.default_rng(3000 + seed)
+    alphabet = [np.array([97, 98], dtype=np.uint8), np.array([0, 1, 255], dtype=np.uint8),
+                np.arange(256, dtype=np.uint8)][seed % 3]
+    hybrids = 0
+    for rep in range(6):
+        npat = int(rng.integers(2, 60))
+        nbytes = int(rng.choice([1, 9, 16, 17, 64, 200, 1000, 4097, 20000]))
+        pats, text = _case(rng, alphabet, npat, 1, 24, nbytes)
+        o, a = build_oracle(pats), build_product(pats)
+        eo, ep, _, _ = o.search(text)
+        split = g.lib().acm_automaton_split_len(a.automaton)
+        hybrids += split > 0
+        variants = [(a, m) for m in [0] + modes_for(a)]
+        if split == 10:
+            a4 = build_product(pats, stride=4)
+            if g.lib().acm_automaton_split_len(a4.automaton) == 7:
+                variants.append((a4, g.MODE_SAMPLED4))
+        for aut, mode in variants:
+            for kw in ({}, {"bucket_shift": 8, "bucket_cap": 32}):
+                off, pat, res = gpu_scan(device, aut, text, mode, **kw)
+                assert_same(off, pat, eo, ep, f"hybrid seed {seed} rep {rep} mode {mode} {kw} n={nbytes} npat={npat}")
+    assert hybrids >= 3
+
+
+@pytest.mark.parametrize("seed", range(6))
 def test_random_ushort_sets(device, seed):
     """AC_ushorts path (iacsm_*, alphabet 2048): random symbol-sequence signatures over random
     packet-size trains with out-of-alphabet separators, ragged lengths, every chunk size of the

@@ -87,6 +87,11 @@ if __name__ == "__main__":
         run(dev, "clamav10k", clamav_pats(10000), n, [1], plants=int(100000 * per_gib), iters=iters)
     if "10k-noplant" in which:
         run(dev, "clamav10k-noplant", clamav_pats(10000), n, [1], plants=0, iters=iters)
+    if "10k-mixed" in which:
+        # a mixed set: ClamAV 10k plus a few short patterns -> sampled filter + start-filter pass (mode 1)
+        short = [(b"MZ", 20000), (b"\x7fEL", 20001), (b"PE\x00\x00", 20002), (b"%PDF-", 20003), (b"virus!", 20004),
+                 (b"\xe8\x00\x00\x00\x00\x5d\x81", 20005), (b"\x90\x90\x90\x90\x90\x90\x90\x90\x90", 20006)]
+        run(dev, "clamav10k+7short", clamav_pats(10000) + short, n, [1, 2], plants=int(100000 * per_gib), iters=iters)
     if "15k" in which:
         run(dev, "clamav15k", clamav_pats(15000), n, [1, 2], plants=int(100000 * per_gib), iters=iters)
     if "dfa" in which:
