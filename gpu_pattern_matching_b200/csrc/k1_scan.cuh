@@ -969,7 +969,12 @@ k_resolve_queue(const __grid_constant__ AutDev A, const __grid_constant__ EmitCt
 /* ------------------------------------------------------------------------- */
 
 #define S2_THREADS 512
-#define S2_UNROLL  2
+#ifndef S2_UNROLL
+#define S2_UNROLL  4
+#endif
+#ifndef S2_PREFETCH
+#define S2_PREFETCH 1              /* pull the CTA's next tile into L2 while this one is processed */
+#endif
 #define S2_SMEM_BYTES (65536 / 8 + 16 + (S2_THREADS / 32) * (WQ_CAP * 8 + 16))
 
 __global__ void __launch_bounds__(S2_THREADS, 2)
@@ -1003,12 +1008,28 @@ k_scan_start2(const AutDev A, const EmitCtx E, const uint8_t *__restrict__ data,
 
 	for (uint64_t first = vec_lo + (uint64_t)blockIdx.x * tile_vecs; first < vec_hi;
 	     first += (uint64_t)gridDim.x * tile_vecs) {
+		/* all loads of the tile first: S2_UNROLL x 16 bytes in flight per thread */
+		uint4 vv[S2_UNROLL];
+#pragma unroll
+		for (int u = 0; u < S2_UNROLL; ++u) {
+			const uint64_t idx = first + (uint64_t)u * S2_THREADS + threadIdx.x;
+			vv[u] = idx < vec_hi ? load_vec(data, idx) : make_uint4(0, 0, 0, 0);
+		}
+#if S2_PREFETCH
+		if (lane < S2_UNROLL) {
+			/* lane u: the 512 bytes this warp reads as part u of the CTA's next tile */
+			const uint64_t nidx = first + (uint64_t)gridDim.x * tile_vecs + (uint64_t)lane * S2_THREADS +
+			    (threadIdx.x & ~31u);
+			if ((nidx + 32) * 16 <= n)
+				prefetch_l2_bulk(data + nidx * 16, 512);
+		}
+#endif
 #pragma unroll
 		for (int u = 0; u < S2_UNROLL; ++u) {
 			const uint64_t idx = first + (uint64_t)u * S2_THREADS + threadIdx.x;
 			/* whole warps fall off the end together except in the last tile */
 			const bool live = idx < vec_hi;
-			uint4 v = live ? load_vec(data, idx) : make_uint4(0, 0, 0, 0);
+			const uint4 v = vv[u];
 			/* first word of the next vector: the neighbour lane has it */
 			uint32_t nxt = __shfl_down_sync(0xffffffffu, v.x, 1);
 			if (lane == 31) {
