@@ -142,7 +142,7 @@ acm_tables_free(struct acm_tables *t)
 {
 	free(t->T); free(t->level_start); free(t->own_begin); free(t->own_pat);
 	free(t->olink); free(t->fail); free(t->pat_len); free(t->pat_iid);
-	free(t->bfs_to_ref); free(t->f1); free(t->f2); free(t->grams); free(t->b2); free(t->b2s);
+	free(t->bfs_to_ref); free(t->f1); free(t->f2); free(t->grams); free(t->b2); free(t->b2s); free(t->b3);
 	free(t->cand); free(t->pat_blob); free(t->pat_off);
 	free(t->cd_cls); free(t->cd_tab); free(t->cd_flat_begin); free(t->cd_flat_pat);
 	free(t->cd_rec); free(t->cd_t16); free(t->cd_flat4);
@@ -163,6 +163,10 @@ acm_tables_device_bytes(const struct acm_tables *t)
 		    ((size_t)t->cand_count + ACM_CAND_PAD) * sizeof(struct acm_cand) +
 		    t->pat_blob_bytes + (size_t)t->num_patterns * 4;
 	if (t->b2)
+		b += 65536 / 8;
+	if (t->b3)
+		b += ACM_B3_WORDS * 4;
+	if (t->b2s)
 		b += 65536 / 8;
 	if (t->cd_tab)
 		b += (size_t)t->num_states * t->cd_classes * 2 + 256 + (size_t)(t->num_states + 1) * 4 +
@@ -477,6 +481,33 @@ out:
 	return rc;
 }
 
+/* first-three-bytes Bloom bitmap (k_scan_start2<false>): three bits per key in one 32-bit word;
+ * a pattern of one or two bytes enters every completion */
+static uint32_t *
+build_b3(const struct acm_core *c)
+{
+	uint32_t *b3 = calloc(ACM_B3_WORDS, 4);
+
+	if (!b3)
+		return NULL;
+	for (int k = 0; k < c->npats; k++) {
+		const unsigned char *p = c->pats[k].syms;
+		const uint32_t n = (uint32_t)c->pats[k].n;
+		if (n == 0)
+			continue;
+		const uint32_t fixed = n < 3 ? n : 3;
+		uint32_t g0 = 0;
+		for (uint32_t b = 0; b < fixed; b++)
+			g0 |= (uint32_t)p[b] << (8 * b);
+		for (uint32_t rest = 0; rest < (1u << (8 * (3 - fixed))); rest++) {
+			const uint32_t g = g0 | (rest << (8 * fixed));
+			const uint32_t h = g * ACM_HASH2_MUL;
+			b3[h >> 18] |= (1u << (h & 31)) | (1u << ((h >> 5) & 31)) | (1u << ((h >> 10) & 31));
+		}
+	}
+	return b3;
+}
+
 static int
 build_filters(struct acm_core *c)
 {
@@ -511,6 +542,10 @@ build_filters(struct acm_core *c)
 			}
 		}
 	}
+
+	t->b3 = build_b3(c);
+	if (!t->b3)
+		return ACM_ERR_NOMEM;
 
 	/*
 	 * Mixed sets: a few patterns shorter than the sampled filter can index (7 bytes at stride

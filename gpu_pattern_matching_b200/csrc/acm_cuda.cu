@@ -133,8 +133,10 @@ set_kernel_attrs(int ordinal)
 	    S4_SMEM_BYTES));
 	CUDA_TRY(cudaFuncSetAttribute(k_scan_sampled<8>, cudaFuncAttributeMaxDynamicSharedMemorySize,
 	    S4_SMEM_BYTES));
-	CUDA_TRY(cudaFuncSetAttribute(k_scan_start2, cudaFuncAttributeMaxDynamicSharedMemorySize,
-	    S2_SMEM_BYTES));
+	CUDA_TRY(cudaFuncSetAttribute(k_scan_start2<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+	    S2_SMEM_BYTES(0)));
+	CUDA_TRY(cudaFuncSetAttribute(k_scan_start2<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+	    S2_SMEM_BYTES(1)));
 	CUDA_TRY(cudaFuncSetAttribute(k_bucket_sort_compact, cudaFuncAttributeMaxDynamicSharedMemorySize,
 	    65536));
 	CUDA_TRY(cudaFuncSetAttribute(k_scan_cdfa<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -426,6 +428,8 @@ acm_automaton_upload(struct acm_device *dev, const struct acm_tables *t, struct 
 		UP(b2, t->b2, 65536 / 8);
 	if (t->b2s)
 		UP(b2s, t->b2s, 65536 / 8);
+	if (t->b3)
+		UP(b3, t->b3, ACM_B3_WORDS * 4);
 	if (t->f1) {
 		UP(f1, t->f1, (1u << ACM_F1_BITS_LOG2) / 8);
 		UP(f2, t->f2, ACM_F2_WORDS * 4);
@@ -982,8 +986,8 @@ launch_k1(struct acm_scanner *s, cudaStream_t st, const void *d_data, uint64_t n
 			uint64_t b2 = (vec_hi - v2 + tile - 1) / tile;
 			if (b2 > (uint64_t)s->dev->sm_count * 2)
 				b2 = (uint64_t)s->dev->sm_count * 2;
-			k_scan_start2<<<(unsigned)b2, S2_THREADS, S2_SMEM_BYTES, st>>>(a->d, E, (const uint8_t *)d_data,
-			    n, v2, vec_hi, limit, a->d.b2s, a->d.split_len - 1);
+			k_scan_start2<true><<<(unsigned)b2, S2_THREADS, S2_SMEM_BYTES(1), st>>>(a->d, E,
+			    (const uint8_t *)d_data, n, v2, vec_hi, limit, a->d.b2s, a->d.split_len - 1);
 			*launches += 1;
 		}
 	} else if (s->p.mode == ACM_MODE_CDFA) {
@@ -1012,8 +1016,8 @@ launch_k1(struct acm_scanner *s, cudaStream_t st, const void *d_data, uint64_t n
 		uint64_t blocks = (vec_hi - vec_lo + tile - 1) / tile;
 		if (blocks > (uint64_t)s->dev->sm_count * 2)
 			blocks = (uint64_t)s->dev->sm_count * 2;
-		k_scan_start2<<<(unsigned)blocks, S2_THREADS, S2_SMEM_BYTES, st>>>(a->d, E,
-		    (const uint8_t *)d_data, n, vec_lo, vec_hi, limit, a->d.b2, 0xFFFFFFFFu);
+		k_scan_start2<false><<<(unsigned)blocks, S2_THREADS, S2_SMEM_BYTES(0), st>>>(a->d, E,
+		    (const uint8_t *)d_data, n, vec_lo, vec_hi, limit, a->d.b3, 0xFFFFFFFFu);
 	} else {
 		const uint64_t chunk = scan_dfa_chunk(s, limit - E.emit_lo);
 		const uint64_t nthreads = (limit - E.emit_lo + chunk - 1) / chunk;

@@ -43,6 +43,7 @@ enum {
 
 #define ACM_F1_BITS_LOG2   20              /* level-1 gram bitmap: 128 KiB smem */
 #define ACM_F2_WORDS       24576u          /* level-2 gram bitmap:  96 KiB smem, word = mulhi(hash, words) */
+#define ACM_B3_WORDS       16384u          /* level-2 start bitmap:  64 KiB smem, word = hash >> 18 */
 #define ACM_HASH1_MUL 0x9E3779B1u
 #define ACM_HASH2_MUL 0x85EBCA6Bu
 #define ACM_HASH3_MUL 0xC2B2AE35u
@@ -111,6 +112,8 @@ struct acm_tables {
 	uint32_t *b2;                /* 2^16-bit exact start bitmap: bit (b0 | b1<<8) */
 	int       split_len;         /* > 0: patterns shorter than this are not in the sampled filter (mixed sets) */
 	uint32_t *b2s;               /* start bitmap of those short patterns alone; NULL when split_len == 0 */
+	uint32_t *b3;                /* start filter of mode 2: 2^19-bit blocked Bloom bitmap (k = 3) of the first THREE
+	                                bytes of every pattern (a pattern of 1 or 2 bytes enters all completions) */
 
 	/* --- byte alphabet, <= 2^14 states, <= 63 distinct pattern bytes: class-compressed DFA --- */
 	uint32_t  cd_classes;        /* C = columns per row; column C-1 = "a byte that occurs in no pattern"; 0 = not built */

@@ -58,6 +58,7 @@ struct AutDev {
 	const uint32_t *pat_len;
 	const uint32_t *b2;
 	const uint32_t *b2s;        /* start bitmap of the patterns shorter than split_len (mixed sets) */
+	const uint32_t *b3;         /* start filter of mode 2: first-three-bytes Bloom bitmap of all patterns */
 	uint32_t split_len;         /* 0: every pattern is in the sampled filter */
 	const uint16_t *cd_tab;        /* class-compressed DFA (k_scan_cdfa), NULL if not built */
 	const uint8_t  *cd_cls;
@@ -975,19 +976,28 @@ k_resolve_queue(const __grid_constant__ AutDev A, const __grid_constant__ EmitCt
 #ifndef S2_PREFETCH
 #define S2_PREFETCH 1              /* pull the CTA's next tile into L2 while this one is processed */
 #endif
-#define S2_SMEM_BYTES (65536 / 8 + 16 + (S2_THREADS / 32) * (WQ_CAP * 8 + 16))
+#define S2_SMEM_BYTES(pair) (((pair) ? 65536 / 8 : ACM_B3_WORDS * 4) + 16 + (S2_THREADS / 32) * (WQ_CAP * 8 + 16))
 
+/*
+ * PAIR = true:  the filter is an exact 2^16-bit bitmap of (byte, next byte) -- 8 KiB; right when few
+ *               patterns stand behind it (the short patterns of a mixed set: hardly any position passes);
+ * PAIR = false: a 2^19-bit blocked Bloom bitmap (three bits per key, all in one word) of the first
+ *               THREE bytes -- 64 KiB; with thousands of patterns the pair bitmap lets 3 .. 15 % of all
+ *               positions through and every one of them costs a trie walk of dependent L2 reads.
+ */
+template <bool PAIR>
 __global__ void __launch_bounds__(S2_THREADS, 2)
 k_scan_start2(const AutDev A, const EmitCtx E, const uint8_t *__restrict__ data, uint64_t n,
-    uint64_t vec_lo, uint64_t vec_hi, uint64_t limit, const uint32_t *__restrict__ start_bitmap,
+    uint64_t vec_lo, uint64_t vec_hi, uint64_t limit, const uint32_t *__restrict__ start_filter,
     uint32_t max_depth)
 {
+	constexpr uint32_t FILTER_BYTES = PAIR ? 65536 / 8 : ACM_B3_WORDS * 4;
 	extern __shared__ __align__(128) uint32_t s2_smem[];
-	uint32_t *b2 = s2_smem;
-	uint64_t *bar = reinterpret_cast<uint64_t *>(s2_smem + 2048);
+	uint32_t *b3 = s2_smem;
+	uint64_t *bar = reinterpret_cast<uint64_t *>(s2_smem + FILTER_BYTES / 4);
 	WarpQueue Q;
 	{
-		uint8_t *qbase = reinterpret_cast<uint8_t *>(s2_smem) + 65536 / 8 + 16 +
+		uint8_t *qbase = reinterpret_cast<uint8_t *>(s2_smem) + FILTER_BYTES + 16 +
 		    (threadIdx.x >> 5) * (WQ_CAP * 8 + 16);
 		Q.rec = reinterpret_cast<uint64_t *>(qbase + 16);
 		Q.count = reinterpret_cast<uint32_t *>(qbase);
@@ -997,8 +1007,13 @@ k_scan_start2(const AutDev A, const EmitCtx E, const uint8_t *__restrict__ data,
 
 	if (threadIdx.x == 0) {
 		mbar_init(bar, 1);
-		mbar_expect_tx(bar, 8192);
-		bulk_g2s(b2, start_bitmap, 8192, bar);
+		mbar_expect_tx(bar, FILTER_BYTES);
+		if (PAIR) {
+			bulk_g2s(b3, start_filter, 8192, bar);
+		} else {
+			bulk_g2s(b3, start_filter, 32768, bar);
+			bulk_g2s(b3 + 8192, start_filter + 8192, 32768, bar);
+		}
 	}
 	__syncthreads();
 	mbar_wait(bar, 0);
@@ -1048,11 +1063,20 @@ k_scan_start2(const AutDev A, const EmitCtx E, const uint8_t *__restrict__ data,
 			uint32_t hits = 0;
 #pragma unroll
 			for (int p = 0; p < 16; ++p) {
-				/* low 16 bits: bytes p, p+1 */
+				/* low 24 bits: bytes p, p+1, p+2 (whatever lies past the end of the buffer is
+				 * harmless: patterns of one or two bytes are in the bitmap with every completion) */
 				const uint32_t x = __funnelshift_r(w[p >> 2], w[(p >> 2) + 1], 8 * (p & 3));
-				const uint32_t word = b2[(x >> 5) & 0x7FF];
-				const uint32_t t = __funnelshift_l(0u, word, x);
-				hits = __funnelshift_l(t, hits, 1);
+				if (PAIR) {
+					/* low 16 bits: bytes p, p+1; words are bit-reversed (tested bit -> MSB) */
+					const uint32_t word = b3[(x >> 5) & 0x7FF];
+					const uint32_t t = __funnelshift_l(0u, word, x);
+					hits = __funnelshift_l(t, hits, 1);
+				} else {
+					const uint32_t h = (x & 0x00FFFFFFu) * ACM_HASH2_MUL;
+					const uint32_t word = b3[h >> 18];
+					const uint32_t t = (word >> (h & 31)) & (word >> ((h >> 5) & 31)) & (word >> ((h >> 10) & 31)) & 1u;
+					hits = (hits << 1) | t;
+				}
 			}
 			if (!live)
 				hits = 0;
