@@ -64,7 +64,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(
-                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "50",
                  "-i", str(self.index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
         except OSError:
             self.proc = None
@@ -72,7 +72,7 @@ class ClockSampler:
     def stop(self):
         if not self.proc:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.25)
+        time.sleep(0.05)
         self.proc.terminate()
         try:
             out, _ = self.proc.communicate(timeout=5)
@@ -305,7 +305,6 @@ def main():
     if world > 1:
         dist.barrier()
     ms = ev0.elapsed_time(ev1)
-    clocks = sampler.stop() if rank == 0 else None
     k1_avg = sum(k1_ms) / len(k1_ms)
     launches, matches, fallback, mode = stats["launches"], stats["matches"], stats["fallback"], stats["mode"]
     if world > 1:
@@ -315,6 +314,19 @@ def main():
         t = torch.tensor([launches], dtype=torch.int64, device=tdev)
         dist.all_reduce(t, op=dist.ReduceOp.SUM)
         launches = int(t.item())
+    # K steps of this workload last a few milliseconds, nvidia-smi samples every 50 ms: the same
+    # steps keep running, untimed, for ~0.6 s more so that the clock / throttle samples are taken
+    # under the load that was just timed (same count on every rank: ms is the max over ranks)
+    tail_steps = int(min(20000, max(args.steps, 600.0 / max(ms / args.steps, 1e-3))))
+    saved = (list(k1_ms), dict(stats))
+    run_steps(tail_steps)
+    torch.cuda.synchronize()
+    k1_ms[:] = saved[0]
+    stats.update(saved[1])
+    clocks = sampler.stop() if rank == 0 else None
+    if clocks is not None:
+        clocks["window"] = (f"the {args.steps} timed steps ({ms:.1f} ms) and {tail_steps} identical untimed steps "
+                            f"that follow them, sampled every 50 ms")
     ms_per_step = ms / args.steps
     value = total / (ms_per_step * 1e-3) / 1e9
 
