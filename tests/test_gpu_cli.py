@@ -125,3 +125,44 @@ def test_flow_grep_ushort_application(tmp_path):
     assert expect["10.0.0.1_1_10.0.0.2_2_udp"] == [] and expect["10.0.0.1_1_10.0.0.3_2_udp"] == [2]
     assert sum(len(v) for v in expect.values()) >= 3
     assert f"Alerts:              {sum(len(v) for v in expect.values())}".encode() in out.stdout
+
+
+def test_cli_follow_mode_sees_appended_data(tmp_path):
+    """-F (reference ocl_aho_grep.c:60-141): the tool keeps reading what is appended to the file
+    until SIGINT; a match whose bytes arrive in two instalments is reported once (the carry
+    between buffers is the last Lmax-1 bytes)."""
+    import signal
+    import time
+    pf = materialize("kat_pat_a.txt", tmp_path)
+    pats = load_patterns("kat_pat_a.txt")
+    text = bytearray(read_fixture("kat_text_a.txt.gz"))
+    # an occurrence that straddles the cut; the cut is a whole number of 256-byte chunks -- like the
+    # reference (databuf.c:327-400), a partial last chunk is zero-padded before it is scanned, so only
+    # a read that ends on a chunk boundary can be continued
+    pat = max((p for p, _ in pats), key=len)
+    cut = 512
+    text[cut - len(pat) // 2:cut - len(pat) // 2 + len(pat)] = pat
+    text = bytes(text)
+    o = build_oracle(pats)
+    eo, ep, _, _ = o.search(text)
+    assert any(e >= cut > e + 1 - len(pats[i][0]) for e, i in zip(eo.tolist(), ep.tolist()))
+    f = tmp_path / "growing.txt"
+    f.write_bytes(text[:cut])
+    p = subprocess.Popen([CLI, "-f", str(f), "-p", pf, "-v", "-F", "-w", "1", "-B", "256", "-G", "8"],
+                         stdout=subprocess.PIPE, stderr=subprocess.PIPE)
+    try:
+        time.sleep(3.0)                               # device init + first pass over the file
+        assert p.poll() is None, p.stderr.read().decode()
+        with open(f, "ab") as fh:
+            fh.write(text[cut:])
+        time.sleep(1.5)
+        p.send_signal(signal.SIGINT)
+        out, err = p.communicate(timeout=60)
+    finally:
+        if p.poll() is None:
+            p.kill()
+    assert p.returncode == 0, err.decode()
+    got = sorted((int(m.group(1)), m.group(2)) for m in (LINE.match(l) for l in out.split(b"\n")) if m)
+    assert got == sorted((pats[i][1], pats[i][0]) for i in ep)
+    st = stats(out)
+    assert st["Matches"] == eo.size and st["Processed bytes"] == len(text)
