@@ -205,6 +205,7 @@ SIGNATURES = {
     "databuf_status": (C.c_int, [C.POINTER(Databuf)]),
     "databuf_match_count": (C.c_size_t, [C.POINTER(Databuf)]),
     "databuf_alloc_postpass": (C.c_int, [C.POINTER(Databuf)]),
+    "databuf_read_fd": (C.c_long, [C.c_int, vp, C.c_size_t]),
     # ocl_aho_match.h
     "ocl_aho_match_init": (None, [C.POINTER(Clconf)]),
     "ocl_aho_match_close": (None, [C.POINTER(Clconf)]),

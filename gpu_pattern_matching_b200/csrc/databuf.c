@@ -12,6 +12,9 @@
 #include <stdlib.h>
 #include <string.h>
 #include <unistd.h>
+#include <pthread.h>
+#include <sys/stat.h>
+#include <sys/types.h>
 
 #include "../../include/acm.h"
 #include "../../include/databuf.h"
@@ -102,6 +105,95 @@ fail:
 	return NULL;
 }
 
+/* ---- parallel read of a regular file ---- */
+
+#define READ_PAR_MIN   ((size_t)8 << 20)      /* below this one read() is as fast */
+#define READ_PAR_MAX   16
+
+struct read_seg {
+	int     fd;
+	char   *dst;
+	off_t   off;
+	size_t  want;
+	ssize_t got;                              /* bytes read, contiguous from off; -1 on error */
+};
+
+static void *
+read_seg_main(void *arg)
+{
+	struct read_seg *s = arg;
+	size_t done = 0;
+
+	while (done < s->want) {
+		const ssize_t r = pread(s->fd, s->dst + done, s->want - done, s->off + (off_t)done);
+		if (r < 0) {
+			s->got = done ? (ssize_t)done : -1;
+			return NULL;
+		}
+		if (r == 0)
+			break;                            /* end of file */
+		done += (size_t)r;
+	}
+	s->got = (ssize_t)done;
+	return NULL;
+}
+
+long
+databuf_read_fd(int fd, void *buf, size_t want)
+{
+	struct read_seg seg[READ_PAR_MAX];
+	pthread_t th[READ_PAR_MAX];
+	struct stat st;
+	const char *env = getenv("ACM_READ_THREADS");
+	int nt = env ? atoi(env) : 4, started = 0, i;
+	off_t off;
+	size_t per, total = 0;
+
+	if (nt > READ_PAR_MAX)
+		nt = READ_PAR_MAX;
+	if (nt < 2 || want < READ_PAR_MIN || fstat(fd, &st) != 0 || !S_ISREG(st.st_mode) ||
+	    (off = lseek(fd, 0, SEEK_CUR)) == (off_t)-1)
+		return (long)read(fd, buf, want);
+	if (off >= st.st_size)
+		return (long)read(fd, buf, want);     /* at (what was) the end: 0, or freshly appended data */
+	if ((size_t)(st.st_size - off) < want)
+		want = (size_t)(st.st_size - off);    /* what the file holds now; a later call sees what is appended */
+	if (want < READ_PAR_MIN)
+		return (long)read(fd, buf, want);
+	per = ((want + (size_t)nt - 1) / (size_t)nt + 4095) & ~(size_t)4095;
+	for (i = 0; i < nt && (size_t)i * per < want; i++) {
+		seg[i].fd = fd;
+		seg[i].dst = (char *)buf + (size_t)i * per;
+		seg[i].off = off + (off_t)((size_t)i * per);
+		seg[i].want = want - (size_t)i * per < per ? want - (size_t)i * per : per;
+		seg[i].got = 0;
+	}
+	nt = i;
+	for (i = 1; i < nt; i++) {
+		if (pthread_create(&th[i], NULL, read_seg_main, &seg[i]) != 0)
+			break;
+		started = i;
+	}
+	read_seg_main(&seg[0]);
+	for (i = 1; i <= started; i++)
+		pthread_join(th[i], NULL);
+	for (i = started + 1; i < nt; i++)        /* threads that could not be created: read here */
+		read_seg_main(&seg[i]);
+	/* the contiguous prefix: everything up to and including the first short segment */
+	for (i = 0; i < nt; i++) {
+		if (seg[i].got < 0)
+			break;
+		total += (size_t)seg[i].got;
+		if ((size_t)seg[i].got < seg[i].want)
+			break;
+	}
+	if (total == 0 && seg[0].got < 0)
+		return -1;
+	if (lseek(fd, off + (off_t)total, SEEK_SET) == (off_t)-1)
+		return -1;
+	return (long)total;
+}
+
 /* reference databuf.c:327-407 */
 int
 databuf_add_fd(struct databuf *db, int fd, int id, size_t *rd_bytes)
@@ -113,7 +205,7 @@ databuf_add_fd(struct databuf *db, int fd, int id, size_t *rd_bytes)
 	if (db->chunks >= db->max_chunks)
 		return -1;
 	/* chunks are fixed size in this mode: chunk k starts at k * max_chunk_size */
-	got = read(fd, db->h_data + db->chunks * db->max_chunk_size,
+	got = databuf_read_fd(fd, db->h_data + db->chunks * db->max_chunk_size,
 	    (db->max_chunks - db->chunks) * db->max_chunk_size);
 	if (got <= 0)
 		return 0;

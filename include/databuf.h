@@ -121,6 +121,14 @@ int    databuf_status(struct databuf *);            /* 0 or the last negative AC
 size_t databuf_match_count(struct databuf *);       /* matches of the last ocl_aho_match() */
 /* allocates d_results, d_results2, d_prefixsum, d_results_comp, d_results2_comp (reference shapes) */
 int    databuf_alloc_postpass(struct databuf *);
+/*
+ * What databuf_add_fd() reads with: like read(fd, buf, want), but a regular file is read by several
+ * threads with pread() on adjacent segments (one read() of a 128 MiB buffer copies out of the page
+ * cache at 3 GB/s on one core; ACM_READ_THREADS, default 4, 1 = plain read) and the file offset is
+ * advanced by what was read.  Pipes, FIFOs and small requests take the plain read().  Returns the
+ * number of contiguous bytes read, 0 at end of file, -1 on error.
+ */
+long   databuf_read_fd(int fd, void *buf, size_t want);
 
 #ifdef __cplusplus
 }

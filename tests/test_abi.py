@@ -119,3 +119,47 @@ def test_struct_layouts(tmp_path):
         assert C.sizeof(cls) == next(out), ctype
         for f in fields:
             assert getattr(cls, f).offset == next(out), f"{ctype}.{f}"
+
+
+def test_databuf_read_fd_parallel_reader(tmp_path, monkeypatch):
+    """databuf_read_fd (what databuf_add_fd reads with): several pread() threads on a regular
+    file give the same bytes and file offset as read(); short files, end of file, appended data,
+    pipes and ACM_READ_THREADS=1 take the plain path."""
+    import ctypes as C
+    import numpy as np
+    L = g.lib()
+    rng = np.random.default_rng(5)
+    data = rng.integers(0, 256, size=(40 << 20) + 12345, dtype=np.uint8)
+    f = tmp_path / "big.bin"
+    data.tofile(f)
+    buf = np.zeros(48 << 20, dtype=np.uint8)
+    for threads in ("4", "16", "3", "1"):
+        monkeypatch.setenv("ACM_READ_THREADS", threads)
+        fd = os.open(f, os.O_RDONLY)
+        try:
+            # a first call that does not reach the end, from an odd offset
+            os.lseek(fd, 777, os.SEEK_SET)
+            buf[:] = 0
+            got = L.databuf_read_fd(fd, buf.ctypes.data_as(C.c_void_p), 16 << 20)
+            assert got == 16 << 20 and np.array_equal(buf[:got], data[777:777 + got])
+            assert os.lseek(fd, 0, os.SEEK_CUR) == 777 + got
+            # the rest: less than asked for
+            pos = 777 + got
+            got = L.databuf_read_fd(fd, buf.ctypes.data_as(C.c_void_p), buf.size)
+            assert got == data.size - pos and np.array_equal(buf[:got], data[pos:])
+            assert L.databuf_read_fd(fd, buf.ctypes.data_as(C.c_void_p), buf.size) == 0      # end of file
+            # appended data is seen by the next call (follow mode)
+            with open(f, "ab") as fh:
+                fh.write(b"tail")
+            assert L.databuf_read_fd(fd, buf.ctypes.data_as(C.c_void_p), buf.size) == 4
+            assert bytes(buf[:4]) == b"tail"
+        finally:
+            os.close(fd)
+            data.tofile(f)
+    # a pipe: plain read
+    r, w = os.pipe()
+    os.write(w, b"hello")
+    os.close(w)
+    assert L.databuf_read_fd(r, buf.ctypes.data_as(C.c_void_p), buf.size) == 5 and bytes(buf[:5]) == b"hello"
+    assert L.databuf_read_fd(r, buf.ctypes.data_as(C.c_void_p), buf.size) == 0
+    os.close(r)
