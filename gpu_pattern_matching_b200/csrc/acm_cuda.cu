@@ -920,7 +920,7 @@ grow(uint64_t **buf, uint64_t *cap, uint64_t need, const char *what)
 
 /*
  * Symbols per thread of k_scan_dfa.  The walk is latency bound, so a scan is cut into one chunk
- * per thread the GPU can hold (6 CTAs of 256 per SM) -- but never below twice the halo (the
+ * per thread the GPU can hold (DFA_MINB CTAs of 256 per SM) -- but never below twice the halo (the
  * cold-start walk every chunk repeats) or 128 symbols, and no more than 4096.
  */
 static uint64_t
@@ -928,7 +928,7 @@ scan_dfa_chunk(const struct acm_scanner *s, uint64_t span)
 {
 	if (s->p.dfa_chunk > 0)
 		return (uint64_t)s->p.dfa_chunk;
-	const uint64_t resident = (uint64_t)s->dev->sm_count * 1536;
+	const uint64_t resident = (uint64_t)s->dev->sm_count * 256 * DFA_MINB;
 	const uint64_t halo = s->aut->max_len > 0 ? (uint64_t)(s->aut->max_len - 1) : 0;
 	uint64_t chunk = (span + resident - 1) / resident;
 	if (chunk < 2 * halo)

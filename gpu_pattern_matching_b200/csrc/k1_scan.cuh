@@ -6,31 +6,36 @@
  * work-item one chunk and does one dependent, uncoalesced 4-byte global load per
  * input byte into a table of up to 1.29 GiB (ahomatch.cl:56-65).  Here:
  *
- *   k_scan_sampled4  (all patterns >= 7 bytes, e.g. the ClamAV sets)
- *       Every occurrence of a pattern of length >= 7 contains a 4-byte window
- *       that starts at a multiple of 4.  The kernel streams the input once with
- *       coalesced 16-byte loads and tests only those aligned windows against a
- *       hashed bitmap of all pattern 4-grams at byte offsets 0..3 (128 KiB,
- *       shared memory, loaded with TMA bulk copies).  Survivors (a few %) are
- *       re-tested against a second 64 KiB shared-memory bitmap, then against an
- *       exact gram table in L2, and only then is the automaton entered: a walk of
- *       the DFA table from the candidate start, following trie edges, reporting
- *       the patterns that end at each node.  0.25 shared-memory lookups per
- *       input byte instead of one table gather per byte.
+ *   k_scan_sampled<STRIDE> + k_resolve_queue  (patterns >= 7 bytes, e.g. the ClamAV sets)
+ *       Every occurrence of a pattern of length >= 7 contains a 4-byte window that starts
+ *       at a multiple of 4 (>= 10: at a multiple of 8).  The kernel streams the input once
+ *       with coalesced 16-byte loads and tests only those aligned windows against f1, a
+ *       blocked Bloom bitmap of one indexed window per (pattern, alignment) (128 KiB of
+ *       shared memory, staged by TMA bulk copies).  Survivors (a few %) are re-tested
+ *       lane-locally against f2 (96 KiB, second hash) and the few that remain are written
+ *       to the scanning warp's queue region; k_resolve_queue then probes the exact gram
+ *       table, fetches the candidate records and compares the candidate patterns with the
+ *       text in CTA-wide phases.  0.125 shared-memory lookups per input byte instead of one
+ *       table gather per byte.  Dense (repetitive) chunks fall back to a bounded DFA walk.
  *
- *   k_scan_start2    (any pattern length)
- *       Same structure with an exact 64-Kbit bitmap over (byte, next byte) tested
- *       at every position: "can an automaton walk started here report anything".
+ *   k_scan_start2<PAIR>  (any pattern length)
+ *       A filter tested at every position ("can an automaton walk started here report
+ *       anything"), hits walk the trie edges of T.  PAIR = false: blocked Bloom bitmap of the
+ *       first three bytes of every pattern (mode 2); PAIR = true: exact bitmap over (byte,
+ *       next byte) of the short patterns of a MIXED set, whose long patterns go through
+ *       k_scan_sampled (both passes emit into the same buckets).
  *
- *   k_scan_dfa       (bytes or ushort symbols; cross-check and AC_ushorts path)
+ *   k_scan_dfa<SYM>  (bytes or ushort symbols; cross-check and AC_ushorts path)
  *       The textbook form: one thread per chunk, cold start Lmax-1 symbols early
  *       (SURVEY.md A.5), one table lookup per symbol, matches reported through the
- *       output links.
+ *       output links; chunks sized so that every resident thread has one.
  *
- * All three report exactly the set { (end offset, pattern index) } that a serial
- * walk of the reference's automaton reports with full match lists (SURVEY.md
- * A.3): an occurrence is found from its start position by following trie edges,
- * and a trie edge is a DFA edge whose target lies one level deeper.
+ *   k_scan_cdfa<RANGE, COMP>  (small automata over few distinct bytes: word lists over text)
+ *       The same walk out of a class-compressed, delta-encoded 16-bit table that lives
+ *       entirely in shared memory; hits are stored in order, the post-pass only expands.
+ *
+ * All of them report exactly the set { (end offset, pattern index) } that a serial walk
+ * of the reference's automaton reports with full match lists.
  *
  * Match emission: records go to the bucket of their END offset
  * ((end - emit_lo) >> shift); lanes of a warp that emit into the same bucket at
@@ -1130,8 +1135,11 @@ __device__ __forceinline__ void dfa_step(const AutDev &A, const EmitCtx &E, uint
  * (scan_dfa_chunk), and the symbols arrive 16 bytes at a time (one sector per lane per two loads)
  * instead of one load per symbol.
  */
+#ifndef DFA_MINB
+#define DFA_MINB 6                 /* resident CTAs of 256 per SM (40 registers) */
+#endif
 template <typename SYM>
-__global__ void __launch_bounds__(256, 6)
+__global__ void __launch_bounds__(256, DFA_MINB)
 k_scan_dfa(const AutDev A, const EmitCtx E, const SYM *__restrict__ data, uint64_t n, uint64_t chunk,
     uint64_t nthreads, uint32_t *final_state)
 {

@@ -86,7 +86,7 @@ if __name__ == "__main__":
     if "10k-s4" in which:
         run(dev, "clamav10k", clamav_pats(10000), n, [1], plants=int(100000 * per_gib), iters=iters)
     if "10k-noplant" in which:
-        run(dev, "clamav10k-noplant", clamav_pats(10000), n, [1], plants=0, iters=iters)
+        run(dev, "clamav10k-noplant", clamav_pats(10000), n, [1, 2], plants=0, iters=iters)
     if "10k-mixed" in which:
         # a mixed set: ClamAV 10k plus a few short patterns -> sampled filter + start-filter pass (mode 1)
         short = [(b"MZ", 20000), (b"\x7fEL", 20001), (b"PE\x00\x00", 20002), (b"%PDF-", 20003), (b"virus!", 20004),
