@@ -126,6 +126,11 @@ def cpu_reference_rate(sample_bytes, threads, steps=1, warmup=0):
         if it >= warmup:
             times.append(dt)
     sec = sum(times) / len(times)
+    # the same walk on ONE thread over the first 64 MiB (per-core figure)
+    one = buf[:min(sample_bytes, 64 << 20)]
+    t0 = time.perf_counter()
+    m.walk_count_mt(one, 1)
+    cpu_reference_rate.single_thread_gbs = one.size / (time.perf_counter() - t0) / 1e9
     return sample_bytes / sec / 1e9, kind, int(found), sec
 
 
@@ -147,7 +152,8 @@ def run_reference(args, rank):
                            "pthread-sharded with Lmax-1 halo (oracle/_ref = reference acsmx.c compiled here)"
                            if kind == "reference" else "oracle port of the reference walk (oracle/acsm_oracle.c)"},
         "cpu_baseline": {"value": rate, "unit": "GB/s", "cores": cores, "kind": kind,
-                         "sample": f"first {sample >> 20} MiB of the workload stream, {found} matches"},
+                         "sample": f"first {sample >> 20} MiB of the workload stream, {found} matches",
+                         "single_thread_gbs": cpu_reference_rate.single_thread_gbs},
         "e2e": {"value": rate, "unit": "GB/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -424,7 +430,8 @@ def main():
         rate, kind, found, sec = cpu_reference_rate(sample, cores)
         line["cpu_baseline"] = {"value": rate, "unit": "GB/s", "cores": cores, "kind": kind,
                                 "sample": f"first {sample >> 20} MiB of rank 0's stream, "
-                                          f"{found} matches, {sec:.2f} s"}
+                                          f"{found} matches, {sec:.2f} s",
+                                "single_thread_gbs": cpu_reference_rate.single_thread_gbs}
     emit(line)
     if world > 1:
         dist.destroy_process_group()
