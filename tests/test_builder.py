@@ -169,3 +169,58 @@ def test_filter_tables_cover_every_pattern():
     pats = clamav_pats(2000)
     a = build_product(pats, upload=False)
     assert a.get_min_pattern_size() == 10 and a.get_max_pattern_size() == 159
+
+
+def _random_pats(rng, alphabet, npat, lo, hi):
+    pats = [(bytes(rng.choice(alphabet, size=int(rng.integers(lo, hi + 1))).tolist()), int(rng.integers(-9, 999)))
+            for _ in range(npat)]
+    if npat >= 4:                                    # duplicates, prefixes, suffixes, infixes on purpose
+        p0 = pats[0][0]
+        pats[1] = (p0, 7)
+        pats[2] = (p0[:max(1, len(p0) // 2)], 8)
+        pats[3] = (p0[-max(1, len(p0) // 2):], 9)
+    return pats
+
+
+@pytest.mark.parametrize("seed", range(8))
+def test_random_sets_builder_equals_oracle_and_reference(seed):
+    """Randomised differential test of the builder (no GPU): tiny alphabets make patterns overlap,
+    nest and repeat; the exported table -- reference layout, reference numbering, head index of every
+    final state -- must equal the oracle's and, where oracle/_ref is built, the table the
+    reference's own acsm_compile / acsm_gen_state_table produce."""
+    rng = np.random.default_rng(4000 + seed)
+    alphabet = [np.array([97, 98], dtype=np.uint8), np.array([0, 1, 255], dtype=np.uint8),
+                np.arange(256, dtype=np.uint8), np.array([0], dtype=np.uint8)][seed % 4]
+    for rep in range(5):
+        pats = _random_pats(rng, alphabet, int(rng.integers(1, 80)), 1, [6, 12, 40, 3][rep % 4])
+        o, a = build_oracle(pats), build_product(pats, upload=False)
+        assert a.get_states() == o.num_states - 1 and a.get_max_pattern_size() == o.max_pattern_len
+        assert _same_table(a.export_ref_table(), o.ref_table()), f"seed {seed} rep {rep}: builder != oracle"
+        if ref_available():
+            r = RefAcsm()
+            for p, iid in pats:
+                r.add(p, iid)
+            r.compile()
+            assert _same_table(a.export_ref_table(), r.h_trans()), f"seed {seed} rep {rep}: builder != reference"
+            r.close()
+        a.free()
+        o.close()
+
+
+@pytest.mark.parametrize("seed", range(4))
+def test_random_ushort_sets_builder_equals_oracle(seed):
+    rng = np.random.default_rng(5000 + seed)
+    tokens = [np.array([0, 1], dtype=np.uint16), np.array([0, 40, 52, 1448, 2047], dtype=np.uint16),
+              np.arange(2048, dtype=np.uint16)][seed % 3]
+    for rep in range(3):
+        o, m = Oracle(2048), g.Iacsm()
+        sigs = [rng.choice(tokens, size=int(rng.integers(1, 20))).astype(np.uint16) for _ in range(int(rng.integers(1, 40)))]
+        if len(sigs) >= 2:
+            sigs[1] = sigs[0].copy()
+        for k, s in enumerate(sigs):
+            o.add(s, 100 + k)
+            m.add_pattern(s, 100 + k)
+        o.compile()
+        m.compile()
+        assert m.get_states() == o.num_states - 1
+        assert _same_table(m.export_ref_table(), o.ref_table(), 2048), f"seed {seed} rep {rep}"

@@ -194,3 +194,36 @@ def test_ushort_oracle_equals_compiled_reference():
     ro, ri, rfin = r.search(toks)
     assert np.array_equal(eo, ro) and fin == rfin
     assert [o.pattern_iid(int(p)) for p in ep] == ri.tolist()
+
+
+@pytest.mark.parametrize("seed", range(6))
+def test_oracle_equals_naive_search(seed):
+    """The oracle's match list against the definition itself -- every (end offset, pattern index)
+    such that the pattern occurs ending there, found by brute force -- on small random cases with
+    overlapping, nested and duplicate patterns (bytes and ushort symbols)."""
+    rng = np.random.default_rng(6000 + seed)
+    ushort = seed % 2 == 1
+    alpha = 2048 if ushort else 256
+    symbols = [np.array([1, 2]), np.array([0, 7, 200]), np.arange(alpha)][seed % 3]
+    dtype = np.uint16 if ushort else np.uint8
+    for rep in range(8):
+        npat = int(rng.integers(1, 30))
+        pats = [rng.choice(symbols, size=int(rng.integers(1, 9))).astype(dtype) for _ in range(npat)]
+        if npat >= 3:
+            pats[1] = pats[0].copy()
+            pats[2] = pats[0][-max(1, pats[0].size // 2):].copy()
+        text = rng.choice(symbols, size=int(rng.choice([1, 5, 64, 700]))).astype(dtype)
+        for _ in range(10):
+            p = pats[int(rng.integers(0, npat))]
+            if p.size <= text.size:
+                pos = int(rng.integers(0, text.size - p.size + 1))
+                text[pos:pos + p.size] = p
+        o = Oracle(alpha)
+        for i, p in enumerate(pats):
+            o.add(p.tobytes() if not ushort else p, i)
+        o.compile()
+        eo, ep, _, _ = o.search(text)
+        want = sorted((s + p.size - 1, i) for i, p in enumerate(pats)
+                      for s in range(text.size - p.size + 1) if np.array_equal(text[s:s + p.size], p))
+        assert list(zip(eo.tolist(), ep.tolist())) == want, f"seed {seed} rep {rep}"
+        o.close()
