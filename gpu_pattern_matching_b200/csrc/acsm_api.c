@@ -111,6 +111,10 @@ acsm_get_patterns_table(acsm_t *a)
 	for (int k = 0; k < c->npats; k++) {
 		const struct acm_pat *p = &c->pats[k];
 		if (!p->syms) {             /* after acsm_cleanup() */
+			for (int j = 0; j < k; j++) {
+				free(tab[j].pattern);
+				free(tab[j].casepattern);
+			}
 			free(tab);
 			acm_set_error("acsm_get_patterns_table: call it before acsm_cleanup");
 			return NULL;

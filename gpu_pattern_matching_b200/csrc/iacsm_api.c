@@ -150,6 +150,8 @@ iacsm_cleanup(iacsm_t *m)
 {
 	struct acm_core *c = core_of(m);
 
+	if (!m)
+		return;
 	if (c)
 		acm_core_cleanup(c);
 	m->patterns = NULL;
