@@ -339,7 +339,7 @@ def main():
     # ---- e2e: same shard from pinned host memory through acm_scan_host ----
     e2e = None
     if not args.no_e2e:
-        host, owner = g.matcher.pinned_empty(per + 64)
+        host, owner = g.matcher.pinned_empty(per + 64, dev)      # on the GPU's own NUMA node where allowed
         # identical bytes: copy the kept range of the device shard back once (outside timing)
         g._lib.check(g.lib().acm_memcpy_d2h(dev.handle, C.c_void_p(host.ctypes.data),
                                        C.c_void_p(data.data_ptr() + emit_lo), per), "d2h")

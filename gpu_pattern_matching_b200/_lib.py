@@ -110,6 +110,7 @@ SIGNATURES = {
     "acm_dev_alloc": (C.c_int, [vp, C.c_size_t, C.POINTER(vp)]),
     "acm_dev_free": (None, [vp, vp]),
     "acm_host_alloc_pinned": (C.c_int, [C.c_size_t, C.POINTER(vp)]),
+    "acm_host_alloc_pinned_near": (C.c_int, [vp, C.c_size_t, C.POINTER(vp)]),
     "acm_host_free_pinned": (None, [vp]),
     "acm_memcpy_h2d": (C.c_int, [vp, vp, vp, C.c_size_t]),
     "acm_memcpy_d2h": (C.c_int, [vp, vp, vp, C.c_size_t]),

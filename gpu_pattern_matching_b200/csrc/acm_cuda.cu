@@ -11,6 +11,8 @@
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
+#include <sys/syscall.h>
+#include <unistd.h>
 
 #include "../../include/acm.h"
 #include "acm_core.h"
@@ -260,11 +262,79 @@ acm_dev_free(struct acm_device *d, void *p)
 	cudaFree(p);
 }
 
+/*
+ * NUMA node the GPU hangs off (/sys/bus/pci/devices/<bus id>/numa_node), -1 if unknown.  On a
+ * two-socket 8-GPU box a pinned buffer on the other socket makes every H2D copy cross the
+ * socket interconnect; eight ranks that all allocate on the node their process happens to run
+ * on share that one node's memory controllers and links.
+ */
+static int
+numa_node_of_device(int ordinal)
+{
+	char bus[32], path[128];
+	int node = -1;
+	FILE *f;
+
+	if (cudaDeviceGetPCIBusId(bus, (int)sizeof(bus), ordinal) != cudaSuccess) {
+		cudaGetLastError();
+		return -1;
+	}
+	for (char *c = bus; *c; ++c)
+		if (*c >= 'A' && *c <= 'Z')
+			*c = (char)(*c - 'A' + 'a');
+	snprintf(path, sizeof(path), "/sys/bus/pci/devices/%s/numa_node", bus);
+	f = fopen(path, "r");
+	if (!f)
+		return -1;
+	if (fscanf(f, "%d", &node) != 1)
+		node = -1;
+	fclose(f);
+	return node;
+}
+
+/* pinned host memory, preferably on the NUMA node of GPU `ordinal` (ACM_NUMA=0: wherever the
+ * calling thread's policy puts it).  The preference is a hint: where the node is not allowed
+ * (cpuset) or unknown, the call is a plain cudaHostAlloc. */
+static int
+alloc_pinned_near(int ordinal, size_t bytes, void **p)
+{
+	const char *env = getenv("ACM_NUMA");
+	const int node = (env && atoi(env) == 0) ? -1 : numa_node_of_device(ordinal);
+	int preferred = 0;
+
+	if (node >= 0 && node < 1024) {
+		unsigned long mask[1024 / (8 * sizeof(unsigned long))];
+		memset(mask, 0, sizeof(mask));
+		mask[node / (8 * sizeof(unsigned long))] |= 1ul << (node % (8 * sizeof(unsigned long)));
+		preferred = syscall(SYS_set_mempolicy, 1 /* MPOL_PREFERRED */, mask, 1024ul + 1) == 0;
+	}
+	const cudaError_t e = cudaHostAlloc(p, bytes ? bytes : 16, cudaHostAllocDefault);
+	if (preferred)
+		syscall(SYS_set_mempolicy, 0 /* MPOL_DEFAULT */, NULL, 0ul);
+	if (e != cudaSuccess) {
+		acm_set_error("cudaHostAlloc(%zu): %s", bytes, cudaGetErrorString(e));
+		cudaGetLastError();
+		return ACM_ERR_CUDA;
+	}
+	return ACM_OK;
+}
+
 extern "C" int
 acm_host_alloc_pinned(size_t bytes, void **p)
 {
-	CUDA_TRY(cudaHostAlloc(p, bytes ? bytes : 16, cudaHostAllocDefault));
-	return ACM_OK;
+	int ordinal = 0;
+
+	if (cudaGetDevice(&ordinal) != cudaSuccess) {
+		cudaGetLastError();
+		ordinal = 0;
+	}
+	return alloc_pinned_near(ordinal, bytes, p);
+}
+
+extern "C" int
+acm_host_alloc_pinned_near(struct acm_device *d, size_t bytes, void **p)
+{
+	return alloc_pinned_near(d ? d->ordinal : 0, bytes, p);
 }
 
 extern "C" void

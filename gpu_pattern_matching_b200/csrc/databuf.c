@@ -65,7 +65,7 @@ databuf_new(size_t max_chunks, size_t max_chunk_size, int max_results, int mappe
 	db->size = max_chunks * max_chunk_size;
 	nres = (size_t)max_results * max_chunks + 1;
 
-	if (acm_host_alloc_pinned(db->size + 64, &p) != ACM_OK)
+	if (acm_host_alloc_pinned_near(dev, db->size + 64, &p) != ACM_OK)
 		goto fail;
 	db->h_data = p;
 	if (acm_dev_alloc(dev, DATABUF_CARRY_CAP + db->size + 64, &p) != ACM_OK)

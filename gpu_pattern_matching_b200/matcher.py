@@ -178,11 +178,15 @@ class Scanner:
             pass
 
 
-def pinned_empty(nbytes):
-    """uint8 numpy view over pinned host memory (caller keeps the returned owner alive)."""
+def pinned_empty(nbytes, device=None):
+    """uint8 numpy view over pinned host memory (caller keeps the returned owner alive); with a
+    Device, preferably on that GPU's NUMA node."""
     L = lib()
     p = C.c_void_p()
-    check(L.acm_host_alloc_pinned(nbytes, C.byref(p)), "acm_host_alloc_pinned")
+    if device is not None:
+        check(L.acm_host_alloc_pinned_near(device.handle, nbytes, C.byref(p)), "acm_host_alloc_pinned_near")
+    else:
+        check(L.acm_host_alloc_pinned(nbytes, C.byref(p)), "acm_host_alloc_pinned")
     buf = (C.c_ubyte * nbytes).from_address(p.value)
     arr = np.frombuffer(buf, dtype=np.uint8)
 

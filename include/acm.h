@@ -58,7 +58,11 @@ struct acm_device *acm_default_device(void);
 /* raw memory helpers (bindings that cannot call the CUDA runtime themselves) */
 int   acm_dev_alloc(struct acm_device *, size_t bytes, void **d_ptr);
 void  acm_dev_free(struct acm_device *, void *d_ptr);
+/* pinned host memory, preferably on the NUMA node of the calling thread's current CUDA device (of `dev`
+ * in the _near form): on a two-socket multi-GPU host the H2D copies then stay on the GPU's own socket.
+ * A hint only (set_mempolicy(MPOL_PREFERRED) around the allocation); ACM_NUMA=0 turns it off. */
 int   acm_host_alloc_pinned(size_t bytes, void **h_ptr);
+int   acm_host_alloc_pinned_near(struct acm_device *dev, size_t bytes, void **h_ptr);
 void  acm_host_free_pinned(void *h_ptr);
 int   acm_memcpy_h2d(struct acm_device *, void *d_dst, const void *h_src, size_t bytes);  /* async on the stream */
 int   acm_memcpy_d2h(struct acm_device *, void *h_dst, const void *d_src, size_t bytes);  /* async on the stream */
