@@ -163,3 +163,26 @@ def test_databuf_read_fd_parallel_reader(tmp_path, monkeypatch):
     assert L.databuf_read_fd(r, buf.ctypes.data_as(C.c_void_p), buf.size) == 5 and bytes(buf[:5]) == b"hello"
     assert L.databuf_read_fd(r, buf.ctypes.data_as(C.c_void_p), buf.size) == 0
     os.close(r)
+
+
+def test_reference_style_caller_compiles_and_links(tmp_path):
+    """examples/worker_loop.c -- the reference's cpu_worker loop written against include/*.h --
+    compiles as C11 with -Wall -Werror and links against the shared library; without a GPU it
+    must fail loudly (no CPU path), with the library's error text."""
+    import subprocess
+    src = os.path.join(ROOT, "examples", "worker_loop.c")
+    exe = str(tmp_path / "worker_loop")
+    libdir = os.path.join(ROOT, "gpu_pattern_matching_b200")
+    subprocess.run(["gcc", "-std=gnu11", "-Wall", "-Werror", "-I", os.path.join(ROOT, "include"), src,
+                    "-L", libdir, "-lacmatch_b200", "-lpthread", f"-Wl,-rpath,{libdir}", "-o", exe], check=True)
+    # the CLI tools exist and refuse to run without their arguments
+    for tool in ("b200_aho_grep", "b200_flow_grep"):
+        p = subprocess.run([os.path.join(ROOT, "cli", tool), "-h"], capture_output=True, timeout=60)
+        assert p.returncode != 0 and (b"Usage" in p.stdout + p.stderr or b"usage" in p.stdout + p.stderr)
+    if g.lib().acm_device_count() <= 0:
+        pf = tmp_path / "p.txt"
+        pf.write_text("needle\n")
+        df = tmp_path / "d.txt"
+        df.write_text("hay needle hay\n")
+        p = subprocess.run([exe, str(pf), str(df)], capture_output=True, timeout=60)
+        assert p.returncode != 0 and p.stderr.strip(), "a caller without a GPU must fail with an error message"
