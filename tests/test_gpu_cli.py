@@ -150,12 +150,29 @@ def test_cli_follow_mode_sees_appended_data(tmp_path):
     f.write_bytes(text[:cut])
     p = subprocess.Popen([CLI, "-f", str(f), "-p", pf, "-v", "-F", "-w", "1", "-B", "256", "-G", "8"],
                          stdout=subprocess.PIPE, stderr=subprocess.PIPE)
+    def wait_until_read(upto, timeout=120.0):
+        """until the tool's file offset on the growing file has reached `upto` (/proc/<pid>/fdinfo)"""
+        t0 = time.time()
+        while time.time() - t0 < timeout:
+            assert p.poll() is None, p.stderr.read().decode()
+            try:
+                for fd in os.listdir(f"/proc/{p.pid}/fd"):
+                    if os.path.realpath(f"/proc/{p.pid}/fd/{fd}") == os.path.realpath(str(f)):
+                        pos = int(re.search(r"pos:\s+(\d+)", open(f"/proc/{p.pid}/fdinfo/{fd}").read()).group(1))
+                        if pos >= upto:
+                            return
+            except (OSError, AttributeError):
+                pass
+            time.sleep(0.05)
+        raise AssertionError(f"the tool did not read {upto} bytes within {timeout} s")
+
     try:
-        time.sleep(3.0)                               # device init + first pass over the file
-        assert p.poll() is None, p.stderr.read().decode()
+        wait_until_read(cut)                          # device init + first pass over the file
+        time.sleep(1.0)                               # ... and its buffer processed (follow sleeps 20 ms per pass)
         with open(f, "ab") as fh:
             fh.write(text[cut:])
-        time.sleep(1.5)
+        wait_until_read(len(text))
+        time.sleep(0.3)
         p.send_signal(signal.SIGINT)
         out, err = p.communicate(timeout=60)
     finally:
