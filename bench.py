@@ -185,8 +185,8 @@ def main():
     guard_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
-    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--bytes-per-gpu", type=int, default=GIB)
     ap.add_argument("--sigs", type=int, default=SIGS, choices=[2000, 10000, 15000],
