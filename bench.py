@@ -20,6 +20,10 @@ N GiB, rank r holds bytes [r, r+1) GiB plus a leading halo of Lmax-1 bytes (weak
   cpu_baseline  the reference's CPU path (oracle/_ref when present, else the oracle port) on a
              bounded sample of the same stream, all host cores
 
+  clocks     nvidia-smi SM clock / throttle reasons, sampled every 50 ms while the timed steps and
+             ~0.6 s of identical untimed steps that follow them run (K steps last milliseconds)
+
+Defaults: N = 1, 50 timed steps after 5 warm-up steps (about 15 s in all, most of it the CPU baseline).
 --impl reference times that CPU path as the arm itself.
 """
 import argparse
