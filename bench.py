@@ -1,38 +1,52 @@
 #!/usr/bin/env python
-"""bench.py -- GB/s scanned by the B200 Aho-Corasick hot path, with roofline and CPU baseline.
+"""bench.py -- GB/s scanned by the B200 Aho-Corasick hot path, with roofline, parity and CPU baseline.
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+    (python bench.py --gpus N without torchrun re-launches itself under torch.distributed.run)
 
-A step = one pass of the hot path (scan -> prefix sum -> compaction + sort -> match count;
-at N > 1 also the count exchange and the gather of the sorted lists to rank 0) over one batch
-of synthetic input.  Workload per GPU (BASELINE.json configs[1]): ClamAV 10000 signatures over
-a 1 GiB seeded random byte stream with ~10^5 signatures planted (pure random
-bytes contain no match, so parity and emission would be vacuous).  At N GPUs the stream is
-N GiB, rank r holds bytes [r, r+1) GiB plus a leading halo of Lmax-1 bytes (weak scaling).
+A step = one pass of the hot path (scan -> prefix sum -> compaction + sort -> push of the sorted
+keys into rank 0's gather buffer -> D2H of the gathered list) over one batch of synthetic input.
+Headline workload per GPU (BASELINE.json configs[1]): ClamAV 10000 signatures over a 1 GiB seeded
+random byte stream with ~10^5 signatures planted (pure random bytes contain no
+match, so parity and emission would be vacuous).  At N GPUs the stream is N GiB, rank r holds bytes
+[r, r+1) GiB plus a leading halo of Lmax-1 bytes (weak scaling).
 
-  value      whole-job GB/s with the input already resident in HBM
+  value      whole-job GB/s with the input already resident in HBM (mean over the K timed steps;
+             step_ms gives best / median / p95 of the per-step device times)
   e2e        the same stream scanned through the C ABI from a pinned HOST buffer
              (acm_scan_host: chunked H2D overlapped with the scan, D2H of the match list)
-  roofline   the scan stage alone (CUDA events inside the library around the streaming filter
-             kernel and the kernel that resolves its survivors) against the measured HBM copy
-             bandwidth in MEASURED_PEAKS.json; algorithmic traffic = 1 B per input byte
+  e2e_databuf  the same through the reference-shaped entry points, one 128 MiB databuf at a time:
+             databuf_copy_host_to_device -> ocl_aho_match -> databuf_copy_device_to_host ->
+             databuf_process_results (reference ocl_aho_grep.c:116-137)
+  roofline   the scan stage alone (CUDA events inside the library around the scan kernels) against
+             the measured HBM copy bandwidth in MEASURED_PEAKS.json; algorithmic traffic = 1 B per
+             input byte
+  parity     checked IN THIS RUN, at every N, on the gathered list of the last timed step: strictly
+             sorted; every planted (end offset, pattern) present; the matches inside a window that
+             straddles the first shard cut (the whole stream at N = 1) counted by the reference CPU
+             walk over the same bytes; the full list on a 64 MiB prefix against the oracle's list.
+             Any mismatch makes the exit code non-zero.
+  other_configs  short runs of BASELINE.json configs 1, 3, 4 (and 5 at N = 8), each with GB/s,
+             roofline fraction and its own parity block (see run_other_configs)
   cpu_baseline  the reference's CPU path (oracle/_ref when present, else the oracle port) on a
              bounded sample of the same stream, all host cores
-
   clocks     nvidia-smi SM clock / throttle reasons, sampled every 50 ms while the timed steps and
              ~0.6 s of identical untimed steps that follow them run (K steps last milliseconds)
 
-Defaults: N = 1, 50 timed steps after 5 warm-up steps (about 15 s in all, most of it the CPU baseline).
---impl reference times that CPU path as the arm itself.
+Defaults: N = 1, 50 timed steps after 5 warm-up steps.  --impl reference times the CPU path as the arm
+itself.  --only-main skips other_configs.
 """
 import argparse
 import ctypes as C
+import hashlib
 import json
 import os
 import statistics
 import subprocess
 import sys
+import tempfile
+import threading
 import time
 
 import numpy as np
@@ -42,10 +56,12 @@ sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
 
 GIB = 1 << 30
+MIB = 1 << 20
 SEED = 2
 PLANTS_PER_GIB = 100000
 SIGS = 10000
 METRIC = "GB/s scanned"
+KEY_BITS = 24
 
 
 def peaks():
@@ -53,6 +69,18 @@ def peaks():
     if os.path.exists(p):
         return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
     return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def traffic_for(tag):
+    """DRAM bytes per launch of the dominant kernel from the committed ncu capture of config `tag`
+    (profiles/traffic.json), or None when that config was never captured -- never a guess."""
+    tp = os.path.join(ROOT, "profiles", "traffic.json")
+    if not os.path.exists(tp):
+        return None, None
+    ent = json.load(open(tp)).get("configs", {}).get(tag)
+    if not ent:
+        return None, None
+    return ent.get("dram_bytes_per_launch"), ent.get("source")
 
 
 class ClockSampler:
@@ -102,26 +130,39 @@ class ClockSampler:
                 "reasons": sorted(reasons)}
 
 
-def plants_for(sigs, total_bytes, seed):
+def plants_for(sigs, total_bytes, seed, per_gib=PLANTS_PER_GIB):
     from gpu_pattern_matching_b200 import synth
-    return synth.Plants(sigs, total_bytes, int(PLANTS_PER_GIB * total_bytes / GIB), seed)
+    return synth.Plants(sigs, total_bytes, int(per_gib * total_bytes / GIB), seed)
+
+
+_CPU_MATCHERS = {}
+
+
+def cpu_matcher(nsigs):
+    """The reference's CPU automaton for the first nsigs ClamAV signatures (oracle/_ref = the
+    reference's acsmx.c compiled here; else the oracle port), built once per signature set."""
+    if nsigs not in _CPU_MATCHERS:
+        from oracle_lib import Oracle, RefAcsm, clamav_signatures, ref_available
+        if ref_available():
+            kind, m = "reference", RefAcsm()
+        else:
+            kind, m = "port", Oracle(256)
+        for i, s in enumerate(clamav_signatures(nsigs)):
+            m.add(s, i)
+        m.compile()
+        _CPU_MATCHERS[nsigs] = (kind, m)
+    return _CPU_MATCHERS[nsigs]
 
 
 def cpu_reference_rate(sample_bytes, threads, steps=1, warmup=0):
     """GB/s of the reference's CPU walk (all threads) over the first sample_bytes of the
     workload stream.  Returns (GB/s, kind, matches, seconds per step)."""
     from gpu_pattern_matching_b200 import synth
-    from oracle_lib import Oracle, RefAcsm, clamav_signatures, ref_available
+    from oracle_lib import clamav_signatures
     sigs = clamav_signatures(SIGS)
     buf = synth.stream(sample_bytes, SEED)
     plants_for(sigs, GIB, SEED).apply_host(buf)       # same plants as the GPU arm's first GiB
-    if ref_available():
-        kind, m = "reference", RefAcsm()
-    else:
-        kind, m = "port", Oracle(256)
-    for i, s in enumerate(sigs):
-        m.add(s, i)
-    m.compile()
+    kind, m = cpu_matcher(SIGS)
     times, found = [], 0
     for it in range(warmup + steps):
         t0 = time.perf_counter()
@@ -184,9 +225,563 @@ def emit(line):
     out.flush()
 
 
+def log(*a):
+    print("[bench]", *a, file=sys.stderr, flush=True)
+
+
+# --------------------------------------------------------------------------------------------
+# one sharded stream configuration: build, run the step pipeline, check parity
+# --------------------------------------------------------------------------------------------
+
+class Ctx:
+    """Per-process state shared by all configurations."""
+
+    def __init__(self, rank, local_rank, world):
+        import torch
+        import gpu_pattern_matching_b200 as g
+        self.torch, self.g = torch, g
+        self.rank, self.local_rank, self.world = rank, local_rank, world
+        self.tdev = torch.device("cuda", local_rank)
+        self.stream = torch.cuda.current_stream()
+        self.dev = g.Device(local_rank, stream=self.stream.cuda_stream)
+        self.automata = {}
+
+    def automaton(self, nsigs):
+        """(Acsm, signature list) for the first nsigs ClamAV signatures, uploaded once."""
+        if nsigs not in self.automata:
+            from oracle_lib import clamav_signatures      # fixture reader only (signature list)
+            sigs = clamav_signatures(nsigs)
+            a = self.g.Acsm()
+            for i, s in enumerate(sigs):
+                a.add_pattern(s, i)
+            a.compile()
+            a.gen_state_table(0, self.dev.handle, None)
+            self.automata[nsigs] = (a, sigs)
+        return self.automata[nsigs]
+
+    def barrier(self):
+        if self.world > 1:
+            import torch.distributed as dist
+            dist.barrier()
+
+    def allreduce_max(self, vals):
+        if self.world == 1:
+            return [float(v) for v in vals]
+        import torch.distributed as dist
+        t = self.torch.tensor(list(vals), dtype=self.torch.float64, device=self.tdev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return [float(x) for x in t.tolist()]
+
+    def allreduce_sum(self, val):
+        if self.world == 1:
+            return int(val)
+        import torch.distributed as dist
+        t = self.torch.tensor([int(val)], dtype=self.torch.int64, device=self.tdev)
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        return int(t.item())
+
+
+def step_stats(ms):
+    if not ms:
+        return None
+    s = sorted(ms)
+    return {"best": s[0], "median": statistics.median(s), "p95": s[min(len(s) - 1, int(round(0.95 * (len(s) - 1))))],
+            "mean": sum(s) / len(s), "n": len(s)}
+
+
+def check_parity(ctx, nsigs, sigs, keys, plants, total, lmax, cuts, prefix_bytes=64 * MIB, seed=SEED):
+    """Rank 0: the checks of the module docstring on `keys` (uint64 (global end offset << 24) |
+    pattern index, the gathered list of one step).  Returns the parity dict; ["ok"] is the verdict."""
+    from gpu_pattern_matching_b200 import sharded
+    g, dev = ctx.g, ctx.dev
+    t_start = time.perf_counter()
+    out = {"ok": False, "matches": int(keys.size)}
+    keys = np.array(keys, dtype=np.uint64, copy=True)
+    out["sorted_strict"] = bool(keys.size < 2 or np.all(keys[1:] > keys[:-1]))
+    ends = plants.pos + plants.length.astype(np.uint64) - np.uint64(1)
+    want = (ends << np.uint64(KEY_BITS)) | plants.pid.astype(np.uint64)
+    out["plants"] = int(plants.count)
+    out["plants_found"] = int(np.isin(want, keys).sum())
+    off = keys >> np.uint64(KEY_BITS)
+    pid = (keys & np.uint64((1 << KEY_BITS) - 1)).astype(np.int64)
+    out["in_range"] = bool(keys.size == 0 or int(off.max()) < total)
+
+    # window straddling the first shard cut (whole stream when it is at most 1 GiB): regenerate the
+    # bytes on this GPU, copy them to the host, reference CPU walk; the walk starts cold at w_lo, so
+    # it is compared with the listed matches that START inside the window as well
+    kind, m = cpu_matcher(nsigs)
+    if total <= GIB or not cuts:
+        w_lo, w_hi = 0, min(total, GIB)
+    else:
+        w_lo = max(0, cuts[0] - GIB // 2) // 16 * 16
+        w_hi = min(total, w_lo + GIB)
+    wn = w_hi - w_lo
+    host, owner = g.matcher.pinned_empty(wn + 64, dev)
+    d = dev.alloc(wn + 64)
+    dev.synth_fill(d, (wn + 7) // 8 * 8, seed, w_lo)
+    dev.plant(d, wn, w_lo, plants)
+    g._lib.check(g.lib().acm_memcpy_d2h(dev.handle, C.c_void_p(host.ctypes.data), C.c_void_p(d), wn), "d2h")
+    dev.sync()
+    dev.free(d)
+    window = host[:wn]
+    cpu_count = int(m.walk_count_mt(window, os.cpu_count() or 1))
+    lens = np.array([len(s) for s in sigs], dtype=np.int64)
+    i0, i1 = np.searchsorted(off, [np.uint64(w_lo), np.uint64(w_hi)])
+    starts = off[i0:i1].astype(np.int64) - lens[pid[i0:i1]] + 1
+    gpu_count = int((starts >= w_lo).sum())
+    out["window"] = {"lo": int(w_lo), "hi": int(w_hi), "straddles_cut": bool(cuts and w_lo < cuts[0] < w_hi),
+                     "cpu_walk": kind, "cpu_count": cpu_count, "gpu_count": gpu_count}
+
+    # full list on the first prefix_bytes of the window against the CPU list
+    pn = min(prefix_bytes, wn)
+    eo, ep, _, _ = m.search(window[:pn], base=w_lo)
+    j1 = np.searchsorted(off, np.uint64(w_lo + pn))
+    sel = starts[:j1 - i0] >= w_lo
+    go, gp = off[i0:j1][sel], pid[i0:j1][sel]
+    out["prefix_list"] = {"bytes": int(pn), "cpu_matches": int(eo.size), "gpu_matches": int(go.size),
+                          "equal": bool(go.size == eo.size and np.array_equal(go, eo) and np.array_equal(gp, ep))}
+    del window, host, owner
+    out["ok"] = bool(out["sorted_strict"] and out["in_range"] and out["plants_found"] == out["plants"] and
+                     cpu_count == gpu_count and out["prefix_list"]["equal"])
+    out["seconds"] = round(time.perf_counter() - t_start, 2)
+    return out
+
+
+def run_stream_config(ctx, nsigs, per, seed, steps, warmup, tail_for_clocks=False, want_e2e=False,
+                      want_databuf=False):
+    """ClamAV nsigs x (per bytes per GPU) seeded random stream through the step pipeline on every
+    rank.  Returns a dict on rank 0 (value, step stats, roofline numbers, parity, ...), None elsewhere."""
+    from gpu_pattern_matching_b200 import sharded
+    torch, g, dev = ctx.torch, ctx.g, ctx.dev
+    rank, world = ctx.rank, ctx.world
+    acsm, sigs = ctx.automaton(nsigs)
+    lmax = acsm.get_max_pattern_size()
+    total = per * world
+    read_lo, lo, hi = sharded.shard_window(total, world, rank, lmax)
+    n = hi - read_lo
+    data = torch.empty(n + 64, dtype=torch.uint8, device=ctx.tdev)
+    dev.synth_fill(data.data_ptr(), (n + 7) // 8 * 8, seed, read_lo)
+    plants = plants_for(sigs, total, seed)
+    dev.plant(data.data_ptr(), n, read_lo, plants)
+    dev.sync()
+
+    emit_lo = lo - read_lo
+    key_add = read_lo << sharded.KEY_PAT_BITS
+    cap_keys = max(1 << 21, int(2.5 * PLANTS_PER_GIB * per / GIB))
+    pipe = sharded.StepPipeline(dev, acsm.automaton, hi - lo, cap_keys, rank, world,
+                                scanner_kwargs={"timing": 0 if os.environ.get("BENCH_NO_KERNEL_TIMING") else 2})
+    k1_ms, stats = [], {"launches": 0, "fallback": 0, "matches": 0, "mode": 0, "list_bytes": 0, "keys": None}
+
+    def note(out):
+        res, tot, keys = out
+        k1_ms.append(res.ms_scan)
+        stats["launches"] += res.launches
+        stats["fallback"] |= res.fallback
+        stats["mode"] = res.mode
+        if tot is not None:
+            stats["matches"] = tot
+            stats["list_bytes"] = int(keys.nbytes)
+            stats["keys"] = keys
+
+    def run_steps(k, events=None):
+        for i in range(k):
+            pipe.submit(data.data_ptr(), n, emit_lo, n, key_add)
+            if events is not None:
+                events[i + 1].record(ctx.stream)
+            if i > 0:
+                note(pipe.complete())
+        if k > 0:
+            note(pipe.complete())
+
+    run_steps(warmup)
+    k1_ms.clear()
+    stats["launches"] = 0
+    sampler = ClockSampler(ctx.local_rank) if tail_for_clocks and rank == 0 else None
+    if sampler:
+        sampler.start()
+    ctx.barrier()
+    torch.cuda.synchronize()
+    evs = [torch.cuda.Event(enable_timing=True) for _ in range(steps + 1)]
+    ev_end = torch.cuda.Event(enable_timing=True)
+    evs[0].record(ctx.stream)
+    run_steps(steps, evs)            # the last complete() has waited for the last step and its D2H
+    ev_end.record(ctx.stream)
+    torch.cuda.synchronize()
+    ctx.barrier()
+    ms = evs[0].elapsed_time(ev_end)
+    per_step = [evs[i].elapsed_time(evs[i + 1]) for i in range(steps)]
+    k1_avg = sum(k1_ms) / max(1, len(k1_ms))
+    keys_last = None if stats["keys"] is None else np.array(stats["keys"], copy=True)
+    matches, fallback, mode = stats["matches"], stats["fallback"], stats["mode"]
+    ms, k1_avg = ctx.allreduce_max([ms, k1_avg])
+    launches = ctx.allreduce_sum(stats["launches"])
+    clocks = None
+    if tail_for_clocks:
+        # K steps of this workload last a few milliseconds, nvidia-smi samples every 50 ms: the same
+        # steps keep running, untimed, for ~0.6 s more so that the clock / throttle samples are taken
+        # under the load that was just timed (same count on every rank: ms is the max over ranks)
+        tail_steps = int(min(20000, max(steps, 600.0 / max(ms / steps, 1e-3))))
+        run_steps(tail_steps)
+        torch.cuda.synchronize()
+        if sampler:
+            clocks = sampler.stop()
+            clocks["window"] = (f"the {steps} timed steps ({ms:.1f} ms) and {tail_steps} identical untimed steps "
+                                f"that follow them, sampled every 50 ms")
+    ms_per_step = ms / steps
+
+    e2e = e2e_db = None
+    if want_e2e:
+        e2e = e2e_scan_host(ctx, acsm, data, emit_lo, per, lo, lmax, steps, warmup, total)
+    if want_databuf:
+        e2e_db = e2e_databuf(ctx, nsigs, data, emit_lo, per, steps, total)
+    pipe.close()
+    ctx.barrier()
+    if rank != 0:
+        del data
+        return None
+    peak, peak_src = peaks()
+    achieved = per / (max(k1_avg, 1e-9) * 1e-3) / 1e9
+    cuts = [sharded.shard_bounds(total, world, r)[0] for r in range(1, world)]
+    parity = check_parity(ctx, nsigs, sigs, keys_last, plants, total, lmax, cuts, seed=seed)
+    del data
+    stride = g.lib().acm_automaton_sample_stride(acsm.automaton)
+    return {
+        "value": total / (ms_per_step * 1e-3) / 1e9, "ms_per_step": ms_per_step, "step_ms": step_stats(per_step),
+        "per": per, "total": total, "lmax": lmax, "states": acsm.get_states(), "mode": mode,
+        "matches": matches, "fallback": int(fallback), "list_bytes": stats["list_bytes"],
+        "launches": launches, "k1_ms": k1_avg, "k1_stats": step_stats(k1_ms), "achieved": achieved, "peak": peak,
+        "peak_src": peak_src, "clocks": clocks, "parity": parity, "e2e": e2e, "e2e_databuf": e2e_db,
+        "kernel": "k_scan_" + g.MODE_NAMES[mode] + (
+            f"<{stride}> + k_resolve_queue (scan stage: both launches inside one event pair)" if mode == 1 else ""),
+    }
+
+
+def e2e_scan_host(ctx, acsm, data, emit_lo, per, lo, lmax, steps, warmup, total):
+    """The same shard from pinned host memory through acm_scan_host (all ranks; max over ranks)."""
+    g, dev, torch = ctx.g, ctx.dev, ctx.torch
+    host, owner = g.matcher.pinned_empty(per + 64, dev)      # on the GPU's own NUMA node where allowed
+    # identical bytes: copy the kept range of the device shard back once (outside timing)
+    g._lib.check(g.lib().acm_memcpy_d2h(dev.handle, C.c_void_p(host.ctypes.data),
+                                   C.c_void_p(data.data_ptr() + emit_lo), per), "d2h")
+    dev.sync()
+    seg = 64 << 20
+    hs = g.Scanner(dev, acsm.automaton, seg)
+    cap = 1 << 22
+    off = np.empty(cap, dtype=np.uint64)
+    pat = np.empty(cap, dtype=np.uint32)
+    r = g._lib.ScanResult()
+
+    def e2e_step():
+        got = g.lib().acm_scan_host(hs._h, C.c_void_p(host.ctypes.data), per, lo,
+                                    off.ctypes.data_as(g._lib.u64p), pat.ctypes.data_as(g._lib.u32p),
+                                    cap, C.byref(r))
+        g._lib.check(got, "acm_scan_host")
+        return int(got)
+    for _ in range(max(1, min(warmup, 3))):
+        e2e_matches = e2e_step()
+    ctx.barrier()
+    torch.cuda.synchronize()
+    e_steps = max(3, min(steps, 5))
+    t0 = time.perf_counter()
+    for _ in range(e_steps):
+        e2e_matches = e2e_step()
+    torch.cuda.synchronize()
+    dt = (time.perf_counter() - t0) / e_steps
+    (dt,) = ctx.allreduce_max([dt])
+    nseg = (per + seg - 1) // seg
+    hs.close()
+    del owner
+    return {"value": total / dt / 1e9, "unit": "GB/s",
+            "h2d_bytes_per_step": int(per + (nseg - 1) * (lmax - 1)),
+            "d2h_bytes_per_step": int(e2e_matches * 8 + nseg * 16),
+            "ms_per_step": dt * 1e3, "matches": e2e_matches,
+            "api": "acm_scan_host (pinned host buffer, 64 MiB segments, H2D overlapped with the scan)"}
+
+
+def e2e_databuf(ctx, nsigs, data, emit_lo, per, steps, total):
+    """The same shard through the reference's own call sequence (ocl_aho_grep.c:116-137), one
+    ocl_worker_ctx per rank: the pinned host stream is handed to the databuf 128 MiB at a time
+    (db->h_data points into it, as if databuf_add_fd had just read those bytes), then
+    databuf_copy_host_to_device -> ocl_aho_match(stream = 1) -> databuf_copy_device_to_host ->
+    databuf_process_results -> databuf_reset.  H2D, scan, D2H of the list and the result decoding
+    are all inside the timed region."""
+    g, dev, torch = ctx.g, ctx.dev, ctx.torch
+    L = g.lib()
+    from oracle_lib import read_fixture
+    chunk, chunks = 4096, 32768                   # README shape: 128 MiB buffers
+    size = chunk * chunks
+    nbuf = per // size
+    if nbuf == 0:
+        return None
+    host, owner = g.matcher.pinned_empty(per + 64, dev)
+    g._lib.check(L.acm_memcpy_d2h(dev.handle, C.c_void_p(host.ctypes.data),
+                                  C.c_void_p(data.data_ptr() + emit_lo), per), "d2h")
+    dev.sync()
+    with tempfile.NamedTemporaryFile(prefix="acm_sigs_", suffix=".hex", delete=False) as f:
+        f.write(b"\n".join(read_fixture("clamav_sigs_15000.hex.gz").split(b"\n")[:nsigs]) + b"\n")
+        pat_path = f.name
+    w = L.ocl_worker_ctx_create(ctx.local_rank)
+    if not w:
+        raise SystemExit("bench: ocl_worker_ctx_create: " + g._lib.last_error())
+    names = (C.c_char_p * 1)(b"stream")
+    fds = (C.c_int * 1)(-1)
+    rc = L.ocl_worker_ctx_init(w, ctx.local_rank, 1024, chunks, 0, pat_path.encode(), 1, -1, chunk, 16,
+                               0, 0, 0, 0, 1, 1, fds, names)
+    os.unlink(pat_path)
+    if rc != 0:
+        raise SystemExit("bench: ocl_worker_ctx_init: " + g._lib.last_error())
+    wc = w.contents
+    db = wc.db
+    own_h_data = C.cast(db.contents.h_data, C.c_void_p).value
+    null_cb = g._lib.MATCH_CB()                  # NULL: count only (a Python callback per match would be the bottleneck)
+
+    def one_pass():
+        found = 0
+        for k in range(nbuf):
+            db.contents.h_data = C.cast(C.c_void_p(host.ctypes.data + k * size), g._lib.u8p)
+            db.contents.chunks = chunks
+            db.contents.bytes = size
+            L.databuf_copy_host_to_device(db, wc.cl.queue)
+            # stream = 0 on the first buffer of a pass drops the carry of the previous pass
+            L.ocl_aho_match(C.byref(wc.cl), db, wc.acsm, 1024, 1 if k else 0)
+            L.databuf_copy_device_to_host(db, wc.cl.queue)
+            if L.databuf_status(db) != 0:
+                raise SystemExit("bench: databuf path: " + g._lib.last_error())
+            found += L.databuf_process_results(db, null_cb, None)
+            L.databuf_reset(db)
+        return found
+    db.contents.h_data = C.cast(C.c_void_p(host.ctypes.data), g._lib.u8p)
+    found = one_pass()
+    ctx.barrier()
+    torch.cuda.synchronize()
+    e_steps = max(3, min(steps, 5))
+    t0 = time.perf_counter()
+    for _ in range(e_steps):
+        found = one_pass()
+    dt = (time.perf_counter() - t0) / e_steps
+    (dt,) = ctx.allreduce_max([dt])
+    db.contents.h_data = C.cast(C.c_void_p(own_h_data), g._lib.u8p)
+    L.ocl_worker_ctx_free(w)
+    del owner
+    return {"value": total / dt / 1e9, "unit": "GB/s", "h2d_bytes_per_step": int(nbuf * size),
+            "d2h_bytes_per_step": int(found * 12), "ms_per_step": dt * 1e3, "matches": int(found),
+            "buffers_per_step": int(nbuf), "buffer_bytes": size,
+            "api": "databuf_copy_host_to_device -> ocl_aho_match -> databuf_copy_device_to_host -> "
+                   "databuf_process_results -> databuf_reset, 128 MiB databufs (32768 x 4096), one worker"}
+
+
+# --------------------------------------------------------------------------------------------
+# BASELINE.json configs other than the headline
+# --------------------------------------------------------------------------------------------
+
+def config1_small(ctx):
+    """configs[0]: ClamAV 2000 x 32 MiB (seed 7, 4096 planted), one GPU, FULL list against the
+    CPU list.  32 MiB fits the 126 MB L2, so a 256 MiB buffer is overwritten between iterations."""
+    torch, g, dev = ctx.torch, ctx.g, ctx.dev
+    nsigs, n, seed = 2000, 32 * MIB, 7
+    acsm, sigs = ctx.automaton(nsigs)
+    data = torch.empty(n + 64, dtype=torch.uint8, device=ctx.tdev)
+    dev.synth_fill(data.data_ptr(), n, seed, 0)
+    from gpu_pattern_matching_b200 import synth
+    plants = synth.Plants(sigs, n, 4096, seed)
+    dev.plant(data.data_ptr(), n, 0, plants)
+    flush = torch.empty(256 * MIB, dtype=torch.uint8, device=ctx.tdev)
+    sc = g.Scanner(dev, acsm.automaton, n, timing=1)
+    tot, k1 = [], []
+    for it in range(3 + 10):
+        flush.fill_(it & 0xFF)
+        res = sc.scan_device(data.data_ptr(), n)
+        if it >= 3:
+            tot.append(res.ms_total)
+            k1.append(res.ms_scan)
+    off, pat = sc.fetch()
+    host = dev.d2h(data.data_ptr(), n)
+    kind, m = cpu_matcher(nsigs)
+    eo, ep, _, _ = m.search(host)
+    equal = bool(off.size == eo.size and np.array_equal(off, eo) and np.array_equal(pat, ep))
+    sc.close()
+    del data, flush
+    peak, _ = peaks()
+    best = min(tot)
+    return {"config": "configs[0]: clamav2000 x 32 MiB seeded random stream (seed 7), 4096 planted, 1 GPU",
+            "value": n / (statistics.median(tot) * 1e-3) / 1e9, "unit": "GB/s", "n_gpus": 1,
+            "ms_scan_prefix_compact": step_stats(tot), "ms_scan_stage": step_stats(k1),
+            "roofline_frac": n / (statistics.median(k1) * 1e-3) / 1e9 / peak,
+            "best_gbs": n / (best * 1e-3) / 1e9, "kernel": g.MODE_NAMES[res.mode],
+            "l2_policy": "input (32 MiB) fits L2: a 256 MiB buffer is overwritten before every iteration",
+            "parity": {"ok": equal, "full_list": True, "cpu_walk": kind, "cpu_matches": int(eo.size),
+                       "gpu_matches": int(off.size)}}
+
+
+def _cpu_list_mt(m, buf, halo, threads):
+    """Sorted (offsets, patterns) of the CPU walk over buf, sharded over `threads` python threads
+    (the C search releases the GIL); shard i starts `halo` bytes early and keeps matches ending in
+    its own range."""
+    n = buf.size
+    cuts = [n * i // threads for i in range(threads + 1)]
+    res = [None] * threads
+
+    def work(i):
+        lo, hi = cuts[i], cuts[i + 1]
+        s = max(0, lo - halo)
+        o, p, _, _ = m.search(buf[s:hi], emit_from=lo - s, base=s, cap=max(1024, (hi - lo) // 4))
+        res[i] = (o, p)
+    th = [threading.Thread(target=work, args=(i,)) for i in range(threads)]
+    for t in th:
+        t.start()
+    for t in th:
+        t.join()
+    return np.concatenate([r[0] for r in res]), np.concatenate([r[1] for r in res])
+
+
+def config4_lexicon(ctx, nbytes):
+    """configs[3]: sentiment lexicon (4 376 words) over English-like text, one match per ~9 bytes:
+    the config that stresses scan + prefix sum + compaction.  K1 alone and K1+K2+K3, full list
+    against the CPU list (python-thread-sharded oracle walk)."""
+    torch, g, dev = ctx.torch, ctx.g, ctx.dev
+    from gpu_pattern_matching_b200 import synth
+    from helpers import build_oracle, load_patterns
+    from oracle_lib import read_fixture
+    lex = load_patterns("sentiment_categorical.pat.gz")
+    a = g.Acsm()
+    for p, iid in lex:
+        a.add_pattern(p, iid)
+    a.compile()
+    a.gen_state_table(0, dev.handle, None)
+    words = [l.split(b"\t")[0] for l in read_fixture("english_top5000.txt.gz").split(b"\n") if l]
+    tile = synth.english_like(words, 32 * MIB, seed=4)
+    text = np.tile(tile, nbytes // tile.size + 1)[:nbytes]
+    data = torch.empty(nbytes + 64, dtype=torch.uint8, device=ctx.tdev)
+    dev.h2d(data.data_ptr(), text)
+    sc = g.Scanner(dev, a.automaton, nbytes, timing=1)
+    k1, k2, k3, tot = [], [], [], []
+    for it in range(2 + 5):
+        res = sc.scan_device(data.data_ptr(), nbytes)
+        if it >= 2:
+            k1.append(res.ms_scan)
+            k2.append(res.ms_prefix)
+            k3.append(res.ms_compact)
+            tot.append(res.ms_total)
+    t0 = time.perf_counter()
+    off, pat = sc.fetch()
+    t_fetch = time.perf_counter() - t0
+    o = build_oracle(lex)
+    t0 = time.perf_counter()
+    eo, ep = _cpu_list_mt(o, text, a.get_max_pattern_size() - 1, os.cpu_count() or 4)
+    t_cpu = time.perf_counter() - t0
+    equal = bool(off.size == eo.size and np.array_equal(off, eo) and np.array_equal(pat, ep))
+    h = hashlib.sha256()
+    h.update(off.tobytes())
+    h.update(pat.tobytes())
+    sc.close()
+    del data
+    peak, _ = peaks()
+    med = statistics.median
+    return {"config": f"configs[3]: sentiment lexicon ({len(lex)} patterns, {a.get_states()} states) x "
+                      f"{nbytes / GIB:g} GiB English-like text (32 MiB Zipf tile repeated), 1 GPU",
+            "value": nbytes / (med(tot) * 1e-3) / 1e9, "unit": "GB/s", "n_gpus": 1,
+            "k1_gbs": nbytes / (med(k1) * 1e-3) / 1e9, "k1_k2_k3_gbs": nbytes / (med(tot) * 1e-3) / 1e9,
+            "ms": {"k1": step_stats(k1), "k2": step_stats(k2), "k3": step_stats(k3), "total": step_stats(tot)},
+            "roofline_frac": nbytes / (med(k1) * 1e-3) / 1e9 / peak,
+            "roofline_frac_with_output": (nbytes + 8 * int(off.size)) / (med(tot) * 1e-3) / 1e9 / peak,
+            "kernel": g.MODE_NAMES[res.mode], "matches": int(off.size), "bytes_per_match": nbytes / max(1, off.size),
+            "fallback": int(res.fallback),
+            "parity": {"ok": equal, "full_list": True, "cpu_walk": "port (oracle/acsm_oracle.c, python-thread-sharded)",
+                       "cpu_matches": int(eo.size), "gpu_matches": int(off.size), "sha256": h.hexdigest(),
+                       "cpu_seconds": round(t_cpu, 1), "fetch_seconds": round(t_fetch, 1)}}
+
+
+def summarize_stream(r, label, scaling, steps, warmup):
+    peak = r["peak"]
+    return {"config": label, "value": r["value"], "unit": "GB/s", "n_gpus": None, "scaling": scaling,
+            "steps": steps, "warmup": warmup, "ms_per_step": r["ms_per_step"], "step_ms": r["step_ms"],
+            "bytes_per_gpu": r["per"], "kernel": r["kernel"], "scan_stage_ms": r["k1_ms"],
+            "scan_stage_gbs_per_gpu": r["achieved"], "roofline_frac": r["achieved"] / peak,
+            "whole_step_frac_per_gpu": r["per"] / (r["ms_per_step"] * 1e-3) / 1e9 / peak,
+            "matches": r["matches"], "fallback": r["fallback"], "parity": r["parity"]}
+
+
+def run_other_configs(ctx, args):
+    """Short runs of the BASELINE.json configs that are not the headline.  Collective: every rank
+    takes part in the sharded ones; rank 0 alone runs the single-GPU ones."""
+    out = []
+    world, rank = ctx.world, ctx.rank
+    steps, warmup = 10, 3
+    if rank == 0 and world == 1:
+        t0 = time.perf_counter()
+        out.append(config1_small(ctx))
+        log(f"config 1 done in {time.perf_counter() - t0:.1f} s")
+    # configs[2]: 15000 signatures over a FIXED 4 GiB stream split over the N GPUs (strong scaling)
+    t0 = time.perf_counter()
+    r = run_stream_config(ctx, 15000, 4 * GIB // world, 3, steps, warmup)
+    if r:
+        e = summarize_stream(r, f"configs[2]: clamav15000 x 4 GiB seeded random stream (seed 3) split over "
+                                f"{world} GPU(s) ({4 / world:g} GiB each, halo {r['lmax'] - 1} B), "
+                                f"{PLANTS_PER_GIB} planted/GiB", "strong", steps, warmup)
+        e["n_gpus"] = world
+        out.append(e)
+        log(f"config 3 done in {time.perf_counter() - t0:.1f} s")
+    if world == 1 and not args.no_dfa_leg:
+        e = config3_dfa_leg(ctx)
+        if rank == 0 and e:
+            out.append(e)
+    if rank == 0 and world == 1:
+        t0 = time.perf_counter()
+        out.append(config4_lexicon(ctx, args.text_bytes))
+        log(f"config 4 done in {time.perf_counter() - t0:.1f} s")
+    if world == 8:
+        t0 = time.perf_counter()
+        r = run_stream_config(ctx, 15000, 4 * GIB, 5, steps, warmup)
+        if r:
+            e = summarize_stream(r, "configs[4]: clamav15000 x 32 GiB seeded random stream (seed 5), 4 GiB per GPU "
+                                    f"x 8 GPUs, halo {r['lmax'] - 1} B, sorted list gathered to the host every step",
+                                 "weak", steps, warmup)
+            e["n_gpus"] = world
+            out.append(e)
+            log(f"config 5 done in {time.perf_counter() - t0:.1f} s")
+    return out
+
+
+def config3_dfa_leg(ctx):
+    """configs[2] in its literal form: the same 15000-signature automaton walked as a DFA (one
+    table lookup per byte, k_scan_dfa: compact transition table, hot rows in shared memory) over
+    a 256 MiB slice of the stream; list against the sampled kernel's on the same slice."""
+    torch, g, dev = ctx.torch, ctx.g, ctx.dev
+    if ctx.rank != 0:
+        return None
+    nsigs, n, seed = 15000, 256 * MIB, 3
+    acsm, sigs = ctx.automaton(nsigs)
+    data = torch.empty(n + 64, dtype=torch.uint8, device=ctx.tdev)
+    dev.synth_fill(data.data_ptr(), n, seed, 0)
+    plants = plants_for(sigs, 4 * GIB, seed)
+    dev.plant(data.data_ptr(), n, 0, plants)
+    ref = g.Scanner(dev, acsm.automaton, n)
+    ref.scan_device(data.data_ptr(), n)
+    ro, rp = ref.fetch()
+    ref.close()
+    sc = g.Scanner(dev, acsm.automaton, n, mode=g.MODE_DFA, timing=1)
+    k1 = []
+    for it in range(1 + 3):
+        res = sc.scan_device(data.data_ptr(), n)
+        if it >= 1:
+            k1.append(res.ms_scan)
+    off, pat = sc.fetch()
+    sc.close()
+    del data
+    peak, _ = peaks()
+    equal = bool(off.size == ro.size and np.array_equal(off, ro) and np.array_equal(pat, rp))
+    return {"config": "configs[2], DFA form: clamav15000 walked one table lookup per byte (k_scan_dfa) over the "
+                      "first 256 MiB of the seed-3 stream, 1 GPU",
+            "value": n / (statistics.median(k1) * 1e-3) / 1e9, "unit": "GB/s", "n_gpus": 1,
+            "ms_scan": step_stats(k1), "roofline_frac": n / (statistics.median(k1) * 1e-3) / 1e9 / peak,
+            "kernel": "k_scan_dfa", "states": acsm.get_states(), "matches": int(off.size),
+            "parity": {"ok": equal, "against": "the sampled kernel's list on the same bytes (itself checked "
+                                               "against the CPU walk in configs[2])",
+                       "gpu_matches": int(off.size), "expected": int(ro.size)}}
+
+
 def main():
     global SIGS
-    guard_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=50)
@@ -194,17 +789,27 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--bytes-per-gpu", type=int, default=GIB)
     ap.add_argument("--sigs", type=int, default=SIGS, choices=[2000, 10000, 15000],
-                    help="ClamAV signature set (default 10000 = BASELINE configs[1]; 15000 with "
-                         "--bytes-per-gpu 4294967296 is configs[2])")
+                    help="ClamAV signature set of the headline run (default 10000 = BASELINE configs[1])")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--only-main", action="store_true", help="skip other_configs")
+    ap.add_argument("--no-dfa-leg", action="store_true")
+    ap.add_argument("--text-bytes", type=int, default=GIB, help="size of the configs[3] text")
     args = ap.parse_args()
-    args.warmup = max(args.warmup, 0)
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else max(args.warmup, 0)
     SIGS = args.sigs
 
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
+
+    if args.impl == "ours" and args.gpus > 1 and "WORLD_SIZE" not in os.environ:
+        # python bench.py --gpus N: one process per GPU needs a launcher
+        port = 29500 + os.getpid() % 2000
+        cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={args.gpus}",
+               "--master-addr", "127.0.0.1", "--master-port", str(port), os.path.abspath(__file__)] + sys.argv[1:]
+        raise SystemExit(subprocess.call(cmd))
+    guard_stdout()
 
     if args.impl == "reference":
         run_reference(args, rank)
@@ -212,222 +817,64 @@ def main():
 
     import torch
     import torch.distributed as dist
-    import gpu_pattern_matching_b200 as g
-    from gpu_pattern_matching_b200 import sharded
-    from oracle_lib import clamav_signatures      # fixture reader only (signature list)
 
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device; the product has no CPU path")
+    if world != args.gpus:
+        raise SystemExit(f"bench.py: --gpus {args.gpus} but WORLD_SIZE is {world}: launch one process per GPU "
+                         "(torchrun --nproc-per-node N), or run `python bench.py --gpus N` without torchrun")
     torch.cuda.set_device(local_rank)
-    tdev = torch.device("cuda", local_rank)
     if world > 1:
-        dist.init_process_group("nccl", device_id=tdev)
-    assert world == args.gpus or world == 1, "launch with torchrun --nproc-per-node == --gpus"
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    ctx = Ctx(rank, local_rank, world)
 
-    # ---- automaton (replicated) ----
-    sigs = clamav_signatures(SIGS)
-    acsm = g.Acsm()
-    for i, s in enumerate(sigs):
-        acsm.add_pattern(s, i)
-    acsm.compile()
-    stream = torch.cuda.current_stream()
-    dev = g.Device(local_rank, stream=stream.cuda_stream)
-    conf_ctx = dev.handle
-    acsm.gen_state_table(0, conf_ctx, None)
-    lmax = acsm.get_max_pattern_size()
-
-    # ---- this rank's shard of the world*bytes stream, generated in HBM ----
     per = args.bytes_per_gpu
-    total = per * world
-    read_lo, lo, hi = sharded.shard_window(total, world, rank, lmax)
-    n = hi - read_lo
-    data = torch.empty(n + 64, dtype=torch.uint8, device=tdev)
-    dev.synth_fill(data.data_ptr(), (n + 7) // 8 * 8, SEED, read_lo)
-    plants = plants_for(sigs, total, SEED)
-    dev.plant(data.data_ptr(), n, read_lo, plants)
-    dev.sync()
-
-    emit_lo = lo - read_lo
-    key_add = read_lo << sharded.KEY_PAT_BITS
-    use_nccl = world > 1 and os.environ.get("BENCH_GATHER", "peer") == "nccl"
-    k1_ms, stats = [], {"launches": 0, "fallback": 0, "matches": 0, "mode": 0, "list_bytes": 0}
-
-    if not use_nccl:
-        # default: pipelined steps, keys pushed into rank 0's HBM by the step itself (NVLink IPC
-        # stores at N > 1), D2H of the gathered list on rank 0's side stream, every step
-        pipe = sharded.StepPipeline(dev, acsm.automaton, hi - lo, 1 << 21, rank, world,
-                                    scanner_kwargs={"timing": 0 if os.environ.get("BENCH_NO_KERNEL_TIMING") else 2})
-
-        def note(out):
-            res, total, keys = out
-            k1_ms.append(res.ms_scan)
-            stats["launches"] += res.launches
-            stats["fallback"] |= res.fallback
-            stats["mode"] = res.mode
-            if total is not None:
-                stats["matches"] = total
-                stats["list_bytes"] = int(keys.nbytes)
-
-        def run_steps(k):
-            for i in range(k):
-                pipe.submit(data.data_ptr(), n, emit_lo, n, key_add)
-                if i > 0:
-                    note(pipe.complete())
-            if k > 0:
-                note(pipe.complete())
-    else:
-        # portable path: NCCL all-gather of the counts + grouped send/recv of the keys, synchronous
-        scanner = g.Scanner(dev, acsm.automaton, hi - lo, timing=True)
-        pinned_out = torch.empty(1 << 22, dtype=torch.int64).pin_memory() if rank == 0 else None
-
-        def run_steps(k):
-            for _ in range(k):
-                res = scanner.scan_device(data.data_ptr(), n, emit_lo, n)
-                counts = sharded.exchange_counts(res.n_matches, tdev)
-                keys = sharded._as_tensor(scanner.keys_ptr(), max(1, int(res.n_matches)), tdev)
-                keys = keys[:int(res.n_matches)] + key_add
-                out = sharded.gather_keys(keys, counts, 0)
-                if rank == 0:
-                    pinned_out[:sum(counts)].copy_(out, non_blocking=True)
-                    stream.synchronize()
-                k1_ms.append(res.ms_scan)
-                stats["launches"] += res.launches
-                stats["fallback"] |= res.fallback
-                stats["mode"] = res.mode
-                stats["matches"] = sum(counts)
-                stats["list_bytes"] = sum(counts) * 8
-
-    run_steps(args.warmup)
-    k1_ms.clear()
-    stats["launches"] = 0
-
-    sampler = ClockSampler(local_rank)
+    t0 = time.perf_counter()
+    r = run_stream_config(ctx, SIGS, per, SEED, args.steps, args.warmup, tail_for_clocks=True,
+                          want_e2e=not args.no_e2e, want_databuf=not args.no_e2e)
     if rank == 0:
-        sampler.start()
-    if world > 1:
-        dist.barrier()
-    torch.cuda.synchronize()
-    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    ev0.record(stream)
-    run_steps(args.steps)            # the last complete() has waited for the last step and its D2H
-    ev1.record(stream)
-    torch.cuda.synchronize()
-    if world > 1:
-        dist.barrier()
-    ms = ev0.elapsed_time(ev1)
-    k1_avg = sum(k1_ms) / len(k1_ms)
-    launches, matches, fallback, mode = stats["launches"], stats["matches"], stats["fallback"], stats["mode"]
-    if world > 1:
-        t = torch.tensor([ms, k1_avg], dtype=torch.float64, device=tdev)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms, k1_avg = float(t[0].item()), float(t[1].item())
-        t = torch.tensor([launches], dtype=torch.int64, device=tdev)
-        dist.all_reduce(t, op=dist.ReduceOp.SUM)
-        launches = int(t.item())
-    # K steps of this workload last a few milliseconds, nvidia-smi samples every 50 ms: the same
-    # steps keep running, untimed, for ~0.6 s more so that the clock / throttle samples are taken
-    # under the load that was just timed (same count on every rank: ms is the max over ranks)
-    tail_steps = int(min(20000, max(args.steps, 600.0 / max(ms / args.steps, 1e-3))))
-    saved = (list(k1_ms), dict(stats))
-    run_steps(tail_steps)
-    torch.cuda.synchronize()
-    k1_ms[:] = saved[0]
-    stats.update(saved[1])
-    clocks = sampler.stop() if rank == 0 else None
-    if clocks is not None:
-        clocks["window"] = (f"the {args.steps} timed steps ({ms:.1f} ms) and {tail_steps} identical untimed steps "
-                            f"that follow them, sampled every 50 ms")
-    ms_per_step = ms / args.steps
-    value = total / (ms_per_step * 1e-3) / 1e9
-
-    # ---- e2e: same shard from pinned host memory through acm_scan_host ----
-    e2e = None
-    if not args.no_e2e:
-        host, owner = g.matcher.pinned_empty(per + 64, dev)      # on the GPU's own NUMA node where allowed
-        # identical bytes: copy the kept range of the device shard back once (outside timing)
-        g._lib.check(g.lib().acm_memcpy_d2h(dev.handle, C.c_void_p(host.ctypes.data),
-                                       C.c_void_p(data.data_ptr() + emit_lo), per), "d2h")
-        dev.sync()
-        seg = 64 << 20
-        hs = g.Scanner(dev, acsm.automaton, seg)
-        cap = 1 << 22
-        off = np.empty(cap, dtype=np.uint64)
-        pat = np.empty(cap, dtype=np.uint32)
-        r = g._lib.ScanResult()
-
-        def e2e_step():
-            got = g.lib().acm_scan_host(hs._h, C.c_void_p(host.ctypes.data), per, lo,
-                                        off.ctypes.data_as(g._lib.u64p), pat.ctypes.data_as(g._lib.u32p),
-                                        cap, C.byref(r))
-            g._lib.check(got, "acm_scan_host")
-            return int(got)
-        for _ in range(max(1, args.warmup)):
-            e2e_matches = e2e_step()
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-        e_steps = max(3, min(args.steps, 5))
-        t0 = time.perf_counter()
-        for _ in range(e_steps):
-            e2e_matches = e2e_step()
-        torch.cuda.synchronize()
-        dt = (time.perf_counter() - t0) / e_steps
-        if world > 1:
-            t = torch.tensor([dt], dtype=torch.float64, device=tdev)
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            dt = float(t.item())
-        nseg = (per + seg - 1) // seg
-        e2e = {"value": total / dt / 1e9, "unit": "GB/s",
-               "h2d_bytes_per_step": int(per + (nseg - 1) * (lmax - 1)),
-               "d2h_bytes_per_step": int(e2e_matches * 8 + nseg * 16),
-               "ms_per_step": dt * 1e3, "matches": e2e_matches,
-               "api": "acm_scan_host (pinned host buffer, 64 MiB segments, H2D overlapped with the scan)"}
-        hs.close()
-        del owner
-
-    if not use_nccl:
-        pipe.close()
+        log(f"headline config done in {time.perf_counter() - t0:.1f} s: {r['value']:.0f} GB/s, parity ok = "
+            f"{r['parity']['ok']}")
+    others = [] if args.only_main else run_other_configs(ctx, args)
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
         return
 
-    peak, peak_src = peaks()
-    achieved = per / (max(k1_avg, 1e-9) * 1e-3) / 1e9
-    traffic = None
-    tp = os.path.join(ROOT, "profiles", "traffic.json")
-    if os.path.exists(tp):
-        traffic = json.load(open(tp)).get("k_scan_sampled_dram_bytes_per_launch")
+    total = r["total"]
+    traffic, traffic_src = traffic_for(f"clamav{SIGS}")
     line = {
-        "metric": METRIC, "value": value, "unit": "GB/s", "n_gpus": world, "steps": args.steps,
-        "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
+        "metric": METRIC, "value": r["value"], "unit": "GB/s", "n_gpus": world, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": r["ms_per_step"], "step_ms": r["step_ms"],
+        "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "u8", "data": "synthetic",
         "config": {"workload": f"clamav{SIGS} x {total / GIB:g} GiB seeded random stream "
-                               f"({per / GIB:g} GiB per GPU, halo {lmax - 1} B), {PLANTS_PER_GIB} planted signatures/GiB",
-                   "signatures": SIGS, "states": acsm.get_states(), "kernel": g.MODE_NAMES[mode],
-                   "bytes_per_gpu": per, "matches": matches, "fallback": int(fallback),
+                               f"({per / GIB:g} GiB per GPU, halo {r['lmax'] - 1} B), {PLANTS_PER_GIB} planted signatures/GiB",
+                   "signatures": SIGS, "states": r["states"], "kernel": ctx.g.MODE_NAMES[r["mode"]],
+                   "bytes_per_gpu": per, "matches": r["matches"], "fallback": r["fallback"],
                    "l2_policy": (f"input ({per / GIB:g} GiB per GPU) is larger than L2 (126 MB); no flush needed"
                                  if per > (256 << 20) else
                                  f"WARNING: input ({per >> 20} MiB per GPU) is not much larger than L2 (126 MB)"),
-                   "step": ("scan + prefix sum + compaction/sort + NCCL count all-gather + key send/recv to "
-                            "rank 0 + D2H of the list" if use_nccl else
-                            "scan + prefix sum + compaction/sort + push of the sorted keys into rank 0's gather "
+                   "step": ("scan + prefix sum + compaction/sort + push of the sorted keys into rank 0's gather "
                             "buffer (NVLink IPC stores at N > 1) + D2H of the gathered list to pinned host "
                             "memory, every step; steps are queued two deep (acm_scan_device_async / "
                             "acm_scan_finish), so the host round trip overlaps the next step's scan"),
-                   "list_d2h_bytes_per_step": stats["list_bytes"]},
-        "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                     "frac": achieved / peak, "traffic": traffic,
-                     "kernel": "k_scan_" + g.MODE_NAMES[mode] + (
-                         f"<{g.lib().acm_automaton_sample_stride(acsm.automaton)}> + k_resolve_queue "
-                         "(scan stage: both launches inside one event pair; the streaming kernel alone "
-                         "is ~80 % of it, see profiles/)" if mode == 1 else ""),
-                     "kernel_ms": k1_avg, "algorithmic_bytes_per_launch": per, "peak_source": peak_src},
-        "gpu_launches": int(launches),
-        "clocks": clocks,
+                   "list_d2h_bytes_per_step": r["list_bytes"]},
+        "roofline": {"bound": "hbm", "achieved": r["achieved"], "peak": r["peak"], "unit": "GB/s",
+                     "frac": r["achieved"] / r["peak"], "traffic": traffic, "traffic_source": traffic_src,
+                     "kernel": r["kernel"], "kernel_ms": r["k1_ms"], "kernel_ms_stats": r["k1_stats"],
+                     "algorithmic_bytes_per_launch": per, "peak_source": r["peak_src"],
+                     "whole_step_frac": per / (r["ms_per_step"] * 1e-3) / 1e9 / r["peak"]},
+        "gpu_launches": int(r["launches"]),
+        "clocks": r["clocks"],
+        "parity": r["parity"],
     }
-    if e2e:
-        line["e2e"] = e2e
+    if r["e2e"]:
+        line["e2e"] = r["e2e"]
+        line["parity"]["e2e_matches_equal"] = bool(world > 1 or r["e2e"]["matches"] == r["matches"])
+    if r["e2e_databuf"]:
+        line["e2e_databuf"] = r["e2e_databuf"]
+        line["parity"]["e2e_databuf_matches_equal"] = bool(world > 1 or r["e2e_databuf"]["matches"] == r["matches"])
     if not args.no_cpu_baseline and world == 1:
         cores = os.cpu_count() or 1
         sample = int(min(GIB, max(32 << 20, int(cores * 60e6 * 8) // (1 << 20) * (1 << 20))))
@@ -436,9 +883,17 @@ def main():
                                 "sample": f"first {sample >> 20} MiB of rank 0's stream, "
                                           f"{found} matches, {sec:.2f} s",
                                 "single_thread_gbs": cpu_reference_rate.single_thread_gbs}
+    if others:
+        line["other_configs"] = others
+    ok = bool(line["parity"]["ok"] and all(v for k, v in line["parity"].items() if k.endswith("_equal")) and
+              all(o["parity"]["ok"] for o in others))
+    line["parity"]["all_configs_ok"] = ok
     emit(line)
     if world > 1:
         dist.destroy_process_group()
+    if not ok:
+        log("PARITY FAILURE -- see the parity blocks of the JSON line")
+        raise SystemExit(3)
 
 
 if __name__ == "__main__":
