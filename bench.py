@@ -242,8 +242,13 @@ class Ctx:
         self.torch, self.g = torch, g
         self.rank, self.local_rank, self.world = rank, local_rank, world
         self.tdev = torch.device("cuda", local_rank)
-        self.stream = torch.cuda.current_stream()
+        # a real (non-default) stream shared by torch and the library: the legacy default stream has
+        # handle 0, which acm_device_set_stream reads as "use your own stream", and events recorded
+        # on torch's stream would then not see the library's kernels
+        self.stream = torch.cuda.Stream(device=self.tdev)
+        torch.cuda.set_stream(self.stream)
         self.dev = g.Device(local_rank, stream=self.stream.cuda_stream)
+        assert self.stream.cuda_stream != 0
         self.automata = {}
 
     def automaton(self, nsigs):
