@@ -173,6 +173,7 @@ SIGNATURES = {
     "acsm_status": (C.c_int, [C.POINTER(AcsmStruct)]),
     "acsm_export_ref_table": (C.c_int, [C.POINTER(AcsmStruct)]),
     "acsm_check_filters": (C.c_int, [C.POINTER(AcsmStruct)]),
+    "acsm_check_cdfa": (C.c_int, [C.POINTER(AcsmStruct), C.POINTER(C.c_uint), C.POINTER(C.c_uint)]),
     "acsm_device_automaton": (vp, [C.POINTER(AcsmStruct)]),
     # iacsmx.h
     "iacsm_new": (C.POINTER(IacsmStruct), []),

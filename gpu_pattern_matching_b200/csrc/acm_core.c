@@ -145,7 +145,7 @@ acm_tables_free(struct acm_tables *t)
 	free(t->bfs_to_ref); free(t->f1); free(t->f2); free(t->grams); free(t->b2); free(t->b2s); free(t->b3);
 	free(t->cand); free(t->pat_blob); free(t->pat_off);
 	free(t->cd_cls); free(t->cd_tab); free(t->cd_flat_begin); free(t->cd_flat_pat);
-	free(t->cd_rec); free(t->cd_t16); free(t->cd_flat4);
+	free(t->rd_tab); free(t->rd_flat4); free(t->cd_flat4);
 	memset(t, 0, sizeof(*t));
 }
 
@@ -171,8 +171,8 @@ acm_tables_device_bytes(const struct acm_tables *t)
 	if (t->cd_tab)
 		b += (size_t)t->num_states * t->cd_classes * 2 + 256 + (size_t)(t->num_states + 1) * 4 +
 		    (size_t)t->cd_flat_total * 4 + (size_t)t->num_states * 16;
-	if (t->cd_rec)
-		b += (size_t)t->num_states * 8 + (size_t)t->cd_t16_count * 2;
+	if (t->rd_tab)
+		b += (size_t)t->rd_len * 20;
 	return b;
 }
 
@@ -227,37 +227,87 @@ cmp_u32(const void *a, const void *b)
 }
 
 /*
- * Delta encoding of cd_tab against the rows of shallow states (see acm_tables.h).  A state's row
- * differs from the row of a state on its failure chain only in the columns where some state in
- * between has a trie child, so deep states keep one or two explicit entries instead of C.
- * fail[] / depth[] are in cd ids.  Picks the dense depth that makes the whole thing smallest;
- * leaves cd_rec NULL when even that does not fit the shared-memory budget or a 16-bit index.
+ * Row-displaced form of cd_tab: ONE 4-byte shared-memory lookup per transition in the common case.
+ *
+ * A state's row differs from the row of a state on its failure chain only in the columns where
+ * some state in between has a trie child, so a deep state needs one or two "explicit" entries
+ * instead of C.  Rows of the states up to depth d ("dense" states, ids 0 .. nd-1) are stored whole,
+ * 33 entries (132 bytes) apart -- 33, not 32, so that column c of different dense rows falls into
+ * different shared-memory banks: text is mostly "the same few letters after different prefixes",
+ * and with a stride of 32 words every lane that reads 'e' out of a dense row would hit one bank;
+ * a deeper state s keeps only the columns where its row differs from
+ * the row of D(s), the first dense state on its failure chain.  All sparse rows are overlaid into
+ * one array by first-fit row displacement (Tarjan & Yao): s gets a base rd_off[s], unique among
+ * all states, such that its explicit column c lives at rd_tab[rd_off[s] + c] and nobody else's
+ * entry does.  An entry carries the column it was stored for, so
+ *
+ *     e = rd_tab[off(s) + c];  if (column(e) != c)  e = rd_tab[33 * drow(s) + c];
+ *
+ * is the transition: the entry found at off(s) + c with column field c can only belong to the
+ * state whose base is exactly off(s), i.e. to s.  The state IS the entry that led to it:
+ *
+ *     bits  0..4   column the entry is stored for (31 = empty slot)
+ *     bits  5..7   |full match list of the target| (0 .. 4)
+ *     bits  8..15  drow(target): the target's dense row (its own when the target is dense)
+ *     bits 16..31  off(target)
+ *
+ * so no per-state record is read (the delta encoding this replaces read an 8-byte record and
+ * then the entry: two dependent, bank-conflicting loads per byte).  rd_flat4[off] is the full
+ * match list of the state with that base.  Needs the pattern bytes in one range (cd_range_lo),
+ * C <= 31, at most 256 dense rows and 65 504 slots; picks the dense depth that makes the table
+ * smallest; leaves rd_tab NULL when it does not fit the shared-memory budget.
+ * fail[] / depth[] are in cd ids.
  */
+struct rd_row {
+	uint32_t state, n;
+};
+
 static int
-build_cdfa_delta(struct acm_tables *t, const uint32_t *fail, const uint8_t *depth, int max_depth)
+cmp_rd_row(const void *a, const void *b)
 {
-	const uint32_t C = t->cd_classes, n = t->num_states;
-	uint32_t *dflt = malloc((size_t)n * 4);
-	uint32_t s, k;
-	int d, best_d = -1;
+	const struct rd_row *x = a, *y = b;
+
+	if (x->n != y->n)
+		return x->n > y->n ? -1 : 1;
+	return x->state < y->state ? -1 : (x->state > y->state);
+}
+
+static int
+build_cdfa_rd(struct acm_tables *t, const uint32_t *fail, const uint8_t *depth, int max_depth)
+{
+	const uint32_t C = t->cd_classes, n = t->num_states, CAP = 65536;
+	uint32_t *dflt = NULL, *off = NULL, *tab = NULL;
+	uint8_t *occ = NULL, *used_base = NULL;
+	struct rd_row *rows = NULL;
+	uint32_t s, k, nd = 0, len = 0, lowfree;
+	int d, best_d = -1, rc = ACM_OK;
 	size_t best = (size_t)-1;
 
-	if (!dflt)
-		return ACM_ERR_NOMEM;
+	if (t->cd_range_lo < 0 || C > 31)
+		return ACM_OK;
+	dflt = malloc((size_t)n * 4);
+	off = malloc((size_t)n * 4);
+	rows = malloc((size_t)n * sizeof(*rows));
+	occ = calloc(CAP + 64, 1);
+	used_base = calloc(CAP + 64, 1);
+	if (!dflt || !off || !rows || !occ || !used_base) {
+		rc = ACM_ERR_NOMEM;
+		goto out;
+	}
 	/* cd ids keep breadth-first order except that a few deep states sit at the very end:
-	 * "depth <= d" is a prefix of the ids for every d that matters, checked here */
+	 * "depth <= d" must be a prefix of the ids */
 	for (d = 0; d <= max_depth && d < 255; d++) {
-		uint32_t nd = 0;
+		uint32_t m = 0;
 		size_t entries;
 		int prefix = 1;
-		while (nd < n && depth[nd] <= d)
-			nd++;
-		for (s = nd; s < n && prefix; s++)
+		while (m < n && depth[m] <= d)
+			m++;
+		for (s = m; s < n && prefix; s++)
 			prefix = depth[s] > d;
-		if (!prefix)
+		if (!prefix || m > ACM_RD_MAX_DENSE)
 			continue;
-		entries = (size_t)nd * C;
-		for (s = nd; s < n; s++) {
+		entries = (size_t)m * ACM_RD_ROW;
+		for (s = m; s < n; s++) {
 			const uint16_t *a, *b;
 			dflt[s] = depth[fail[s]] <= d ? fail[s] : dflt[fail[s]];
 			a = t->cd_tab + (size_t)s * C;
@@ -265,53 +315,194 @@ build_cdfa_delta(struct acm_tables *t, const uint32_t *fail, const uint8_t *dept
 			for (k = 0; k < C; k++)
 				entries += a[k] != b[k];
 		}
-		if (entries <= 65536 && (size_t)nd * C <= 65536 && entries * 2 < best) {
-			best = entries * 2;
+		if (entries < best) {
+			best = entries;
 			best_d = d;
 		}
 	}
-	if (best_d < 0 || best + (size_t)n * 8 + 64 > ACM_CD_COMP_BUDGET) {
-		free(dflt);
-		return ACM_OK;
-	}
+	if (best_d < 0 || best + 64 > CAP || best * 4 > ACM_RD_SMEM_BUDGET)
+		goto out;
 	d = best_d;
-	t->cd_rec = malloc((size_t)n * 8);
-	t->cd_t16 = malloc(best + 64);
-	if (!t->cd_rec || !t->cd_t16) {
-		free(dflt);
+	while (nd < n && depth[nd] <= d)
+		nd++;
+	for (s = 0; s < n; s++) {
+		const uint16_t *a = t->cd_tab + (size_t)s * C, *b;
+		rows[s].state = s;
+		rows[s].n = 0;
+		if (s < nd) {
+			dflt[s] = s;
+			continue;
+		}
+		dflt[s] = depth[fail[s]] <= d ? fail[s] : dflt[fail[s]];
+		b = t->cd_tab + (size_t)dflt[s] * C;
+		for (k = 0; k < C; k++)
+			rows[s].n += a[k] != b[k];
+	}
+	/* dense rows first, whole; their columns C .. 31 stay free for displaced entries */
+	for (s = 0; s < nd; s++) {
+		off[s] = s * ACM_RD_ROW;
+		used_base[off[s]] = 1;
+		memset(occ + off[s], 1, C);
+	}
+	len = nd * ACM_RD_ROW;
+	/* first fit, rows with the most explicit entries first */
+	qsort(rows + nd, n - nd, sizeof(*rows), cmp_rd_row);
+	lowfree = 0;
+	for (uint32_t r = nd; r < n; r++) {
+		const uint32_t st = rows[r].state;
+		const uint16_t *a = t->cd_tab + (size_t)st * C, *b = t->cd_tab + (size_t)dflt[st] * C;
+		uint32_t cols[32], nc = 0, base, p;
+		int placed = 0;
+
+		for (k = 0; k < C; k++)
+			if (a[k] != b[k])
+				cols[nc++] = k;
+		while (lowfree < CAP && occ[lowfree])
+			lowfree++;
+		if (nc == 0) {
+			/* no entry of its own: any base nobody else uses (identity only) */
+			for (base = 0; base + 32 < CAP && used_base[base]; base++)
+				;
+			if (base + 32 >= CAP)
+				goto out;
+			off[st] = base;
+			used_base[base] = 1;
+			if (base + 32 > len)
+				len = base + 32;
+			continue;
+		}
+		/* the first explicit column goes to a free slot p >= lowfree: base = p - cols[0] */
+		for (p = lowfree > cols[0] ? lowfree : cols[0]; p + 32 < CAP; p++) {
+			if (occ[p])
+				continue;
+			base = p - cols[0];
+			if (used_base[base])
+				continue;
+			for (k = 1; k < nc && !occ[base + cols[k]]; k++)
+				;
+			if (k < nc)
+				continue;
+			placed = 1;
+			break;
+		}
+		if (!placed)
+			goto out;
+		off[st] = base;
+		used_base[base] = 1;
+		for (k = 0; k < nc; k++)
+			occ[base + cols[k]] = 1;
+		if (base + 32 > len)
+			len = base + 32;
+	}
+	if ((size_t)len * 4 > ACM_RD_SMEM_BUDGET)
+		goto out;
+	tab = malloc((size_t)len * 4 + 64);
+	t->rd_flat4 = calloc((size_t)len * 4 + 16, 4);
+	if (!tab || !t->rd_flat4) {
+		rc = ACM_ERR_NOMEM;
+		goto out;
+	}
+	for (k = 0; k < len; k++)
+		tab[k] = ACM_RD_EMPTY;
+	for (s = 0; s < n; s++) {
+		const uint16_t *a = t->cd_tab + (size_t)s * C, *b = t->cd_tab + (size_t)dflt[s] * C;
+		for (k = 0; k < C; k++) {
+			if (s < nd || a[k] != b[k]) {
+				const uint32_t nx = a[k] & ACM_CD_STATE_MASK, recs = t->cd_flat4[(size_t)nx * 4] >> 24;
+				tab[off[s] + k] = k | (recs << 5) | (dflt[nx] << 8) | (off[nx] << 16);
+			}
+		}
+		memcpy(t->rd_flat4 + (size_t)off[s] * 4, t->cd_flat4 + (size_t)s * 4, 16);
+	}
+	t->rd_tab = tab;
+	tab = NULL;
+	t->rd_len = len;
+	t->rd_dense_rows = nd;
+	t->rd_dense_depth = d;
+out:
+	if (rc != ACM_OK || !t->rd_tab) {
+		free(t->rd_flat4);
+		t->rd_flat4 = NULL;
+	}
+	free(dflt); free(off); free(rows); free(occ); free(used_base); free(tab);
+	return rc;
+}
+
+/*
+ * Test support: walks cd_tab and rd_tab in lockstep from the root over every (state, column) and
+ * counts disagreements in target, match-count code or match list.  Every state is a trie node,
+ * hence reachable, so 0 means the row-displaced table IS the automaton.  -1: no rd table.
+ * *slots / *dense report the table shape.
+ */
+int
+acm_core_check_rd(const struct acm_core *c, uint32_t *slots, uint32_t *dense)
+{
+	const struct acm_tables *t = &c->tab;
+	const uint32_t C = t->cd_classes, n = t->num_states;
+	uint32_t *ent, *queue, head = 0, tail = 0, k;
+	int bad = 0;
+
+	if (!t->rd_tab || !t->cd_tab)
+		return -1;
+	if (slots)
+		*slots = t->rd_len;
+	if (dense)
+		*dense = t->rd_dense_rows;
+	ent = malloc((size_t)n * 4);           /* cd id -> the entry (state word) it was reached by */
+	queue = malloc((size_t)n * 4);
+	if (!ent || !queue) {
+		free(ent); free(queue);
 		return ACM_ERR_NOMEM;
 	}
-	{
-		uint32_t nd = 0, w;
-		while (nd < n && depth[nd] <= d)
-			nd++;
-		w = nd * C;
-		memcpy(t->cd_t16, t->cd_tab, (size_t)nd * C * 2);
-		for (s = 0; s < n; s++) {
-			uint32_t bitmap = 0, base = 0, D = s;
-			if (s >= nd) {
-				const uint16_t *a = t->cd_tab + (size_t)s * C, *b;
-				D = dflt[s] = depth[fail[s]] <= d ? fail[s] : dflt[fail[s]];
-				b = t->cd_tab + (size_t)D * C;
-				base = w;
-				for (k = 0; k < C; k++) {
-					if (a[k] != b[k]) {
-						bitmap |= 1u << k;
-						t->cd_t16[w++] = a[k];
-					}
-				}
-				if (!bitmap)
-					base = 0;
+	memset(ent, 0xFF, (size_t)n * 4);
+	ent[0] = 0;                            /* root: base 0, dense row 0 */
+	queue[tail++] = 0;
+	while (head < tail) {
+		const uint32_t s = queue[head++], e = ent[s];
+		const uint32_t off = e >> 16, drow = (e >> 8) & 0xFF;
+		for (k = 0; k < C; k++) {
+			uint32_t x, nx, want = t->cd_tab[(size_t)s * C + k];
+			if (off + k >= t->rd_len) {
+				bad++;
+				continue;
 			}
-			t->cd_rec[2 * s] = bitmap;
-			t->cd_rec[2 * s + 1] = (base & 0xFFFFu) | ((D * C) << 16);
+			x = t->rd_tab[off + k];
+			if ((x & 31) != k)
+				x = t->rd_tab[drow * ACM_RD_ROW + k];
+			if ((x & 31) != k || ((x >> 5) & 7) != (t->cd_flat4[(size_t)(want & ACM_CD_STATE_MASK) * 4] >> 24)) {
+				bad++;
+				continue;
+			}
+			nx = want & ACM_CD_STATE_MASK;
+			if (ent[nx] == 0xFFFFFFFFu) {
+				ent[nx] = x;
+				queue[tail++] = nx;
+			} else if ((ent[nx] >> 8) != (x >> 8)) {
+				bad++;                     /* same target must mean same base and dense row */
+			}
+			if (memcmp(t->rd_flat4 + (size_t)(x >> 16) * 4, t->cd_flat4 + (size_t)nx * 4, 16) != 0)
+				bad++;
 		}
-		t->cd_t16_count = w;
-		t->cd_dense_states = nd;
 	}
-	t->cd_dense_depth = d;
-	free(dflt);
-	return ACM_OK;
+	if (tail != n)
+		bad += (int)(n - tail);
+	/* bases are unique */
+	{
+		uint8_t *seen = calloc(65536, 1);
+		uint32_t s;
+		if (seen) {
+			for (s = 0; s < n; s++) {
+				if (ent[s] == 0xFFFFFFFFu)
+					continue;
+				if (seen[ent[s] >> 16])
+					bad++;
+				seen[ent[s] >> 16] = 1;
+			}
+			free(seen);
+		}
+	}
+	free(ent); free(queue);
+	return bad;
 }
 
 /*
@@ -465,8 +656,7 @@ build_cdfa(struct acm_core *c)
 	}
 	t->cd_classes = C;
 	t->cd_thr4 = n4 ? ((3u << ACM_CD_STATE_BITS) | (n - n4)) : 0xFFFFFFFFu;
-	if (C <= 32)
-		rc = build_cdfa_delta(t, fail, depth, t->max_depth);
+	rc = build_cdfa_rd(t, fail, depth, t->max_depth);
 out:
 	free(cnt); free(perm); free(fail); free(depth);
 	if (rc == ACM_OK && !t->cd_classes) {

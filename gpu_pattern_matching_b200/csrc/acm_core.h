@@ -42,6 +42,8 @@ int  acm_core_compile(struct acm_core *);
 int  acm_core_export_ref(struct acm_core *, int **out);
 /* sampled-filter tables against the patterns: number of violations, -1 if no filter was built */
 int  acm_core_check_filters(const struct acm_core *);
+/* row-displaced dense-output table against the class-compressed one: violations, -1 if not built */
+int  acm_core_check_rd(const struct acm_core *, uint32_t *slots, uint32_t *dense);
 /* drop host tables and pattern bytes (device copy stays) */
 void acm_core_cleanup(struct acm_core *);
 void acm_core_free(struct acm_core *);

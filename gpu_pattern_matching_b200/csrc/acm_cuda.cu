@@ -19,6 +19,7 @@
 #include "acm_tables.h"
 #include "k1_scan.cuh"
 #include "k234_post.cuh"
+#include "k1_rd.cuh"
 
 #define CUDA_TRY(expr)                                                              \
 	do {                                                                            \
@@ -63,8 +64,10 @@ struct acm_scanner {
 	struct acm_scan_params p;
 	uint64_t  max_bytes;
 	uint32_t  shift, cap, max_buckets;
-	uint32_t  cd_hot, cd_tab_bytes, cd_rec_bytes;   /* CDFA: shared-memory layout (see k_scan_cdfa) */
-	int       cd_comp;
+	uint32_t  cd_hot, cd_tab_bytes;                 /* CDFA, plain table: shared-memory layout (see k_scan_cdfa) */
+	int       rd;                                   /* CDFA through the row-displaced table (k_scan_rd + k_rd_expand) */
+	uint32_t  rd_warps, rd_tab_bytes, rd_log_cap, rd_regions;
+	uint32_t *rd_loglen;
 	uint64_t *buckets;
 	uint32_t *counts, *offsets;
 	uint8_t  *scratch;          /* one allocation, one memset per scan: flags | bucket_tiles | counts */
@@ -141,14 +144,12 @@ set_kernel_attrs(int ordinal)
 	    S2_SMEM_BYTES(1)));
 	CUDA_TRY(cudaFuncSetAttribute(k_bucket_sort_compact, cudaFuncAttributeMaxDynamicSharedMemorySize,
 	    65536));
-	CUDA_TRY(cudaFuncSetAttribute(k_scan_cdfa<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+	CUDA_TRY(cudaFuncSetAttribute(k_scan_cdfa<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
 	    CD_SMEM_MAX));
-	CUDA_TRY(cudaFuncSetAttribute(k_scan_cdfa<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+	CUDA_TRY(cudaFuncSetAttribute(k_scan_cdfa<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
 	    CD_SMEM_MAX));
-	CUDA_TRY(cudaFuncSetAttribute(k_scan_cdfa<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-	    CD_SMEM_MAX));
-	CUDA_TRY(cudaFuncSetAttribute(k_scan_cdfa<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-	    CD_SMEM_MAX));
+	CUDA_TRY(cudaFuncSetAttribute(k_scan_rd, cudaFuncAttributeMaxDynamicSharedMemorySize, CD_SMEM_MAX));
+	CUDA_TRY(cudaFuncSetAttribute(k_rd_expand, cudaFuncAttributeMaxDynamicSharedMemorySize, RD_K3_SMEM));
 	if (ordinal < 64)
 		g_attr_done[ordinal] = 1;
 	return ACM_OK;
@@ -523,11 +524,10 @@ acm_automaton_upload(struct acm_device *dev, const struct acm_tables *t, struct 
 		a->d.cd_classes = t->cd_classes;
 		a->d.cd_range_lo = t->cd_range_lo;
 		a->d.cd_thr4 = t->cd_thr4;
-		if (t->cd_rec) {
-			UP(cd_rec, t->cd_rec, (size_t)t->num_states * 8);
-			UP(cd_t16, t->cd_t16, (size_t)t->cd_t16_count * 2);
-			a->d.cd_t16_count = t->cd_t16_count;
-			a->d.cd_dense_states = t->cd_dense_states;
+		if (t->rd_tab) {
+			UP(rd_tab, t->rd_tab, (size_t)t->rd_len * 4);
+			UP(rd_flat4, t->rd_flat4, (size_t)t->rd_len * 16);
+			a->d.rd_len = t->rd_len;
 		}
 	}
 #undef UP
@@ -778,7 +778,8 @@ acm_scanner_free(struct acm_scanner *s)
 	free(s);
 }
 
-/* (re)allocates buckets, scratch (flags | tile states | counts) and offsets for s->shift / s->cap */
+/* (re)allocates buckets, scratch (flags | scan tile states | counts | log lengths)
+ * and offsets for s->shift / s->cap */
 static int
 scanner_alloc_buckets(struct acm_scanner *s)
 {
@@ -791,19 +792,29 @@ scanner_alloc_buckets(struct acm_scanner *s)
 	/* CDFA cuts chunks on absolute multiples of 2^shift: one more partial bucket */
 	s->max_buckets = (uint32_t)((s->max_bytes + (1ull << s->shift) - 1) >> s->shift) + 2;
 	s->n_bucket_tiles = (s->max_buckets + SCAN_TILE - 1) / SCAN_TILE + 1;
-	/* CDFA rows hold 4-byte hits (offset in chunk, state); everything else 8-byte record keys */
-	const size_t slot = s->p.mode == ACM_MODE_CDFA ? 4 : 8;
-	if (cudaMalloc((void **)&s->buckets, (size_t)s->max_buckets * s->cap * slot) != cudaSuccess ||
-	    cudaMalloc((void **)&s->scratch, 64 + (size_t)s->n_bucket_tiles * 8 + (size_t)s->max_buckets * 4) !=
-	    cudaSuccess ||
+	/* k_scan_rd: a region = 32 chunks; its log takes the 32 chunk rows (cap hits each) */
+	s->rd_regions = s->rd ? s->max_buckets / 32 + 2 : 0;
+	s->rd_log_cap = 32 * s->cap;
+	/* test hook: a tiny log sends every dense region down the exact two-pass path */
+	if (s->rd && getenv("ACM_RD_LOG_CAP") && atoi(getenv("ACM_RD_LOG_CAP")) > 32 * RD_CHECK &&
+	    (uint32_t)atoi(getenv("ACM_RD_LOG_CAP")) < s->rd_log_cap)
+		s->rd_log_cap = (uint32_t)atoi(getenv("ACM_RD_LOG_CAP")) / RD_LOG_ALIGN * RD_LOG_ALIGN;
+	/* plain CDFA rows hold 4-byte hits; k_scan_rd logs 8-byte hits; everything else 8-byte record keys */
+	const size_t slot = s->p.mode == ACM_MODE_CDFA && !s->rd ? 4 : 8;
+	const size_t rows = s->rd ? (size_t)s->rd_regions * 32 : s->max_buckets;
+	const size_t scratch_bytes = 64 + (size_t)s->n_bucket_tiles * 8 + (size_t)s->max_buckets * 4 +
+	    (size_t)s->rd_regions * 4;
+	if (cudaMalloc((void **)&s->buckets, rows * s->cap * slot) != cudaSuccess ||
+	    cudaMalloc((void **)&s->scratch, scratch_bytes) != cudaSuccess ||
 	    cudaMalloc((void **)&s->offsets, (size_t)s->max_buckets * 4) != cudaSuccess) {
 		acm_set_error("scanner: cannot allocate %zu bytes of result buckets: %s",
-		    (size_t)s->max_buckets * s->cap * slot, cudaGetErrorString(cudaGetLastError()));
+		    rows * s->cap * slot, cudaGetErrorString(cudaGetLastError()));
 		return ACM_ERR_CUDA;
 	}
 	s->flags = (uint32_t *)s->scratch;
 	s->bucket_tiles = (uint64_t *)(s->scratch + 64);
 	s->counts = (uint32_t *)(s->scratch + 64 + (size_t)s->n_bucket_tiles * 8);
+	s->rd_loglen = s->counts + s->max_buckets;
 	return ACM_OK;
 }
 
@@ -856,11 +867,33 @@ acm_scanner_create(struct acm_device *dev, struct acm_automaton *aut, uint64_t m
 	if (mode == ACM_MODE_CDFA) {
 		/*
 		 * A bucket is one thread's chunk: 256 bytes unless the halo (Lmax - 1) asks for more
-		 * (chunk >= 4 x halo keeps the cold-start overhead <= 25 %), room for one record per
+		 * (chunk >= 4 x halo keeps the cold-start overhead <= 25 %), room for one hit per
 		 * 4 bytes before the exact two-pass path takes over.
 		 */
 		const uint32_t halo = aut->max_len > 0 ? (uint32_t)aut->max_len - 1 : 0;
+		const char *plain = getenv("ACM_CD_PLAIN");
+		uint32_t sh_rd = 8;
+		while ((1u << sh_rd) < 4 * halo)
+			sh_rd++;
+		/* the row-displaced table in shared memory with at least 8 warps beside it: k_scan_rd */
+		if (aut->d.rd_tab && !(plain && atoi(plain)) && sh_rd <= RD_MAX_SHIFT) {
+			const uint32_t tab_bytes = (aut->d.rd_len * 4 + 15) & ~15u;
+			const uint32_t tabpad = (tab_bytes + 1023) & ~1023u;
+			uint32_t w = tabpad + 64 < CD_SMEM_MAX ? (CD_SMEM_MAX - 64 - tabpad) / RD_WARP_SMEM : 0;
+			const char *we = getenv("ACM_RD_WARPS");
+			if (w > 32)
+				w = 32;
+			if (we && atoi(we) > 0 && (uint32_t)atoi(we) < w)
+				w = (uint32_t)atoi(we);
+			if (w >= 8 || (we && w >= 1)) {
+				s->rd = 1;
+				s->rd_warps = w;
+				s->rd_tab_bytes = tab_bytes;
+			}
+		}
 		uint32_t sh = s->p.bucket_shift ? (uint32_t)s->p.bucket_shift : 8u;
+		if (s->rd)
+			sh = sh_rd;             /* the chunk size is the kernel's: a caller's bucket shape is a hint */
 		while (sh < 30 && (1u << sh) < 4 * halo)
 			sh++;
 		if (sh > 32 - ACM_CD_STATE_BITS) {
@@ -870,17 +903,10 @@ acm_scanner_create(struct acm_device *dev, struct acm_automaton *aut, uint64_t m
 			return ACM_ERR_ARG;
 		}
 		s->p.bucket_shift = (int)sh;
-		if (!s->p.bucket_cap)
+		if (s->rd || !s->p.bucket_cap)
 			s->p.bucket_cap = (int)((1u << sh) / 4 > 8192 ? 8192 : (1u << sh) / 4);
 		const uint32_t lut_bytes = aut->d.cd_range_lo >= 0 ? 0 : CD_LUT_WORDS * 4;
-		const char *plain = getenv("ACM_CD_PLAIN");
-		if (aut->d.cd_rec && !(plain && atoi(plain))) {
-			/* delta-encoded table: all of it in shared memory */
-			s->cd_comp = 1;
-			s->cd_tab_bytes = (aut->d.cd_t16_count * 2 + 15) & ~15u;
-			s->cd_rec_bytes = (aut->num_states * 8 + 15) & ~15u;
-			s->cd_hot = aut->d.cd_dense_states;
-		} else {
+		if (!s->rd) {
 			const uint32_t row = aut->d.cd_classes * 2;
 			uint32_t budget = CD_SMEM_MAX - 16 - lut_bytes;
 			const char *kb = getenv("ACM_CD_HOT_KB");
@@ -896,7 +922,6 @@ acm_scanner_create(struct acm_device *dev, struct acm_automaton *aut, uint64_t m
 				s->cd_hot = s->cd_hot ? s->cd_hot - 1 : 0;
 				s->cd_tab_bytes = (s->cd_hot * row + 15) & ~15u;
 			}
-			s->cd_rec_bytes = 0;
 		}
 	}
 	/* sparse matches (signature sets): 128 KiB buckets of up to 1024 records keep the
@@ -1060,27 +1085,36 @@ launch_k1(struct acm_scanner *s, cudaStream_t st, const void *d_data, uint64_t n
 			    (const uint8_t *)d_data, n, v2, vec_hi, limit, a->d.b2s, a->d.split_len - 1);
 			*launches += 1;
 		}
+	} else if (s->p.mode == ACM_MODE_CDFA && s->rd) {
+		/* persistent: one CTA per SM holding the whole table, warps take regions of 32 chunks round-robin */
+		const uint64_t regions = (((limit - 1) >> E.shift) - (E.emit_lo >> E.shift) + 32) / 32;
+		uint64_t blocks = (regions + s->rd_warps - 1) / s->rd_warps;
+		if (blocks > (uint64_t)s->dev->sm_count)
+			blocks = s->dev->sm_count;
+		RdCtx R;
+		R.log = (uint2 *)s->buckets;
+		R.loglen = s->rd_loglen;
+		R.log_cap = s->rd_log_cap;
+		R.tab_bytes = s->rd_tab_bytes;
+		R.mode = E.direct ? RD_MODE_DIRECT : RD_MODE_LOG;
+		R.lo = (uint32_t)a->d.cd_range_lo;
+		R.cmax = a->d.cd_classes - 1;
+		R.tabw_out = s->flags + 8;
+		const size_t smem = ((s->rd_tab_bytes + 1023) & ~1023u) + (size_t)s->rd_warps * RD_WARP_SMEM + 64;
+		k_scan_rd<<<(unsigned)blocks, s->rd_warps * 32, smem, st>>>(a->d, E, R, (const uint8_t *)d_data, limit);
 	} else if (s->p.mode == ACM_MODE_CDFA) {
 		/* persistent: one CTA per SM holding the hot rows, threads stride over chunk pairs */
 		const uint64_t pairs = (((limit - 1) >> E.shift) - (E.emit_lo >> E.shift) + 2) / 2;
 		uint64_t blocks = (pairs + CD_THREADS - 1) / CD_THREADS;
 		if (blocks > (uint64_t)s->dev->sm_count)
 			blocks = s->dev->sm_count;
-		const size_t smem = s->cd_tab_bytes + s->cd_rec_bytes + (a->d.cd_range_lo >= 0 ? 0 : CD_LUT_WORDS * 4) + 16;
-#define CD_LAUNCH(R, Cm) k_scan_cdfa<R, Cm><<<(unsigned)blocks, CD_THREADS, smem, st>>>(a->d, E, \
-	    (const uint8_t *)d_data, limit, s->cd_hot, s->cd_tab_bytes, s->cd_rec_bytes)
-		if (a->d.cd_range_lo >= 0) {
-			if (s->cd_comp)
-				CD_LAUNCH(true, true);
-			else
-				CD_LAUNCH(true, false);
-		} else {
-			if (s->cd_comp)
-				CD_LAUNCH(false, true);
-			else
-				CD_LAUNCH(false, false);
-		}
-#undef CD_LAUNCH
+		const size_t smem = s->cd_tab_bytes + (a->d.cd_range_lo >= 0 ? 0 : CD_LUT_WORDS * 4) + 16;
+		if (a->d.cd_range_lo >= 0)
+			k_scan_cdfa<true><<<(unsigned)blocks, CD_THREADS, smem, st>>>(a->d, E, (const uint8_t *)d_data, limit,
+			    s->cd_hot, s->cd_tab_bytes);
+		else
+			k_scan_cdfa<false><<<(unsigned)blocks, CD_THREADS, smem, st>>>(a->d, E, (const uint8_t *)d_data, limit,
+			    s->cd_hot, s->cd_tab_bytes);
 	} else if (s->p.mode == ACM_MODE_START2) {
 		const uint64_t tile = (uint64_t)S2_THREADS * S2_UNROLL;
 		uint64_t blocks = (vec_hi - vec_lo + tile - 1) / tile;
@@ -1106,6 +1140,16 @@ launch_k1(struct acm_scanner *s, cudaStream_t st, const void *d_data, uint64_t n
 static void
 launch_k3(struct acm_scanner *s, cudaStream_t st, uint32_t nb, uint32_t k3_blocks, int with_push)
 {
+	if (s->p.mode == ACM_MODE_CDFA && s->rd) {
+		/* every logged hit expands on its own: grid-stride over the regions, one warp per region */
+		const uint32_t nreg = (nb + 31) / 32, w = RD_K3_THREADS / 32;
+		uint32_t blocks = (nreg + w - 1) / w;
+		if (blocks > (uint32_t)s->dev->sm_count * 8)
+			blocks = (uint32_t)s->dev->sm_count * 8;
+		k_rd_expand<<<blocks, RD_K3_THREADS, RD_K3_SMEM, st>>>((const uint2 *)s->buckets, s->rd_loglen, s->rd_log_cap, nreg,
+		    s->offsets, nb, s->out, s->out_cap, s->flags, s->aut->d.rd_flat4, s->pend.emit_lo >> s->shift, s->shift);
+		return;
+	}
 	if (s->p.mode == ACM_MODE_CDFA) {
 		/* hits are in order already: an expanding copy, one warp per bucket */
 		uint32_t blocks = (nb + 8 * K3X_NB - 1) / (8 * K3X_NB);
@@ -1208,8 +1252,9 @@ scan_launch(struct acm_scanner *s, cudaStream_t st, const void *d_data, uint64_t
 	E.cap = s->cap;
 	E.shift = s->shift;
 
-	/* flags (incl. the K1 work counters and the scan's tile counter), tile states, counts */
-	CUDA_TRY(cudaMemsetAsync(s->scratch, 0, 64 + (size_t)s->n_bucket_tiles * 8 + (size_t)nb * 4, st));
+	/* flags (incl. the K1 work counters and the scan's tile counter), tile states, counts (k_scan_rd
+	 * writes every chunk's count and every region's log length itself) */
+	CUDA_TRY(cudaMemsetAsync(s->scratch, 0, 64 + (size_t)s->n_bucket_tiles * 8 + (s->rd ? 0 : (size_t)nb * 4), st));
 	if (timing)
 		CUDA_TRY(cudaEventRecord(s->ev[0], st));
 	if ((rc = launch_k1(s, st, d_data, n, E, 0, &launches)) != ACM_OK)

@@ -39,7 +39,11 @@ enum {
 #define ACM_CD_STATE_MASK 0x3FFFu
 #define ACM_CD_MAX_STATES (1u << ACM_CD_STATE_BITS)
 #define ACM_CD_MAX_CLASSES 64
-#define ACM_CD_COMP_BUDGET (216 * 1024)   /* bytes of shared memory for cd_rec + cd_t16 */
+/* row-displaced table (k_scan_rd): entry = column | records << 5 | dense row << 8 | base << 16 */
+#define ACM_RD_EMPTY       31u             /* column field of a free slot: never a real column (C <= 31) */
+#define ACM_RD_MAX_DENSE   256u
+#define ACM_RD_ROW         33u             /* slots between dense rows (odd: bank rotation)        */
+#define ACM_RD_SMEM_BUDGET (176 * 1024)    /* bytes of shared memory the table may take (>= 16 warps still fit beside it) */
 
 #define ACM_F1_BITS_LOG2   20              /* level-1 gram bitmap: 128 KiB smem */
 #define ACM_F2_WORDS       24576u          /* level-2 gram bitmap:  96 KiB smem, word = mulhi(hash, words) */
@@ -125,16 +129,13 @@ struct acm_tables {
 	uint32_t  cd_flat_total;
 	uint32_t *cd_flat4;          /* [num_states][4]: the same lists inline (<= 4 entries): word 0 = first | count << 24 */
 	uint32_t  cd_thr4;           /* an entry >= this has FOUR patterns ending (code 3 = three or four) */
-	/* the same table delta-encoded so that ALL of it fits in shared memory (C <= 32 only):
-	 * rows of states up to depth cd_dense_depth are stored whole; a deeper state s keeps only
-	 * the columns where its row differs from the row of D(s), the first state of depth <=
-	 * cd_dense_depth on its failure chain.  cd_rec[s] = { bitmap of explicit columns,
-	 * first explicit entry | (row of D(s)) << 16 }, both indices into cd_t16.  NULL = not built. */
-	uint32_t *cd_rec;            /* [num_states][2]                               */
-	uint16_t *cd_t16;            /* dense rows, then the explicit entries of every state */
-	uint32_t  cd_t16_count;
-	int       cd_dense_depth;
-	uint32_t  cd_dense_states;   /* states of depth <= cd_dense_depth = the first ids */
+	/* the same automaton as ONE row-displaced array of 4-byte entries that fits in shared memory
+	 * (build_cdfa_rd in acm_core.c has the format); NULL = not built */
+	uint32_t *rd_tab;            /* [rd_len] entries                              */
+	uint32_t *rd_flat4;          /* [rd_len][4]: full match list of the state whose base is the slot */
+	uint32_t  rd_len;            /* slots, a multiple of nothing; reads reach rd_len - 1 at most */
+	uint32_t  rd_dense_rows;     /* states 0 .. rd_dense_rows-1 keep whole rows, ACM_RD_ROW slots apart */
+	int       rd_dense_depth;
 };
 
 void acm_tables_free(struct acm_tables *t);

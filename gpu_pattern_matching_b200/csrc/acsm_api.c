@@ -193,6 +193,13 @@ acsm_check_filters(acsm_t *a)
 }
 
 int
+acsm_check_cdfa(acsm_t *a, unsigned int *slots, unsigned int *dense_rows)
+{
+	struct acm_core *c = core_of(a);
+	return c ? acm_core_check_rd(c, slots, dense_rows) : ACM_ERR_ARG;
+}
+
+int
 acsm_export_ref_table(acsm_t *a)
 {
 	struct acm_core *c = core_of(a);

@@ -18,6 +18,7 @@
 #include "../../include/ocl_context.h"
 #include "../../include/ocl_prefix_sum.h"
 #include "acm_core.h"
+#include "acm_tables.h"
 #include "acm_queue.h"
 #include "databuf_priv.h"
 
@@ -92,8 +93,10 @@ match_common(struct databuf *db, struct acm_automaton *aut, int sym_size, int st
 	if (!pv->scanner) {
 		struct acm_scan_params p;
 		memset(&p, 0, sizeof(p));
-		/* db->max_results is per max_chunk_size bytes in the reference; scale it to a bucket */
-		p.bucket_shift = 15;
+		/* 32 KiB result buckets for the sparse-output kernels; the dense-output kernels (word
+		 * lists: a bucket is one thread's chunk there) keep their own shape */
+		if (acm_automaton_default_mode(aut) != ACM_MODE_CDFA)
+			p.bucket_shift = 15;
 		rc = acm_scanner_create(pv->dev, aut, db->size / (uint64_t)sym_size + 1, &p, &pv->scanner);
 		if (rc != ACM_OK) {
 			pv->status = rc;

@@ -30,9 +30,11 @@
  *       (SURVEY.md A.5), one table lookup per symbol, matches reported through the
  *       output links; chunks sized so that every resident thread has one.
  *
- *   k_scan_cdfa<RANGE, COMP>  (small automata over few distinct bytes: word lists over text)
- *       The same walk out of a class-compressed, delta-encoded 16-bit table that lives
- *       entirely in shared memory; hits are stored in order, the post-pass only expands.
+ *   k_scan_rd (k1_rd.cuh) / k_scan_cdfa<RANGE>  (small automata over few distinct bytes: word
+ *       lists over text, one match per ~9 bytes)
+ *       The same walk out of shared memory: k_scan_rd from a row-displaced table of 4-byte
+ *       entries (one lookup per byte); k_scan_cdfa, for automata that table does not fit, from
+ *       the first rows of the class-compressed 16-bit table with the rest served by L1/L2.
  *
  * All of them report exactly the set { (end offset, pattern index) } that a serial walk
  * of the reference's automaton reports with full match lists.
@@ -70,10 +72,9 @@ struct AutDev {
 	const uint32_t *cd_flat_begin;
 	const uint32_t *cd_flat_pat;
 	const uint4    *cd_flat4;      /* [states]: list inline, .x = first | count << 24 */
-	const uint32_t *cd_rec;        /* delta-encoded form (all of it fits in shared memory), NULL if not built */
-	const uint16_t *cd_t16;
-	uint32_t cd_t16_count;
-	uint32_t cd_dense_states;
+	const uint32_t *rd_tab;        /* row-displaced form (k_scan_rd, all of it in shared memory), NULL if not built */
+	const uint4    *rd_flat4;      /* [rd_len]: match list of the state whose base is the slot */
+	uint32_t rd_len;
 	uint32_t cd_thr4;              /* entry >= this: four patterns end there (code 3 = three or four) */
 	uint32_t cd_classes;
 	int      cd_range_lo;
@@ -99,7 +100,7 @@ struct EmitCtx {
 	uint32_t  vq_cap;        /* entries per region                                   */
 	uint32_t  cap;
 	uint32_t  shift;
-	int       direct;
+	int       direct;        /* 1: second pass of the exact two-pass path; 2: k_scan_rd's counting pass before it */
 };
 
 #define F1_WORDS (1u << (ACM_F1_BITS_LOG2 - 5))
@@ -1206,22 +1207,15 @@ k_scan_dfa(const AutDev A, const EmitCtx E, const SYM *__restrict__ data, uint64
 /* ------------------------------------------------------------------------- */
 
 /*
- * k_scan_cdfa -- the dense-output kernel (word lists over text: one match per ~9 bytes).
+ * k_scan_cdfa -- dense-output walk for the automata k_scan_rd (k1_rd.cuh) cannot take: more than
+ * 31 byte classes, pattern bytes not in one range, or a row-displaced table that does not fit
+ * shared memory.
  *
- * With that many matches a filter buys nothing: every byte has to go through the automaton.
- * So this is the plain DFA walk of reference ahomatch.cl:56-65 -- one transition per byte,
- * one thread per chunk, cold start Lmax-1 bytes early -- made cheap:
- *   - the table is class-compressed to uint16[states][C] (acm_core.c build_cdfa): 54 bytes a
- *     row for a lower-case lexicon instead of the reference's 2 KiB, 848 KiB in all instead of
- *     30.7 MiB;
- *   - COMP: that table is delta-encoded against the rows of the shallow states
- *     (build_cdfa_delta: 188 KiB for the sentiment lexicon) and lives ENTIRELY in shared
- *     memory; a transition is two dependent shared-memory loads (the state's 8-byte record,
- *     then the entry) and no branch.  With the plain table a warp step waits for its slowest
- *     lane, and some lane always missed the hot rows: 63 % of all stall samples were the L2
- *     round trip of cold rows (profiles/).
- *     !COMP (the encoding does not fit): first n_hot rows in shared memory, the rest through
- *     L1/L2;
+ * The plain DFA walk of reference ahomatch.cl:56-65 -- one transition per byte, one thread per
+ * chunk, cold start Lmax-1 bytes early:
+ *   - the table is class-compressed to uint16[states][C] (acm_core.c build_cdfa); the first
+ *     n_hot rows (breadth-first order: the shallow, most visited states) live in shared memory,
+ *     the rest is served by L1/L2;
  *   - byte -> column is arithmetic when the pattern bytes span < 64 values, else one lookup in
  *     a 32-way replicated (bank-conflict-free) table;
  *   - every thread walks TWO adjacent chunks in lockstep, two independent dependency chains;
@@ -1256,20 +1250,11 @@ __device__ __forceinline__ uint32_t lds_u16(uint32_t saddr)
 	return v;
 }
 
-__device__ __forceinline__ uint2 lds_v2(uint32_t saddr)
-{
-	uint2 v;
-	asm("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(saddr));
-	return v;
-}
-
 struct CdLook {
-	uint32_t tab_sa;          /* shared address: t16 (COMP) or the hot rows               */
-	uint32_t rec_sa;          /* shared address: state records (COMP)                     */
+	uint32_t tab_sa;          /* shared address: the hot rows                             */
 	uint32_t lut_sa;          /* shared address: replicated class map (!RANGE)            */
-	const uint16_t *tab;      /* !COMP: the whole table in global memory                  */
+	const uint16_t *tab;      /* the whole table in global memory                         */
 	uint32_t C, n_hot, rlo, cmax, lane4;
-	uint32_t crow;            /* COMP: C << 16 (record word 1 of a dense state = state * crow); n_hot = dense states */
 };
 
 template <bool RANGE>
@@ -1282,19 +1267,8 @@ __device__ __forceinline__ uint32_t cd_class(const CdLook &L, uint32_t b)
 	return (w >> ((b & 3u) * 8u)) & 0xFFu;
 }
 
-template <bool COMP>
 __device__ __forceinline__ uint32_t cd_next(const CdLook &L, uint32_t state, uint32_t c)
 {
-	if (COMP) {
-		/* a dense state's record is {no explicit columns, its own row}: computed, not loaded, so
-		 * only the lanes in deep states take part in the (bank-conflicting) 8-byte read */
-		uint2 r = make_uint2(0u, state * L.crow);
-		if (state >= L.n_hot)
-			r = lds_v2(L.rec_sa + state * 8);
-		const uint32_t onehot = 1u << c;
-		const uint32_t idx = (r.x & onehot) ? (r.y & 0xFFFFu) + __popc(r.x & (onehot - 1u)) : (r.y >> 16) + c;
-		return lds_u16(L.tab_sa + idx * 2);
-	}
 	const uint32_t idx = state * L.C + c;
 	return state < L.n_hot ? lds_u16(L.tab_sa + idx * 2) : (uint32_t)__ldg(L.tab + idx);
 }
@@ -1367,7 +1341,7 @@ __device__ __forceinline__ void cd_close(const EmitCtx &E, uint64_t b, const CdO
 }
 
 /* byte-wise walk of chunk k (absolute chunk index): the first / last chunk of a scan, direct mode */
-template <bool RANGE, bool COMP>
+template <bool RANGE>
 __device__ __noinline__ void cd_chunk_bytes(const AutDev *__restrict__ Ap, const EmitCtx *__restrict__ Ep,
     const CdLook *__restrict__ Lp, const uint8_t *__restrict__ data, uint64_t k, uint64_t limit)
 {
@@ -1387,7 +1361,7 @@ __device__ __noinline__ void cd_chunk_bytes(const AutDev *__restrict__ Ap, const
 	CdOut o = cd_open(E, b);
 	uint32_t state = 0;
 	for (; pos < hi; ++pos) {
-		const uint32_t e = cd_next<COMP>(L, state, cd_class<RANGE>(L, __ldg(data + pos)));
+		const uint32_t e = cd_next(L, state, cd_class<RANGE>(L, __ldg(data + pos)));
 		state = e & ACM_CD_STATE_MASK;
 		if ((e >> ACM_CD_STATE_BITS) && pos >= lo)
 			cd_emit(A, o, state, e >> ACM_CD_STATE_BITS, pos, (uint32_t)(pos - (k << E.shift)));
@@ -1396,29 +1370,25 @@ __device__ __noinline__ void cd_chunk_bytes(const AutDev *__restrict__ Ap, const
 }
 
 /*
- * Shared memory: [tab_bytes: t16 or hot rows][rec_bytes: state records (COMP)][class map
- * (!RANGE)][mbarrier]; all sizes multiples of 16.
+ * Shared memory: [tab_bytes: hot rows][class map (!RANGE)][mbarrier]; all sizes multiples of 16.
  */
-template <bool RANGE, bool COMP>
+template <bool RANGE>
 __global__ void __launch_bounds__(CD_THREADS, 1)
 k_scan_cdfa(const __grid_constant__ AutDev A, const __grid_constant__ EmitCtx E,
-    const uint8_t *__restrict__ data, uint64_t limit, uint32_t n_hot, uint32_t tab_bytes, uint32_t rec_bytes)
+    const uint8_t *__restrict__ data, uint64_t limit, uint32_t n_hot, uint32_t tab_bytes)
 {
 	extern __shared__ __align__(128) uint32_t cd_smem[];
 	uint8_t *sm = reinterpret_cast<uint8_t *>(cd_smem);
-	uint32_t *lut = reinterpret_cast<uint32_t *>(sm + tab_bytes + rec_bytes);
-	uint64_t *bar = reinterpret_cast<uint64_t *>(sm + tab_bytes + rec_bytes + (RANGE ? 0 : CD_LUT_WORDS * 4));
+	uint32_t *lut = reinterpret_cast<uint32_t *>(sm + tab_bytes);
+	uint64_t *bar = reinterpret_cast<uint64_t *>(sm + tab_bytes + (RANGE ? 0 : CD_LUT_WORDS * 4));
 
 	/* stage the tables: TMA bulk copies of up to 16 KiB on one mbarrier */
 	if (threadIdx.x == 0) {
-		const uint8_t *src_tab = reinterpret_cast<const uint8_t *>(COMP ? A.cd_t16 : A.cd_tab);
+		const uint8_t *src_tab = reinterpret_cast<const uint8_t *>(A.cd_tab);
 		mbar_init(bar, 1);
-		mbar_expect_tx(bar, tab_bytes + rec_bytes);
+		mbar_expect_tx(bar, tab_bytes);
 		for (uint32_t off = 0; off < tab_bytes; off += 16384)
 			bulk_g2s(sm + off, src_tab + off, min(tab_bytes - off, 16384u), bar);
-		for (uint32_t off = 0; off < rec_bytes; off += 16384)
-			bulk_g2s(sm + tab_bytes + off, reinterpret_cast<const uint8_t *>(A.cd_rec) + off,
-			    min(rec_bytes - off, 16384u), bar);
 	}
 	if (!RANGE) {
 		/* word (b >> 2) of the class map, once per bank */
@@ -1431,7 +1401,6 @@ k_scan_cdfa(const __grid_constant__ AutDev A, const __grid_constant__ EmitCtx E,
 
 	CdLook L;
 	L.tab_sa = smem_u32(sm);
-	L.rec_sa = smem_u32(sm + tab_bytes);
 	L.lut_sa = smem_u32(lut);
 	L.tab = A.cd_tab;
 	L.C = A.cd_classes;
@@ -1439,7 +1408,6 @@ k_scan_cdfa(const __grid_constant__ AutDev A, const __grid_constant__ EmitCtx E,
 	L.rlo = (uint32_t)A.cd_range_lo;
 	L.cmax = A.cd_classes - 1;
 	L.lane4 = (threadIdx.x & 31) * 4;
-	L.crow = A.cd_classes << 16;
 
 	const uint32_t shift = E.shift;
 	const uint64_t chunk = 1ull << shift;
@@ -1455,9 +1423,9 @@ k_scan_cdfa(const __grid_constant__ AutDev A, const __grid_constant__ EmitCtx E,
 		const bool fast = !E.direct && kb <= k_last && a0 >= E.emit_lo && a0 + 2 * chunk <= limit &&
 		    a0 >= halo && a0 - halo >= E.valid_lo;
 		if (!fast) {
-			cd_chunk_bytes<RANGE, COMP>(&A, &E, &L, data, ka, limit);
+			cd_chunk_bytes<RANGE>(&A, &E, &L, data, ka, limit);
 			if (kb <= k_last)
-				cd_chunk_bytes<RANGE, COMP>(&A, &E, &L, data, kb, limit);
+				cd_chunk_bytes<RANGE>(&A, &E, &L, data, kb, limit);
 			continue;
 		}
 		/*
@@ -1488,9 +1456,9 @@ k_scan_cdfa(const __grid_constant__ AutDev A, const __grid_constant__ EmitCtx E,
 				for (int q = 0; q < 16; ++q) {
 					if (v == 0 && (uint32_t)q == skip)
 						sa = sb = 0;
-					sa = cd_next<COMP>(L, sa, cd_class<RANGE>(L, (wa[q >> 2] >> (8 * (q & 3))) & 0xFFu)) &
+					sa = cd_next(L, sa, cd_class<RANGE>(L, (wa[q >> 2] >> (8 * (q & 3))) & 0xFFu)) &
 					    ACM_CD_STATE_MASK;
-					sb = cd_next<COMP>(L, sb, cd_class<RANGE>(L, (wb[q >> 2] >> (8 * (q & 3))) & 0xFFu)) &
+					sb = cd_next(L, sb, cd_class<RANGE>(L, (wb[q >> 2] >> (8 * (q & 3))) & 0xFFu)) &
 					    ACM_CD_STATE_MASK;
 				}
 			}
@@ -1513,8 +1481,8 @@ k_scan_cdfa(const __grid_constant__ AutDev A, const __grid_constant__ EmitCtx E,
 			for (int q = 0; q < 32; ++q) {
 				const uint32_t ca = cd_class<RANGE>(L, (wa[q >> 2] >> (8 * (q & 3))) & 0xFFu);
 				const uint32_t cb = cd_class<RANGE>(L, (wb[q >> 2] >> (8 * (q & 3))) & 0xFFu);
-				const uint32_t ea = cd_next<COMP>(L, sa, ca);
-				const uint32_t eb = cd_next<COMP>(L, sb, cb);
+				const uint32_t ea = cd_next(L, sa, ca);
+				const uint32_t eb = cd_next(L, sb, cb);
 				sa = ea & ACM_CD_STATE_MASK;
 				sb = eb & ACM_CD_STATE_MASK;
 				const uint32_t da = ea >> ACM_CD_STATE_BITS, db = eb >> ACM_CD_STATE_BITS;

@@ -132,6 +132,15 @@ int  acsm_export_ref_table(acsm_t *);
  */
 int  acsm_check_filters(acsm_t *);
 
+/*
+ * Word lists (<= 16 384 states, pattern bytes within one range of < 31 values, <= 4 patterns ending
+ * in a state) also get a row-displaced transition table that lives in shared memory (k_scan_rd).
+ * Checks it against the dense automaton over every (state, byte class): number of violations
+ * (0 = identical), -1 if this automaton has none.  *slots / *dense_rows (may be NULL) report its
+ * shape.  Test support.
+ */
+int  acsm_check_cdfa(acsm_t *, unsigned int *slots, unsigned int *dense_rows);
+
 /* device automaton handle for the native API in acm.h (NULL before upload) */
 struct acm_automaton *acsm_device_automaton(acsm_t *);
 

@@ -288,41 +288,50 @@ def _word_text(rng, pats, nbytes, seps=b" \n.,"):
 
 
 def test_cdfa_windows_shapes_and_class_maps(device):
-    """The class-compressed DFA kernel (mode 4) on its own: both byte->column forms (arithmetic
-    range / replicated lookup table), hot-row budgets from "nothing in shared memory" upwards,
-    ragged lengths, unaligned emit windows with a hidden stale prefix, bucket overflow (exact
-    two-pass path) -- always the oracle's list."""
+    """The dense-output kernels (mode 4) on their own: the row-displaced table in shared memory
+    (k_scan_rd + k_rd_expand, the default for word lists) and the class-compressed table with
+    both byte->column forms (arithmetic range / replicated lookup table) and hot-row budgets from
+    "nothing in shared memory" upwards; ragged lengths around chunk (256 B) and region (8 KiB)
+    cuts, unaligned emit windows with a hidden stale prefix, log / bucket overflow (exact two-pass
+    path), long patterns (halo of two staging pieces, 512-byte chunks) -- always the oracle's list."""
     import os
     rng = np.random.default_rng(77)
     lex = load_patterns("sentiment_categorical.pat.gz")[:1500]
+    # long lower-case patterns: Lmax 120 -> halo 119 (two 64-byte staging pieces), 512-byte chunks
+    longw = [(bytes(rng.integers(97, 123, size=int(rng.integers(2, 121))).tolist()), i) for i in range(120)]
+    longw += [(p[:k], 500 + 10 * i + j) for i, (p, _) in enumerate(longw[:8]) for j, k in enumerate((2, 3, 5, 64, 65))
+              if k < len(p)]
     # wide byte span (> 63 values) but few distinct bytes -> lookup-table form
     sym = np.array([0, 7, 65, 66, 200, 201, 255], dtype=np.uint8)
     wide = [(bytes(rng.choice(sym, size=int(rng.integers(4, 10))).tolist()), i) for i in range(300)]
     # four patterns ending in one state (the most this form takes), one of them twice over
     wide += [(bytes([7, 0, 255, 200, 65]), 900), (bytes([0, 255, 200, 65]), 901), (bytes([255, 200, 65]), 902),
              (bytes([200, 65]), 903), (bytes([66, 66]), 904), (bytes([66, 66]), 905)]
-    for pats, form in ((lex, "range"), (wide, "lut")):
+    hooks = ("ACM_CD_PLAIN", "ACM_CD_HOT_KB", "ACM_RD_WARPS", "ACM_RD_LOG_CAP")
+    for pats, form in ((lex, "range"), (longw, "long"), (wide, "lut")):
         o, a = build_oracle(pats), build_product(pats)
         assert g.lib().acm_automaton_cdfa_classes(a.automaton) > 0
         assert g.lib().acm_automaton_default_mode(a.automaton) == g.MODE_CDFA
-        if form == "range":
+        # the row-displaced table exists exactly for the one-range sets, and is the automaton
+        assert (a.L.acsm_check_cdfa(a._p, None, None) == 0) == (form != "lut")
+        if form != "lut":
             text = _word_text(rng, pats, 300000)
         else:
             text = rng.choice(np.array([0, 7, 65, 66, 200, 201, 255, 33], dtype=np.uint8), size=300000)
-        for n in (1, 15, 16, 255, 256, 257, 511, 513, 4096 + 17, 300000):
+        for n in (1, 15, 16, 255, 256, 257, 511, 513, 4096 + 17, 8191, 8192, 8193, 3 * 8192, 5 * 16384 + 1, 300000):
             t = text[:n]
             eo, ep, _, _ = o.search(t)
-            # delta-encoded table wholly in shared memory (default), then the plain table with
-            # 1 KiB / 64 KiB / the default amount of hot rows in shared memory
-            for env in ({}, {"ACM_CD_PLAIN": "1", "ACM_CD_HOT_KB": "1"},
+            # the row-displaced table wholly in shared memory (default; also with 3 warps per CTA),
+            # then the plain table with 1 KiB / 64 KiB / the default amount of hot rows in shared memory
+            for env in ({}, {"ACM_RD_WARPS": "3"}, {"ACM_CD_PLAIN": "1", "ACM_CD_HOT_KB": "1"},
                         {"ACM_CD_PLAIN": "1", "ACM_CD_HOT_KB": "64"}, {"ACM_CD_PLAIN": "1"}):
-                for k in ("ACM_CD_PLAIN", "ACM_CD_HOT_KB"):
+                for k in hooks:
                     os.environ.pop(k, None)
                 os.environ.update(env)
                 off, pat, res = gpu_scan(device, a, t, g.MODE_CDFA)
                 assert_same(off, pat, eo, ep, f"cdfa {form} n={n} {env}")
-        os.environ.pop("ACM_CD_PLAIN", None)
-        os.environ.pop("ACM_CD_HOT_KB", None)
+        for k in hooks:
+            os.environ.pop(k, None)
         # emit windows: any cut, with the bytes before valid_lo replaced by junk that would match
         eo, ep, _, _ = o.search(text)
         lmax = a.get_max_pattern_size()
@@ -343,10 +352,21 @@ def test_cdfa_windows_shapes_and_class_maps(device):
             keep2 = (eo2 + vlo >= lo) & (eo2 + vlo < hi)
             off, pat, _ = gpu_scan(device, a, junk, g.MODE_CDFA, emit_lo=lo, emit_hi=hi, valid_lo=vlo)
             assert_same(off, pat, eo2[keep2] + np.uint64(vlo), ep2[keep2], f"cdfa {form} valid_lo {vlo} window [{lo},{hi})")
-        # overflow -> exact two-pass path (direct writes, no sort needed)
+        # overflow -> exact two-pass path (direct writes, no sort needed): a 320-entry region log for
+        # k_scan_rd (a region of this text has ~800 hits), 32-hit rows for the plain kernel
+        os.environ["ACM_RD_LOG_CAP"] = "320"
         off, pat, res = gpu_scan(device, a, text, g.MODE_CDFA, bucket_shift=10, bucket_cap=32)
+        os.environ.pop("ACM_RD_LOG_CAP")
         assert res.fallback == 1
         assert_same(off, pat, eo, ep, f"cdfa {form} overflow")
+        # a match list that outgrows the scanner's first output buffer (65 536 keys): grown, post-pass relaunched
+        if form == "range":
+            big = np.tile(text, 8)
+            eb, pb, _, _ = o.search(big)
+            assert eb.size > (1 << 16)
+            off, pat, res = gpu_scan(device, a, big, g.MODE_CDFA)
+            assert res.fallback == 0
+            assert_same(off, pat, eb, pb, "cdfa range, output buffer grown")
 
 
 def _split_len(a):
