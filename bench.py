@@ -373,8 +373,13 @@ def run_stream_config(ctx, nsigs, per, seed, steps, warmup, tail_for_clocks=Fals
     emit_lo = lo - read_lo
     key_add = read_lo << sharded.KEY_PAT_BITS
     cap_keys = max(1 << 21, int(2.5 * PLANTS_PER_GIB * per / GIB))
+    # two scanners on two streams: the small kernels of step i (resolve, prefix sum, compaction) run
+    # under the streaming kernel of step i + 1; timing 3 = events around the streaming kernel alone
+    own = os.environ.get("BENCH_OWN_STREAMS", "1") != "0"
     pipe = sharded.StepPipeline(dev, acsm.automaton, hi - lo, cap_keys, rank, world,
-                                scanner_kwargs={"timing": 0 if os.environ.get("BENCH_NO_KERNEL_TIMING") else 2})
+                                scanner_kwargs={"timing": 0 if os.environ.get("BENCH_NO_KERNEL_TIMING") else
+                                                int(os.environ.get("BENCH_TIMING", "3")), "own_stream": own})
+    step_streams = {}
     k1_ms, stats = [], {"launches": 0, "fallback": 0, "matches": 0, "mode": 0, "list_bytes": 0, "keys": None}
 
     def note(out):
@@ -390,9 +395,12 @@ def run_stream_config(ctx, nsigs, per, seed, steps, warmup, tail_for_clocks=Fals
 
     def run_steps(k, events=None):
         for i in range(k):
-            pipe.submit(data.data_ptr(), n, emit_lo, n, key_add)
+            sid = pipe.submit(data.data_ptr(), n, emit_lo, n, key_add)
             if events is not None:
-                events[i + 1].record(ctx.stream)
+                h = pipe.stream_of(sid)
+                if h not in step_streams:
+                    step_streams[h] = torch.cuda.ExternalStream(h, device=ctx.tdev)
+                events[i + 1].record(step_streams[h])
             if i > 0:
                 note(pipe.complete())
         if k > 0:
@@ -457,7 +465,10 @@ def run_stream_config(ctx, nsigs, per, seed, steps, warmup, tail_for_clocks=Fals
         "launches": launches, "k1_ms": k1_avg, "k1_stats": step_stats(k1_ms), "achieved": achieved, "peak": peak,
         "peak_src": peak_src, "clocks": clocks, "parity": parity, "e2e": e2e, "e2e_databuf": e2e_db,
         "kernel": "k_scan_" + g.MODE_NAMES[mode] + (
-            f"<{stride}> + k_resolve_queue (scan stage: both launches inside one event pair)" if mode == 1 else ""),
+            f"<{stride}>" + (" (the streaming kernel alone: its event pair; k_resolve_queue of a step runs under "
+                             "the streaming kernel of the next step on the other scanner's stream)"
+                             if own and os.environ.get("BENCH_TIMING", "3") == "3" else
+                             " + k_resolve_queue (scan stage: both launches inside one event pair)") if mode == 1 else ""),
     }
 
 

@@ -49,7 +49,8 @@ usage(void)
 	    "  -p file        pattern file, one pattern per line (plain, -x hex, or `ID \"pattern\"`)\n"
 	    "  -F             follow: keep processing data appended to the files (until SIGINT)\n"
 	    "  -B chunk_size  bytes per chunk (default 4096, rounded up to 16)\n"
-	    "  -D devpos      CUDA device ordinal (default 0)\n"
+	    "  -D devpos      CUDA device ordinal, or a comma-separated list: worker t runs on the\n"
+	    "                 (t mod n)-th of them (default 0)\n"
 	    "  -G global_ws   chunks per buffer; buffer = global_ws * chunk_size (default 32768)\n"
 	    "  -L local_ws    accepted for compatibility, ignored\n"
 	    "  -m max         limit patterns to max bytes\n"
@@ -127,6 +128,10 @@ cpu_worker(void *arg)
 		}
 		ctx->bytes += rd_bytes;
 		ctx->lines += rd_lines;
+		if (e == -4) {                      /* the read failed: the reference aborts here */
+			fprintf(stderr, "ERROR: %s: %s\n", ctx->filenames[cur_file], acm_last_error());
+			exit(1);
+		}
 		if (e == -1 || e == -2) {           /* buffer full */
 			process_buffer(ctx);
 			continue;
@@ -207,7 +212,8 @@ int
 main(int argc, char **argv)
 {
 	char *data_path = NULL, *pat_path = NULL, *tok, *save;
-	int opt, text_mode = 0, verbose = 0, hex_pat = 0, follow = 0, mapped = 0, dev_pos = 0;
+	int opt, text_mode = 0, verbose = 0, hex_pat = 0, follow = 0, mapped = 0;
+	int devs[64] = {0}, ndev = 1;
 	int thread_no = 2, pat_size_limit = -1, max_results = MAX_RESULTS, i;
 	size_t max_chunk_size = 4096, global_ws = 32768, local_ws = 1024;
 	struct file_list fl = {0};
@@ -226,7 +232,16 @@ main(int argc, char **argv)
 		case 'v': verbose = 1; break;
 		case 'x': hex_pat = 1; break;
 		case 'B': max_chunk_size = (size_t)atol(optarg); break;
-		case 'D': dev_pos = atoi(optarg); break;
+		case 'D': {
+			char *list = strdup(optarg), *sv, *t;
+			ndev = 0;
+			for (t = strtok_r(list, ",", &sv); t && ndev < 64; t = strtok_r(NULL, ",", &sv))
+				devs[ndev++] = atoi(t);
+			free(list);
+			if (ndev == 0)
+				usage();
+			break;
+		}
 		case 'F': follow = 1; break;
 		case 'G': global_ws = (size_t)atol(optarg); break;
 		case 'L': local_ws = (size_t)atol(optarg); break;
@@ -261,6 +276,9 @@ main(int argc, char **argv)
 	w = calloc((size_t)thread_no, sizeof(*w));
 	threads = calloc((size_t)thread_no, sizeof(*threads));
 	for (i = 0; i < thread_no; i++) {
+		/* workers are striped over the devices like files over the workers (reference
+		 * ocl_aho_grep.c:48,87,498-502: every worker owns a context on its device) */
+		const int dev_pos = devs[i % ndev];
 		w[i] = ocl_worker_ctx_create(dev_pos);
 		if (!w[i]) {
 			fprintf(stderr, "ERROR: %s\n", acm_last_error());

@@ -24,7 +24,7 @@ class AcmError(RuntimeError):
 
 class ScanParams(C.Structure):
     _fields_ = [("mode", C.c_int), ("bucket_shift", C.c_int), ("bucket_cap", C.c_int),
-                ("timing", C.c_int), ("dfa_chunk", C.c_int), ("reserved", C.c_int * 3)]
+                ("timing", C.c_int), ("dfa_chunk", C.c_int), ("own_stream", C.c_int), ("reserved", C.c_int * 2)]
 
 
 class ScanResult(C.Structure):
@@ -112,6 +112,7 @@ SIGNATURES = {
     "acm_host_alloc_pinned": (C.c_int, [C.c_size_t, C.POINTER(vp)]),
     "acm_host_alloc_pinned_near": (C.c_int, [vp, C.c_size_t, C.POINTER(vp)]),
     "acm_host_free_pinned": (None, [vp]),
+    "acm_dev_memset": (C.c_int, [vp, vp, C.c_int, C.c_size_t]),
     "acm_memcpy_h2d": (C.c_int, [vp, vp, vp, C.c_size_t]),
     "acm_memcpy_d2h": (C.c_int, [vp, vp, vp, C.c_size_t]),
     "acm_memcpy_d2h_side": (C.c_int, [vp, vp, vp, C.c_size_t]),
@@ -121,6 +122,7 @@ SIGNATURES = {
     "acm_automaton_free": (None, [vp]),
     "acm_automaton_states": (C.c_uint32, [vp]),
     "acm_automaton_patterns": (C.c_uint32, [vp]),
+    "acm_automaton_pattern_lengths": (u32p, [vp]),
     "acm_automaton_max_pattern_len": (C.c_int, [vp]),
     "acm_automaton_min_pattern_len": (C.c_int, [vp]),
     "acm_automaton_alphabet": (C.c_int, [vp]),
@@ -139,6 +141,7 @@ SIGNATURES = {
                                         C.POINTER(PushTarget)]),
     "acm_scan_finish": (C.c_int, [vp, C.POINTER(ScanResult)]),
     "acm_scan_keys": (vp, [vp]),
+    "acm_scanner_stream": (vp, [vp]),
     "acm_scan_fetch": (C.c_int64, [vp, C.c_uint64, u64p, u32p, C.c_uint64]),
     "acm_scan_histogram": (C.c_int, [vp, vp]),
     "acm_scan_trace": (C.c_int, [vp, u64p, C.c_uint32]),
@@ -148,8 +151,19 @@ SIGNATURES = {
     "acm_scan_push_keys": (C.c_int, [vp, vp, C.c_uint64, C.c_uint64]),
     "acm_scan_host": (C.c_int64, [vp, vp, C.c_uint64, C.c_uint64, u64p, u32p, C.c_uint64,
                                   C.POINTER(ScanResult)]),
+    "acm_scan_host_ex": (C.c_int64, [vp, vp, C.c_uint64, C.c_uint64, C.c_uint64, u64p, u32p, C.c_uint64,
+                                     C.POINTER(ScanResult)]),
+    "acm_multi_open": (C.c_int, [vp, C.POINTER(C.c_int), C.c_int, C.c_uint64, C.POINTER(ScanParams), C.POINTER(vp)]),
+    "acm_multi_close": (None, [vp]),
+    "acm_multi_devices": (C.c_int, [vp]),
+    "acm_multi_device": (vp, [vp, C.c_int]),
+    "acm_multi_shard": (None, [vp, C.c_uint64, C.c_int, u64p, u64p, u64p]),
+    "acm_multi_scan_device": (C.c_int64, [vp, C.POINTER(vp), C.c_uint64, u64p, C.c_uint64, u64p,
+                                          C.POINTER(ScanResult)]),
+    "acm_multi_scan_host": (C.c_int64, [vp, vp, C.c_uint64, C.c_uint64, u64p, u32p, C.c_uint64,
+                                        C.POINTER(ScanResult)]),
     "acm_exclusive_scan_u32": (C.c_int, [vp, vp, vp, C.c_uint32, vp]),
-    "acm_compact_columns_i32": (C.c_int, [vp, vp, vp, vp, C.c_int32, C.c_int32]),
+    "acm_compact_columns_i32": (C.c_int, [vp, vp, vp, vp, C.c_int32, C.c_int32, C.c_int64]),
     "acm_radix_sort_u64": (C.c_int, [vp, vp, vp, C.c_uint64, C.c_int, C.c_int, C.c_int]),
     "acm_sort_pairs_u32": (C.c_int, [vp, vp, vp, vp, vp, C.c_uint32, C.c_int]),
     "acm_synth_fill_device": (C.c_int, [vp, vp, C.c_uint64, C.c_uint64, C.c_uint64]),
@@ -174,6 +188,7 @@ SIGNATURES = {
     "acsm_export_ref_table": (C.c_int, [C.POINTER(AcsmStruct)]),
     "acsm_check_filters": (C.c_int, [C.POINTER(AcsmStruct)]),
     "acsm_check_cdfa": (C.c_int, [C.POINTER(AcsmStruct), C.POINTER(C.c_uint), C.POINTER(C.c_uint)]),
+    "acsm_tables": (vp, [C.POINTER(AcsmStruct)]),
     "acsm_device_automaton": (vp, [C.POINTER(AcsmStruct)]),
     # iacsmx.h
     "iacsm_new": (C.POINTER(IacsmStruct), []),
@@ -207,6 +222,7 @@ SIGNATURES = {
     "databuf_status": (C.c_int, [C.POINTER(Databuf)]),
     "databuf_match_count": (C.c_size_t, [C.POINTER(Databuf)]),
     "databuf_alloc_postpass": (C.c_int, [C.POINTER(Databuf)]),
+    "databuf_set_file_semantics": (None, [C.POINTER(Databuf), C.c_int]),
     "databuf_read_fd": (C.c_long, [C.c_int, vp, C.c_size_t]),
     # ocl_aho_match.h
     "ocl_aho_match_init": (None, [C.POINTER(Clconf)]),

@@ -110,6 +110,8 @@ struct acm_scanner {
 		uint64_t     push_cap, push_add;
 	} pend;
 	cudaEvent_t ev_done;
+	cudaStream_t own_stream;    /* acm_scan_params.own_stream: this scanner's scans run here, not on the device's stream */
+	cudaEvent_t  ev_dep;        /* orders a scan on own_stream behind what the device's stream held at launch */
 };
 
 /* ------------------------------------------------------------------------- */
@@ -409,6 +411,14 @@ acm_side_sync(struct acm_device *d)
 }
 
 extern "C" int
+acm_dev_memset(struct acm_device *d, void *dst, int value, size_t bytes)
+{
+	CUDA_TRY(cudaSetDevice(d->ordinal));
+	CUDA_TRY(cudaMemsetAsync(dst, value, bytes, d->stream));
+	return ACM_OK;
+}
+
+extern "C" int
 acm_memcpy_d2d(struct acm_device *d, void *dst, const void *src, size_t bytes)
 {
 	CUDA_TRY(cudaSetDevice(d->ordinal));
@@ -549,6 +559,7 @@ acm_automaton_upload(struct acm_device *dev, const struct acm_tables *t, struct 
 }
 
 extern "C" uint32_t acm_automaton_states(const struct acm_automaton *a) { return a->num_states; }
+extern "C" const uint32_t *acm_automaton_pattern_lengths(const struct acm_automaton *a) { return a->h_pat_len; }
 extern "C" uint32_t acm_automaton_patterns(const struct acm_automaton *a) { return a->num_patterns; }
 extern "C" int acm_automaton_max_pattern_len(const struct acm_automaton *a) { return a->max_len; }
 extern "C" int acm_automaton_min_pattern_len(const struct acm_automaton *a) { return a->min_len; }
@@ -634,12 +645,12 @@ acm_exclusive_scan_u32(struct acm_device *d, const uint32_t *in, uint32_t *out, 
 
 extern "C" int
 acm_compact_columns_i32(struct acm_device *d, int32_t *dst, const int32_t *src, const int32_t *prefix,
-    int32_t len, int32_t max_results)
+    int32_t len, int32_t max_results, int64_t dst_cap)
 {
 	CUDA_TRY(cudaSetDevice(d->ordinal));
 	if (len <= 0)
 		return ACM_OK;
-	k_compact_columns<<<(len + 255) / 256, 256, 0, d->stream>>>(dst, src, prefix, len, max_results);
+	k_compact_columns<<<(len + 255) / 256, 256, 0, d->stream>>>(dst, src, prefix, len, max_results, dst_cap);
 	CUDA_TRY(cudaGetLastError());
 	return ACM_OK;
 }
@@ -756,6 +767,12 @@ acm_scanner_free(struct acm_scanner *s)
 	cudaSetDevice(s->dev->ordinal);
 	cudaStreamSynchronize(s->dev->stream);
 	cudaStreamSynchronize(s->dev->copy_stream);
+	if (s->own_stream) {
+		cudaStreamSynchronize(s->own_stream);
+		cudaStreamDestroy(s->own_stream);
+	}
+	if (s->ev_dep)
+		cudaEventDestroy(s->ev_dep);
 	cudaFree(s->buckets); cudaFree(s->scratch); cudaFree(s->offsets);
 	cudaFree(s->tile_state); cudaFree(s->out); cudaFree(s->tmp); cudaFree(s->hist);
 	cudaFree(s->stage[0]); cudaFree(s->stage[1]); cudaFree(s->trace);
@@ -828,6 +845,11 @@ acm_scanner_create(struct acm_device *dev, struct acm_automaton *aut, uint64_t m
 	*out = NULL;
 	if (!dev || !aut) {
 		acm_set_error("scanner_create: device and automaton required");
+		return ACM_ERR_ARG;
+	}
+	if (aut->dev != dev && aut->dev->ordinal != dev->ordinal) {
+		acm_set_error("scanner_create: the automaton lives on device %d, the scanner is asked for device %d",
+		    aut->dev->ordinal, dev->ordinal);
 		return ACM_ERR_ARG;
 	}
 	if (max_bytes == 0 || max_bytes > (1ull << 40)) {
@@ -903,8 +925,10 @@ acm_scanner_create(struct acm_device *dev, struct acm_automaton *aut, uint64_t m
 			return ACM_ERR_ARG;
 		}
 		s->p.bucket_shift = (int)sh;
-		if (s->rd || !s->p.bucket_cap)
+		if (!s->p.bucket_cap)
 			s->p.bucket_cap = (int)((1u << sh) / 4 > 8192 ? 8192 : (1u << sh) / 4);
+		if (s->rd && (uint32_t)s->p.bucket_cap > (1u << sh))
+			s->p.bucket_cap = (int)(1u << sh);  /* one hit per byte is all a chunk can log */
 		const uint32_t lut_bytes = aut->d.cd_range_lo >= 0 ? 0 : CD_LUT_WORDS * 4;
 		if (!s->rd) {
 			const uint32_t row = aut->d.cd_classes * 2;
@@ -984,6 +1008,14 @@ acm_scanner_create(struct acm_device *dev, struct acm_automaton *aut, uint64_t m
 	for (int i = 0; i < 4; i++)
 		cudaEventCreate(&s->ev[i]);
 	cudaEventCreateWithFlags(&s->ev_done, cudaEventDisableTiming);
+	if (s->p.own_stream) {
+		if (cudaStreamCreateWithFlags(&s->own_stream, cudaStreamNonBlocking) != cudaSuccess ||
+		    cudaEventCreateWithFlags(&s->ev_dep, cudaEventDisableTiming) != cudaSuccess) {
+			acm_set_error("scanner_create: cannot create the scanner's stream");
+			acm_scanner_free(s);
+			return ACM_ERR_CUDA;
+		}
+	}
 	for (int i = 0; i < 2; i++) {
 		cudaEventCreateWithFlags(&s->ev_copied[i], cudaEventDisableTiming);
 		cudaEventCreateWithFlags(&s->ev_free[i], cudaEventDisableTiming);
@@ -1068,6 +1100,8 @@ launch_k1(struct acm_scanner *s, cudaStream_t st, const void *d_data, uint64_t n
 		else
 			k_scan_sampled<4><<<(unsigned)blocks, S4_THREADS, S4_SMEM_BYTES, st>>>(a->d, Eq,
 			    (const uint8_t *)d_data, n, vec_lo, vec_hi, limit, s->flags + 6);
+		if (s->p.timing == 3)       /* the streaming kernel alone */
+			CUDA_TRY(cudaEventRecord(s->ev[1], st));
 		k_resolve_queue<<<(unsigned)blocks * (S4_THREADS / 32), RQ_THREADS, 0, st>>>(a->d, Eq,
 		    (const uint8_t *)d_data, n, limit);
 		*launches += 1;
@@ -1211,6 +1245,14 @@ scan_launch(struct acm_scanner *s, cudaStream_t st, const void *d_data, uint64_t
 		acm_set_error("scan: more than 2^40 symbols in one call");
 		return ACM_ERR_LIMIT;
 	}
+	/* record counts and offsets are 32-bit: the dense-output kernels can produce four records per
+	 * byte, so one call of theirs covers at most 2^30 bytes (the sparse kernels stay far below
+	 * one record per 2^8 bytes: their limit is the 2^40 above) */
+	if (s->p.mode == ACM_MODE_CDFA && emit_hi - emit_lo > (1ull << 30)) {
+		acm_set_error("scan: the dense-output kernel takes at most 2^30 bytes per call (32-bit record offsets); "
+		    "split the scan");
+		return ACM_ERR_LIMIT;
+	}
 	CUDA_TRY(cudaSetDevice(s->dev->ordinal));
 	if (s->densify) {
 		/*
@@ -1260,7 +1302,7 @@ scan_launch(struct acm_scanner *s, cudaStream_t st, const void *d_data, uint64_t
 	if ((rc = launch_k1(s, st, d_data, n, E, 0, &launches)) != ACM_OK)
 		return rc;
 	launches++;
-	if (timing)
+	if (timing && !(timing == 3 && s->p.mode == ACM_MODE_SAMPLED4))
 		CUDA_TRY(cudaEventRecord(s->ev[1], st));
 	const int cdfa = s->p.mode == ACM_MODE_CDFA;
 	if ((rc = launch_exclusive_scan(st, s->counts, s->offsets, nb, s->bucket_tiles, s->flags + 3,
@@ -1435,6 +1477,21 @@ scan_complete(struct acm_scanner *s, struct acm_scan_result *res)
 	return ACM_OK;
 }
 
+/* the stream a scan of this scanner is queued on; with an own stream, first ordered behind
+ * everything the caller has queued on the device's stream so far (the input, usually) */
+static int
+scanner_stream(struct acm_scanner *s, cudaStream_t *st)
+{
+	*st = s->dev->stream;
+	if (!s->own_stream)
+		return ACM_OK;
+	CUDA_TRY(cudaSetDevice(s->dev->ordinal));
+	CUDA_TRY(cudaEventRecord(s->ev_dep, s->dev->stream));
+	CUDA_TRY(cudaStreamWaitEvent(s->own_stream, s->ev_dep, 0));
+	*st = s->own_stream;
+	return ACM_OK;
+}
+
 static int
 scan_on_stream(struct acm_scanner *s, cudaStream_t st, const void *d_data, uint64_t n, uint64_t valid_lo,
     uint64_t emit_lo, uint64_t emit_hi, struct acm_scan_result *res)
@@ -1453,7 +1510,9 @@ extern "C" int
 acm_scan_device(struct acm_scanner *s, const void *d_data, uint64_t n, uint64_t emit_lo, uint64_t emit_hi,
     struct acm_scan_result *res)
 {
-	return scan_on_stream(s, s->dev->stream, d_data, n, 0, emit_lo, emit_hi, res);
+	cudaStream_t st;
+	int rc = scanner_stream(s, &st);
+	return rc != ACM_OK ? rc : scan_on_stream(s, st, d_data, n, 0, emit_lo, emit_hi, res);
 }
 
 extern "C" int
@@ -1464,7 +1523,9 @@ acm_scan_device_ex(struct acm_scanner *s, const void *d_data, uint64_t n, uint64
 		acm_set_error("scan: valid_lo must not exceed emit_lo");
 		return ACM_ERR_ARG;
 	}
-	return scan_on_stream(s, s->dev->stream, d_data, n, valid_lo, emit_lo, emit_hi, res);
+	cudaStream_t st;
+	int rc = scanner_stream(s, &st);
+	return rc != ACM_OK ? rc : scan_on_stream(s, st, d_data, n, valid_lo, emit_lo, emit_hi, res);
 }
 
 extern "C" int
@@ -1475,7 +1536,9 @@ acm_scan_device_async(struct acm_scanner *s, const void *d_data, uint64_t n, uin
 		acm_set_error("scan: valid_lo must not exceed emit_lo");
 		return ACM_ERR_ARG;
 	}
-	return scan_launch(s, s->dev->stream, d_data, n, valid_lo, emit_lo, emit_hi, push);
+	cudaStream_t st;
+	int rc = scanner_stream(s, &st);
+	return rc != ACM_OK ? rc : scan_launch(s, st, d_data, n, valid_lo, emit_lo, emit_hi, push);
 }
 
 extern "C" int
@@ -1497,6 +1560,12 @@ acm_scan_trace(struct acm_scanner *s, uint64_t *h_out, uint32_t n_ctas)
 	CUDA_TRY(cudaSetDevice(s->dev->ordinal));
 	CUDA_TRY(cudaMemcpy(h_out, s->trace, (size_t)n_ctas * 32, cudaMemcpyDeviceToHost));
 	return ACM_OK;
+}
+
+extern "C" void *
+acm_scanner_stream(struct acm_scanner *s)
+{
+	return (void *)(s->own_stream ? s->own_stream : s->dev->stream);
 }
 
 extern "C" const uint64_t *
@@ -1552,7 +1621,7 @@ extern "C" int64_t
 acm_scan_fetch(struct acm_scanner *s, uint64_t base, uint64_t *h_off, uint32_t *h_pat, uint64_t cap)
 {
 	CUDA_TRY(cudaSetDevice(s->dev->ordinal));
-	return fetch_on_stream(s, s->dev->stream, base, 0, h_off, h_pat, cap);
+	return fetch_on_stream(s, s->own_stream ? s->own_stream : s->dev->stream, base, 0, h_off, h_pat, cap);
 }
 
 /* ---- peer gather (single node): CUDA IPC mapping + a store kernel ---- */
@@ -1596,7 +1665,7 @@ acm_scan_push_keys(struct acm_scanner *s, uint64_t *d_dst, uint64_t dst_index, u
 	uint64_t blocks = (s->last_n + 255) / 256;
 	if (blocks > 592)
 		blocks = 592;
-	k_push_keys<<<(unsigned)blocks, 256, 0, s->dev->stream>>>(s->out, s->last_n, d_dst + dst_index,
+	k_push_keys<<<(unsigned)blocks, 256, 0, s->own_stream ? s->own_stream : s->dev->stream>>>(s->out, s->last_n, d_dst + dst_index,
 	    key_add);
 	CUDA_TRY(cudaGetLastError());
 	return ACM_OK;
@@ -1611,7 +1680,7 @@ acm_scan_histogram(struct acm_scanner *s, uint64_t *d_counts)
 	uint64_t blocks = (s->last_n + 255) / 256;
 	if (blocks > 1184)
 		blocks = 1184;
-	k_histogram<<<(unsigned)blocks, 256, 0, s->dev->stream>>>(s->out, s->last_n,
+	k_histogram<<<(unsigned)blocks, 256, 0, s->own_stream ? s->own_stream : s->dev->stream>>>(s->out, s->last_n,
 	    (unsigned long long *)d_counts);
 	CUDA_TRY(cudaGetLastError());
 	return ACM_OK;
@@ -1627,12 +1696,20 @@ extern "C" int64_t
 acm_scan_host(struct acm_scanner *s, const void *h_data, uint64_t n, uint64_t base, uint64_t *h_off,
     uint32_t *h_pat, uint64_t cap, struct acm_scan_result *res)
 {
+	return acm_scan_host_ex(s, h_data, n, 0, base, h_off, h_pat, cap, res);
+}
+
+/* the same with lead0 symbols of valid context in front of h_data (a shard of a longer host stream) */
+extern "C" int64_t
+acm_scan_host_ex(struct acm_scanner *s, const void *h_data, uint64_t n, uint64_t lead0, uint64_t base,
+    uint64_t *h_off, uint32_t *h_pat, uint64_t cap, struct acm_scan_result *res)
+{
 	const uint8_t *src = (const uint8_t *)h_data;
 	const uint64_t sym = s->aut->alpha == 256 ? 1 : 2;
 	const uint64_t halo = s->aut->max_len > 0 ? (uint64_t)(s->aut->max_len - 1) : 0;
 	uint64_t seg = s->max_bytes;
 	uint64_t written = 0, found = 0, launches = 0;
-	cudaStream_t ks = s->dev->stream, cs = s->dev->copy_stream;
+	cudaStream_t ks = s->own_stream ? s->own_stream : s->dev->stream, cs = s->dev->copy_stream;
 	struct acm_scan_result r1;
 	int rc, fallback = 0;
 
@@ -1659,7 +1736,7 @@ acm_scan_host(struct acm_scanner *s, const void *h_data, uint64_t n, uint64_t ba
 	/* segment i travels with its `lead` symbols of context: [lo - lead, hi) -> stage[i & 1] */
 	auto enqueue_copy = [&](uint64_t i) -> int {
 		const uint64_t lo = i * seg, hi = (lo + seg < n) ? lo + seg : n;
-		const uint64_t lead = lo < halo ? lo : halo;
+		const uint64_t lead = lo + lead0 < halo ? lo + lead0 : halo;
 		const int b = (int)(i & 1);
 		if (i >= 2)
 			CUDA_TRY(cudaStreamWaitEvent(cs, s->ev_free[b], 0));
@@ -1673,7 +1750,7 @@ acm_scan_host(struct acm_scanner *s, const void *h_data, uint64_t n, uint64_t ba
 		return rc;
 	for (uint64_t i = 0; i < nseg; i++) {
 		const uint64_t lo = i * seg, hi = (lo + seg < n) ? lo + seg : n;
-		const uint64_t lead = lo < halo ? lo : halo;
+		const uint64_t lead = lo + lead0 < halo ? lo + lead0 : halo;
 		const int b = (int)(i & 1);
 
 		if (i + 1 < nseg && (rc = enqueue_copy(i + 1)) != ACM_OK)

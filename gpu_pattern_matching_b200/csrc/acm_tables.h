@@ -46,7 +46,9 @@ enum {
 #define ACM_RD_SMEM_BUDGET (176 * 1024)    /* bytes of shared memory the table may take (>= 16 warps still fit beside it) */
 
 #define ACM_F1_BITS_LOG2   20              /* level-1 gram bitmap: 128 KiB smem */
+#ifndef ACM_F2_WORDS
 #define ACM_F2_WORDS       24576u          /* level-2 gram bitmap:  96 KiB smem, word = mulhi(hash, words) */
+#endif
 #define ACM_B3_WORDS       16384u          /* level-2 start bitmap:  64 KiB smem, word = hash >> 18 */
 #define ACM_HASH1_MUL 0x9E3779B1u
 #define ACM_HASH2_MUL 0x85EBCA6Bu

@@ -192,6 +192,14 @@ acsm_check_filters(acsm_t *a)
 	return c ? acm_core_check_filters(c) : ACM_ERR_ARG;
 }
 
+const struct acm_tables *
+acsm_tables(acsm_t *a)
+{
+	struct acm_core *c = core_of(a);
+
+	return c && c->compiled && c->tab.T ? &c->tab : NULL;
+}
+
 int
 acsm_check_cdfa(acsm_t *a, unsigned int *slots, unsigned int *dense_rows)
 {

@@ -77,8 +77,9 @@ match_common(struct databuf *db, struct acm_automaton *aut, int sym_size, int st
 	uint64_t halo, keep;
 	int rc;
 
-	pv->n_matches = 0;
+	pv->n_matches = pv->n_valid = 0;
 	pv->fetched = 0;
+	pv->buckets_on_device = 0;
 	if (!aut) {
 		acm_set_error("ocl_aho_match: automaton has no device tables (acsm_gen_state_table not called or failed)");
 		pv->status = ACM_ERR_STATE;
@@ -107,8 +108,13 @@ match_common(struct databuf *db, struct acm_automaton *aut, int sym_size, int st
 	halo = (uint64_t)(acm_automaton_max_pattern_len(aut) > 0 ? acm_automaton_max_pattern_len(aut) - 1 : 0);
 	if (halo > carry_cap)
 		halo = carry_cap;
-	if (!stream)
+	if (!stream) {
 		pv->carry_len = 0;
+		pv->carry_real = 0;
+		pv->carry_file = -1;
+	}
+	pv->filt_carry_real = pv->carry_real;
+	pv->filt_carry_file = pv->carry_file;
 	if (nsym == 0)
 		return;
 	rc = acm_scan_device_ex(pv->scanner, pv->d_base, carry_cap + nsym, carry_cap - pv->carry_len,
@@ -118,6 +124,7 @@ match_common(struct databuf *db, struct acm_automaton *aut, int sym_size, int st
 		return;
 	}
 	pv->n_matches = res.n_matches;
+	pv->have_match = 1;
 
 	/* new carry = last `halo` symbols of (old carry + this buffer), right-aligned before d_data */
 	keep = pv->carry_len + nsym;
@@ -136,6 +143,34 @@ match_common(struct databuf *db, struct acm_automaton *aut, int sym_size, int st
 		}
 	}
 	pv->carry_len = stream ? keep : 0;
+	/*
+	 * Per-file semantics: which of the carried symbols are real, contiguous bytes of the file the
+	 * buffer ends with -- the stretch of chunks of that file that runs up to the very end of the
+	 * buffer (plus, if it also starts the buffer and continues the previous carry's file, that
+	 * carry).  A padded last chunk, or nothing carried, leaves 0: nothing of the next buffer may
+	 * reach back.
+	 */
+	if (stream && keep && db->chunks > 0) {
+		size_t c = db->chunks - 1;
+		const int fid = db->file_ids[c];
+		uint64_t real = 0;
+		if ((size_t)db->h_indices[c] + (size_t)db->h_sizes[c] == db->bytes) {
+			real = (uint64_t)db->h_sizes[c];
+			while (c > 0 && db->file_ids[c - 1] == fid &&
+			    db->h_indices[c - 1] + db->h_sizes[c - 1] == db->h_indices[c]) {
+				c--;
+				real += (uint64_t)db->h_sizes[c];
+			}
+			if (c == 0 && db->h_indices[0] == 0 && pv->carry_file == fid)
+				real += pv->carry_real * (uint64_t)sym_size;
+		}
+		real /= (uint64_t)sym_size;
+		pv->carry_real = real < keep ? real : keep;
+		pv->carry_file = fid;
+	} else {
+		pv->carry_real = 0;
+		pv->carry_file = -1;
+	}
 	/* the reference blocks in clFinish (ocl_aho_match.c:128) */
 	pv->status = acm_device_sync(pv->dev);
 }
@@ -156,14 +191,60 @@ ocl_aho_match_ushort(struct clconf *cl, struct databuf *db, iacsm_t *iacsm, size
 	match_common(db, iacsm_device_automaton(iacsm), 2, 1);
 }
 
+/*
+ * The reference's COMPACT_RESULTS order (databuf.c:648-651) is ocl_aho_match -> ocl_prefix_sum ->
+ * ocl_compact_array -> databuf_copy_device_to_host, with the match kernel itself filling the
+ * device buckets.  Here the device holds one sorted list, so the bucket view the two post-passes
+ * work on is built from it first (the host does that in databuf_copy_device_to_host) and
+ * uploaded: they never see memory nobody wrote.
+ */
+static int
+upload_bucket_view(struct databuf *db)
+{
+	struct databuf_priv *pv = (struct databuf_priv *)db->priv;
+	const size_t nres = ((size_t)db->max_results * db->max_chunks + 1) * sizeof(int);
+	int rc;
+
+	/* no match has run on this databuf: the buckets on the device are the caller's own
+	 * (the reference's self-test, databuf.c:935-1021, fills them by hand) */
+	if (pv->buckets_on_device || !pv->have_match)
+		return ACM_OK;
+	if (!pv->fetched)
+		databuf_copy_device_to_host(db, NULL);
+	if (pv->status != ACM_OK)
+		return pv->status;
+	/* rows 1.. of the host view are only valid below a chunk's count: clear the device copy first */
+	if ((rc = acm_dev_memset(pv->dev, db->d_results, 0, nres)) != ACM_OK ||
+	    (rc = acm_dev_memset(pv->dev, db->d_results2, 0, nres)) != ACM_OK)
+		return pv->status = rc;
+	{
+		const size_t C = db->chunks, R = (size_t)db->max_results;
+		size_t k;
+		/* the count row, the rows in use, and the tail word (last state) */
+		for (k = 0; k < R && C; k++) {
+			if ((rc = acm_memcpy_h2d(pv->dev, (int *)db->d_results + k * C, db->h_results + k * C, C * sizeof(int))) != ACM_OK ||
+			    (rc = acm_memcpy_h2d(pv->dev, (int *)db->d_results2 + k * C, db->h_results2 + k * C, C * sizeof(int))) != ACM_OK)
+				return pv->status = rc;
+		}
+		if ((rc = acm_memcpy_h2d(pv->dev, (int *)db->d_results + R * C, db->h_results + R * C, sizeof(int))) != ACM_OK)
+			return pv->status = rc;
+	}
+	if ((rc = acm_device_sync(pv->dev)) != ACM_OK)
+		return pv->status = rc;
+	pv->buckets_on_device = 1;
+	return ACM_OK;
+}
+
 void
 ocl_prefix_sum(struct clconf *cl, struct databuf *db, unsigned int n)
 {
 	struct databuf_priv *pv = (struct databuf_priv *)db->priv;
 
 	(void)cl;
-	if (databuf_alloc_postpass(db) != ACM_OK)
+	if (databuf_alloc_postpass(db) != ACM_OK || upload_bucket_view(db) != ACM_OK)
 		return;
+	if (n > db->max_chunks)
+		n = (unsigned int)db->max_chunks;
 	pv->status = acm_exclusive_scan_u32(pv->dev, (const uint32_t *)db->d_results,
 	    (uint32_t *)db->d_prefixsum, n, NULL);
 	if (pv->status == ACM_OK)
@@ -177,15 +258,15 @@ ocl_compact_array(struct clconf *cl, struct databuf *db, size_t local)
 
 	(void)cl;
 	(void)local;
-	if (databuf_alloc_postpass(db) != ACM_OK || db->chunks == 0)
+	if (databuf_alloc_postpass(db) != ACM_OK || db->chunks == 0 || upload_bucket_view(db) != ACM_OK)
 		return;
 	pv->status = acm_compact_columns_i32(pv->dev, (int32_t *)db->d_results_comp,
 	    (const int32_t *)db->d_results, (const int32_t *)db->d_prefixsum, (int32_t)db->chunks,
-	    db->max_results);
+	    db->max_results, (int64_t)db->size + 2);
 	if (pv->status == ACM_OK)
 		pv->status = acm_compact_columns_i32(pv->dev, (int32_t *)db->d_results2_comp,
 		    (const int32_t *)db->d_results2, (const int32_t *)db->d_prefixsum, (int32_t)db->chunks,
-		    db->max_results);
+		    db->max_results, (int64_t)db->size + 2);
 	if (pv->status == ACM_OK)
 		pv->status = acm_device_sync(pv->dev);
 }

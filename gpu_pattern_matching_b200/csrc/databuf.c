@@ -8,6 +8,7 @@
  * through acm.h.
  */
 #define _GNU_SOURCE
+#include <errno.h>
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
@@ -57,6 +58,14 @@ databuf_new(size_t max_chunks, size_t max_chunk_size, int max_results, int mappe
 	db->priv = pv;
 	pv->dev = dev;
 	pv->sym_size = 1;
+	{
+		/* ACM_DATABUF_STREAM_QUIRK=1: one stream across files and padding, as the reference scans it */
+		const char *q = getenv("ACM_DATABUF_STREAM_QUIRK");
+		pv->file_semantics = !(q && atoi(q));
+	}
+	pv->carry_file = -1;
+	pthread_mutex_init(&pv->ra.lock, NULL);
+	pthread_cond_init(&pv->ra.cond, NULL);
 	db->cl = conf;
 	db->mapped = mapped;
 	db->max_results = max_results;
@@ -82,11 +91,12 @@ databuf_new(size_t max_chunks, size_t max_chunk_size, int max_results, int mappe
 	db->h_results = calloc(nres, sizeof(int));
 	db->h_results2 = calloc(nres, sizeof(int));
 	db->h_prefixsum = calloc(max_chunks, sizeof(int));
+	pv->run_id = malloc(max_chunks * sizeof(int));
 	db->results_comp_size = db->results2_comp_size = MIN(db->size + 2, (size_t)1 << 16);
 	db->h_results_comp = calloc(db->results_comp_size, sizeof(int));
 	db->h_results2_comp = calloc(db->results2_comp_size, sizeof(int));
 	if (!db->h_indices || !db->h_sizes || !db->file_ids || !db->h_results || !db->h_results2 ||
-	    !db->h_prefixsum || !db->h_results_comp || !db->h_results2_comp) {
+	    !db->h_prefixsum || !db->h_results_comp || !db->h_results2_comp || !pv->run_id) {
 		acm_set_error("databuf_new: out of memory");
 		goto fail;
 	}
@@ -194,22 +204,166 @@ databuf_read_fd(int fd, void *buf, size_t want)
 	return (long)total;
 }
 
-/* reference databuf.c:327-407 */
+/* ---- read-ahead of the next whole buffer (see databuf_priv.h) ---- */
+
+static void *
+readahead_main(void *arg)
+{
+	struct databuf_readahead *ra = arg;
+
+	pthread_mutex_lock(&ra->lock);
+	for (;;) {
+		while (!ra->busy && !ra->quit)
+			pthread_cond_wait(&ra->cond, &ra->lock);
+		if (ra->quit)
+			break;
+		{
+			const int fd = ra->fd;
+			const off_t off = ra->off;
+			const size_t want = ra->want;
+			size_t done = 0;
+			long got = 0;
+			pthread_mutex_unlock(&ra->lock);
+			while (done < want) {
+				const ssize_t r = pread(fd, ra->buf + done, want - done, off + (off_t)done);
+				if (r < 0) {
+					got = done ? (long)done : -1;
+					break;
+				}
+				if (r == 0)
+					break;
+				done += (size_t)r;
+				got = (long)done;
+			}
+			pthread_mutex_lock(&ra->lock);
+			ra->got = got;
+			ra->have = 1;
+			ra->busy = 0;
+			pthread_cond_broadcast(&ra->cond);
+		}
+	}
+	pthread_mutex_unlock(&ra->lock);
+	return NULL;
+}
+
+/* ask for [off, off + want) of fd; needs the second buffer, which is allocated on first use */
+static void
+readahead_start(struct databuf *db, int fd, off_t off, size_t want)
+{
+	struct databuf_priv *pv = priv_of(db);
+	struct databuf_readahead *ra = &pv->ra;
+	const char *env = getenv("ACM_READAHEAD");
+	void *p;
+
+	if (env && atoi(env) == 0)
+		return;
+	if (!ra->buf) {
+		if (acm_host_alloc_pinned_near(pv->dev, db->size + 64, &p) != ACM_OK)
+			return;
+		ra->buf = p;
+	}
+	pthread_mutex_lock(&ra->lock);
+	if (!ra->started) {
+		if (pthread_create(&ra->thread, NULL, readahead_main, ra) != 0) {
+			pthread_mutex_unlock(&ra->lock);
+			return;
+		}
+		ra->started = 1;
+	}
+	while (ra->busy)
+		pthread_cond_wait(&ra->cond, &ra->lock);
+	ra->fd = fd;
+	ra->off = off;
+	ra->want = want;
+	ra->have = 0;
+	ra->busy = 1;
+	pthread_cond_broadcast(&ra->cond);
+	pthread_mutex_unlock(&ra->lock);
+}
+
+/* the read-ahead result if it is exactly what is asked for now: swaps the buffers, returns the bytes; -2 = none */
+static long
+readahead_take(struct databuf *db, int fd, off_t off, size_t want)
+{
+	struct databuf_priv *pv = priv_of(db);
+	struct databuf_readahead *ra = &pv->ra;
+	long got = -2;
+
+	if (!ra->started)
+		return -2;
+	pthread_mutex_lock(&ra->lock);
+	while (ra->busy)
+		pthread_cond_wait(&ra->cond, &ra->lock);
+	if (ra->have && ra->fd == fd && ra->off == off && ra->want == want && ra->got >= 0) {
+		unsigned char *t = db->h_data;
+		db->h_data = ra->buf;
+		ra->buf = t;
+		got = ra->got;
+	}
+	ra->have = 0;
+	pthread_mutex_unlock(&ra->lock);
+	return got;
+}
+
+static void
+readahead_stop(struct databuf_priv *pv)
+{
+	struct databuf_readahead *ra = &pv->ra;
+
+	if (ra->started) {
+		pthread_mutex_lock(&ra->lock);
+		while (ra->busy)
+			pthread_cond_wait(&ra->cond, &ra->lock);
+		ra->quit = 1;
+		pthread_cond_broadcast(&ra->cond);
+		pthread_mutex_unlock(&ra->lock);
+		pthread_join(ra->thread, NULL);
+		ra->started = 0;
+	}
+	acm_host_free_pinned(ra->buf);
+	ra->buf = NULL;
+}
+
+/*
+ * reference databuf.c:327-407.  Returns what the reference returns, and -4 (with the reason in
+ * acm_last_error()) when the read itself fails: the reference aborts there; "0 = end of file"
+ * would silently truncate the scan.
+ */
 int
 databuf_add_fd(struct databuf *db, int fd, int id, size_t *rd_bytes)
 {
 	size_t i, cur_chunks, tail;
-	ssize_t got;
+	const size_t room = (db->max_chunks - db->chunks) * db->max_chunk_size;
+	ssize_t got = -2;
+	struct stat st;
+	off_t pos = (off_t)-1;
+	int regular;
 
 	*rd_bytes = 0;
 	if (db->chunks >= db->max_chunks)
 		return -1;
+	regular = fstat(fd, &st) == 0 && S_ISREG(st.st_mode) && (pos = lseek(fd, 0, SEEK_CUR)) != (off_t)-1;
 	/* chunks are fixed size in this mode: chunk k starts at k * max_chunk_size */
-	got = databuf_read_fd(fd, db->h_data + db->chunks * db->max_chunk_size,
-	    (db->max_chunks - db->chunks) * db->max_chunk_size);
-	if (got <= 0)
+	/* (priv is NULL for a caller-built, host-only struct: no read-ahead there) */
+	if (regular && db->chunks == 0 && db->priv) {
+		got = readahead_take(db, fd, pos, room);
+		if (got >= 0 && lseek(fd, pos + (off_t)got, SEEK_SET) == (off_t)-1)
+			got = -1;
+	}
+	if (got == -2)
+		got = databuf_read_fd(fd, db->h_data + db->chunks * db->max_chunk_size, room);
+	if (got < 0) {
+		acm_set_error("databuf_add_fd: read failed: %s", strerror(errno));
+		if (db->priv)
+			priv_of(db)->status = ACM_ERR_IO;
+		return -4;
+	}
+	if (got == 0)
 		return 0;
 	*rd_bytes = (size_t)got;
+	/* a whole buffer in one go and more of the file behind it: fetch the next one meanwhile */
+	if (regular && db->priv && db->chunks == 0 && (size_t)got == db->size && pos + (off_t)got < st.st_size)
+		readahead_start(db, fd, pos + (off_t)got, db->size);
 
 	cur_chunks = (size_t)got / db->max_chunk_size;
 	for (i = db->chunks; i < db->chunks + cur_chunks; i++) {
@@ -325,7 +479,9 @@ databuf_clear(struct databuf *db)
 	memset(db->h_results2_comp, 0, db->results2_comp_size * sizeof(int));
 	memset(db->file_ids, 0, db->max_chunks * sizeof(int));
 	pv->carry_len = 0;
-	pv->n_matches = 0;
+	pv->carry_real = 0;
+	pv->carry_file = -1;
+	pv->n_matches = pv->n_valid = 0;
 	db->last_state = 0;
 	databuf_reset(db);
 }
@@ -357,17 +513,40 @@ chunk_of(const struct databuf *db, long off)
 	return (int)lo;
 }
 
+/*
+ * Chunks of one contiguous stretch of real bytes of one file get the same id: consecutive chunks
+ * continue a run when the file id is the same and the earlier chunk is filled to where the later
+ * one starts (no zero padding in between).
+ */
+static void
+label_runs(const struct databuf *db, int *run_id)
+{
+	size_t c;
+	int run = 0;
+
+	for (c = 0; c < db->chunks; c++) {
+		if (c && !(db->file_ids[c] == db->file_ids[c - 1] &&
+		    db->h_indices[c - 1] + db->h_sizes[c - 1] == db->h_indices[c]))
+			run++;
+		run_id[c] = run;
+	}
+}
+
 void
 databuf_copy_device_to_host(struct databuf *db, cl_command_queue queue)
 {
 	struct databuf_priv *pv = priv_of(db);
 	const size_t R = (size_t)db->max_results, C = db->chunks;
-	uint64_t n = pv->n_matches, i;
+	const uint64_t n = pv->n_matches;
+	const uint32_t *plen = (pv->file_semantics && pv->sym_size == 1 && pv->scanner_aut) ?
+	    acm_automaton_pattern_lengths(pv->scanner_aut) : NULL;
+	uint64_t i, kept = 0;
 	int64_t got;
 
 	(void)queue;
-	memset(db->h_results, 0, (R * db->max_chunks + 1) * sizeof(int));
-	memset(db->h_results2, 0, (R * db->max_chunks + 1) * sizeof(int));
+	/* bucket rows 1.. are only ever read below a chunk's count: clearing the counts is enough */
+	memset(db->h_results, 0, db->max_chunks * sizeof(int));
+	memset(db->h_results2, 0, db->max_chunks * sizeof(int));
 	if (n + 2 > db->results_comp_size) {
 		size_t nc = db->results_comp_size;
 		int *a, *b;
@@ -403,15 +582,35 @@ databuf_copy_device_to_host(struct databuf *db, cl_command_queue queue)
 		pv->status = (int)got;
 		return;
 	}
-	db->h_results_comp[0] = db->h_results2_comp[0] = (int)n;
+	if (plen && n)
+		label_runs(db, pv->run_id);
 	for (i = 0; i < n; i++) {
 		const long off = (long)(pv->h_off[i] - DATABUF_CARRY_CAP / pv->sym_size);
 		const int pat = (int)pv->h_pat[i];
 		const int c = chunk_of(db, off * pv->sym_size);
 		int k;
 
-		db->h_results_comp[i + 1] = pat;
-		db->h_results2_comp[i + 1] = (int)off;
+		if (plen) {
+			/*
+			 * Per-file semantics: every byte of the match is a real byte of ONE file.  The end
+			 * must not lie in a chunk's zero padding; the start must lie in the same contiguous
+			 * run of chunks -- or in the carried tail of the previous buffer when that tail is the
+			 * same file, ran up to that buffer's end and this run starts the buffer.
+			 */
+			const long start = off - (long)plen[pat] + 1;
+			if (off >= (long)db->h_indices[c] + db->h_sizes[c])
+				continue;
+			if (start >= 0) {
+				if (pv->run_id[chunk_of(db, start)] != pv->run_id[c])
+					continue;
+			} else if (pv->run_id[c] != 0 || db->h_indices[0] != 0 || db->file_ids[0] != pv->filt_carry_file ||
+			    (uint64_t)(-start) > pv->filt_carry_real) {
+				continue;
+			}
+		}
+		db->h_results_comp[kept + 1] = pat;
+		db->h_results2_comp[kept + 1] = (int)off;
+		kept++;
 		/* reference bucket layout, ahomatch.cl:67-73: row 0 = counts, row k = k-th match */
 		k = ++db->h_results[c];
 		db->h_results2[c] = k;
@@ -420,7 +619,8 @@ databuf_copy_device_to_host(struct databuf *db, cl_command_queue queue)
 			db->h_results2[(size_t)k * C + c] = (int)off;
 		}
 	}
-	db->h_results_comp[n + 1] = db->h_results2_comp[n + 1] = (int)db->last_state;
+	db->h_results_comp[0] = db->h_results2_comp[0] = (int)kept;
+	db->h_results_comp[kept + 1] = db->h_results2_comp[kept + 1] = (int)db->last_state;
 	db->h_results[C * R] = (int)db->last_state;
 	{
 		int run = 0;
@@ -429,6 +629,7 @@ databuf_copy_device_to_host(struct databuf *db, cl_command_queue queue)
 			run += db->h_results[i];
 		}
 	}
+	pv->n_valid = kept;
 	pv->fetched = 1;
 }
 
@@ -461,6 +662,10 @@ databuf_free(struct databuf *db, int mapped, cl_command_queue queue)
 		return;
 	pv = priv_of(db);
 	if (pv) {
+		readahead_stop(pv);
+		pthread_mutex_destroy(&pv->ra.lock);
+		pthread_cond_destroy(&pv->ra.cond);
+		free(pv->run_id);
 		if (pv->scanner)
 			acm_scanner_free(pv->scanner);
 		if (pv->dev) {
@@ -492,7 +697,15 @@ databuf_status(struct databuf *db)
 size_t
 databuf_match_count(struct databuf *db)
 {
-	return (size_t)priv_of(db)->n_matches;
+	struct databuf_priv *pv = priv_of(db);
+
+	return (size_t)(pv->fetched ? pv->n_valid : pv->n_matches);
+}
+
+void
+databuf_set_file_semantics(struct databuf *db, int on)
+{
+	priv_of(db)->file_semantics = on != 0;
 }
 
 int
@@ -516,5 +729,12 @@ databuf_alloc_postpass(struct databuf *db)
 	PP(d_results_comp, ncomp);
 	PP(d_results2_comp, ncomp);
 #undef PP
+	/* nothing on the device has filled these yet: never let a post-pass read raw memory */
+	if ((rc = acm_dev_memset(pv->dev, db->d_results, 0, nres)) != ACM_OK ||
+	    (rc = acm_dev_memset(pv->dev, db->d_results2, 0, nres)) != ACM_OK ||
+	    (rc = acm_dev_memset(pv->dev, db->d_prefixsum, 0, db->max_chunks * sizeof(int) + 16)) != ACM_OK ||
+	    (rc = acm_dev_memset(pv->dev, db->d_results_comp, 0, ncomp)) != ACM_OK ||
+	    (rc = acm_dev_memset(pv->dev, db->d_results2_comp, 0, ncomp)) != ACM_OK)
+		return pv->status = rc;
 	return ACM_OK;
 }

@@ -291,7 +291,9 @@ __device__ __forceinline__ uint4 load_vec(const uint8_t *__restrict__ data, uint
 /* sampled 4-gram entry filter                                               */
 /* ------------------------------------------------------------------------- */
 
+#ifndef S4_THREADS
 #define S4_THREADS 1024
+#endif
 #define S4_UNROLL  4
 #ifndef S4_UNIT_CHUNKS
 #define S4_UNIT_CHUNKS 8                 /* chunks per run (16 KiB) while plenty of work is left */

@@ -352,22 +352,27 @@ k_bucket_expand_compact(const uint32_t *__restrict__ buckets, const uint32_t *__
 	}
 }
 
-/* reference bucket format -> [total, values..., tail]  (reference compactarray.cl:40-68) */
+/* reference bucket format -> [total, values..., tail]  (reference compactarray.cl:40-68).
+ * dst holds dst_cap ints: counts that would run past it (garbage in, or a caller's short buffer)
+ * are cut off instead of written out of bounds. */
 __global__ void k_compact_columns(int32_t *__restrict__ dst, const int32_t *__restrict__ src,
-    const int32_t *__restrict__ prefix, int32_t len, int32_t max_results)
+    const int32_t *__restrict__ prefix, int32_t len, int32_t max_results, int64_t dst_cap)
 {
 	const int64_t gid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
 	if (gid == 0) {
-		const int32_t total = prefix[len - 1] + src[len - 1];
-		dst[0] = total;
-		dst[(int64_t)total + 1] = src[(int64_t)max_results * len];
+		const int64_t total = (int64_t)prefix[len - 1] + src[len - 1];
+		dst[0] = (int32_t)total;
+		if (total >= 0 && total + 1 < dst_cap)
+			dst[total + 1] = src[(int64_t)max_results * len];
 	}
 	if (gid >= len)
 		return;
-	const int32_t off = prefix[gid];
+	const int64_t off = prefix[gid];
 	const int32_t m = src[gid];
-	for (int32_t i = 0; i < m && i < max_results - 1; ++i)
-		dst[(int64_t)off + 1 + i] = src[(int64_t)len * (i + 1) + gid];
+	if (off < 0)
+		return;
+	for (int32_t i = 0; i < m && i < max_results - 1 && off + 1 + i < dst_cap; ++i)
+		dst[off + 1 + i] = src[(int64_t)len * (i + 1) + gid];
 }
 
 /* ------------------------------------------------------------------------- */

@@ -86,12 +86,12 @@ class Scanner:
     """struct acm_scanner: scratch + result buffers for scans of up to max_bytes symbols."""
 
     def __init__(self, device, automaton, max_bytes, mode=MODE_AUTO, bucket_shift=0, bucket_cap=0,
-                 timing=False, dfa_chunk=0):
+                 timing=False, dfa_chunk=0, own_stream=False):
         self.L = lib()
         self.device = device
         self.automaton = automaton
         p = ScanParams(mode=mode, bucket_shift=bucket_shift, bucket_cap=bucket_cap,
-                       timing=int(timing), dfa_chunk=dfa_chunk)
+                       timing=int(timing), dfa_chunk=dfa_chunk, own_stream=int(own_stream))
         h = C.c_void_p()
         check(self.L.acm_scanner_create(device.handle, automaton, max_bytes, C.byref(p), C.byref(h)),
               "acm_scanner_create")
@@ -142,6 +142,10 @@ class Scanner:
 
     def keys_ptr(self):
         return self.L.acm_scan_keys(self._h)
+
+    def stream(self):
+        """cudaStream_t (int) this scanner's scans are queued on."""
+        return self.L.acm_scanner_stream(self._h)
 
     def histogram_into(self, d_counts_ptr):
         check(self.L.acm_scan_histogram(self._h, C.c_void_p(d_counts_ptr)), "acm_scan_histogram")

@@ -344,6 +344,10 @@ class StepPipeline:
         self.launched = s
         return s
 
+    def stream_of(self, step):
+        """cudaStream_t (int) the kernels of `step` were queued on."""
+        return self.scanners[step & 1].stream()
+
     def complete(self):
         """Finish the oldest queued step.  Returns (ScanResult of this rank, total matches of the
         step over all ranks or None, keys) -- total and keys (a uint64 view of pinned memory,

@@ -30,7 +30,7 @@ extern "C" {
 #define ACM_ERR_NOMEM         -11
 #define ACM_ERR_ARG           -12
 #define ACM_ERR_STATE         -13   /* call made in the wrong order            */
-#define ACM_ERR_LIMIT         -14   /* > 2^24-1 patterns, > 2^30 states, > 2^40 bytes per scan */
+#define ACM_ERR_LIMIT         -14   /* > 2^24-1 patterns, > 2^30 states, > 2^40 bytes per scan (2^30 for the dense-output kernels) */
 #define ACM_ERR_EMPTY_PATTERN -15   /* zero-length pattern (kept, never matches) */
 #define ACM_ERR_IO            -16
 #define ACM_ERR_NO_DEVICE     -17   /* no CUDA device: there is no CPU fallback */
@@ -64,6 +64,7 @@ void  acm_dev_free(struct acm_device *, void *d_ptr);
 int   acm_host_alloc_pinned(size_t bytes, void **h_ptr);
 int   acm_host_alloc_pinned_near(struct acm_device *dev, size_t bytes, void **h_ptr);
 void  acm_host_free_pinned(void *h_ptr);
+int   acm_dev_memset(struct acm_device *, void *d_dst, int value, size_t bytes);         /* async on the stream */
 int   acm_memcpy_h2d(struct acm_device *, void *d_dst, const void *h_src, size_t bytes);  /* async on the stream */
 int   acm_memcpy_d2h(struct acm_device *, void *h_dst, const void *d_src, size_t bytes);  /* async on the stream */
 /* D2H on a side stream (ordered after the work queued so far), so it overlaps later kernels; acm_side_sync waits for it */
@@ -79,6 +80,8 @@ int   acm_automaton_upload(struct acm_device *, const struct acm_tables *, struc
 void  acm_automaton_free(struct acm_automaton *);
 uint32_t acm_automaton_states(const struct acm_automaton *);
 uint32_t acm_automaton_patterns(const struct acm_automaton *);
+/* host array [patterns]: length of every pattern by index (add order); lives as long as the automaton */
+const uint32_t *acm_automaton_pattern_lengths(const struct acm_automaton *);
 int      acm_automaton_max_pattern_len(const struct acm_automaton *);
 int      acm_automaton_min_pattern_len(const struct acm_automaton *);
 int      acm_automaton_alphabet(const struct acm_automaton *);
@@ -103,9 +106,13 @@ struct acm_scan_params {
 	int      mode;          /* 0 auto, 1 sampled4, 2 start2, 3 dfa, 4 cdfa                */
 	int      bucket_shift;  /* log2 bytes of input per result bucket; 0 = default (17 sampled, 15 otherwise) */
 	int      bucket_cap;    /* records per bucket before the exact 2-pass fallback; 0 = default */
-	int      timing;        /* 1: CUDA events around each kernel; 2: around the scan kernel only (ms_scan) */
+	int      timing;        /* 1: CUDA events around each kernel; 2: around the scan stage only (ms_scan);
+	                           3: sampled mode: around the streaming kernel alone, without the resolve kernel */
 	int      dfa_chunk;     /* symbols per thread in DFA mode; 0 = sized to fill the GPU */
-	int      reserved[3];
+	int      own_stream;    /* 1: the scanner gets a stream of its own; each of its scans is ordered behind
+	                           what the device's stream holds when it is queued, but two scanners' scans
+	                           overlap (the small kernels of step i run under the streaming kernel of i+1) */
+	int      reserved[2];
 };
 
 struct acm_scan_result {
@@ -169,6 +176,9 @@ int  acm_scan_device_async(struct acm_scanner *, const void *d_data, uint64_t n,
          uint64_t emit_lo, uint64_t emit_hi, const struct acm_push_target *push);
 int  acm_scan_finish(struct acm_scanner *, struct acm_scan_result *res);
 
+/* the cudaStream_t this scanner's scans are queued on (its own, or the device's) */
+void *acm_scanner_stream(struct acm_scanner *);
+
 /* device pointer to the sorted u64 keys of the last scan: (end offset relative to d_data) << 24 | pattern index */
 const uint64_t *acm_scan_keys(struct acm_scanner *);
 
@@ -210,14 +220,53 @@ int  acm_scan_histogram(struct acm_scanner *, uint64_t *d_counts);
  */
 int64_t acm_scan_host(struct acm_scanner *, const void *h_data, uint64_t n, uint64_t base,
             uint64_t *h_off, uint32_t *h_pat, uint64_t cap, struct acm_scan_result *res);
+/* the same for a range in the middle of a longer host stream: lead symbols in front of h_data are
+ * valid context (h_data - lead is readable); matches ENDING in [0, n) are reported */
+int64_t acm_scan_host_ex(struct acm_scanner *, const void *h_data, uint64_t n, uint64_t lead, uint64_t base,
+            uint64_t *h_off, uint32_t *h_pat, uint64_t cap, struct acm_scan_result *res);
+
+/*
+ * ---- several GPUs in one process (no torch, no MPI): one host thread per device ----
+ * What the reference gets from `-w` worker threads that each own a context on device `dev_pos`
+ * (ocl_aho_grep.c:498-502, ocl_worker.c:32), for ONE stream: the automaton is replicated, device g
+ * of P takes bytes [g N/P, (g+1) N/P) (cuts multiples of 16) plus Lmax-1 bytes of leading context
+ * and keeps the matches that END in its own range, so the global sorted list is the concatenation
+ * of the per-device lists in device order.  There is no collective: the devices
+ * exchange nothing but their match counts, through host memory; every device copies its own sorted
+ * list into its slice of the caller's buffer over its own PCIe link.
+ * The same ordinal may be listed more than once (two "devices" on one GPU: separate streams and
+ * buffers) -- that is how the logic is tested on a single-GPU box.
+ */
+struct acm_multi;
+int   acm_multi_open(const struct acm_tables *, const int *ordinals, int n_devices, uint64_t max_bytes_per_device,
+          const struct acm_scan_params *, struct acm_multi **out);
+void  acm_multi_close(struct acm_multi *);
+int   acm_multi_devices(const struct acm_multi *);
+struct acm_device *acm_multi_device(struct acm_multi *, int g);
+/* shard g of a stream of `total` symbols: device g reads [read_lo, hi) and keeps matches ending in [lo, hi) */
+void  acm_multi_shard(const struct acm_multi *, uint64_t total, int g, uint64_t *read_lo, uint64_t *lo, uint64_t *hi);
+/*
+ * Shards already in device memory: d_data[g] holds stream[read_lo_g, hi_g) on device g (16-byte
+ * aligned).  All devices scan at once; h_keys (pinned recommended) receives the global sorted
+ * list, (stream end offset << 24) | pattern index, each device's part copied by that device;
+ * counts[g] (may be NULL) = matches of device g.  Returns the total, or a negative error; more
+ * than cap matches: the total is returned, nothing beyond cap is written.
+ */
+int64_t acm_multi_scan_device(struct acm_multi *, const void *const *d_data, uint64_t total,
+            uint64_t *h_keys, uint64_t cap, uint64_t *counts, struct acm_scan_result *res);
+/* a host stream (pinned for full rate): every device streams its own shard through its own
+ * double-buffered H2D pipeline; results as acm_scan_host */
+int64_t acm_multi_scan_host(struct acm_multi *, const void *h_data, uint64_t n, uint64_t base,
+            uint64_t *h_off, uint32_t *h_pat, uint64_t cap, struct acm_scan_result *res);
 
 /* ---- post-pass primitives (reference ocl_prefix_sum / ocl_compact_array / ocl_bitonic_sort) ---- */
 /* exclusive prefix sum, single-pass decoupled look-back; d_total may be NULL */
 int  acm_exclusive_scan_u32(struct acm_device *, const uint32_t *d_in, uint32_t *d_out,
          uint32_t n, uint32_t *d_total);
-/* column-major bucket compaction (reference compactarray.cl:40-68): dst = [total, values..., tail] */
+/* column-major bucket compaction (reference compactarray.cl:40-68): dst = [total, values..., tail];
+ * nothing is written at or beyond d_dst[dst_capacity_ints] */
 int  acm_compact_columns_i32(struct acm_device *, int32_t *d_dst, const int32_t *d_src,
-         const int32_t *d_prefix, int32_t len, int32_t max_results);
+         const int32_t *d_prefix, int32_t len, int32_t max_results, int64_t dst_capacity_ints);
 /* LSD radix sort of u64 keys on bits [begin_bit, end_bit); d_tmp has n entries */
 int  acm_radix_sort_u64(struct acm_device *, uint64_t *d_keys, uint64_t *d_tmp, uint64_t n,
          int begin_bit, int end_bit, int descending);

@@ -141,6 +141,10 @@ int  acsm_check_filters(acsm_t *);
  */
 int  acsm_check_cdfa(acsm_t *, unsigned int *slots, unsigned int *dense_rows);
 
+/* the compiled host tables (acm_automaton_upload, acm_multi_open); NULL before acsm_compile and after acsm_cleanup */
+struct acm_tables;
+const struct acm_tables *acsm_tables(acsm_t *);
+
 /* device automaton handle for the native API in acm.h (NULL before upload) */
 struct acm_automaton *acsm_device_automaton(acsm_t *);
 

@@ -87,7 +87,8 @@ struct databuf *databuf_new(size_t, size_t, int, int, struct clconf *);
 /*
  * read() as much of fd as fits, in max_chunk_size chunks, zero-padding a short
  * last chunk.  Returns >0 (bytes read, buffer can take more), 0 (EOF), -1 (all
- * chunks used), -2 (all bytes used); *rd_bytes always set.  reference databuf.c:327
+ * chunks used), -2 (all bytes used), -4 (the read failed: acm_last_error(); the reference
+ * aborts); *rd_bytes always set.  reference databuf.c:327
  */
 int  databuf_add_fd(struct databuf *, int, int, size_t *);
 
@@ -118,7 +119,16 @@ void databuf_free(struct databuf *, int, cl_command_queue);   /* reference datab
 
 /* additions */
 int    databuf_status(struct databuf *);            /* 0 or the last negative ACM_ERR_* */
-size_t databuf_match_count(struct databuf *);       /* matches of the last ocl_aho_match() */
+size_t databuf_match_count(struct databuf *);       /* matches of the last ocl_aho_match() (after databuf_copy_device_to_host: those that passed the per-file rule) */
+/*
+ * Per-file semantics (default on; off = the reference's behaviour, also ACM_DATABUF_STREAM_QUIRK=1
+ * in the environment at databuf_new): a match is reported only if all its bytes are real bytes of
+ * ONE file -- not a chunk's zero padding, not the tail of one file plus the head of the next --
+ * and a match may reach back into the previous buffer only where that buffer ended with bytes
+ * of the same file.  The reference carries one DFA state across chunks, buffers and files alike
+ * (ahomatch.cl:38-45,86-93, databuf.c:610,622).
+ */
+void   databuf_set_file_semantics(struct databuf *, int on);
 /* allocates d_results, d_results2, d_prefixsum, d_results_comp, d_results2_comp (reference shapes) */
 int    databuf_alloc_postpass(struct databuf *);
 /*

@@ -183,3 +183,25 @@ def test_cli_follow_mode_sees_appended_data(tmp_path):
     assert got == sorted((pats[i][1], pats[i][0]) for i in ep)
     st = stats(out)
     assert st["Matches"] == eo.size and st["Processed bytes"] == len(text)
+
+
+def test_cli_device_list_stripes_workers(tmp_path):
+    """-D a,b,...: worker t opens the (t mod n)-th device of the list (reference ocl_aho_grep.c:498-502:
+    every worker owns a context on its device).  The same GPU twice on a single-GPU box."""
+    import torch
+    ngpu = max(1, torch.cuda.device_count())
+    pats = clamav_pats(2000)
+    o = build_oracle(pats)
+    pf = tmp_path / "sigs.hex"
+    pf.write_bytes(b"\n".join(read_fixture("clamav_sigs_15000.hex.gz").split(b"\n")[:2000]) + b"\n")
+    d = tmp_path / "in"
+    d.mkdir()
+    expect = 0
+    for k in range(4):
+        buf, _ = planted_stream(pats, 1 << 18, seed=60 + k, plants=30)
+        (d / f"f{k}.bin").write_bytes(buf.tobytes())
+        expect += o.search(buf)[0].size                   # per-file semantics: every file on its own
+    devs = ",".join(str(i % ngpu) for i in range(2))
+    out = run(["-f", str(d), "-p", str(pf), "-x", "-w", "4", "-D", devs, "-B", "4096", "-G", "16"])
+    st = stats(out)
+    assert st["Matches"] == expect and st["Processed files"] == 4

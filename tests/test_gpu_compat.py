@@ -313,3 +313,86 @@ def test_radix_sort_and_pair_sort(lib, device):
             device.free(p)
     assert L.ocl_bitonic_sort(C.byref(conf), None, None, None, None, 1, 1, 1) == -2
     L.clfreectx(C.byref(conf))
+
+
+def _five_calls(L, w, chunks_bytes=None):
+    """copy_h2d -> match(stream=1) -> copy_d2h -> process_results (collect) -> reset; returns the callbacks"""
+    ctx = w.contents
+    db = ctx.db
+    got = []
+
+    @_lib.MATCH_CB
+    def cb(file_idx, pat_idx, chunk_idx, offset, uarg):
+        got.append((file_idx, pat_idx, chunk_idx, offset))
+        return 0
+    L.databuf_copy_host_to_device(db, ctx.cl.queue)
+    L.ocl_aho_match(C.byref(ctx.cl), db, ctx.acsm, 1024, 1)
+    assert L.databuf_status(db) == 0, _lib.last_error()
+    L.databuf_copy_device_to_host(db, ctx.cl.queue)
+    n = L.databuf_process_results(db, cb, None)
+    assert n == len(got) == L.databuf_match_count(db)
+    L.databuf_reset(db)
+    return got
+
+
+def test_per_file_semantics_and_the_reference_quirk(lib, tmp_path):
+    """the carry is reset and the stream cut at every file change.  A signature whose
+    halves are the end of file A and the start of file B must NOT be reported; the same split
+    across two buffers of ONE file must; a signature completed by a chunk's zero padding must not.
+    With the quirk switched back on (databuf_set_file_semantics(db, 0)) the reference's one-stream
+    behaviour returns (ahomatch.cl:38-45,86-93: one state carried across everything)."""
+    L = lib
+    pf = tmp_path / "p.txt"
+    pf.write_bytes(b"HELLOWORLD\nabcdefgh\nzz\n")
+    # "tail0" ends with a zero byte: matches only if padding counts as stream
+    pfx = tmp_path / "px.txt"
+    pfx.write_bytes(b"48454c4c4f574f524c44\n6162636465666768\n7a7a\n7461696c00\n")      # the same three + "tail\0" (hex)
+    chunk, chunks = 64, 4                                  # 256-byte buffers
+    for quirk in (0, 1):
+        w, keep = _worker(L, pfx, True, chunks, chunk)
+        db = w.contents.db
+        L.databuf_set_file_semantics(db, 0 if quirk else 1)
+        fa = tmp_path / "a.bin"
+        fb = tmp_path / "b.bin"
+        # file A: exactly two chunks, ends with "HELLO"; file B starts with "WORLD"
+        fa.write_bytes(b"." * (2 * chunk - 5) + b"HELLO")
+        fb.write_bytes(b"WORLD" + b"." * 20 + b"zz" + b"." * 10 + b"tail")           # 41 bytes: padded chunk, ends "tail" + zeros
+        rd = C.c_size_t(0)
+        for fid, f in ((0, fa), (1, fb)):
+            fd = os.open(f, os.O_RDONLY)
+            L.databuf_add_fd(db, fd, fid, C.byref(rd))
+            os.close(fd)
+        assert db.contents.chunks == 3
+        got = _five_calls(L, w)
+        names = sorted((g_[0], g_[1]) for g_ in got)
+        if quirk:
+            # one stream: HELLO|WORLD across the files (pattern 0, reported in file 1), zz, and "tail\\0" made of padding
+            assert names == [(1, 0), (1, 2), (1, 3)]
+        else:
+            assert names == [(1, 2)]                                   # only zz, inside file B
+        # --- one file over two buffers: the split signature IS found, once, in the second buffer
+        fc = tmp_path / "c.bin"
+        fc.write_bytes(b"." * (chunks * chunk - 4) + b"abcdefgh" + b"." * 60)         # "abcd" | "efgh" across the buffer cut
+        fd = os.open(fc, os.O_RDONLY)
+        e = L.databuf_add_fd(db, fd, 5, C.byref(rd))
+        assert e in (-1, -2) and rd.value == chunks * chunk
+        first = _five_calls(L, w)
+        L.databuf_add_fd(db, fd, 5, C.byref(rd))
+        second = _five_calls(L, w)
+        os.close(fd)
+        assert [g_[1] for g_ in first] == [] and [(g_[0], g_[1], g_[3]) for g_ in second] == [(5, 1, 4)]
+        # --- a different file right behind it: its first bytes complete nothing that file 5 left in the carry
+        fd2 = tmp_path / "d.bin"
+        fd2.write_bytes(b"." * (chunks * chunk - 5) + b"HELLO")
+        fd3 = tmp_path / "e.bin"
+        fd3.write_bytes(b"WORLD" + b"." * 59)
+        fd = os.open(fd2, os.O_RDONLY)
+        L.databuf_add_fd(db, fd, 7, C.byref(rd))
+        os.close(fd)
+        assert _five_calls(L, w) == []
+        fd = os.open(fd3, os.O_RDONLY)
+        L.databuf_add_fd(db, fd, 8, C.byref(rd))
+        os.close(fd)
+        cross = _five_calls(L, w)
+        assert [(g_[0], g_[1]) for g_ in cross] == ([(8, 0)] if quirk else [])
+        L.ocl_worker_ctx_free(w)

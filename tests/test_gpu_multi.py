@@ -137,3 +137,77 @@ def test_peer_gather_two_ranks(world, tmp_path):
     mp.spawn(_worker, args=(world, _free_port(), total, str(tmp_path)), nprocs=world, join=True)
     ok, n = open(tmp_path / "result").read().split()
     assert ok == "1" and int(n) >= 256
+
+
+def test_multi_device_c_api_in_one_process():
+    """acm_multi_*: one host thread per device, no torch.distributed.  Devices are distinct GPUs when
+    the box has them, else the same GPU three times (separate streams and buffers).  Device-resident
+    shards and the host-stream form, both against the whole-stream oracle walk; plants across every cut."""
+    if not torch.cuda.is_available():
+        pytest.fail("gpu test selected but no CUDA device is visible")
+    import ctypes as C
+    import gpu_pattern_matching_b200 as g
+    from gpu_pattern_matching_b200 import _lib, sharded, synth
+    from helpers import build_oracle, build_product, clamav_pats
+    L = g.lib()
+    pats = clamav_pats(2000)
+    o, a = build_oracle(pats), build_product(pats, upload=False)
+    ngpu = torch.cuda.device_count()
+    for ndev in (1, 2, 3):
+        ords = (C.c_int * ndev)(*[i % ngpu for i in range(ndev)])
+        total = (5 << 20) + 16 * 7 + 3
+        m = C.c_void_p()
+        p = _lib.ScanParams()
+        _lib.check(L.acm_multi_open(L.acsm_tables(a._p), ords, ndev, total // ndev + 4096, C.byref(p), C.byref(m)),
+                   "acm_multi_open")
+        assert L.acm_multi_devices(m) == ndev
+        cuts = []
+        rl, lo, hi = C.c_uint64(), C.c_uint64(), C.c_uint64()
+        for gdev in range(ndev):
+            L.acm_multi_shard(m, total, gdev, C.byref(rl), C.byref(lo), C.byref(hi))
+            cuts.append((rl.value, lo.value, hi.value))
+        assert cuts[0][1] == 0 and cuts[-1][2] == total and all(c[2] == d[1] for c, d in zip(cuts, cuts[1:]))
+        forced = [(c[1] - 300, 40 + k) for k, c in enumerate(cuts[1:])] + [(c[1] - 4, 70 + k) for k, c in enumerate(cuts[1:])]
+        plants = synth.Plants([p_ for p_, _ in pats], total, 400, 11, forced)
+        whole = synth.stream(total, 11)
+        plants.apply_host(whole)
+        eo, ep, _, _ = o.search(whole)
+        # device-resident shards
+        ptrs = (C.c_void_p * ndev)()
+        devs = []
+        for gdev, (read_lo, lo_, hi_) in enumerate(cuts):
+            d = g.Device.__new__(g.Device)
+            d.L, d._h, d.ordinal = L, C.c_void_p(L.acm_multi_device(m, gdev)), ords[gdev]
+            n = hi_ - read_lo
+            ptr = d.alloc(n + 64)
+            d.h2d(ptr, whole[read_lo:hi_])
+            ptrs[gdev] = ptr
+            devs.append((d, ptr))
+        cap = int(eo.size) + 16
+        keys, owner = g.matcher.pinned_empty(cap * 8)
+        keys = keys.view(np.uint64)
+        counts = (C.c_uint64 * ndev)()
+        res = _lib.ScanResult()
+        for _ in range(3):                                   # the workers and their buffers are reused
+            keys[:] = 0
+            tot = L.acm_multi_scan_device(m, ptrs, total, keys.ctypes.data_as(_lib.u64p), cap, counts, C.byref(res))
+            assert tot == eo.size == sum(counts), (tot, eo.size, list(counts))
+            goff, gpat = sharded.unpack_keys(keys[:tot].copy())
+            assert np.array_equal(goff, eo) and np.array_equal(gpat, ep)
+        # a buffer that is too small: the total is still reported, nothing is written beyond cap
+        keys[:] = 0
+        tot = L.acm_multi_scan_device(m, ptrs, total, keys.ctypes.data_as(_lib.u64p), 10, counts, C.byref(res))
+        assert tot == eo.size and not keys[10:].any()
+        # host stream
+        host, owner2 = g.matcher.pinned_empty(total + 64)
+        host[:total] = whole
+        off = np.empty(cap, dtype=np.uint64)
+        pat = np.empty(cap, dtype=np.uint32)
+        tot = L.acm_multi_scan_host(m, C.c_void_p(host.ctypes.data), total, 1000, off.ctypes.data_as(_lib.u64p),
+                                    pat.ctypes.data_as(_lib.u32p), cap, C.byref(res))
+        assert tot == eo.size
+        assert np.array_equal(off[:tot], eo + np.uint64(1000)) and np.array_equal(pat[:tot], ep)
+        for d, ptr in devs:
+            d.free(ptr)
+        L.acm_multi_close(m)
+        del owner, owner2
