@@ -188,6 +188,7 @@ SIGNATURES = {
     "acsm_export_ref_table": (C.c_int, [C.POINTER(AcsmStruct)]),
     "acsm_check_filters": (C.c_int, [C.POINTER(AcsmStruct)]),
     "acsm_check_cdfa": (C.c_int, [C.POINTER(AcsmStruct), C.POINTER(C.c_uint), C.POINTER(C.c_uint)]),
+    "acsm_check_xd": (C.c_int, [C.POINTER(AcsmStruct), C.POINTER(C.c_uint)]),
     "acsm_tables": (vp, [C.POINTER(AcsmStruct)]),
     "acsm_device_automaton": (vp, [C.POINTER(AcsmStruct)]),
     # iacsmx.h
@@ -203,6 +204,7 @@ SIGNATURES = {
     "iacsm_free": (None, [C.POINTER(IacsmStruct)]),
     "iacsm_status": (C.c_int, [C.POINTER(IacsmStruct)]),
     "iacsm_export_ref_table": (C.c_int, [C.POINTER(IacsmStruct)]),
+    "iacsm_check_xd": (C.c_int, [C.POINTER(IacsmStruct), C.POINTER(C.c_uint)]),
     "iacsm_device_automaton": (vp, [C.POINTER(IacsmStruct)]),
     # ocl_context.h
     "clinitctx": (None, [C.POINTER(Clconf), C.c_int, C.c_int]),

@@ -145,7 +145,7 @@ acm_tables_free(struct acm_tables *t)
 	free(t->bfs_to_ref); free(t->f1); free(t->f2); free(t->grams); free(t->b2); free(t->b2s); free(t->b3);
 	free(t->cand); free(t->pat_blob); free(t->pat_off);
 	free(t->cd_cls); free(t->cd_tab); free(t->cd_flat_begin); free(t->cd_flat_pat);
-	free(t->rd_tab); free(t->rd_flat4); free(t->cd_flat4);
+	free(t->rd_tab); free(t->rd_flat4); free(t->cd_flat4); free(t->xd_tab); free(t->xd_sid);
 	memset(t, 0, sizeof(*t));
 }
 
@@ -173,6 +173,8 @@ acm_tables_device_bytes(const struct acm_tables *t)
 		    (size_t)t->cd_flat_total * 4 + (size_t)t->num_states * 16;
 	if (t->rd_tab)
 		b += (size_t)t->rd_len * 20;
+	if (t->xd_tab)
+		b += (size_t)t->xd_len * 8;
 	return b;
 }
 
@@ -426,6 +428,278 @@ out:
 	}
 	free(dflt); free(off); free(rows); free(occ); free(used_base); free(tab);
 	return rc;
+}
+
+/*
+ * The DFA as ONE small row-displaced array ("xd"): what k_scan_xd walks instead of the dense
+ * T[states][alpha] (370 MiB for 10 000 ClamAV signatures, one 4-byte gather per input byte into
+ * 2-5 x the L2: reference ahomatch.cl:56-65 does exactly that out of a table twice that size).
+ *
+ * A DFA row is the failure state's row with the state's own trie edges on top, so it differs from
+ * the row of a shallow state on its failure chain only where the states in between have trie
+ * children.  Which shallow state?  For bytes, the depth-1 state of the LAST INPUT BYTE: the
+ * failure chain of any state ends in (the state of its last byte, or the root when no pattern
+ * starts with it) -> root.  So with b the byte that led to state s,
+ *
+ *     T[s][c] = xd[off(s) + c]               if that slot carries symbol c (then it is s's own:
+ *                                             bases are unique, see build_cdfa_rd), else
+ *             = xd[off(d1(b)) + c]           d1(b) = T[root][b], if that slot carries c, else
+ *             = xd[c]                        the root row, stored whole at base 0.
+ *
+ * The second and third lookups depend on the INPUT only, not on the walk: the kernel computes
+ * them a step ahead, and only the first is on the state's dependency chain.  Explicit entries
+ * (row differs from that default): 1.6 M for 10 000 ClamAV signatures = 6.8 MB with everything.
+ * The same holds for ushort symbols (alphabet 2048) with "the previous symbol"; stored against
+ * the root row alone, the depth-1 states of a few popular symbols would put ~40 inherited entries
+ * into every deeper state's row (1.4 M entries for 2 000 packet-size signatures instead of ~0.1 M).
+ * entry = symbol | any-match flag << sym_bits | base(target) << (sym_bits + 1); the root's row
+ * comes first, then the states in breadth-first order (first fit, lowest free slot; no base is
+ * congruent to alpha-1 modulo alpha, which is what lets free slots be marked unreadable), so a prefix
+ * of the array -- what k_scan_xd keeps in shared memory -- holds the shallow states.
+ * xd_sid[base] = breadth-first id of the state with that base (emission needs olink / own lists).
+ */
+/* the first free slot at or behind p; nxt[] is a union-find "next" array with path halving */
+static uint32_t
+xd_next_free(uint32_t *nxt, uint32_t p)
+{
+	while (nxt[p] != p) {
+		nxt[p] = nxt[nxt[p]];
+		p = nxt[p];
+	}
+	return p;
+}
+
+static int
+build_xd(struct acm_tables *t)
+{
+	const uint32_t A = (uint32_t)t->alpha, n = t->num_states;
+	const uint32_t sym_bits = A == 256 ? 8u : 11u;
+	const uint32_t max_slots = 1u << (31 - sym_bits);
+	const int levels = 1;
+	uint32_t *off = NULL, *tab = NULL, *sid = NULL, *cols = NULL, *nxt = NULL;
+	uint8_t *occ = NULL, *used_base = NULL, *depth1 = NULL;
+	uint32_t s, k, len, lowfree, cap, hint[17], d1_end = 0;
+	uint64_t est = 0;
+	int rc = ACM_OK;
+
+	if (!t->T || !t->fail || n == 0)
+		return ACM_OK;
+	for (k = 0; k < 17; k++)
+		hint[k] = A;
+	cols = malloc((size_t)A * 4);
+	off = malloc((size_t)n * 4);
+	depth1 = calloc(n, 1);                         /* 1: depth <= 1 */
+	if (!cols || !off || !depth1) {
+		rc = ACM_ERR_NOMEM;
+		goto out;
+	}
+	for (s = 0; s < t->level_start[2 <= t->max_depth + 1 ? 2 : t->max_depth + 1] && s < n; s++)
+		depth1[s] = 1;
+	/* how many slots at most: the root row plus every explicit entry (+ slack for first fit) */
+	for (s = 1; s < n; s++) {
+		const uint32_t *row = t->T + (size_t)s * A, *def;
+		uint32_t d = 0;
+		if (levels && !depth1[s]) {
+			d = t->fail[s];
+			while (!depth1[d])
+				d = t->fail[d];
+		}
+		def = t->T + (size_t)d * A;
+		for (k = 0; k < A; k++)
+			est += (row[k] & ACM_T_MASK) != (def[k] & ACM_T_MASK);
+	}
+	cap = (uint32_t)(2 * est + 8 * A < max_slots ? 2 * est + 8 * A : max_slots);
+	if (est + est / 2 + 2 * A >= max_slots)
+		goto out;                                   /* does not fit the entry format: no xd table */
+	occ = calloc((size_t)cap + A + 8, 1);
+	used_base = calloc((size_t)cap + A + 8, 1);
+	nxt = malloc(((size_t)cap + A + 8) * 4);        /* nxt[p]: a free slot >= p is at or behind nxt[p] (path-compressed) */
+	if (!occ || !used_base || !nxt) {
+		rc = ACM_ERR_NOMEM;
+		goto out;
+	}
+	for (k = 0; k < cap + A + 8; k++)
+		nxt[k] = k;
+	off[0] = 0;
+	used_base[0] = 1;
+	memset(occ, 1, A);
+	for (k = 0; k < A; k++)
+		nxt[k] = A;
+	len = A;
+	d1_end = A;
+	lowfree = A;
+	for (s = 1; s < n; s++) {
+		const uint32_t *row = t->T + (size_t)s * A, *def;
+		uint32_t d = 0, nc = 0, base = 0, p;
+		int placed = 0;
+		if (levels && !depth1[s]) {
+			d = t->fail[s];
+			while (!depth1[d])
+				d = t->fail[d];
+		}
+		def = t->T + (size_t)d * A;
+		for (k = 0; k < A; k++)
+			if ((row[k] & ACM_T_MASK) != (def[k] & ACM_T_MASK))
+				cols[nc++] = k;
+		lowfree = xd_next_free(nxt, lowfree);
+		if (nc == 0) {
+			/* identity only: any base nobody else uses, near the front of the free area */
+			for (base = lowfree > A ? lowfree - A : 0; base < cap && (used_base[base] || base % A == A - 1); base++)
+				;
+			if (base >= cap)
+				goto out;
+			placed = 1;
+		} else {
+			/* first fit over the free slots from where the last row with as many entries went (rows
+			 * with one entry fit any hole; wide rows would test every hole of the crowded front each
+			 * time), at most 4096 tries; then behind everything placed so far */
+			uint32_t tries = 0;
+			uint32_t *hp = &hint[nc < 16 ? nc : 16];
+			if (*hp < lowfree)
+				*hp = lowfree;
+			for (p = xd_next_free(nxt, *hp > cols[0] ? *hp : cols[0]); p < cap && tries < 4096;
+			     p = xd_next_free(nxt, p + 1), tries++) {
+				base = p - cols[0];
+				if (used_base[base] || base % A == A - 1)
+					continue;
+				for (k = 1; k < nc && !occ[base + cols[k]]; k++)
+					;
+				if (k < nc)
+					continue;
+				placed = 1;
+				if (nc > 1)
+					*hp = p;
+				break;
+			}
+			if (!placed) {
+				for (base = len; base + A < cap && (used_base[base] || base % A == A - 1); base++)
+					;
+				placed = base + A < cap;
+				if (placed && nc > 1)
+					*hp = base + cols[0];
+			}
+		}
+		if (!placed)
+			goto out;                               /* ran out of slots: leave xd unbuilt */
+		off[s] = base;
+		used_base[base] = 1;
+		for (k = 0; k < nc; k++) {
+			occ[base + cols[k]] = 1;
+			nxt[base + cols[k]] = base + cols[k] + 1;
+		}
+		if (base + A > len)
+			len = base + A;
+		if (depth1[s])
+			d1_end = len;                           /* every lookup from a state of depth <= 1 stays below this */
+	}
+	if (len > max_slots)
+		goto out;
+	tab = malloc((size_t)len * 4 + 64);
+	sid = calloc((size_t)len + 16, 4);
+	if (!tab || !sid) {
+		rc = ACM_ERR_NOMEM;
+		goto out;
+	}
+	memset(tab, 0, (size_t)len * 4);
+	for (s = 0; s < n; s++) {
+		const uint32_t *row = t->T + (size_t)s * A, *def;
+		uint32_t d = 0;
+		if (s && levels && !depth1[s]) {
+			d = t->fail[s];
+			while (!depth1[d])
+				d = t->fail[d];
+		}
+		def = t->T + (size_t)d * A;
+		sid[off[s]] = s;
+		for (k = 0; k < A; k++) {
+			if (s == 0 || (row[k] & ACM_T_MASK) != (def[k] & ACM_T_MASK)) {
+				const uint32_t nx = row[k] & ACM_T_MASK;
+				tab[off[s] + k] = k | ((row[k] & ACM_T_ANY) ? 1u << sym_bits : 0u) | (off[nx] << (sym_bits + 1));
+			}
+		}
+	}
+	/* A free slot p must fail the check of EVERY state that can read it -- the state with base
+	 * p - c reads it for symbol c -- so it claims a symbol whose implied base no state has: bases
+	 * congruent to alpha-1 modulo alpha are never handed out (see the placement above), and
+	 * c = (p + 1) mod alpha implies exactly such a base (or a negative one). */
+	for (k = 0; k < len; k++)
+		if (!occ[k])
+			tab[k] = (k + 1) % A;                   /* next = root, no flag: never selected anyway */
+	t->xd_tab = tab;
+	t->xd_sid = sid;
+	t->xd_len = len;
+	t->xd_d1_end = d1_end;
+	t->xd_levels = levels;
+	t->xd_sym_bits = sym_bits;
+	tab = sid = NULL;
+out:
+	free(cols); free(off); free(depth1); free(occ); free(used_base); free(nxt); free(tab); free(sid);
+	return rc;
+}
+
+/*
+ * Test support: every transition of the dense table T through the xd lookup rule (with the
+ * previous symbol that leads to each state), over all states.  Violations, or -1 if not built.
+ */
+int
+acm_core_check_xd(const struct acm_core *c, uint32_t *slots)
+{
+	const struct acm_tables *t = &c->tab;
+	const uint32_t A = (uint32_t)t->alpha, n = t->num_states;
+	uint32_t *off, *last, s, k;
+	int bad = 0;
+
+	if (!t->xd_tab || !t->T)
+		return -1;
+	if (slots)
+		*slots = t->xd_len;
+	off = malloc((size_t)n * 4);
+	last = malloc((size_t)n * 4);
+	if (!off || !last) {
+		free(off); free(last);
+		return ACM_ERR_NOMEM;
+	}
+	memset(off, 0xFF, (size_t)n * 4);
+	for (k = 0; k < t->xd_len; k++)
+		if (t->xd_sid[k] || k == 0)
+			off[t->xd_sid[k]] = k;
+	/* the symbol on the trie edge into s (breadth-first order: parents first) */
+	last[0] = 0;
+	for (s = 0; s < n; s++) {
+		uint32_t d = 0;
+		while (d + 1 <= (uint32_t)t->max_depth && s >= t->level_start[d + 1])
+			d++;
+		for (k = 0; k < A; k++) {
+			const uint32_t nx = t->T[(size_t)s * A + k] & ACM_T_MASK;
+			if (nx >= t->level_start[d + 1] && nx < t->level_start[d + 2 <= (uint32_t)t->max_depth + 1 ? d + 2 : (uint32_t)t->max_depth + 1])
+				last[nx] = k;
+		}
+	}
+	const uint32_t sb = t->xd_sym_bits, smask = (1u << sb) - 1u;
+	for (s = 0; s < n; s++) {
+		if (off[s] == 0xFFFFFFFFu) {
+			bad++;
+			continue;
+		}
+		for (k = 0; k < A; k++) {
+			const uint32_t want = t->T[(size_t)s * A + k];
+			uint32_t x = t->xd_tab[off[s] + k];
+			if ((x & smask) != k) {
+				x = t->xd_tab[k];                                       /* the root row */
+				if (t->xd_levels && s) {
+					const uint32_t r = t->xd_tab[last[s]];              /* root row entry of the previous symbol */
+					const uint32_t y = t->xd_tab[(r >> (sb + 1)) + k];   /* the row of its depth-1 state */
+					if ((y & smask) == k)
+						x = y;
+				}
+			}
+			if ((x & smask) != k || (x >> (sb + 1)) != off[want & ACM_T_MASK] ||
+			    (((x >> sb) & 1u) != 0) != ((want & ACM_T_ANY) != 0))
+				bad++;
+		}
+	}
+	free(off); free(last);
+	return bad;
 }
 
 /*
@@ -1310,6 +1584,8 @@ acm_core_compile(struct acm_core *c)
 		rc = build_filters(c);
 	if (A == 256 && rc == ACM_OK)
 		rc = build_cdfa(c);
+	if (rc == ACM_OK)
+		rc = build_xd(t);
 
 out:
 	trie_free(&tr);

@@ -44,6 +44,8 @@ int  acm_core_export_ref(struct acm_core *, int **out);
 int  acm_core_check_filters(const struct acm_core *);
 /* row-displaced dense-output table against the class-compressed one: violations, -1 if not built */
 int  acm_core_check_rd(const struct acm_core *, uint32_t *slots, uint32_t *dense);
+/* the row-displaced DFA (xd) against the dense table over every (state, symbol): violations, -1 if not built */
+int  acm_core_check_xd(const struct acm_core *, uint32_t *slots);
 /* drop host tables and pattern bytes (device copy stays) */
 void acm_core_cleanup(struct acm_core *);
 void acm_core_free(struct acm_core *);

@@ -54,7 +54,7 @@ struct acm_automaton {
 	size_t    bytes;
 	uint32_t *h_pat_len;        /* host copies that outlive acsm_cleanup() */
 	int32_t  *h_pat_iid;
-	void     *allocs[24];
+	void     *allocs[32];
 	int       n_allocs;
 };
 
@@ -151,6 +151,8 @@ set_kernel_attrs(int ordinal)
 	CUDA_TRY(cudaFuncSetAttribute(k_scan_cdfa<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
 	    CD_SMEM_MAX));
 	CUDA_TRY(cudaFuncSetAttribute(k_scan_rd, cudaFuncAttributeMaxDynamicSharedMemorySize, CD_SMEM_MAX));
+	CUDA_TRY(cudaFuncSetAttribute(k_scan_xd<uint8_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, XD_SMEM_MAX));
+	CUDA_TRY(cudaFuncSetAttribute(k_scan_xd<uint16_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, XD_SMEM_MAX));
 	CUDA_TRY(cudaFuncSetAttribute(k_rd_expand, cudaFuncAttributeMaxDynamicSharedMemorySize, RD_K3_SMEM));
 	if (ordinal < 64)
 		g_attr_done[ordinal] = 1;
@@ -437,7 +439,7 @@ upload(struct acm_automaton *a, const void *src, size_t bytes, const void **dst)
 	size_t padded = (bytes + 255) & ~(size_t)255;
 
 	*dst = NULL;
-	if (a->n_allocs >= 24)
+	if (a->n_allocs >= 32)
 		return ACM_ERR_LIMIT;
 	CUDA_TRY(cudaMalloc(&p, padded ? padded : 256));
 	a->allocs[a->n_allocs++] = p;
@@ -539,6 +541,13 @@ acm_automaton_upload(struct acm_device *dev, const struct acm_tables *t, struct 
 			UP(rd_flat4, t->rd_flat4, (size_t)t->rd_len * 16);
 			a->d.rd_len = t->rd_len;
 		}
+	}
+	if (t->xd_tab) {
+		UP(xd_tab, t->xd_tab, (size_t)t->xd_len * 4);
+		UP(xd_sid, t->xd_sid, (size_t)t->xd_len * 4);
+		a->d.xd_len = t->xd_len;
+		a->d.xd_d1_end = t->xd_d1_end;
+		a->d.xd_sym_bits = t->xd_sym_bits;
 	}
 #undef UP
 	a->d.num_states = t->num_states;
@@ -1051,11 +1060,11 @@ grow(uint64_t **buf, uint64_t *cap, uint64_t need, const char *what)
  * cold-start walk every chunk repeats) or 128 symbols, and no more than 4096.
  */
 static uint64_t
-scan_dfa_chunk(const struct acm_scanner *s, uint64_t span)
+scan_dfa_chunk(const struct acm_scanner *s, uint64_t span, uint64_t chains_per_sm)
 {
 	if (s->p.dfa_chunk > 0)
 		return (uint64_t)s->p.dfa_chunk;
-	const uint64_t resident = (uint64_t)s->dev->sm_count * 256 * DFA_MINB;
+	const uint64_t resident = (uint64_t)s->dev->sm_count * chains_per_sm;
 	const uint64_t halo = s->aut->max_len > 0 ? (uint64_t)(s->aut->max_len - 1) : 0;
 	uint64_t chunk = (span + resident - 1) / resident;
 	if (chunk < 2 * halo)
@@ -1156,8 +1165,33 @@ launch_k1(struct acm_scanner *s, cudaStream_t st, const void *d_data, uint64_t n
 			blocks = (uint64_t)s->dev->sm_count * 2;
 		k_scan_start2<false><<<(unsigned)blocks, S2_THREADS, S2_SMEM_BYTES(0), st>>>(a->d, E,
 		    (const uint8_t *)d_data, n, vec_lo, vec_hi, limit, a->d.b3, 0xFFFFFFFFu);
+	} else if (a->d.xd_tab && (size_t)a->d.xd_d1_end * 4 + 64 <= XD_SMEM_MAX &&
+	    !(getenv("ACM_DFA_DENSE") && atoi(getenv("ACM_DFA_DENSE")))) {
+		/* the row-displaced table, its first ~200 KiB in shared memory: one persistent CTA per SM,
+		 * threads take chunks round-robin (ACM_DFA_DENSE=1: the dense-table kernel below instead) */
+		const uint64_t chunk = scan_dfa_chunk(s, limit - E.emit_lo, 2 * XD_THREADS);      /* two chunks per thread */
+		const uint64_t nthreads = (limit - E.emit_lo + chunk - 1) / chunk;
+		uint64_t blocks = ((nthreads + 1) / 2 + 1 + XD_THREADS - 1) / XD_THREADS;
+		if (blocks > (uint64_t)s->dev->sm_count)
+			blocks = s->dev->sm_count;
+		/* half of the SM's 256 KiB for the staged prefix, the other half stays L1 for the slots behind
+		 * it (measured: 10 000 ClamAV signatures 720 GB/s with 64-128 KiB staged, 700 with 224; 2 000
+		 * packet-size signatures 1 231 GB/s with 128, 951 with 224) */
+		uint32_t slots = a->d.xd_len < XD_SMEM_DEFAULT / 4 ? a->d.xd_len : XD_SMEM_DEFAULT / 4;
+		slots &= ~3u;
+		if (getenv("ACM_XD_SMEM_KB") && (uint32_t)atoi(getenv("ACM_XD_SMEM_KB")) * 256 < slots)
+			slots = (uint32_t)atoi(getenv("ACM_XD_SMEM_KB")) * 256;      /* experiments: smaller staged prefix */
+		if (slots < ((a->d.xd_d1_end + 3) & ~3u))
+			slots = (a->d.xd_d1_end + 3) & ~3u;         /* the rows of depth <= 1 at least: the kernel reads them unconditionally from shared memory */
+		const size_t smem = (size_t)slots * 4 + 64;
+		if (a->alpha == 256)
+			k_scan_xd<uint8_t><<<(unsigned)blocks, XD_THREADS, smem, st>>>(a->d, E, (const uint8_t *)d_data, n,
+			    chunk, nthreads, s->flags + 2, slots);
+		else
+			k_scan_xd<uint16_t><<<(unsigned)blocks, XD_THREADS, smem, st>>>(a->d, E, (const uint16_t *)d_data,
+			    n, chunk, nthreads, s->flags + 2, slots);
 	} else {
-		const uint64_t chunk = scan_dfa_chunk(s, limit - E.emit_lo);
+		const uint64_t chunk = scan_dfa_chunk(s, limit - E.emit_lo, 256 * DFA_MINB);
 		const uint64_t nthreads = (limit - E.emit_lo + chunk - 1) / chunk;
 		const uint64_t blocks = (nthreads + 1 + 255) / 256;
 		if (a->alpha == 256)

@@ -136,6 +136,14 @@ struct acm_tables {
 	uint32_t *rd_tab;            /* [rd_len] entries                              */
 	uint32_t *rd_flat4;          /* [rd_len][4]: full match list of the state whose base is the slot */
 	uint32_t  rd_len;            /* slots, a multiple of nothing; reads reach rd_len - 1 at most */
+	/* the whole DFA as one row-displaced array of 4-byte entries (build_xd in acm_core.c has the
+	 * format); NULL = not built (more slots than the entry format addresses) */
+	uint32_t *xd_tab;            /* [xd_len] entries: symbol | any-match << sym_bits | base << (sym_bits + 1) */
+	uint32_t *xd_sid;            /* [xd_len]: breadth-first id of the state whose base is the slot */
+	uint32_t  xd_len;
+	uint32_t  xd_d1_end;         /* slots [0, xd_d1_end) hold every row of the states of depth <= 1 (k_scan_xd keeps at least these in shared memory) */
+	int       xd_levels;         /* 1 (bytes): miss -> row of the previous byte's depth-1 state -> root row; 0: miss -> root row */
+	uint32_t  xd_sym_bits;       /* 8 or 11 */
 	uint32_t  rd_dense_rows;     /* states 0 .. rd_dense_rows-1 keep whole rows, ACM_RD_ROW slots apart */
 	int       rd_dense_depth;
 };

@@ -192,6 +192,13 @@ acsm_check_filters(acsm_t *a)
 	return c ? acm_core_check_filters(c) : ACM_ERR_ARG;
 }
 
+int
+acsm_check_xd(acsm_t *a, unsigned int *slots)
+{
+	struct acm_core *c = core_of(a);
+	return c ? acm_core_check_xd(c, slots) : ACM_ERR_ARG;
+}
+
 const struct acm_tables *
 acsm_tables(acsm_t *a)
 {

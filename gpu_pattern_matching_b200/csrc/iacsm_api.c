@@ -138,6 +138,13 @@ iacsm_export_ref_table(iacsm_t *m)
 	return rc;
 }
 
+int
+iacsm_check_xd(iacsm_t *a, unsigned int *slots)
+{
+	struct acm_core *c = a ? (struct acm_core *)a->priv : NULL;
+	return c ? acm_core_check_xd(c, slots) : ACM_ERR_ARG;
+}
+
 struct acm_automaton *
 iacsm_device_automaton(iacsm_t *m)
 {

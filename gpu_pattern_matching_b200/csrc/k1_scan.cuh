@@ -75,6 +75,11 @@ struct AutDev {
 	const uint32_t *rd_tab;        /* row-displaced form (k_scan_rd, all of it in shared memory), NULL if not built */
 	const uint4    *rd_flat4;      /* [rd_len]: match list of the state whose base is the slot */
 	uint32_t rd_len;
+	const uint32_t *xd_tab;        /* the whole DFA row-displaced (k_scan_xd; acm_core.c:build_xd), NULL if not built */
+	const uint32_t *xd_sid;        /* [xd_len]: breadth-first id of the state whose base is the slot */
+	uint32_t xd_len;
+	uint32_t xd_d1_end;            /* the rows of the states of depth <= 1 end here */
+	uint32_t xd_sym_bits;          /* 8 (bytes) or 11 (ushort symbols) */
 	uint32_t cd_thr4;              /* entry >= this: four patterns end there (code 3 = three or four) */
 	uint32_t cd_classes;
 	int      cd_range_lo;
@@ -1202,6 +1207,203 @@ k_scan_dfa(const AutDev A, const EmitCtx E, const SYM *__restrict__ data, uint64
 	}
 	for (; pos < b; ++pos)
 		dfa_step(A, E, alpha, state, data[pos], pos, a);
+}
+
+/* ------------------------------------------------------------------------- */
+/* the DFA walk out of the row-displaced table: hot rows in shared memory     */
+/* ------------------------------------------------------------------------- */
+
+/*
+ * k_scan_xd -- reference ahomatch.cl:56-65 (AC_ushorts/ahomatch.cl:37-66) in the form north_star
+ * names: one thread per chunk, cold start Lmax-1 symbols early, "the hot rows of the transition
+ * table in shared memory, cold states served from L2".
+ *
+ * The table is acm_core.c:build_xd's: the whole DFA as ONE array of 4-byte entries, root row
+ * first, then the states in breadth-first order (9.5 MB for 10 000 ClamAV signatures where the
+ * dense table is 370 MiB; 0.9 MB where the reference's ushort table is 528 MiB).  Its first
+ * `smem_slots` entries -- root, depth 1, depth 2, ... as far as 128 KiB reach -- are staged into
+ * shared memory with TMA bulk copies; a lookup whose slot lies beyond comes from L1 / L2.
+ *
+ * Transition on symbol c from the state with base o, b the previous symbol:
+ *     x = xd[o + c]                       is it this state's entry for c?  (carries c, bases unique)
+ *     g = xd[base(xd[b]) + c]             else the entry of the depth-1 state of b
+ *     r = xd[c]                           else the root row
+ * g and r depend on the input only -- r is next step's xd[b] -- so they are off the walk's
+ * dependency chain; when the walk sits in that depth-1 state itself (random input: most of the
+ * time) x IS g and the lane skips the third lookup.
+ * A symbol outside the alphabet sends the automaton to the root (cli/b200_flow_grep separates
+ * flows that way).  Matches: the entry's flag says "the target reports something"; the state's
+ * breadth-first id (xd_sid) leads to the own lists along the output links as in k_scan_dfa.
+ */
+#define XD_THREADS 1024
+#define XD_SMEM_MAX (224 * 1024)
+#define XD_SMEM_DEFAULT (128 * 1024)
+
+struct XdLook {
+	uint32_t tab_sa;          /* shared address of the staged prefix                  */
+	uint32_t smem_slots;      /* >= xd_d1_end: the rows of all states of depth <= 1 are in it */
+	const uint32_t *tab;      /* the whole table in global memory                     */
+	uint32_t sym_mask, base_shift;
+};
+
+/* the rare part of a step, out of line: every pattern the state with base `os` reports */
+__device__ __noinline__ void xd_report(const AutDev *__restrict__ Ap, const EmitCtx *__restrict__ Ep, uint32_t os,
+    uint64_t pos)
+{
+	for (uint32_t v = __ldg(Ap->xd_sid + os); v; v = __ldg(&Ap->olink[v]))
+		emit_own(*Ap, *Ep, v, pos);
+}
+
+struct XdState {
+	uint32_t os;              /* base of the current state                            */
+	uint32_t ob;              /* base of the depth-1 state of the previous symbol     */
+};
+
+/*
+ * One step, branch-free up to the (rare) report: r and g always come from shared memory, the
+ * state's own entry x from shared memory or, beyond the staged prefix, from L1 / L2 -- two
+ * predicated loads, of which at most one executes, none when the walk sits in the depth-1 state
+ * of the previous symbol (x is g then).
+ */
+__device__ __forceinline__ void xd_step(const AutDev &A, const EmitCtx &E, const XdLook &L, XdState &S, uint32_t c,
+    uint64_t pos, uint64_t a)
+{
+	uint32_t r, g, x;
+	asm("ld.shared.u32 %0, [%1];" : "=r"(r) : "r"(L.tab_sa + c * 4));
+	asm("ld.shared.u32 %0, [%1];" : "=r"(g) : "r"(L.tab_sa + (S.ob + c) * 4));
+	const uint32_t slot = S.os + c;
+	x = g;
+	asm("{\n"
+	    ".reg .pred ps, pg;\n"
+	    ".reg .b32 sa;\n"
+	    ".reg .b64 ga;\n"
+	    "setp.ne.u32 ps, %1, %2;\n"                 /* the state is not that depth-1 state     */
+	    "setp.lt.and.u32 pg, %3, %4, ps;\n"         /* ... and its slot is in shared memory    */
+	    "setp.ge.and.u32 ps, %3, %4, ps;\n"         /* ... or beyond it                        */
+	    "mad.lo.u32 sa, %3, 4, %5;\n"
+	    "mad.wide.u32 ga, %3, 4, %6;\n"
+	    "@pg ld.shared.u32 %0, [sa];\n"
+	    "@ps ld.global.nc.u32 %0, [ga];\n"
+	    "}\n" : "+r"(x) : "r"(S.os), "r"(S.ob), "r"(slot), "r"(L.smem_slots), "r"(L.tab_sa), "l"(L.tab));
+	const bool okx = (x & L.sym_mask) == c, okg = (g & L.sym_mask) == c;
+	const uint32_t nx = okx ? x : (okg ? g : r);
+	S.os = nx >> L.base_shift;
+	S.ob = r >> L.base_shift;
+	if (((nx >> (L.base_shift - 1)) & 1u) && pos >= a)
+		xd_report(&A, &E, S.os, pos);
+}
+
+template <typename SYM>
+__global__ void __launch_bounds__(XD_THREADS, 1)
+k_scan_xd(const __grid_constant__ AutDev A, const __grid_constant__ EmitCtx E, const SYM *__restrict__ data,
+    uint64_t n, uint64_t chunk, uint64_t nthreads, uint32_t *final_state, uint32_t smem_slots)
+{
+	extern __shared__ __align__(128) uint32_t xd_smem[];
+	constexpr uint64_t VS = 16 / sizeof(SYM);          /* symbols per 16-byte vector */
+	constexpr uint32_t PER_WORD = 4 / sizeof(SYM);
+	constexpr uint32_t SYM_BITS = 8 * sizeof(SYM);
+	constexpr uint32_t SYM_MASK = (1u << SYM_BITS) - 1u;
+	uint64_t *bar = reinterpret_cast<uint64_t *>(xd_smem + smem_slots);
+	const uint32_t alpha = (uint32_t)A.alpha;
+	const uint64_t limit = E.emit_hi < n ? E.emit_hi : n;
+
+	if (threadIdx.x == 0) {
+		const uint32_t bytes = smem_slots * 4;
+		mbar_init(bar, 1);
+		mbar_expect_tx(bar, bytes);
+		for (uint32_t off = 0; off < bytes; off += 16384)
+			bulk_g2s(reinterpret_cast<uint8_t *>(xd_smem) + off, reinterpret_cast<const uint8_t *>(A.xd_tab) + off,
+			    min(bytes - off, 16384u), bar);
+	}
+	__syncthreads();
+	mbar_wait(bar, 0);
+
+	XdLook L;
+	L.tab_sa = smem_u32(xd_smem);
+	L.smem_slots = smem_slots;
+	L.tab = A.xd_tab;
+	L.sym_mask = (1u << A.xd_sym_bits) - 1u;
+	L.base_shift = A.xd_sym_bits + 1;
+	const uint64_t halo = A.max_len > 0 ? (uint64_t)(A.max_len - 1) : 0;
+
+	/* a symbol outside the alphabet (ushort streams only: flow separators) sends the walk to the root */
+	auto step = [&](XdState &S, uint32_t c, uint64_t p, uint64_t a) {
+		if (sizeof(SYM) > 1 && c >= alpha)
+			S.os = S.ob = 0;
+		else
+			xd_step(A, E, L, S, c, p, a);
+	};
+	/*
+	 * Every thread walks TWO chunks at a time, vector by vector in lockstep: two independent
+	 * dependency chains per lane (a deep state's entry may come from L2).  Chunk pairs are taken
+	 * round-robin; u == npairs is the extra job "state after the last symbol".
+	 */
+	const uint64_t npairs = (nthreads + 1) / 2;
+	for (uint64_t u = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; u <= npairs;
+	     u += (uint64_t)gridDim.x * blockDim.x) {
+		if (u == npairs) {
+			/* the true state after the last symbol (breadth-first id): the longest suffix that is a
+			 * pattern prefix fits in the last Lmax symbols */
+			const uint64_t back = (uint64_t)A.max_len;
+			uint64_t p0 = n > back ? n - back : 0;
+			if (p0 < E.valid_lo)
+				p0 = E.valid_lo;
+			XdState S = {0u, 0u};
+			for (uint64_t pos = p0; pos < n; ++pos)
+				step(S, data[pos], pos, ~0ull);
+			*final_state = __ldg(A.xd_sid + S.os);
+			continue;
+		}
+		uint64_t a[2], b[2], pos[2];
+		XdState S[2] = {{0u, 0u}, {0u, 0u}};
+#pragma unroll
+		for (int q = 0; q < 2; ++q) {
+			a[q] = E.emit_lo + (2 * u + q) * chunk;
+			b[q] = a[q] + chunk;
+			if (b[q] > limit)
+				b[q] = limit;
+			if (a[q] > limit)
+				a[q] = limit;                           /* empty */
+			pos[q] = a[q] > halo ? a[q] - halo : 0;
+			if (pos[q] < E.valid_lo)
+				pos[q] = E.valid_lo;
+			if (a[q] >= b[q])
+				pos[q] = b[q];
+			/* head: symbol by symbol up to the next 16-byte boundary (all of it when the buffer itself
+			 * is not 16-byte aligned) */
+			uint64_t head_end = (pos[q] + VS - 1) / VS * VS;
+			if (head_end > b[q] || ((uintptr_t)data & 15) != 0)
+				head_end = b[q];
+			for (; pos[q] < head_end; ++pos[q])
+				step(S[q], data[pos[q]], pos[q], a[q]);
+		}
+		/* body: whole vectors of both chunks in lockstep */
+		while (pos[0] + VS <= b[0] && pos[1] + VS <= b[1]) {
+			const uint4 v0 = __ldg(reinterpret_cast<const uint4 *>(data + pos[0]));
+			const uint4 v1 = __ldg(reinterpret_cast<const uint4 *>(data + pos[1]));
+			const uint32_t w0[4] = {v0.x, v0.y, v0.z, v0.w}, w1[4] = {v1.x, v1.y, v1.z, v1.w};
+#pragma unroll
+			for (uint32_t k = 0; k < (uint32_t)VS; ++k) {
+				step(S[0], (w0[k / PER_WORD] >> ((k % PER_WORD) * SYM_BITS)) & SYM_MASK, pos[0] + k, a[0]);
+				step(S[1], (w1[k / PER_WORD] >> ((k % PER_WORD) * SYM_BITS)) & SYM_MASK, pos[1] + k, a[1]);
+			}
+			pos[0] += VS;
+			pos[1] += VS;
+		}
+		/* what is left of either (the other one ended): vectors, then the tail */
+#pragma unroll
+		for (int q = 0; q < 2; ++q) {
+			for (; pos[q] + VS <= b[q]; pos[q] += VS) {
+				const uint4 v = __ldg(reinterpret_cast<const uint4 *>(data + pos[q]));
+				const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+				for (uint32_t k = 0; k < (uint32_t)VS; ++k)
+					step(S[q], (w[k / PER_WORD] >> ((k % PER_WORD) * SYM_BITS)) & SYM_MASK, pos[q] + k, a[q]);
+			}
+			for (; pos[q] < b[q]; ++pos[q])
+				step(S[q], data[pos[q]], pos[q], a[q]);
+		}
+	}
 }
 
 /* ------------------------------------------------------------------------- */

@@ -141,6 +141,13 @@ int  acsm_check_filters(acsm_t *);
  */
 int  acsm_check_cdfa(acsm_t *, unsigned int *slots, unsigned int *dense_rows);
 
+/*
+ * Every automaton also gets its DFA as one small row-displaced array (k_scan_xd walks it; 6.8 MB
+ * instead of the 370 MiB dense table for 10 000 ClamAV signatures).  Checks it against the dense
+ * table over every (state, symbol): violations (0 = identical), -1 if none was built.  Test support.
+ */
+int  acsm_check_xd(acsm_t *, unsigned int *slots);
+
 /* the compiled host tables (acm_automaton_upload, acm_multi_open); NULL before acsm_compile and after acsm_cleanup */
 struct acm_tables;
 const struct acm_tables *acsm_tables(acsm_t *);

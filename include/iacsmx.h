@@ -76,6 +76,8 @@ void     iacsm_free(iacsm_t *);
 /* additions */
 int      iacsm_status(iacsm_t *);
 int      iacsm_export_ref_table(iacsm_t *);      /* int32[num_states][4096], second half = iid */
+/* the row-displaced DFA (k_scan_xd) against the dense table: violations, -1 if not built.  Test support. */
+int  iacsm_check_xd(iacsm_t *, unsigned int *slots);
 struct acm_automaton *iacsm_device_automaton(iacsm_t *);
 
 #ifdef __cplusplus
