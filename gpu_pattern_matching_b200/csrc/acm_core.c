@@ -143,7 +143,7 @@ acm_tables_free(struct acm_tables *t)
 	free(t->T); free(t->level_start); free(t->own_begin); free(t->own_pat);
 	free(t->olink); free(t->fail); free(t->pat_len); free(t->pat_iid);
 	free(t->bfs_to_ref); free(t->f1); free(t->f2); free(t->grams); free(t->b2); free(t->b2s); free(t->b3);
-	free(t->cand); free(t->pat_blob); free(t->pat_off);
+	free(t->cand); free(t->pat_blob); free(t->pat_off); free(t->pat_win);
 	free(t->cd_cls); free(t->cd_tab); free(t->cd_flat_begin); free(t->cd_flat_pat);
 	free(t->rd_tab); free(t->rd_flat4); free(t->cd_flat4); free(t->xd_tab); free(t->xd_sid);
 	memset(t, 0, sizeof(*t));
@@ -1093,7 +1093,8 @@ build_filters(struct acm_core *c)
 		t->grams = calloc(slots, sizeof(*t->grams));
 		tr = malloc((ntr_max + 1) * sizeof(*tr));
 		t->pat_off = calloc((size_t)c->npats + 1, 4);
-		if (!t->grams || !tr || !t->pat_off) {
+		t->pat_win = calloc((size_t)c->npats * 8 + 8, 1);
+		if (!t->grams || !tr || !t->pat_off || !t->pat_win) {
 			free(tr);
 			return ACM_ERR_NOMEM;
 		}
@@ -1195,6 +1196,9 @@ build_filters(struct acm_core *c)
 				 * Hashing only 3 bytes for everybody made 0.45 % of all random windows TRUE gram hits
 				 * (75 k grams of 2^24) that only the exact table could reject.
 				 */
+				t->pat_win[(size_t)k * 8 + j] = (uint8_t)o;
+				if (o > t->max_win)
+					t->max_win = o;
 				const uint32_t fixed = o + 4 <= n ? 4 : 3;
 				for (uint32_t b = 0; b < fixed; b++)
 					g |= (uint32_t)p[o + b] << (8 * b);

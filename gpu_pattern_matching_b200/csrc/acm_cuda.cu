@@ -96,6 +96,9 @@ struct acm_scanner {
 	uint4    *vq;               /* sampled mode: verification queue, one region per scanning warp */
 	uint32_t *vq_count;
 	uint32_t  vq_cap;
+	uint32_t *dq;               /* sampled mode: per-warp lists of dense chunks */
+	uint32_t *dq_count;
+	uint32_t  dq_cap;
 	uint64_t *h_keys;           /* pinned bounce buffer for results */
 	uint64_t  h_keys_cap;
 	/* a scan queued by acm_scan_device_async and not yet finished */
@@ -520,6 +523,7 @@ acm_automaton_upload(struct acm_device *dev, const struct acm_tables *t, struct 
 		UP(cand, t->cand, ((size_t)t->cand_count + ACM_CAND_PAD) * sizeof(struct acm_cand));
 		UP(pat_blob, t->pat_blob, t->pat_blob_bytes);
 		UP(pat_off, t->pat_off, (size_t)t->num_patterns * 4);
+		UP(pat_win, t->pat_win, (size_t)t->num_patterns * 8);
 		UP(pat_len, t->pat_len, (size_t)t->num_patterns * 4);
 		a->d.gram_mask = t->gram_slots - 1;
 		uint32_t lg = 0;
@@ -554,6 +558,7 @@ acm_automaton_upload(struct acm_device *dev, const struct acm_tables *t, struct 
 	a->d.alpha = t->alpha;
 	a->d.max_len = t->max_pattern_len;
 	a->d.sample_stride = t->sample_stride;
+	a->d.max_win = t->max_win;
 	a->d.split_len = t->b2s ? (uint32_t)t->split_len : 0u;
 	if (rc == ACM_OK && cudaStreamSynchronize(dev->stream) != cudaSuccess) {
 		acm_set_error("automaton_upload: %s", cudaGetErrorString(cudaGetLastError()));
@@ -785,7 +790,7 @@ acm_scanner_free(struct acm_scanner *s)
 	cudaFree(s->buckets); cudaFree(s->scratch); cudaFree(s->offsets);
 	cudaFree(s->tile_state); cudaFree(s->out); cudaFree(s->tmp); cudaFree(s->hist);
 	cudaFree(s->stage[0]); cudaFree(s->stage[1]); cudaFree(s->trace);
-	cudaFree(s->vq); cudaFree(s->vq_count);
+	cudaFree(s->vq); cudaFree(s->vq_count); cudaFree(s->dq); cudaFree(s->dq_count);
 	if (s->h_flags)
 		cudaFreeHost(s->h_flags);
 	if (s->h_keys)
@@ -1006,6 +1011,13 @@ acm_scanner_create(struct acm_device *dev, struct acm_automaton *aut, uint64_t m
 			s->vq_cap = (uint32_t)atoi(getenv("ACM_VQ_CAP"));
 		SALLOC(s->vq, (size_t)regions * s->vq_cap * sizeof(uint4));
 		SALLOC(s->vq_count, (size_t)regions * 4);
+		/* dense chunks (2 KiB) a warp may have to hand on: all of its share and then some (the work
+		 * hand-out is dynamic); a full list makes the scanning warp walk the chunk itself */
+		s->dq_cap = (uint32_t)(2 * ((max_bytes >> 11) / regions) + 64);
+		if (getenv("ACM_DQ_CAP") && atoi(getenv("ACM_DQ_CAP")) >= 0)
+			s->dq_cap = (uint32_t)atoi(getenv("ACM_DQ_CAP"));   /* test hook */
+		SALLOC(s->dq, ((size_t)regions * s->dq_cap + 1) * 4);
+		SALLOC(s->dq_count, (size_t)regions * 4);
 	}
 #undef SALLOC
 	if (cudaHostAlloc((void **)&s->h_flags, 64, cudaHostAllocMapped) != cudaSuccess ||
@@ -1103,6 +1115,9 @@ launch_k1(struct acm_scanner *s, cudaStream_t st, const void *d_data, uint64_t n
 		Eq.vq = s->vq;
 		Eq.vq_count = s->vq_count;
 		Eq.vq_cap = s->vq_cap;
+		Eq.dq = s->dq;
+		Eq.dq_count = s->dq_count;
+		Eq.dq_cap = s->dq_cap;
 		if (a->d.sample_stride == 8)
 			k_scan_sampled<8><<<(unsigned)blocks, S4_THREADS, S4_SMEM_BYTES, st>>>(a->d, Eq,
 			    (const uint8_t *)d_data, n, vec_lo, vec_hi, limit, s->flags + 6);
@@ -1112,7 +1127,7 @@ launch_k1(struct acm_scanner *s, cudaStream_t st, const void *d_data, uint64_t n
 		if (s->p.timing == 3)       /* the streaming kernel alone */
 			CUDA_TRY(cudaEventRecord(s->ev[1], st));
 		k_resolve_queue<<<(unsigned)blocks * (S4_THREADS / 32), RQ_THREADS, 0, st>>>(a->d, Eq,
-		    (const uint8_t *)d_data, n, limit);
+		    (const uint8_t *)d_data, n, limit, vec_lo, (uint32_t)a->d.sample_stride);
 		*launches += 1;
 		if (a->d.split_len) {
 			/* mixed set: the patterns shorter than split_len, second pass into the same buckets */

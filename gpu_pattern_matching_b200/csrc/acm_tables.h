@@ -115,6 +115,8 @@ struct acm_tables {
 	uint8_t  *pat_blob;          /* pattern bytes, each pattern 4-byte aligned, zero padded */
 	uint32_t  pat_blob_bytes;
 	uint32_t *pat_off;           /* [num_patterns] byte offset into pat_blob      */
+	uint32_t  max_win;           /* largest entry of pat_win                       */
+	uint8_t  *pat_win;           /* [num_patterns][8]: offset of the indexed window of (pattern, alignment j = (-start) mod stride) */
 	uint32_t *b2;                /* 2^16-bit exact start bitmap: bit (b0 | b1<<8) */
 	int       split_len;         /* > 0: patterns shorter than this are not in the sampled filter (mixed sets) */
 	uint32_t *b2s;               /* start bitmap of those short patterns alone; NULL when split_len == 0 */

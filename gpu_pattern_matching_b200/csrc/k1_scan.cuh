@@ -63,6 +63,7 @@ struct AutDev {
 	const uint8_t  *pat_blob;
 	const uint32_t *pat_off;
 	const uint32_t *pat_len;
+	const uint8_t  *pat_win;    /* [patterns][8]: offset of the indexed window per alignment (sampled filter) */
 	const uint32_t *b2;
 	const uint32_t *b2s;        /* start bitmap of the patterns shorter than split_len (mixed sets) */
 	const uint32_t *b3;         /* start filter of mode 2: first-three-bytes Bloom bitmap of all patterns */
@@ -89,6 +90,7 @@ struct AutDev {
 	int      alpha;
 	int      max_len;
 	int      sample_stride;
+	uint32_t max_win;        /* largest indexed window offset of the sampled filter (<= ACM_CAND_O_MAX) */
 };
 
 struct EmitCtx {
@@ -103,6 +105,9 @@ struct EmitCtx {
 	uint4    *vq;            /* sampled kernel: per-warp regions of candidates awaiting the full compare */
 	uint32_t *vq_count;      /* [regions] entries written (<= vq_cap)                */
 	uint32_t  vq_cap;        /* entries per region                                   */
+	uint32_t *dq;            /* sampled kernel: per-warp lists of DENSE chunks (first vector index), left to k_resolve_queue */
+	uint32_t *dq_count;      /* [regions]                                            */
+	uint32_t  dq_cap;
 	uint32_t  cap;
 	uint32_t  shift;
 	int       direct;        /* 1: second pass of the exact two-pass path; 2: k_scan_rd's counting pass before it */
@@ -349,49 +354,103 @@ __device__ __forceinline__ void s4_verify(const AutDev &A, const EmitCtx &E, con
 }
 
 /*
- * Dense-hit fallback.  On repetitive input (zero pages, period-4/8 fills) almost every
- * aligned window is a pattern gram with a long candidate list, and filter + verify would
- * degenerate to (windows x candidates).  A chunk whose level-1 hit count says "this is not
- * random-looking data" is handed to the automaton instead, which is linear whatever the
- * text: lane l owns the starts whose first aligned window lies in its 64 bytes,
- * s in [lo - 3, lo + 60], walks the DFA cold from the first of them until no match that
- * started there can still be open, and keeps a match iff its start is one of its own.
+ * Dense-hit fallback.  On repetitive input (zero pages, period-4/8 fills, code padding) almost
+ * every aligned window is a pattern gram with a long candidate list, and filter + verify would
+ * degenerate to (windows x candidates).  A 2 KiB chunk whose level-1 hit count says "this is not
+ * random-looking data" is handed to the automaton instead, which is linear whatever the text.
+ *
+ * WHO REPORTS WHAT.  The filter finds an occurrence through its INDEXED window -- one per
+ * (pattern, alignment of the start), not necessarily the first aligned one: the builder moves it
+ * to a rarer later window when the first one's gram is popular (zero runs, common prologues:
+ * exactly the material dense chunks are made of).  So an occurrence belongs to the chunk its
+ * indexed window lies in, and the walk of a dense chunk reports exactly the occurrences whose
+ * indexed window lies in that chunk -- whether they start before it (by up to ACM_CAND_O_MAX
+ * bytes) or end far behind it.  (Round 1 let the walk own "starts whose FIRST aligned window lies
+ * in the chunk": next to a filter-scanned chunk that reported some occurrences twice and lost
+ * others; tools/density_sweep.py found it.)
+ *
+ * The scanning warp only queues the chunk; threads of k_resolve_queue walk it, in 1 to 8 slices
+ * (a few dense chunks in a region: many short walks, so that a CTA does not wait for three threads;
+ * all chunks dense: one long walk per thread, little overlap): cold start max_win bytes -- the
+ * largest window offset in the index -- in front (nothing that starts earlier can have its window inside), the
+ * row-displaced table (acm_core.c:build_xd) through L1 -- zero pages keep every lane on the same
+ * few entries -- or the dense table when there is none, until no occurrence that began inside the
+ * chunk can still be open.
  */
-/* a quarter of the chunk's windows hit: random data sees 3..6 % */
-
-__device__ __noinline__ void s4_chunk_dfa(const AutDev *__restrict__ Ap, const EmitCtx *__restrict__ Ep,
-    const uint8_t *__restrict__ data, uint64_t chunk_lo, uint64_t limit, int lane, uint32_t stride)
+__device__ __noinline__ void s4_dense_chunk(const AutDev *__restrict__ Ap, const EmitCtx *__restrict__ Ep,
+    const uint8_t *__restrict__ data, uint64_t chunk_lo, uint64_t chunk_hi, uint64_t limit, uint32_t stride)
 {
+	/* [chunk_lo, chunk_hi): the chunk, or the slice of it this thread owns the windows of */
 	const AutDev &A = *Ap;
 	const EmitCtx &E = *Ep;
-	const uint64_t lo = chunk_lo + 64ull * (uint64_t)lane;
-	/* starts whose first stride-aligned window lies in [lo, lo + 64) */
-	uint64_t s_min = lo >= stride - 1 ? lo - (stride - 1) : 0;
-	if (s_min < E.valid_lo)
-		s_min = E.valid_lo;
-	const uint64_t s_max = lo + 64 - stride;
-	uint64_t end = s_max + (uint64_t)A.max_len;
+	uint64_t pos = chunk_lo > A.max_win ? chunk_lo - A.max_win : 0;
+	if (pos < E.valid_lo)
+		pos = E.valid_lo;
+	uint64_t end = chunk_hi + (uint64_t)A.max_len;
 	if (end > limit)
 		end = limit;
-	uint32_t state = 0;
-	for (uint64_t pos = s_min; pos < end; ++pos) {
-		const uint32_t e = __ldg(&A.T[(size_t)state * 256 + __ldg(&data[pos])]);
-		state = e & ACM_T_MASK;
-		if (e & ACM_T_ANY) {
+	const bool use_xd = A.xd_tab != nullptr;
+	const uint32_t sh = A.xd_sym_bits + 1, smask = (1u << A.xd_sym_bits) - 1u;
+	uint32_t os = 0, ob = 0, state = 0;
+	/* the text comes 16 bytes per load and is shifted out of a 128-bit register: a 1-byte load per
+	 * step from 32 different sectors per warp instruction made the L1 the bound of the whole walk */
+	uint4 tv = make_uint4(0, 0, 0, 0);
+	uint32_t have = 0;                                /* bytes left in tv */
+	for (; pos < end; ++pos) {
+		if (have == 0) {
+			tv = __ldg(reinterpret_cast<const uint4 *>(data + (pos & ~15ull)));
+			have = 16;
+			for (uint32_t skip = (uint32_t)(pos & 15); skip; --skip) {      /* only before the first byte */
+				tv.x = __funnelshift_r(tv.x, tv.y, 8);
+				tv.y = __funnelshift_r(tv.y, tv.z, 8);
+				tv.z = __funnelshift_r(tv.z, tv.w, 8);
+				tv.w >>= 8;
+				--have;
+			}
+		}
+		const uint32_t c = tv.x & 0xFFu;
+		tv.x = __funnelshift_r(tv.x, tv.y, 8);
+		tv.y = __funnelshift_r(tv.y, tv.z, 8);
+		tv.z = __funnelshift_r(tv.z, tv.w, 8);
+		tv.w >>= 8;
+		--have;
+		bool any;
+		if (use_xd) {
+			const uint32_t r = __ldg(A.xd_tab + c), g = __ldg(A.xd_tab + ob + c);
+			uint32_t x = g;
+			if (os != ob)
+				x = __ldg(A.xd_tab + os + c);
+			if ((x & smask) != c)
+				x = (g & smask) == c ? g : r;
+			os = x >> sh;
+			ob = r >> sh;
+			any = (x >> (sh - 1)) & 1u;
+			if (any || pos >= chunk_hi)
+				state = __ldg(A.xd_sid + os);
+		} else {
+			const uint32_t e = __ldg(&A.T[(size_t)state * 256 + c]);
+			state = e & ACM_T_MASK;
+			any = (e & ACM_T_ANY) != 0;
+		}
+		if (any) {
 			for (uint32_t v = state; v; v = __ldg(&A.olink[v])) {
 				const uint32_t b = __ldg(&A.own_begin[v]), t = __ldg(&A.own_begin[v + 1]);
 				for (uint32_t k = b; k < t; ++k) {
 					const uint32_t pid = __ldg(&A.own_pat[k]);
 					const uint64_t len = __ldg(&A.pat_len[pid]);
 					/* mixed sets: the short patterns belong to the start-filter pass */
-					if (pos + 1 >= len + s_min && pos + 1 - len <= s_max && len >= A.split_len)
+					if (len < A.split_len || pos + 1 < len)
+						continue;
+					const uint64_t s = pos + 1 - len;
+					const uint64_t w = s + __ldg(&A.pat_win[(size_t)pid * 8 + ((stride - (uint32_t)(s % stride)) % stride)]);
+					if (s >= E.valid_lo && w >= chunk_lo && w < chunk_hi)
 						emit_record(E, pos, pid);
 				}
 			}
 		}
-		/* past the last owned start: stop once the longest open prefix began after it */
-		if (pos >= s_max) {
-			const uint64_t d = pos - s_max;          /* symbols read beyond s_max */
+		/* past the chunk: stop once the longest open prefix began behind it */
+		if (pos >= chunk_hi) {
+			const uint64_t d = pos - chunk_hi + 1;       /* symbols read beyond the chunk */
 			if (state < __ldg(&A.level_start[d + 1 <= (uint64_t)A.max_len ? d + 1 : (uint64_t)A.max_len]))
 				break;
 		}
@@ -556,6 +615,8 @@ k_scan_sampled(const __grid_constant__ AutDev A, const __grid_constant__ EmitCtx
 	const uint32_t vq_region = blockIdx.x * (S4_THREADS / 32) + (threadIdx.x >> 5);
 	uint4 *const vq_mine = E.vq + (size_t)vq_region * E.vq_cap;
 	uint32_t vq_n = 0;
+	uint32_t *const dq_mine = E.dq + (size_t)vq_region * E.dq_cap;
+	uint32_t dq_n = 0;                                /* lane 0 only */
 	auto load_chunk = [&](uint4 (&d)[S4_UNROLL], uint64_t f) {
 		if (f + chunk_vecs <= vec_hi) {                  /* all but the last chunk */
 			const uint4 *p = reinterpret_cast<const uint4 *>(data) + f + lane;
@@ -637,7 +698,13 @@ k_scan_sampled(const __grid_constant__ AutDev A, const __grid_constant__ EmitCtx
 					hits &= ~((((1u << WPV) - 1u) << (NW - WPV)) >> (WPV * u));
 		}
 		if (__reduce_add_sync(FULL_MASK, (uint32_t)__popc(hits)) >= NW * 32 / 4) {
-			s4_chunk_dfa(&A, &E, data, cur_first * 16, limit, lane, STRIDE);
+			/* dense: queue the chunk for k_resolve_queue (a full list: walk it here, one lane, slowly) */
+			if (lane == 0) {
+				if (dq_n < E.dq_cap)
+					dq_mine[dq_n++] = (uint32_t)(cur_first - vec_lo);
+				else
+					s4_dense_chunk(&A, &E, data, cur_first * 16, cur_first * 16 + chunk_vecs * 16, limit, STRIDE);
+			}
 			continue;
 		}
 		/*
@@ -782,8 +849,10 @@ k_scan_sampled(const __grid_constant__ AutDev A, const __grid_constant__ EmitCtx
 			}
 		}
 	}
-	if (lane == 0)
+	if (lane == 0) {
 		E.vq_count[vq_region] = vq_n;
+		E.dq_count[vq_region] = dq_n;
+	}
 	if (E.trace && lane == 0) {
 		atomicMax((unsigned long long *)&E.trace[blockIdx.x * 4 + 2], (unsigned long long)globaltimer_ns());
 		atomicAdd((unsigned long long *)&E.trace[blockIdx.x * 4 + 3], (unsigned long long)trace_chunks);
@@ -814,7 +883,7 @@ k_scan_sampled(const __grid_constant__ AutDev A, const __grid_constant__ EmitCtx
  */
 #define RQ_THREADS 128
 #ifndef RQ_MINB
-#define RQ_MINB 1
+#define RQ_MINB 10                          /* <= 51 registers: the (rare, out-of-line) dense-chunk walk may spill, the resolve phases must not grow */
 #endif
 #define RQ_WORK    512                      /* candidate work items per CTA round */
 #define RQ_LIST    (2 * RQ_THREADS)         /* candidates awaiting the full compare: one batch of 1b + overflow of 1a */
@@ -871,8 +940,19 @@ __device__ __forceinline__ bool rq_candidate(const AutDev &A, const EmitCtx &E, 
 
 __global__ void __launch_bounds__(RQ_THREADS, RQ_MINB)
 k_resolve_queue(const __grid_constant__ AutDev A, const __grid_constant__ EmitCtx E,
-    const uint8_t *__restrict__ data, uint64_t n, uint64_t limit)
+    const uint8_t *__restrict__ data, uint64_t n, uint64_t limit, uint64_t vec_lo, uint32_t stride)
 {
+	/* the region's dense chunks first (usually none): one thread each */
+	{
+		const uint32_t nd = min(E.dq_count[blockIdx.x], E.dq_cap);
+		const uint32_t *dl = E.dq + (size_t)blockIdx.x * E.dq_cap;
+		const uint32_t per = nd >= 96 ? 1u : (nd >= 48 ? 2u : (nd >= 24 ? 4u : 8u));   /* slices per chunk */
+		const uint32_t slice = 32u * S4_UNROLL * 16u / per;
+		for (uint32_t i = threadIdx.x; i < nd * per; i += RQ_THREADS) {
+			const uint64_t lo = (vec_lo + dl[i / per]) * 16 + (uint64_t)(i % per) * slice;
+			s4_dense_chunk(&A, &E, data, lo, lo + slice, limit, stride);
+		}
+	}
 	__shared__ RqShared S;
 	const uint4 *q = E.vq + (size_t)blockIdx.x * E.vq_cap;
 	/* the first entry is fetched before the count is known (the region exists either way) */

@@ -224,3 +224,34 @@ def test_random_ushort_sets_builder_equals_oracle(seed):
         m.compile()
         assert m.get_states() == o.num_states - 1
         assert _same_table(m.export_ref_table(), o.ref_table(), 2048), f"seed {seed} rep {rep}"
+
+
+def test_row_displaced_tables_are_the_automaton():
+    """The two compact forms the DFA kernels walk -- xd (every automaton: k_scan_xd) and rd (word
+    lists: k_scan_rd) -- against the dense table, over every (state, symbol), on the host."""
+    import ctypes as C
+    from helpers import build_product, clamav_pats, load_patterns
+    import gpu_pattern_matching_b200 as g
+    for name, hexp in (("kat_pat_a.txt", False), ("kat_pat_b.txt", False), ("kat_pat_c.txt", False),
+                       ("kat_pat_two_words.txt", False), ("sentiment_categorical.pat.gz", False)):
+        a = build_product(load_patterns(name, hexp), upload=False)
+        slots = C.c_uint(0)
+        assert a.L.acsm_check_xd(a._p, C.byref(slots)) == 0 and slots.value >= 256, name
+        assert a.L.acsm_check_cdfa(a._p, None, None) in (0, -1), name        # -1: not a one-range word list
+    a = build_product(load_patterns("sentiment_categorical.pat.gz"), upload=False)
+    slots, dense = C.c_uint(0), C.c_uint(0)
+    assert a.L.acsm_check_cdfa(a._p, C.byref(slots), C.byref(dense)) == 0
+    assert slots.value * 4 < 176 * 1024 and 0 < dense.value <= 256          # fits shared memory
+    a = build_product(clamav_pats(2000), upload=False)
+    slots = C.c_uint(0)
+    assert a.L.acsm_check_xd(a._p, C.byref(slots)) == 0
+    assert slots.value * 4 < 4 << 20                                        # ~0.8 MB where the dense table is 87 MiB
+    # ushort symbols (AC_ushorts): random sequences over a skewed alphabet
+    rng = np.random.default_rng(6)
+    w = 1.0 / np.arange(1, 2049) ** 1.1
+    w /= w.sum()
+    m = g.Iacsm()
+    for i in range(300):
+        m.add_pattern(rng.choice(2048, size=int(rng.integers(2, 17)), p=w).astype(np.uint16), i)
+    m.compile()
+    assert m.L.iacsm_check_xd(m._p, C.byref(slots)) == 0 and slots.value >= 2048

@@ -209,6 +209,48 @@ def test_repetitive_input_dense_hit_fallback(device):
     assert_same(off, pat, eo, ep, "repetitive sampled stride 4")
 
 
+@pytest.mark.parametrize("dq_cap", [None, 0, 1])
+def test_dense_chunks_next_to_filter_chunks_own_by_indexed_window(device, dq_cap, monkeypatch):
+    """A dense 2 KiB chunk is walked by the automaton, its neighbours go through the gram filter,
+    and an occurrence belongs to the chunk its INDEXED window lies in -- which for signatures that
+    start with popular bytes (zero runs, common prologues) is not their first aligned window.
+    Zero runs that cover part of a chunk, with signatures planted over every kind of border: the
+    oracle's list, neither short nor with duplicates (tools/density_sweep.py found both in round 1's
+    ownership rule).  ACM_DQ_CAP = 0 / 1: the scanning warp walks the chunk itself when its list
+    of dense chunks is full."""
+    if dq_cap is not None:
+        monkeypatch.setenv("ACM_DQ_CAP", str(dq_cap))
+    pats = clamav_pats(10000)
+    o, a = build_oracle(pats), build_product(pats)
+    n = 8 << 20
+    buf = synth.stream(n, 2)
+    # what the sweep does: the first 2 % / 5 % of every 64 KiB block zeroed -> one dense chunk, the
+    # next one partly dense, then random-looking ones
+    v = buf.reshape(-1, 64 << 10)
+    v[0::2, :1296] = 0
+    v[1::2, :3264] = 0
+    # signatures that start with zeros or with the popular prologues, over the borders of the zero runs
+    zsig = [i for i, (p, _) in enumerate(pats) if p[:4] == b"\0\0\0\0" or p[:4] == bytes.fromhex("e800005d")][:64]
+    assert len(zsig) >= 8
+    rng = np.random.default_rng(4)
+    planted = 0
+    for b in range(0, n >> 16):
+        base = b << 16
+        edge = 1296 if b % 2 == 0 else 3264
+        for k, i in enumerate(zsig[:6] + list(rng.integers(0, len(pats), 6))):
+            s = np.frombuffer(pats[int(i)][0], dtype=np.uint8)
+            pos = base + edge - s.size // 2 + 7 * k if k % 3 == 0 else base + (2048 * (1 + k)) - s.size // 3 + k
+            if pos + s.size < base + (64 << 10):
+                buf[pos:pos + s.size] = s
+                planted += 1
+    eo, ep, _, _ = o.search(buf)
+    assert eo.size >= planted // 2
+    off, pat, res = gpu_scan(device, a, buf, g.MODE_SAMPLED4)
+    assert_same(off, pat, eo, ep, f"mixed dense / filter chunks, dq_cap {dq_cap}")
+    off, pat, res = gpu_scan(device, build_product(pats, stride=4), buf, g.MODE_SAMPLED4)
+    assert_same(off, pat, eo, ep, f"mixed dense / filter chunks, stride 4, dq_cap {dq_cap}")
+
+
 @pytest.mark.parametrize("cap", [1, 3, 16])
 def test_resolve_queue_overflow_takes_inline_path(device, cap, monkeypatch):
     """The sampled kernel queues its filter survivors for k_resolve_queue; when a warp's region is
