@@ -156,6 +156,7 @@ set_kernel_attrs(int ordinal)
 	CUDA_TRY(cudaFuncSetAttribute(k_scan_rd, cudaFuncAttributeMaxDynamicSharedMemorySize, CD_SMEM_MAX));
 	CUDA_TRY(cudaFuncSetAttribute(k_scan_xd<uint8_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, XD_SMEM_MAX));
 	CUDA_TRY(cudaFuncSetAttribute(k_scan_xd<uint16_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, XD_SMEM_MAX));
+	CUDA_TRY(cudaFuncSetAttribute(k_dense_walk, cudaFuncAttributeMaxDynamicSharedMemorySize, XD_SMEM_MAX));
 	CUDA_TRY(cudaFuncSetAttribute(k_rd_expand, cudaFuncAttributeMaxDynamicSharedMemorySize, RD_K3_SMEM));
 	if (ordinal < 64)
 		g_attr_done[ordinal] = 1;
@@ -1126,9 +1127,35 @@ launch_k1(struct acm_scanner *s, cudaStream_t st, const void *d_data, uint64_t n
 			    (const uint8_t *)d_data, n, vec_lo, vec_hi, limit, s->flags + 6);
 		if (s->p.timing == 3)       /* the streaming kernel alone */
 			CUDA_TRY(cudaEventRecord(s->ev[1], st));
+		/* dense chunks (zero pages, padding, repeated prologues): their own kernel, hot rows of the
+		 * row-displaced table in shared memory, launched as the programmatic dependent of
+		 * k_resolve_queue so that it costs nothing when no chunk was queued (ACM_DENSE_KERNEL=0, or no
+		 * such table: k_resolve_queue walks them, table through L1) */
+		const int dense_kernel = a->d.xd_tab && (size_t)a->d.xd_d1_end * 4 + 64 <= XD_SMEM_MAX &&
+		    !(getenv("ACM_DENSE_KERNEL") && !atoi(getenv("ACM_DENSE_KERNEL")));
 		k_resolve_queue<<<(unsigned)blocks * (S4_THREADS / 32), RQ_THREADS, 0, st>>>(a->d, Eq,
-		    (const uint8_t *)d_data, n, limit, vec_lo, (uint32_t)a->d.sample_stride);
+		    (const uint8_t *)d_data, n, limit, vec_lo, (uint32_t)a->d.sample_stride, dense_kernel ? 0u : 1u);
 		*launches += 1;
+		if (dense_kernel) {
+			uint32_t slots = a->d.xd_len < XD_SMEM_DEFAULT / 4 ? a->d.xd_len : XD_SMEM_DEFAULT / 4;
+			slots &= ~3u;
+			if (slots < ((a->d.xd_d1_end + 3) & ~3u))
+				slots = (a->d.xd_d1_end + 3) & ~3u;
+			cudaLaunchConfig_t cfg;
+			cudaLaunchAttribute at[1];
+			memset(&cfg, 0, sizeof cfg);
+			cfg.gridDim = dim3((unsigned)blocks);
+			cfg.blockDim = dim3(XD_THREADS);
+			cfg.dynamicSmemBytes = (size_t)slots * 4 + 64;
+			cfg.stream = st;
+			at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+			at[0].val.programmaticStreamSerializationAllowed = 1;
+			cfg.attrs = at;
+			cfg.numAttrs = (getenv("ACM_DENSE_PDL") && !atoi(getenv("ACM_DENSE_PDL"))) ? 0 : 1;
+			CUDA_TRY(cudaLaunchKernelEx(&cfg, k_dense_walk, a->d, Eq, (const uint8_t *)d_data, limit, vec_lo,
+			    (uint32_t)a->d.sample_stride, (uint32_t)(S4_THREADS / 32), slots));
+			*launches += 1;
+		}
 		if (a->d.split_len) {
 			/* mixed set: the patterns shorter than split_len, second pass into the same buckets */
 			const uint64_t lead = (uint64_t)a->d.split_len - 2;      /* longest short pattern - 1 */

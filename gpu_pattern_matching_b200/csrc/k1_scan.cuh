@@ -940,10 +940,14 @@ __device__ __forceinline__ bool rq_candidate(const AutDev &A, const EmitCtx &E, 
 
 __global__ void __launch_bounds__(RQ_THREADS, RQ_MINB)
 k_resolve_queue(const __grid_constant__ AutDev A, const __grid_constant__ EmitCtx E,
-    const uint8_t *__restrict__ data, uint64_t n, uint64_t limit, uint64_t vec_lo, uint32_t stride)
+    const uint8_t *__restrict__ data, uint64_t n, uint64_t limit, uint64_t vec_lo, uint32_t stride, uint32_t walk_dense)
 {
-	/* the region's dense chunks first (usually none): one thread each */
-	{
+	/* k_dense_walk, launched behind this kernel as its programmatic dependent, needs nothing from it:
+	 * its CTAs may take the SMs this grid's last wave leaves */
+	asm volatile("griddepcontrol.launch_dependents;");
+	/* the region's dense chunks first (usually none), when k_dense_walk cannot take them (no
+	 * row-displaced table): one thread per slice, table entries through L1 */
+	if (walk_dense) {
 		const uint32_t nd = min(E.dq_count[blockIdx.x], E.dq_cap);
 		const uint32_t *dl = E.dq + (size_t)blockIdx.x * E.dq_cap;
 		const uint32_t per = nd >= 96 ? 1u : (nd >= 48 ? 2u : (nd >= 24 ? 4u : 8u));   /* slices per chunk */
@@ -1334,6 +1338,30 @@ __device__ __noinline__ void xd_report(const AutDev *__restrict__ Ap, const Emit
 		emit_own(*Ap, *Ep, v, pos);
 }
 
+/*
+ * The same for a dense chunk of the sampled filter (k_dense_walk): of the patterns that end here only
+ * the occurrences whose INDEXED window lies in [lo, lo + len) are this walk's (s4_dense_chunk tells why).
+ */
+__device__ __noinline__ void xd_report_win(const AutDev *__restrict__ Ap, const EmitCtx *__restrict__ Ep, uint32_t os,
+    uint64_t pos, uint64_t lo, uint32_t len, uint32_t stride)
+{
+	const AutDev &A = *Ap;
+	for (uint32_t v = __ldg(A.xd_sid + os); v; v = __ldg(&A.olink[v])) {
+		const uint32_t b = __ldg(&A.own_begin[v]), t = __ldg(&A.own_begin[v + 1]);
+		for (uint32_t k = b; k < t; ++k) {
+			const uint32_t pid = __ldg(&A.own_pat[k]);
+			const uint64_t plen = __ldg(&A.pat_len[pid]);
+			/* mixed sets: the short patterns belong to the start-filter pass */
+			if (plen < A.split_len || pos + 1 < plen)
+				continue;
+			const uint64_t s = pos + 1 - plen;
+			const uint64_t w = s + __ldg(&A.pat_win[(size_t)pid * 8 + ((stride - (uint32_t)(s % stride)) % stride)]);
+			if (s >= Ep->valid_lo && w >= lo && w < lo + len)
+				emit_record(*Ep, pos, pid);
+		}
+	}
+}
+
 struct XdState {
 	uint32_t os;              /* base of the current state                            */
 	uint32_t ob;              /* base of the depth-1 state of the previous symbol     */
@@ -1345,8 +1373,9 @@ struct XdState {
  * predicated loads, of which at most one executes, none when the walk sits in the depth-1 state
  * of the previous symbol (x is g then).
  */
+template <bool WIN = false>
 __device__ __forceinline__ void xd_step(const AutDev &A, const EmitCtx &E, const XdLook &L, XdState &S, uint32_t c,
-    uint64_t pos, uint64_t a)
+    uint64_t pos, uint64_t a, uint32_t win_len = 0, uint32_t stride = 0)
 {
 	uint32_t r, g, x;
 	asm("ld.shared.u32 %0, [%1];" : "=r"(r) : "r"(L.tab_sa + c * 4));
@@ -1369,8 +1398,12 @@ __device__ __forceinline__ void xd_step(const AutDev &A, const EmitCtx &E, const
 	const uint32_t nx = okx ? x : (okg ? g : r);
 	S.os = nx >> L.base_shift;
 	S.ob = r >> L.base_shift;
-	if (((nx >> (L.base_shift - 1)) & 1u) && pos >= a)
-		xd_report(&A, &E, S.os, pos);
+	if (((nx >> (L.base_shift - 1)) & 1u) && pos >= a) {
+		if (WIN)
+			xd_report_win(&A, &E, S.os, pos, a, win_len, stride);
+		else
+			xd_report(&A, &E, S.os, pos);
+	}
 }
 
 template <typename SYM>
@@ -1484,6 +1517,145 @@ k_scan_xd(const __grid_constant__ AutDev A, const __grid_constant__ EmitCtx E, c
 				step(S[q], data[pos[q]], pos[q], a[q]);
 		}
 	}
+}
+
+/*
+ * k_dense_walk -- the dense chunks k_scan_sampled queued (per scanning warp: E.dq; see s4_dense_chunk),
+ * walked out of the row-displaced table with its hot rows in shared memory, the way k_scan_xd walks a
+ * whole buffer.
+ *
+ * CTA b takes the lists of scanning CTA b's warps (`rpc` regions).  No dense chunk -- random-looking
+ * input, the usual case: the CTA is done after reading its `rpc` counters, before anything is staged.
+ * The kernel is launched as the programmatic dependent of k_resolve_queue (it needs k_scan_sampled's
+ * lists only, and those are complete before k_resolve_queue starts), so its launch and the empty
+ * check hide behind that kernel's last wave; griddepcontrol.wait before the exit keeps "this grid
+ * done" meaning "k_resolve_queue done" for what follows in the stream.
+ * Otherwise the T chunks are cut into `per` slices each, 1 <= per <= 8, so that every thread has up to
+ * two walks in lockstep (a handful of zero pages in a buffer must not become a handful of 2 KiB walks on
+ * one lane each); a slice is never shorter than the cold start in front of it.  A walk: cold start
+ * max_win bytes before the slice (nothing that starts earlier can have its indexed window inside),
+ * report the occurrences whose indexed window lies in the slice, and run on behind it until no
+ * occurrence that began inside can still be open.
+ */
+__global__ void __launch_bounds__(XD_THREADS, 1)
+k_dense_walk(const __grid_constant__ AutDev A, const __grid_constant__ EmitCtx E, const uint8_t *__restrict__ data,
+    uint64_t limit, uint64_t vec_lo, uint32_t stride, uint32_t rpc, uint32_t smem_slots)
+{
+	extern __shared__ __align__(128) uint32_t xd_smem[];
+	__shared__ uint32_t pre[33];                     /* chunks in the regions before region r of this CTA */
+	if (threadIdx.x < 32) {
+		uint32_t sum = threadIdx.x < rpc ? min(E.dq_count[blockIdx.x * rpc + threadIdx.x], E.dq_cap) : 0u;
+#pragma unroll
+		for (int d = 1; d < 32; d <<= 1) {
+			const uint32_t t = __shfl_up_sync(FULL_MASK, sum, d);
+			if ((int)threadIdx.x >= d)
+				sum += t;
+		}
+		pre[threadIdx.x + 1] = sum;
+		if (threadIdx.x == 0)
+			pre[0] = 0;
+	}
+	__syncthreads();
+	const uint32_t T = pre[32];
+	if (T == 0) {
+		asm volatile("griddepcontrol.wait;" ::: "memory");
+		return;
+	}
+	uint64_t *bar = reinterpret_cast<uint64_t *>(xd_smem + smem_slots);
+	if (threadIdx.x == 0) {
+		const uint32_t bytes = smem_slots * 4;
+		mbar_init(bar, 1);
+		mbar_expect_tx(bar, bytes);
+		for (uint32_t off = 0; off < bytes; off += 16384)
+			bulk_g2s(reinterpret_cast<uint8_t *>(xd_smem) + off, reinterpret_cast<const uint8_t *>(A.xd_tab) + off,
+			    min(bytes - off, 16384u), bar);
+	}
+	__syncthreads();
+	mbar_wait(bar, 0);
+
+	XdLook L;
+	L.tab_sa = smem_u32(xd_smem);
+	L.smem_slots = smem_slots;
+	L.tab = A.xd_tab;
+	L.sym_mask = (1u << A.xd_sym_bits) - 1u;
+	L.base_shift = A.xd_sym_bits + 1;
+
+	constexpr uint32_t CHUNK = 32u * S4_UNROLL * 16u;
+	uint32_t per_log = 0;
+	while (per_log < 3 && (T << per_log) < 2 * XD_THREADS && (CHUNK >> (per_log + 1)) >= A.max_win)
+		++per_log;
+	const uint32_t slice = CHUNK >> per_log;
+	const uint32_t items = T << per_log, half = (items + 1) / 2;
+
+	for (uint32_t u = threadIdx.x; u < half; u += XD_THREADS) {
+		uint64_t a[2], b[2], pos[2];
+		XdState S[2] = {{0u, 0u}, {0u, 0u}};
+#pragma unroll
+		for (int q = 0; q < 2; ++q) {
+			const uint32_t item = u + q * half;
+			a[q] = b[q] = pos[q] = 0;
+			if (item >= items)
+				continue;
+			const uint32_t ci = item >> per_log;
+			uint32_t r = 0;
+#pragma unroll
+			for (uint32_t st = 16; st; st >>= 1)
+				if (pre[r + st] <= ci)
+					r += st;
+			const uint32_t first = E.dq[(size_t)(blockIdx.x * rpc + r) * E.dq_cap + (ci - pre[r])];
+			a[q] = (vec_lo + first) * 16 + (uint64_t)(item & ((1u << per_log) - 1u)) * slice;
+			b[q] = a[q] + slice < limit ? a[q] + slice : limit;
+			if (a[q] >= b[q]) {
+				a[q] = b[q] = 0;
+				continue;
+			}
+			pos[q] = a[q] > A.max_win ? a[q] - A.max_win : 0;
+			if (pos[q] < E.valid_lo)
+				pos[q] = E.valid_lo;
+			/* head: byte by byte up to the next 16-byte boundary */
+			uint64_t head_end = (pos[q] + 15) & ~15ull;
+			if (head_end > b[q])
+				head_end = b[q];
+			for (; pos[q] < head_end; ++pos[q])
+				xd_step<true>(A, E, L, S[q], data[pos[q]], pos[q], a[q], slice, stride);
+		}
+		/* body: whole vectors of both slices in lockstep */
+		while (pos[0] + 16 <= b[0] && pos[1] + 16 <= b[1]) {
+			const uint4 v0 = __ldg(reinterpret_cast<const uint4 *>(data + pos[0]));
+			const uint4 v1 = __ldg(reinterpret_cast<const uint4 *>(data + pos[1]));
+			const uint32_t w0[4] = {v0.x, v0.y, v0.z, v0.w}, w1[4] = {v1.x, v1.y, v1.z, v1.w};
+#pragma unroll
+			for (uint32_t k = 0; k < 16; ++k) {
+				xd_step<true>(A, E, L, S[0], (w0[k / 4] >> ((k % 4) * 8)) & 0xFFu, pos[0] + k, a[0], slice, stride);
+				xd_step<true>(A, E, L, S[1], (w1[k / 4] >> ((k % 4) * 8)) & 0xFFu, pos[1] + k, a[1], slice, stride);
+			}
+			pos[0] += 16;
+			pos[1] += 16;
+		}
+#pragma unroll
+		for (int q = 0; q < 2; ++q) {
+			for (; pos[q] + 16 <= b[q]; pos[q] += 16) {
+				const uint4 v = __ldg(reinterpret_cast<const uint4 *>(data + pos[q]));
+				const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+				for (uint32_t k = 0; k < 16; ++k)
+					xd_step<true>(A, E, L, S[q], (w[k / 4] >> ((k % 4) * 8)) & 0xFFu, pos[q] + k, a[q], slice, stride);
+			}
+			for (; pos[q] < b[q]; ++pos[q])
+				xd_step<true>(A, E, L, S[q], data[pos[q]], pos[q], a[q], slice, stride);
+			/* behind the slice: until the longest open prefix began behind it */
+			if (a[q] < b[q]) {
+				const uint64_t end = b[q] + (uint64_t)A.max_len < limit ? b[q] + (uint64_t)A.max_len : limit;
+				for (; pos[q] < end; ++pos[q]) {
+					xd_step<true>(A, E, L, S[q], data[pos[q]], pos[q], a[q], slice, stride);
+					const uint64_t d = pos[q] - b[q] + 1;
+					if (__ldg(A.xd_sid + S[q].os) < __ldg(&A.level_start[d + 1 <= (uint64_t)A.max_len ? d + 1 : (uint64_t)A.max_len]))
+						break;
+				}
+			}
+		}
+	}
+	asm volatile("griddepcontrol.wait;" ::: "memory");
 }
 
 /* ------------------------------------------------------------------------- */

@@ -209,7 +209,7 @@ def test_repetitive_input_dense_hit_fallback(device):
     assert_same(off, pat, eo, ep, "repetitive sampled stride 4")
 
 
-@pytest.mark.parametrize("dq_cap", [None, 0, 1])
+@pytest.mark.parametrize("dq_cap", [None, 0, 1, "resolve"])
 def test_dense_chunks_next_to_filter_chunks_own_by_indexed_window(device, dq_cap, monkeypatch):
     """A dense 2 KiB chunk is walked by the automaton, its neighbours go through the gram filter,
     and an occurrence belongs to the chunk its INDEXED window lies in -- which for signatures that
@@ -217,8 +217,11 @@ def test_dense_chunks_next_to_filter_chunks_own_by_indexed_window(device, dq_cap
     Zero runs that cover part of a chunk, with signatures planted over every kind of border: the
     oracle's list, neither short nor with duplicates (tools/density_sweep.py found both in round 1's
     ownership rule).  ACM_DQ_CAP = 0 / 1: the scanning warp walks the chunk itself when its list
-    of dense chunks is full."""
-    if dq_cap is not None:
+    of dense chunks is full; "resolve": k_resolve_queue walks them (the path of automata without a
+    row-displaced table) instead of the scanning CTA at its end (s4_dense_phase)."""
+    if dq_cap == "resolve":
+        monkeypatch.setenv("ACM_DENSE_KERNEL", "0")
+    elif dq_cap is not None:
         monkeypatch.setenv("ACM_DQ_CAP", str(dq_cap))
     pats = clamav_pats(10000)
     o, a = build_oracle(pats), build_product(pats)

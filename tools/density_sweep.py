@@ -104,6 +104,11 @@ def main():
                 best = g._lib.ScanResult.from_buffer_copy(r)
         off, pat = sc.fetch()
         sc.close()
+        k1 = None
+        if best.mode == g.MODE_SAMPLED4:
+            sc = g.Scanner(dev, a.automaton, n, timing=3)          # the streaming kernel alone
+            k1 = min(sc.scan_device(d, n).ms_scan for _ in range(3))
+            sc.close()
         t0 = time.time()
         want = cpu.walk_count_mt(buf, os.cpu_count() or 4)
         pn = min(n, 32 << 20)
@@ -111,7 +116,7 @@ def main():
         k = int(np.searchsorted(off, pn))
         ok = bool(want == off.size and np.array_equal(off[:k], eo) and np.array_equal(pat[:k], ep))
         row = {"input": label, "mib": mib, "signatures": nsig, "mode": g.MODE_NAMES[best.mode], "matches": int(off.size),
-               "fallback": int(best.fallback), "scan_stage_ms": round(best.ms_scan, 4), "post_ms": round(best.ms_prefix + best.ms_compact, 4),
+               "fallback": int(best.fallback), "scan_stage_ms": round(best.ms_scan, 4), "k_scan_sampled_ms": None if k1 is None else round(k1, 4), "post_ms": round(best.ms_prefix + best.ms_compact, 4),
                "total_ms": round(best.ms_total, 4), "scan_gbs": round(n / best.ms_scan / 1e6, 1),
                "total_gbs": round(n / best.ms_total / 1e6, 1), "parity": ok, "cpu_check_s": round(time.time() - t0, 1)}
         rows.append(row)
