@@ -373,9 +373,11 @@ def run_stream_config(ctx, nsigs, per, seed, steps, warmup, tail_for_clocks=Fals
     emit_lo = lo - read_lo
     key_add = read_lo << sharded.KEY_PAT_BITS
     cap_keys = max(1 << 21, int(2.5 * PLANTS_PER_GIB * per / GIB))
-    # two scanners on two streams: the small kernels of step i (resolve, prefix sum, compaction) run
-    # under the streaming kernel of step i + 1; timing 3 = events around the streaming kernel alone
-    own = os.environ.get("BENCH_OWN_STREAMS", "1") != "0"
+    # two scanners, one stream: every kernel of a step is the programmatic dependent of the one before
+    # it (launch set-up and CTA residency under the predecessor's tail); timing 3 = events around the
+    # streaming kernel alone.  BENCH_OWN_STREAMS=1: a stream per scanner instead (measured: no gain --
+    # the small kernels of step i only take from the streaming kernel of step i + 1 what they use)
+    own = os.environ.get("BENCH_OWN_STREAMS", "0") != "0"
     pipe = sharded.StepPipeline(dev, acsm.automaton, hi - lo, cap_keys, rank, world,
                                 scanner_kwargs={"timing": 0 if os.environ.get("BENCH_NO_KERNEL_TIMING") else
                                                 int(os.environ.get("BENCH_TIMING", "3")), "own_stream": own})
@@ -465,9 +467,8 @@ def run_stream_config(ctx, nsigs, per, seed, steps, warmup, tail_for_clocks=Fals
         "launches": launches, "k1_ms": k1_avg, "k1_stats": step_stats(k1_ms), "achieved": achieved, "peak": peak,
         "peak_src": peak_src, "clocks": clocks, "parity": parity, "e2e": e2e, "e2e_databuf": e2e_db,
         "kernel": "k_scan_" + g.MODE_NAMES[mode] + (
-            f"<{stride}>" + (" (the streaming kernel alone: its event pair; k_resolve_queue of a step runs under "
-                             "the streaming kernel of the next step on the other scanner's stream)"
-                             if own and os.environ.get("BENCH_TIMING", "3") == "3" else
+            f"<{stride}>" + (" (the streaming kernel alone: its event pair)"
+                             if os.environ.get("BENCH_TIMING", "3") == "3" else
                              " + k_resolve_queue (scan stage: both launches inside one event pair)") if mode == 1 else ""),
     }
 

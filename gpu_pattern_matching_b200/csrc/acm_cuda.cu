@@ -132,6 +132,33 @@ acm_device_count(void)
 	return n;
 }
 
+/*
+ * Launch as the programmatic dependent of the kernel before it in the stream (k1_scan.cuh:pdl_wait):
+ * set-up and CTA residency overlap the predecessor's tail.  ACM_PDL=0: plain launches.
+ */
+static int g_pdl = -1;
+
+template <typename... KArgs, typename... Args>
+static cudaError_t
+launch_dep(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args... args)
+{
+	cudaLaunchConfig_t cfg;
+	cudaLaunchAttribute at[1];
+
+	if (g_pdl < 0)
+		g_pdl = !(getenv("ACM_PDL") && !atoi(getenv("ACM_PDL")));
+	memset(&cfg, 0, sizeof cfg);
+	cfg.gridDim = grid;
+	cfg.blockDim = block;
+	cfg.dynamicSmemBytes = smem;
+	cfg.stream = st;
+	at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+	at[0].val.programmaticStreamSerializationAllowed = 1;
+	cfg.attrs = at;
+	cfg.numAttrs = g_pdl ? 1 : 0;
+	return cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
+}
+
 static int g_attr_done[64];
 
 static int
@@ -626,8 +653,8 @@ launch_exclusive_scan(cudaStream_t st, const uint32_t *in, uint32_t *out, uint32
 		CUDA_TRY(cudaMemsetAsync(tile_state, 0, (size_t)tiles * 8, st));
 		CUDA_TRY(cudaMemsetAsync(tile_counter, 0, 4, st));
 	}
-	k_scan_lookback<<<tiles, SCAN_THREADS, 0, st>>>(in, out, n, tile_state, tile_counter, total);
-	CUDA_TRY(cudaGetLastError());
+	CUDA_TRY(launch_dep(k_scan_lookback, dim3(tiles), dim3(SCAN_THREADS), 0, st, in, out, n, tile_state, tile_counter,
+	    total));
 	return ACM_OK;
 }
 
@@ -1120,11 +1147,11 @@ launch_k1(struct acm_scanner *s, cudaStream_t st, const void *d_data, uint64_t n
 		Eq.dq_count = s->dq_count;
 		Eq.dq_cap = s->dq_cap;
 		if (a->d.sample_stride == 8)
-			k_scan_sampled<8><<<(unsigned)blocks, S4_THREADS, S4_SMEM_BYTES, st>>>(a->d, Eq,
-			    (const uint8_t *)d_data, n, vec_lo, vec_hi, limit, s->flags + 6);
+			CUDA_TRY(launch_dep(k_scan_sampled<8>, dim3((unsigned)blocks), dim3(S4_THREADS), S4_SMEM_BYTES, st, a->d, Eq,
+			    (const uint8_t *)d_data, n, vec_lo, vec_hi, limit, s->flags + 6));
 		else
-			k_scan_sampled<4><<<(unsigned)blocks, S4_THREADS, S4_SMEM_BYTES, st>>>(a->d, Eq,
-			    (const uint8_t *)d_data, n, vec_lo, vec_hi, limit, s->flags + 6);
+			CUDA_TRY(launch_dep(k_scan_sampled<4>, dim3((unsigned)blocks), dim3(S4_THREADS), S4_SMEM_BYTES, st, a->d, Eq,
+			    (const uint8_t *)d_data, n, vec_lo, vec_hi, limit, s->flags + 6));
 		if (s->p.timing == 3)       /* the streaming kernel alone */
 			CUDA_TRY(cudaEventRecord(s->ev[1], st));
 		/* dense chunks (zero pages, padding, repeated prologues): their own kernel, hot rows of the
@@ -1133,27 +1160,16 @@ launch_k1(struct acm_scanner *s, cudaStream_t st, const void *d_data, uint64_t n
 		 * such table: k_resolve_queue walks them, table through L1) */
 		const int dense_kernel = a->d.xd_tab && (size_t)a->d.xd_d1_end * 4 + 64 <= XD_SMEM_MAX &&
 		    !(getenv("ACM_DENSE_KERNEL") && !atoi(getenv("ACM_DENSE_KERNEL")));
-		k_resolve_queue<<<(unsigned)blocks * (S4_THREADS / 32), RQ_THREADS, 0, st>>>(a->d, Eq,
-		    (const uint8_t *)d_data, n, limit, vec_lo, (uint32_t)a->d.sample_stride, dense_kernel ? 0u : 1u);
+		CUDA_TRY(launch_dep(k_resolve_queue, dim3((unsigned)blocks * (S4_THREADS / 32)), dim3(RQ_THREADS), 0, st, a->d, Eq,
+		    (const uint8_t *)d_data, n, limit, vec_lo, (uint32_t)a->d.sample_stride, dense_kernel ? 0u : 1u));
 		*launches += 1;
 		if (dense_kernel) {
 			uint32_t slots = a->d.xd_len < XD_SMEM_DEFAULT / 4 ? a->d.xd_len : XD_SMEM_DEFAULT / 4;
 			slots &= ~3u;
 			if (slots < ((a->d.xd_d1_end + 3) & ~3u))
 				slots = (a->d.xd_d1_end + 3) & ~3u;
-			cudaLaunchConfig_t cfg;
-			cudaLaunchAttribute at[1];
-			memset(&cfg, 0, sizeof cfg);
-			cfg.gridDim = dim3((unsigned)blocks);
-			cfg.blockDim = dim3(XD_THREADS);
-			cfg.dynamicSmemBytes = (size_t)slots * 4 + 64;
-			cfg.stream = st;
-			at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-			at[0].val.programmaticStreamSerializationAllowed = 1;
-			cfg.attrs = at;
-			cfg.numAttrs = (getenv("ACM_DENSE_PDL") && !atoi(getenv("ACM_DENSE_PDL"))) ? 0 : 1;
-			CUDA_TRY(cudaLaunchKernelEx(&cfg, k_dense_walk, a->d, Eq, (const uint8_t *)d_data, limit, vec_lo,
-			    (uint32_t)a->d.sample_stride, (uint32_t)(S4_THREADS / 32), slots));
+			CUDA_TRY(launch_dep(k_dense_walk, dim3((unsigned)blocks), dim3(XD_THREADS), (size_t)slots * 4 + 64, st, a->d, Eq,
+			    (const uint8_t *)d_data, limit, vec_lo, (uint32_t)a->d.sample_stride, (uint32_t)(S4_THREADS / 32), slots));
 			*launches += 1;
 		}
 		if (a->d.split_len) {
@@ -1256,8 +1272,9 @@ launch_k3(struct acm_scanner *s, cudaStream_t st, uint32_t nb, uint32_t k3_block
 		uint32_t blocks = (nreg + w - 1) / w;
 		if (blocks > (uint32_t)s->dev->sm_count * 8)
 			blocks = (uint32_t)s->dev->sm_count * 8;
-		k_rd_expand<<<blocks, RD_K3_THREADS, RD_K3_SMEM, st>>>((const uint2 *)s->buckets, s->rd_loglen, s->rd_log_cap, nreg,
-		    s->offsets, nb, s->out, s->out_cap, s->flags, s->aut->d.rd_flat4, s->pend.emit_lo >> s->shift, s->shift);
+		launch_dep(k_rd_expand, dim3(blocks), dim3(RD_K3_THREADS), RD_K3_SMEM, st, (const uint2 *)s->buckets, s->rd_loglen,
+		    s->rd_log_cap, nreg, s->offsets, nb, s->out, s->out_cap, s->flags, s->aut->d.rd_flat4,
+		    s->pend.emit_lo >> s->shift, s->shift);
 		return;
 	}
 	if (s->p.mode == ACM_MODE_CDFA) {
@@ -1265,14 +1282,14 @@ launch_k3(struct acm_scanner *s, cudaStream_t st, uint32_t nb, uint32_t k3_block
 		uint32_t blocks = (nb + 8 * K3X_NB - 1) / (8 * K3X_NB);
 		if (blocks > (uint32_t)s->dev->sm_count * 8)
 			blocks = (uint32_t)s->dev->sm_count * 8;
-		k_bucket_expand_compact<<<blocks, 256, 0, st>>>((const uint32_t *)s->buckets, s->counts, s->offsets,
-		    s->out, s->cap, nb, s->out_cap, s->flags, s->aut->d.cd_flat4, s->pend.emit_lo >> s->shift, s->shift);
+		launch_dep(k_bucket_expand_compact, dim3(blocks), dim3(256), 0, st, (const uint32_t *)s->buckets, s->counts,
+		    s->offsets, s->out, s->cap, nb, s->out_cap, s->flags, s->aut->d.cd_flat4, s->pend.emit_lo >> s->shift, s->shift);
 		return;
 	}
 	/* with_push: the step's own launch also stores the keys into the gather region; the relaunch
 	 * after the output buffer grew does not (the host pushes then, scan_complete) */
-	k_bucket_sort_compact<<<k3_blocks, K3_THREADS, (size_t)s->cap * 8, st>>>(s->buckets, s->counts,
-	    s->offsets, s->out, s->cap, nb, s->out_cap, s->flags, with_push ? s->pend.push_dst : NULL,
+	launch_dep(k_bucket_sort_compact, dim3(k3_blocks), dim3(K3_THREADS), (size_t)s->cap * 8, st, s->buckets, s->counts,
+	    s->offsets, s->out, s->cap, nb, s->out_cap, s->flags, with_push ? s->pend.push_dst : (uint64_t *)NULL,
 	    s->pend.push_cap, s->pend.push_add);
 }
 
@@ -1415,8 +1432,7 @@ scan_launch(struct acm_scanner *s, cudaStream_t st, const void *d_data, uint64_t
 	 * pinned memory: a 32-byte cudaMemcpyAsync here put a copy-engine round trip between every
 	 * two steps queued on this stream (1 GiB step 0.2255 -> 0.2190 ms).
 	 */
-	k_publish_flags<<<1, 32, 0, st>>>(s->flags, s->h_flags_dev);
-	CUDA_TRY(cudaGetLastError());
+	CUDA_TRY(launch_dep(k_publish_flags, dim3(1), dim3(32), 0, st, s->flags, s->h_flags_dev));
 	launches++;
 	CUDA_TRY(cudaEventRecord(s->ev_done, st));
 	s->pend.active = 1;

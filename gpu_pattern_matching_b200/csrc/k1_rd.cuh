@@ -366,6 +366,8 @@ k_rd_expand(const uint2 *__restrict__ log, const uint32_t *__restrict__ loglen, 
 	uint64_t *win = rx_smem + (size_t)(threadIdx.x >> 5) * RD_K3_WIN;
 	const uint32_t gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nw = (gridDim.x * blockDim.x) >> 5;
 
+	pdl_trigger();
+	pdl_wait();
 	if (*(volatile uint32_t *)flags)
 		return;
 	/* hits carry the ABSOLUTE base of k_scan_rd's shared-memory table: flags[8] = its word address */

@@ -121,6 +121,26 @@ __device__ __forceinline__ uint32_t smem_u32(const void *p)
 	return (uint32_t)__cvta_generic_to_shared(p);
 }
 
+/*
+ * Programmatic dependent launch.  The kernels of a step are launched with
+ * cudaLaunchAttributeProgrammaticStreamSerialization (acm_cuda.cu:launch_dep): a kernel may be set up
+ * and its CTAs made resident while its predecessor in the stream still runs, as soon as every CTA of
+ * the predecessor has passed pdl_trigger() (or ended).  EVERY such kernel calls pdl_wait() before it
+ * touches anything a predecessor wrote -- it returns when the predecessor grid has completed and its
+ * stores are visible -- and on every path before it ends, so that "this grid is done" keeps
+ * implying "everything before it in the stream is done" along the chain.  Both are no-ops in a
+ * kernel launched the plain way.
+ */
+__device__ __forceinline__ void pdl_wait()
+{
+	asm volatile("griddepcontrol.wait;" ::: "memory");
+}
+
+__device__ __forceinline__ void pdl_trigger()
+{
+	asm volatile("griddepcontrol.launch_dependents;");
+}
+
 __device__ __forceinline__ uint64_t globaltimer_ns()
 {
 	uint64_t t;
@@ -477,6 +497,7 @@ k_scan_sampled(const __grid_constant__ AutDev A, const __grid_constant__ EmitCtx
 	constexpr int WPV = 16 / STRIDE;                 /* windows per 16-byte vector */
 	constexpr int NW = S4_UNROLL * WPV;              /* windows per lane per chunk */
 
+	pdl_trigger();            /* k_resolve_queue's CTAs follow on every SM as its scanning CTA ends */
 	if (E.trace && threadIdx.x == 0)
 		E.trace[blockIdx.x * 4 + 0] = globaltimer_ns();
 	/* stage both bitmaps with TMA bulk copies, 32 KiB each */
@@ -488,6 +509,9 @@ k_scan_sampled(const __grid_constant__ AutDev A, const __grid_constant__ EmitCtx
 		for (uint32_t off = 0; off < F2_WORDS; off += 8192)
 			bulk_g2s(f2 + off, A.f2 + off, 32768, bar);
 	}
+	/* the bitmaps belong to the automaton; everything below -- work counter, text, queues -- may
+	 * have been written by what precedes this kernel in the stream */
+	pdl_wait();
 	__syncthreads();
 
 	/*
@@ -942,9 +966,11 @@ __global__ void __launch_bounds__(RQ_THREADS, RQ_MINB)
 k_resolve_queue(const __grid_constant__ AutDev A, const __grid_constant__ EmitCtx E,
     const uint8_t *__restrict__ data, uint64_t n, uint64_t limit, uint64_t vec_lo, uint32_t stride, uint32_t walk_dense)
 {
-	/* k_dense_walk, launched behind this kernel as its programmatic dependent, needs nothing from it:
-	 * its CTAs may take the SMs this grid's last wave leaves */
-	asm volatile("griddepcontrol.launch_dependents;");
+	pdl_wait();               /* the queues of k_scan_sampled */
+	/* k_dense_walk, launched behind this kernel as its programmatic dependent, needs nothing from it,
+	 * only k_scan_sampled's lists -- complete once every CTA here is past its wait: its CTAs may take
+	 * the SMs this grid's last wave leaves */
+	pdl_trigger();
 	/* the region's dense chunks first (usually none), when k_dense_walk cannot take them (no
 	 * row-displaced table): one thread per slice, table entries through L1 */
 	if (walk_dense) {
@@ -1557,8 +1583,9 @@ k_dense_walk(const __grid_constant__ AutDev A, const __grid_constant__ EmitCtx E
 	}
 	__syncthreads();
 	const uint32_t T = pre[32];
+	pdl_trigger();
 	if (T == 0) {
-		asm volatile("griddepcontrol.wait;" ::: "memory");
+		pdl_wait();
 		return;
 	}
 	uint64_t *bar = reinterpret_cast<uint64_t *>(xd_smem + smem_slots);
@@ -1655,7 +1682,7 @@ k_dense_walk(const __grid_constant__ AutDev A, const __grid_constant__ EmitCtx E
 			}
 		}
 	}
-	asm volatile("griddepcontrol.wait;" ::: "memory");
+	pdl_wait();
 }
 
 /* ------------------------------------------------------------------------- */

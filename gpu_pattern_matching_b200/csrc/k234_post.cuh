@@ -63,6 +63,8 @@ k_scan_lookback(const uint32_t *__restrict__ in, uint32_t *__restrict__ out, uin
 	__shared__ uint32_t s_warp[SCAN_THREADS / 32];
 	__shared__ uint32_t s_prefix;
 
+	pdl_trigger();
+	pdl_wait();
 	if (threadIdx.x == 0)
 		s_tile = atomicAdd(tile_counter, 1u);
 	__syncthreads();
@@ -175,6 +177,8 @@ k_bucket_sort_compact(const uint64_t *__restrict__ buckets, const uint32_t *__re
 	const uint32_t lane = threadIdx.x & 31;
 	const uint32_t warps = K3_THREADS / 32;
 
+	pdl_trigger();
+	pdl_wait();
 	if (*(volatile uint32_t *)flags)        /* overflow: buckets are incomplete */
 		return;
 	for (uint32_t blk = blockIdx.x; blk * warps < n_buckets; blk += gridDim.x) {
@@ -303,6 +307,8 @@ k_bucket_expand_compact(const uint32_t *__restrict__ buckets, const uint32_t *__
 	const uint32_t lane = threadIdx.x & 31;
 	const uint32_t warps = (gridDim.x * blockDim.x) >> 5;
 
+	pdl_trigger();
+	pdl_wait();
 	if (*(volatile uint32_t *)flags)
 		return;
 	for (uint32_t g = ((blockIdx.x * blockDim.x + threadIdx.x) >> 5) * K3X_NB; g < n_buckets;
@@ -551,6 +557,7 @@ __global__ void k_plant(uint8_t *__restrict__ buf, uint64_t n, uint64_t buf_offs
 __global__ void
 k_publish_flags(const uint32_t *__restrict__ flags, uint32_t *__restrict__ h_flags)
 {
+	pdl_wait();
 	if (threadIdx.x < 8) {
 		h_flags[threadIdx.x] = flags[threadIdx.x];
 		__threadfence_system();
