@@ -6,9 +6,11 @@ kernels, C ABI in include/*.h).  These modules are thin ctypes mirrors of that A
 
     acsm      Acsm, Iacsm           builder interface (acsmx.h, iacsmx.h)
     matcher   Device, Scanner       native scan API (acm.h)
-    worker    Worker                databuf / ocl_worker / ocl_aho_match path
-    sharded   sharded_scan          one process per GPU, torch.distributed plumbing
+    sharded   ShardedScan, StepPipeline   one process per GPU, torch.distributed plumbing
     synth     stream, Plants        synthetic inputs for tests and bench
+    _lib      lib(), structs        the ctypes prototypes of every entry point of include/*.h,
+                                    among them the databuf / ocl_worker / ocl_aho_match path
+                                    (databuf.h, common.h), which tests and bench.py call directly
 """
 from ._lib import AcmError, LIB_PATH, lib  # noqa: F401
 from .acsm import Acsm, Iacsm  # noqa: F401

@@ -142,7 +142,7 @@ acm_tables_free(struct acm_tables *t)
 {
 	free(t->T); free(t->level_start); free(t->own_begin); free(t->own_pat);
 	free(t->olink); free(t->fail); free(t->pat_len); free(t->pat_iid);
-	free(t->bfs_to_ref); free(t->f1); free(t->f2); free(t->grams); free(t->b2); free(t->b2s); free(t->b3);
+	free(t->bfs_to_ref); free(t->f1); free(t->f2); free(t->grams); free(t->b2s); free(t->b3);
 	free(t->cand); free(t->pat_blob); free(t->pat_off); free(t->pat_win);
 	free(t->cd_cls); free(t->cd_tab); free(t->cd_flat_begin); free(t->cd_flat_pat);
 	free(t->rd_tab); free(t->rd_flat4); free(t->cd_flat4); free(t->xd_tab); free(t->xd_sid);
@@ -162,8 +162,6 @@ acm_tables_device_bytes(const struct acm_tables *t)
 		    (size_t)t->gram_slots * sizeof(struct acm_gram_slot) +
 		    ((size_t)t->cand_count + ACM_CAND_PAD) * sizeof(struct acm_cand) +
 		    t->pat_blob_bytes + (size_t)t->num_patterns * 4;
-	if (t->b2)
-		b += 65536 / 8;
 	if (t->b3)
 		b += ACM_B3_WORDS * 4;
 	if (t->b2s)
@@ -977,35 +975,6 @@ build_filters(struct acm_core *c)
 {
 	struct acm_tables *t = &c->tab;
 	uint32_t s, k;
-
-	/* exact 2-byte start bitmap: "a walk from this position can report" */
-	t->b2 = calloc(65536 / 32, 4);
-	if (!t->b2)
-		return ACM_ERR_NOMEM;
-	if (t->max_depth >= 1) {
-		for (unsigned b0 = 0; b0 < 256; b0++) {
-			uint32_t e1 = t->T[b0];
-			uint32_t s1 = e1 & ACM_T_MASK;
-			if (s1 < t->level_start[1])
-				continue;                 /* no depth-1 node */
-			if (e1 & ACM_T_OWN) {             /* 1-byte pattern  */
-				for (unsigned b1 = 0; b1 < 256; b1++) {
-					uint32_t idx = b0 | (b1 << 8);
-					t->b2[idx >> 5] |= 0x80000000u >> (idx & 31);
-				}
-				continue;
-			}
-			if (t->max_depth < 2)
-				continue;
-			for (unsigned b1 = 0; b1 < 256; b1++) {
-				uint32_t s2 = t->T[(size_t)s1 * 256 + b1] & ACM_T_MASK;
-				if (s2 >= t->level_start[2]) {
-					uint32_t idx = b0 | (b1 << 8);
-					t->b2[idx >> 5] |= 0x80000000u >> (idx & 31);
-				}
-			}
-		}
-	}
 
 	t->b3 = build_b3(c);
 	if (!t->b3)

@@ -538,8 +538,6 @@ acm_automaton_upload(struct acm_device *dev, const struct acm_tables *t, struct 
 	UP(own_begin, t->own_begin, (size_t)(t->num_states + 1) * 4);
 	UP(own_pat, t->own_pat, (size_t)t->own_total * 4);
 	UP(olink, t->olink, (size_t)t->num_states * 4);
-	if (t->b2)
-		UP(b2, t->b2, 65536 / 8);
 	if (t->b2s)
 		UP(b2s, t->b2s, 65536 / 8);
 	if (t->b3)

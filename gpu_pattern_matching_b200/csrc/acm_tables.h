@@ -117,7 +117,6 @@ struct acm_tables {
 	uint32_t *pat_off;           /* [num_patterns] byte offset into pat_blob      */
 	uint32_t  max_win;           /* largest entry of pat_win                       */
 	uint8_t  *pat_win;           /* [num_patterns][8]: offset of the indexed window of (pattern, alignment j = (-start) mod stride) */
-	uint32_t *b2;                /* 2^16-bit exact start bitmap: bit (b0 | b1<<8) */
 	int       split_len;         /* > 0: patterns shorter than this are not in the sampled filter (mixed sets) */
 	uint32_t *b2s;               /* start bitmap of those short patterns alone; NULL when split_len == 0 */
 	uint32_t *b3;                /* start filter of mode 2: 2^19-bit blocked Bloom bitmap (k = 3) of the first THREE

@@ -64,7 +64,6 @@ struct AutDev {
 	const uint32_t *pat_off;
 	const uint32_t *pat_len;
 	const uint8_t  *pat_win;    /* [patterns][8]: offset of the indexed window per alignment (sampled filter) */
-	const uint32_t *b2;
 	const uint32_t *b2s;        /* start bitmap of the patterns shorter than split_len (mixed sets) */
 	const uint32_t *b3;         /* start filter of mode 2: first-three-bytes Bloom bitmap of all patterns */
 	uint32_t split_len;         /* 0: every pattern is in the sampled filter */
@@ -630,12 +629,6 @@ k_scan_sampled(const __grid_constant__ AutDev A, const __grid_constant__ EmitCtx
 	if (E.trace && threadIdx.x == 0)
 		E.trace[blockIdx.x * 4 + 1] = globaltimer_ns();
 
-#ifdef S4_TRACE_DETAIL
-	/* per-chunk timestamps: the slowest chunk of every CTA with what it did (make EXTRA=-DS4_TRACE_DETAIL,
-	 * ACM_TRACE=1 ACM_TRACE_DETAIL=1 tools/quick_bench.py) */
-	uint64_t td_prev = globaltimer_ns(), td_max = 0, td_slow = 0, td_filter = 0;
-	uint32_t tdc_rounds = 0, tdc_pend = 0, tdc_cand = 0, tdc_verify = 0, td_info = 0;
-#endif
 	const uint32_t vq_region = blockIdx.x * (S4_THREADS / 32) + (threadIdx.x >> 5);
 	uint4 *const vq_mine = E.vq + (size_t)vq_region * E.vq_cap;
 	uint32_t vq_n = 0;
@@ -671,23 +664,6 @@ k_scan_sampled(const __grid_constant__ AutDev A, const __grid_constant__ EmitCtx
 	};
 	while (run_count) {
 		++trace_chunks;
-#ifdef S4_TRACE_DETAIL
-		{
-			const uint64_t now = globaltimer_ns();
-			const uint64_t d = now - td_prev;
-			td_prev = now;
-			if (trace_chunks > 1) {
-				if (d > td_max) {
-					td_max = d;
-					td_info = ((td_filter / 250) > 255 ? 255 : (uint32_t)(td_filter / 250)) | (min(tdc_rounds, 63u) << 8) |
-					    (min(tdc_pend, 63u) << 14) | (min(tdc_cand, 63u) << 20) | (min(tdc_verify, 63u) << 26);
-				}
-				td_slow += d > 8000;
-			}
-			tdc_rounds = tdc_pend = tdc_cand = tdc_verify = 0;
-			td_filter = 0;
-		}
-#endif
 		const uint64_t cur_first = first;
 		load_chunk(v, cur_first);
 		advance();
@@ -706,13 +682,6 @@ k_scan_sampled(const __grid_constant__ AutDev A, const __grid_constant__ EmitCtx
 				hits = __funnelshift_l(t, hits, 1);
 			}
 		}
-#ifdef S4_EXPERIMENT
-		/* roofline experiments (never shipped): 1 = loads only, 2 = loads + level-1 filter, no hit handling */
-		if (S4_EXPERIMENT == 1)
-			hits = ((v[0].x ^ v[1].x ^ v[2].x ^ v[3].x ^ v[0].z ^ v[1].z ^ v[2].z ^ v[3].z) == 0x12345678u) ? 1u : 0u;
-		else if (S4_EXPERIMENT == 2)
-			hits = (hits == 0x00a5a5a5u && v[0].x == 0x12345678u) ? 1u : 0u;
-#endif
 		/* the last chunk may stick out past vec_hi: those vectors were not loaded (zeros) and
 		 * must not be tested -- an all-zero window is a real, and popular, pattern gram */
 		if (cur_first + chunk_vecs > vec_hi) {
@@ -763,10 +732,6 @@ k_scan_sampled(const __grid_constant__ AutDev A, const __grid_constant__ EmitCtx
 		/* Survivors are rare: from here on control flow is warp-uniform and verification is done
 		 * by the whole warp. */
 		while (__any_sync(FULL_MASK, hits != 0)) {
-#ifdef S4_TRACE_DETAIL
-			if (tdc_rounds++ == 0)
-				td_filter = globaltimer_ns() - td_prev;
-#endif
 			uint32_t cbegin = 0, word4 = 0;
 			uint64_t e = 0;
 			const bool has = hits != 0;
@@ -817,9 +782,6 @@ k_scan_sampled(const __grid_constant__ AutDev A, const __grid_constant__ EmitCtx
 				}
 			}
 			uint32_t pend = __ballot_sync(FULL_MASK, cbegin != 0);
-#ifdef S4_TRACE_DETAIL
-			tdc_pend += __popc(pend);
-#endif
 			while (pend) {
 				const int src = __ffs(pend) - 1;
 				pend &= pend - 1;
@@ -833,9 +795,6 @@ k_scan_sampled(const __grid_constant__ AutDev A, const __grid_constant__ EmitCtx
 					/* one candidate per lane (lists are padded, lanes past LAST are ignored) */
 					const uint4 *cp = reinterpret_cast<const uint4 *>(A.cand) + 2 * (size_t)(ci + lane);
 					const uint4 c = __ldg(cp);
-#ifdef S4_TRACE_DETAIL
-					++tdc_cand;
-#endif
 					const uint32_t lastm = __ballot_sync(FULL_MASK, (c.w & ACM_CAND_LAST) != 0);
 					const int nvalid = lastm ? __ffs(lastm) : 32;
 					const uint32_t o = c.x >> ACM_CAND_O_SHIFT;
@@ -860,9 +819,6 @@ k_scan_sampled(const __grid_constant__ AutDev A, const __grid_constant__ EmitCtx
 					while (surv) {
 						const int l = __ffs(surv) - 1;
 						surv &= surv - 1;
-#ifdef S4_TRACE_DETAIL
-						++tdc_verify;
-#endif
 						s4_verify(A, E, data, __shfl_sync(FULL_MASK, c.x, l) & ACM_CAND_ID_MASK,
 						    __shfl_sync(FULL_MASK, len, l), __shfl_sync(FULL_MASK, s, l), lane);
 					}
@@ -880,13 +836,6 @@ k_scan_sampled(const __grid_constant__ AutDev A, const __grid_constant__ EmitCtx
 	if (E.trace && lane == 0) {
 		atomicMax((unsigned long long *)&E.trace[blockIdx.x * 4 + 2], (unsigned long long)globaltimer_ns());
 		atomicAdd((unsigned long long *)&E.trace[blockIdx.x * 4 + 3], (unsigned long long)trace_chunks);
-#ifdef S4_TRACE_DETAIL
-		{
-			uint64_t *x = E.trace + (512 + blockIdx.x) * 4;
-			atomicMax((unsigned long long *)&x[0], (unsigned long long)((td_max / 100) << 32 | td_info));
-			atomicAdd((unsigned long long *)&x[1], (unsigned long long)td_slow);
-		}
-#endif
 	}
 }
 

@@ -51,16 +51,6 @@ def run(dev, name, pats, n, modes, text=None, plants=0, iters=5):
                 (tr[:, 0].min() - t0) / 1e3, (tr[:, 0].max() - t0) / 1e3, (tr[:, 1].min() - t0) / 1e3,
                 (tr[:, 1].max() - t0) / 1e3, (tr[:, 2].min() - t0) / 1e3, (tr[:, 2].max() - t0) / 1e3,
                 tr[:, 3].min(), tr[:, 3].max()), flush=True)
-            if os.environ.get("ACM_TRACE_DETAIL"):      # library built with make EXTRA=-DS4_TRACE_DETAIL
-                t2 = np.zeros(1024 * 4, dtype=np.uint64)
-                g.lib().acm_scan_trace(sc._h, t2.ctypes.data_as(g._lib.u64p), 1024)
-                x = t2.reshape(1024, 4)[512:512 + 148].astype(np.int64)
-                oo = np.argsort(tr[:, 2])
-                print("  slowest chunk per CTA by exit time (us : us until the filter is done / hit-loop rounds / "
-                      "gram hits / candidate rounds / full compares): " + "  ".join(
-                          f"{(x[i, 0] >> 32) / 10:.0f}:{(x[i, 0] & 255) / 4:.1f}/{(x[i, 0] >> 8) & 63}/{(x[i, 0] >> 14) & 63}/"
-                          f"{(x[i, 0] >> 20) & 63}/{(x[i, 0] >> 26) & 63}" for i in oo))
-                print("  chunks above 8 us per CTA: " + " ".join(str(x[i, 1]) for i in oo))
             ex = np.sort((tr[:, 2] - t0) / 1e3)
             print("  exit times (us), sorted: " + " ".join(f"{x:.0f}" for x in ex), flush=True)
             order = np.argsort(tr[:, 2])
