@@ -67,6 +67,64 @@ void ocl_compact_array_close(struct clconf *c) { (void)c; }
 int  ocl_bitonic_sort_init(struct clconf *c) { (void)c; return 0; }
 int  ocl_bitonic_sort_close(struct clconf *c) { (void)c; return 0; }
 
+/* the databuf's scanner for this automaton (one per databuf, replaced when the automaton changes) */
+static int
+ensure_scanner(struct databuf *db, struct acm_automaton *aut, int sym_size)
+{
+	struct databuf_priv *pv = (struct databuf_priv *)db->priv;
+	struct acm_scan_params p;
+	int rc;
+
+	if (pv->scanner && pv->scanner_aut != aut) {
+		acm_scanner_free(pv->scanner);
+		pv->scanner = NULL;
+		pv->carry_len = 0;
+	}
+	if (pv->scanner)
+		return ACM_OK;
+	memset(&p, 0, sizeof(p));
+	/* 32 KiB result buckets for the sparse-output kernels; the dense-output kernels (word
+	 * lists: a bucket is one thread's chunk there) keep their own shape */
+	if (acm_automaton_default_mode(aut) != ACM_MODE_CDFA)
+		p.bucket_shift = 15;
+	rc = acm_scanner_create(pv->dev, aut, db->size / (uint64_t)sym_size + 1, &p, &pv->scanner);
+	if (rc == ACM_OK)
+		pv->scanner_aut = aut;
+	return rc;
+}
+
+/*
+ * What the reference does in its init calls -- build the OpenCL program, create the kernels
+ * (ocl_aho_match.c:25-60, called from ocl_worker_ctx_init before any file is opened) -- has its
+ * counterpart here: create the scanner (result buckets, queues) and run the kernels once over a few
+ * KiB of the still empty device buffer, so that the driver loads their code now and not inside the
+ * first buffer of the scan loop.  Nothing of the databuf's state changes.
+ */
+int
+databuf_prepare(struct databuf *db, struct acm_automaton *aut, int sym_size)
+{
+	struct databuf_priv *pv = db ? (struct databuf_priv *)db->priv : NULL;
+	const uint64_t carry_cap = DATABUF_CARRY_CAP / (uint64_t)sym_size;
+	uint64_t n = 65536;
+	struct acm_scan_result res;
+	int rc;
+
+	if (!pv || !aut)
+		return ACM_ERR_ARG;
+	if ((rc = ensure_scanner(db, aut, sym_size)) != ACM_OK)
+		return rc;
+	if (n > db->size / (uint64_t)sym_size)
+		n = db->size / (uint64_t)sym_size;
+	if (n == 0)
+		return ACM_OK;
+	if ((rc = acm_dev_memset(pv->dev, pv->d_base + DATABUF_CARRY_CAP, 0, (size_t)n * sym_size)) != ACM_OK)
+		return rc;
+	rc = acm_scan_device_ex(pv->scanner, pv->d_base, carry_cap + n, carry_cap, carry_cap, carry_cap + n, &res);
+	if (rc == ACM_OK)
+		rc = acm_device_sync(pv->dev);
+	return rc;
+}
+
 static void
 match_common(struct databuf *db, struct acm_automaton *aut, int sym_size, int stream)
 {
@@ -86,24 +144,9 @@ match_common(struct databuf *db, struct acm_automaton *aut, int sym_size, int st
 		return;
 	}
 	pv->sym_size = sym_size;
-	if (pv->scanner && pv->scanner_aut != aut) {
-		acm_scanner_free(pv->scanner);
-		pv->scanner = NULL;
-		pv->carry_len = 0;
-	}
-	if (!pv->scanner) {
-		struct acm_scan_params p;
-		memset(&p, 0, sizeof(p));
-		/* 32 KiB result buckets for the sparse-output kernels; the dense-output kernels (word
-		 * lists: a bucket is one thread's chunk there) keep their own shape */
-		if (acm_automaton_default_mode(aut) != ACM_MODE_CDFA)
-			p.bucket_shift = 15;
-		rc = acm_scanner_create(pv->dev, aut, db->size / (uint64_t)sym_size + 1, &p, &pv->scanner);
-		if (rc != ACM_OK) {
-			pv->status = rc;
-			return;
-		}
-		pv->scanner_aut = aut;
+	if ((rc = ensure_scanner(db, aut, sym_size)) != ACM_OK) {
+		pv->status = rc;
+		return;
 	}
 	halo = (uint64_t)(acm_automaton_max_pattern_len(aut) > 0 ? acm_automaton_max_pattern_len(aut) - 1 : 0);
 	if (halo > carry_cap)

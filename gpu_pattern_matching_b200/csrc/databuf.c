@@ -12,6 +12,7 @@
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
+#include <time.h>
 #include <unistd.h>
 #include <pthread.h>
 #include <sys/stat.h>
@@ -31,6 +32,10 @@ priv_of(struct databuf *db)
 {
 	return (struct databuf_priv *)db->priv;
 }
+
+#define READ_PAR_MIN   ((size_t)8 << 20)      /* below this one read() is as fast */
+#define READ_PAR_MAX   16
+
 
 struct databuf *
 databuf_new(size_t max_chunks, size_t max_chunk_size, int max_results, int mapped, struct clconf *conf)
@@ -77,6 +82,18 @@ databuf_new(size_t max_chunks, size_t max_chunk_size, int max_results, int mappe
 	if (acm_host_alloc_pinned_near(dev, db->size + 64, &p) != ACM_OK)
 		goto fail;
 	db->h_data = p;
+	/*
+	 * The second pinned buffer of the read-ahead, here and not on first use: pinning 128 MiB takes
+	 * ~50 ms, which inside the scan loop cost more than the overlap gains on anything below a few GiB
+	 * per worker (cli_bench, 4 x 512 MiB: 25 -> 6 GB/s).  Buffers too small for a parallel read do
+	 * not read ahead; ACM_READAHEAD=0 turns it off.
+	 */
+	{
+		const char *env = getenv("ACM_READAHEAD");
+		if (!(env && atoi(env) == 0) && db->size >= READ_PAR_MIN &&
+		    acm_host_alloc_pinned_near(dev, db->size + 64, &p) == ACM_OK)
+			pv->ra.buf = p;
+	}
 	if (acm_dev_alloc(dev, DATABUF_CARRY_CAP + db->size + 64, &p) != ACM_OK)
 		goto fail;
 	pv->d_base = p;
@@ -117,8 +134,6 @@ fail:
 
 /* ---- parallel read of a regular file ---- */
 
-#define READ_PAR_MIN   ((size_t)8 << 20)      /* below this one read() is as fast */
-#define READ_PAR_MAX   16
 
 struct read_seg {
 	int     fd;
@@ -148,28 +163,30 @@ read_seg_main(void *arg)
 	return NULL;
 }
 
-long
-databuf_read_fd(int fd, void *buf, size_t want)
+static int
+read_threads(void)
+{
+	const char *env = getenv("ACM_READ_THREADS");
+	int nt = env ? atoi(env) : 4;
+
+	return nt > READ_PAR_MAX ? READ_PAR_MAX : nt;
+}
+
+/*
+ * [off, off + want) of a regular file into buf with nt threads pread()ing adjacent segments; the file
+ * offset is not touched.  Returns the contiguous bytes read from `off` on (short at the end of the
+ * file), -1 when nothing could be read because of an error.
+ */
+static long
+read_segments(int fd, void *buf, off_t off, size_t want, int nt)
 {
 	struct read_seg seg[READ_PAR_MAX];
 	pthread_t th[READ_PAR_MAX];
-	struct stat st;
-	const char *env = getenv("ACM_READ_THREADS");
-	int nt = env ? atoi(env) : 4, started = 0, i;
-	off_t off;
+	int started = 0, i;
 	size_t per, total = 0;
 
-	if (nt > READ_PAR_MAX)
-		nt = READ_PAR_MAX;
-	if (nt < 2 || want < READ_PAR_MIN || fstat(fd, &st) != 0 || !S_ISREG(st.st_mode) ||
-	    (off = lseek(fd, 0, SEEK_CUR)) == (off_t)-1)
-		return (long)read(fd, buf, want);
-	if (off >= st.st_size)
-		return (long)read(fd, buf, want);     /* at (what was) the end: 0, or freshly appended data */
-	if ((size_t)(st.st_size - off) < want)
-		want = (size_t)(st.st_size - off);    /* what the file holds now; a later call sees what is appended */
-	if (want < READ_PAR_MIN)
-		return (long)read(fd, buf, want);
+	if (nt < 1)
+		nt = 1;
 	per = ((want + (size_t)nt - 1) / (size_t)nt + 4095) & ~(size_t)4095;
 	for (i = 0; i < nt && (size_t)i * per < want; i++) {
 		seg[i].fd = fd;
@@ -197,14 +214,45 @@ databuf_read_fd(int fd, void *buf, size_t want)
 		if ((size_t)seg[i].got < seg[i].want)
 			break;
 	}
-	if (total == 0 && seg[0].got < 0)
-		return -1;
-	if (lseek(fd, off + (off_t)total, SEEK_SET) == (off_t)-1)
+	if (total == 0 && nt > 0 && seg[0].got < 0)
 		return -1;
 	return (long)total;
 }
 
+long
+databuf_read_fd(int fd, void *buf, size_t want)
+{
+	struct stat st;
+	const int nt = read_threads();
+	off_t off;
+	long total;
+
+	if (nt < 2 || want < READ_PAR_MIN || fstat(fd, &st) != 0 || !S_ISREG(st.st_mode) ||
+	    (off = lseek(fd, 0, SEEK_CUR)) == (off_t)-1)
+		return (long)read(fd, buf, want);
+	if (off >= st.st_size)
+		return (long)read(fd, buf, want);     /* at (what was) the end: 0, or freshly appended data */
+	if ((size_t)(st.st_size - off) < want)
+		want = (size_t)(st.st_size - off);    /* what the file holds now; a later call sees what is appended */
+	if (want < READ_PAR_MIN)
+		return (long)read(fd, buf, want);
+	total = read_segments(fd, buf, off, want, nt);
+	if (total < 0)
+		return -1;
+	if (lseek(fd, off + (off_t)total, SEEK_SET) == (off_t)-1)
+		return -1;
+	return total;
+}
+
 /* ---- read-ahead of the next whole buffer (see databuf_priv.h) ---- */
+
+static double
+now_s(void)
+{
+	struct timespec ts;
+	clock_gettime(CLOCK_MONOTONIC, &ts);
+	return (double)ts.tv_sec + 1e-9 * (double)ts.tv_nsec;
+}
 
 static void *
 readahead_main(void *arg)
@@ -220,22 +268,19 @@ readahead_main(void *arg)
 		{
 			const int fd = ra->fd;
 			const off_t off = ra->off;
-			const size_t want = ra->want;
-			size_t done = 0;
+			size_t want = ra->want;
+			struct stat st;
 			long got = 0;
 			pthread_mutex_unlock(&ra->lock);
-			while (done < want) {
-				const ssize_t r = pread(fd, ra->buf + done, want - done, off + (off_t)done);
-				if (r < 0) {
-					got = done ? (long)done : -1;
-					break;
-				}
-				if (r == 0)
-					break;
-				done += (size_t)r;
-				got = (long)done;
+			const double t0 = now_s();
+			/* what the file holds now, in parallel segments like a read in the foreground */
+			if (fstat(fd, &st) == 0 && off < st.st_size) {
+				if ((size_t)(st.st_size - off) < want)
+					want = (size_t)(st.st_size - off);
+				got = read_segments(fd, ra->buf, off, want, want < READ_PAR_MIN ? 1 : read_threads());
 			}
 			pthread_mutex_lock(&ra->lock);
+			ra->t_ra_read += now_s() - t0;
 			ra->got = got;
 			ra->have = 1;
 			ra->busy = 0;
@@ -246,22 +291,15 @@ readahead_main(void *arg)
 	return NULL;
 }
 
-/* ask for [off, off + want) of fd; needs the second buffer, which is allocated on first use */
+/* ask for [off, off + want) of fd; needs the second buffer (databuf_new; ACM_READAHEAD=0: there is none) */
 static void
 readahead_start(struct databuf *db, int fd, off_t off, size_t want)
 {
 	struct databuf_priv *pv = priv_of(db);
 	struct databuf_readahead *ra = &pv->ra;
-	const char *env = getenv("ACM_READAHEAD");
-	void *p;
 
-	if (env && atoi(env) == 0)
+	if (!ra->buf)
 		return;
-	if (!ra->buf) {
-		if (acm_host_alloc_pinned_near(pv->dev, db->size + 64, &p) != ACM_OK)
-			return;
-		ra->buf = p;
-	}
 	pthread_mutex_lock(&ra->lock);
 	if (!ra->started) {
 		if (pthread_create(&ra->thread, NULL, readahead_main, ra) != 0) {
@@ -291,14 +329,19 @@ readahead_take(struct databuf *db, int fd, off_t off, size_t want)
 
 	if (!ra->started)
 		return -2;
+	const double t0 = now_s();
 	pthread_mutex_lock(&ra->lock);
 	while (ra->busy)
 		pthread_cond_wait(&ra->cond, &ra->lock);
+	ra->t_wait += now_s() - t0;
 	if (ra->have && ra->fd == fd && ra->off == off && ra->want == want && ra->got >= 0) {
 		unsigned char *t = db->h_data;
 		db->h_data = ra->buf;
 		ra->buf = t;
 		got = ra->got;
+		ra->n_taken++;
+	} else if (ra->have) {
+		ra->n_missed++;
 	}
 	ra->have = 0;
 	pthread_mutex_unlock(&ra->lock);
@@ -350,8 +393,14 @@ databuf_add_fd(struct databuf *db, int fd, int id, size_t *rd_bytes)
 		if (got >= 0 && lseek(fd, pos + (off_t)got, SEEK_SET) == (off_t)-1)
 			got = -1;
 	}
-	if (got == -2)
+	if (got == -2) {
+		const double t0 = now_s();
 		got = databuf_read_fd(fd, db->h_data + db->chunks * db->max_chunk_size, room);
+		if (db->priv) {
+			priv_of(db)->ra.t_direct += now_s() - t0;
+			priv_of(db)->ra.n_direct++;
+		}
+	}
 	if (got < 0) {
 		acm_set_error("databuf_add_fd: read failed: %s", strerror(errno));
 		if (db->priv)
@@ -663,6 +712,9 @@ databuf_free(struct databuf *db, int mapped, cl_command_queue queue)
 	pv = priv_of(db);
 	if (pv) {
 		readahead_stop(pv);
+		if (getenv("ACM_DATABUF_STATS"))
+			fprintf(stderr, "databuf %p: %ld foreground reads %.3f s, %ld buffers read ahead (%.3f s reading, %.3f s waited for), %ld dropped\n",
+			    (void *)db, pv->ra.n_direct, pv->ra.t_direct, pv->ra.n_taken, pv->ra.t_ra_read, pv->ra.t_wait, pv->ra.n_missed);
 		pthread_mutex_destroy(&pv->ra.lock);
 		pthread_cond_destroy(&pv->ra.cond);
 		free(pv->run_id);

@@ -30,6 +30,9 @@ struct databuf_readahead {
 	long            got;             /* result (< 0: error), valid when !busy && have */
 	int             have;
 	unsigned char  *buf;             /* the second pinned buffer (h_alt)              */
+	/* ACM_DATABUF_STATS=1: printed by databuf_free */
+	double          t_direct, t_wait, t_ra_read;   /* seconds in foreground reads, waiting for the read-ahead, reading ahead */
+	long            n_direct, n_taken, n_missed;
 };
 
 struct databuf_priv {
@@ -58,5 +61,9 @@ struct databuf_priv {
 	int                   buckets_on_device; /* d_results / d_results2 hold the bucket view of the last match */
 	struct databuf_readahead ra;
 };
+
+struct acm_automaton;
+/* compat_ocl.c: scanner creation + first launches ahead of the scan loop (ocl_worker_ctx_init) */
+int databuf_prepare(struct databuf *db, struct acm_automaton *aut, int sym_size);
 
 #endif

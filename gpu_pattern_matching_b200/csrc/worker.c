@@ -20,6 +20,7 @@
 #include "../../include/ocl_worker.h"
 #include "../../include/utils.h"
 #include "acm_core.h"
+#include "databuf_priv.h"
 
 static int
 hex_nibble(int ch)
@@ -201,6 +202,9 @@ ocl_worker_ctx_init(struct ocl_worker_ctx *w, int dev_pos, size_t local_ws, size
 
 	w->db = databuf_new(global_ws, max_chunk_size, max_results, mapped, &w->cl);
 	if (!w->db)
+		return -1;
+	/* scanner and kernel code now, as the reference builds its program here (compat_ocl.c:databuf_prepare) */
+	if (databuf_prepare(w->db, acsm_device_automaton(w->acsm), 1) != ACM_OK)
 		return -1;
 
 	w->local_ws = local_ws;

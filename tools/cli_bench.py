@@ -45,4 +45,7 @@ for extra in sys.argv[3:] or ["-w 1", "-w 2", "-w 4", "-w 4 -G 65536", "-w 4 -G 
     by = float(g("Processed bytes").group(1))
     print(f"{extra:22s} matches {g('Matches').group(1)} time {secs:.3f} s  {by / secs / 1e9:.2f} GB/s  "
           f"launches {g('Kernel launches').group(1)}", flush=True)
+    for line in p.stderr.decode().splitlines():        # ACM_DATABUF_STATS=1: where the workers' time went
+        if line.startswith("databuf"):
+            print("    " + line, flush=True)
 subprocess.run(["rm", "-rf", d])

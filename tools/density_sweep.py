@@ -7,6 +7,7 @@ bytes with such material and, beside it, scans a real corpus (the box's shared l
 concatenated), each with GB/s, the kernel split and parity against the CPU walk:
 
     python tools/density_sweep.py [MiB per point, default 1024] [signatures, default 10000] [--corpus GLOB] [--quick]
+                                  [--only zero:0.2]
 
 prints one line per input class and writes profiles/r02_density_sweep.json (when run from the repo).
 The mixes (fraction f of every 64 KiB block is replaced, the rest stays the seeded random stream):
@@ -76,7 +77,8 @@ def corpus(path_glob, want):
 
 
 def main():
-    args = [a for a in sys.argv[1:] if not a.startswith("--")]
+    skip = {i + 1 for i, a in enumerate(sys.argv) if a in ("--corpus", "--only")}
+    args = [a for i, a in enumerate(sys.argv) if i >= 1 and not a.startswith("--") and i not in skip]
     mib = int(args[0]) if args else 1024
     nsig = int(args[1]) if len(args) > 1 else 10000
     cdir = sys.argv[sys.argv.index("--corpus") + 1] if "--corpus" in sys.argv else "/usr/lib/**/*.so*"
@@ -124,6 +126,11 @@ def main():
 
     base = synth.stream(n, 2)
     plants.apply_host(base)
+    if "--only" in sys.argv:                     # one point, e.g. --only zero:0.2 (for ncu)
+        kind, frac = sys.argv[sys.argv.index("--only") + 1].split(":")
+        point(f"{kind} {int(float(frac) * 100)} % of every 64 KiB", mix(base.copy(), kind, float(frac), pats, rng))
+        del owner
+        return
     point("random + planted (bench workload)", base)
     quick = "--quick" in sys.argv
     for kind in ("zero", "prologue", "text"):
