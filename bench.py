@@ -701,7 +701,9 @@ def config4_lexicon(ctx, nbytes):
             "ms": {"k1": step_stats(k1), "k2": step_stats(k2), "k3": step_stats(k3), "total": step_stats(tot)},
             "roofline_frac": nbytes / (med(k1) * 1e-3) / 1e9 / peak,
             "roofline_frac_with_output": (nbytes + 8 * int(off.size)) / (med(tot) * 1e-3) / 1e9 / peak,
-            "kernel": g.MODE_NAMES[res.mode], "matches": int(off.size), "bytes_per_match": nbytes / max(1, off.size),
+            "kernel": "k_scan_rd + k_scan_lookback + k_rd_expand" if res.mode == g.MODE_CDFA else g.MODE_NAMES[res.mode],
+            "traffic": traffic_for("sentiment")[0] if nbytes == GIB else None, "traffic_source": traffic_for("sentiment")[1],
+            "matches": int(off.size), "bytes_per_match": nbytes / max(1, off.size),
             "fallback": int(res.fallback),
             "parity": {"ok": equal, "full_list": True, "cpu_walk": "port (oracle/acsm_oracle.c, python-thread-sharded)",
                        "cpu_matches": int(eo.size), "gpu_matches": int(off.size), "sha256": h.hexdigest(),
@@ -787,11 +789,11 @@ def config3_dfa_leg(ctx):
     del data
     peak, _ = peaks()
     equal = bool(off.size == ro.size and np.array_equal(off, ro) and np.array_equal(pat, rp))
-    return {"config": "configs[2], DFA form: clamav15000 walked one table lookup per byte (k_scan_dfa) over the "
+    return {"config": "configs[2], DFA form: clamav15000 walked one table lookup per byte (k_scan_xd: row-displaced table, hot rows in shared memory) over the "
                       "first 256 MiB of the seed-3 stream, 1 GPU",
             "value": n / (statistics.median(k1) * 1e-3) / 1e9, "unit": "GB/s", "n_gpus": 1,
             "ms_scan": step_stats(k1), "roofline_frac": n / (statistics.median(k1) * 1e-3) / 1e9 / peak,
-            "kernel": "k_scan_dfa", "states": acsm.get_states(), "matches": int(off.size),
+            "kernel": "k_scan_xd<uint8_t>", "states": acsm.get_states(), "matches": int(off.size),
             "parity": {"ok": equal, "against": "the sampled kernel's list on the same bytes (itself checked "
                                                "against the CPU walk in configs[2])",
                        "gpu_matches": int(off.size), "expected": int(ro.size)}}
@@ -881,6 +883,9 @@ def main():
                      "frac": r["achieved"] / r["peak"], "traffic": traffic, "traffic_source": traffic_src,
                      "kernel": r["kernel"], "kernel_ms": r["k1_ms"], "kernel_ms_stats": r["k1_stats"],
                      "algorithmic_bytes_per_launch": per, "peak_source": r["peak_src"],
+                     "note": "peak is the measured COPY bandwidth (half reads, half writes); this kernel only reads, "
+                             "and a read-only sweep with its loads and no other work runs at 7.08 TB/s on this part "
+                             "(profiles/README.md), so frac can exceed 1; whole_step_frac is the step as the caller sees it",
                      "whole_step_frac": per / (r["ms_per_step"] * 1e-3) / 1e9 / r["peak"]},
         "gpu_launches": int(r["launches"]),
         "clocks": r["clocks"],

@@ -1158,8 +1158,9 @@ launch_k1(struct acm_scanner *s, cudaStream_t st, const void *d_data, uint64_t n
 		 * such table: k_resolve_queue walks them, table through L1) */
 		const int dense_kernel = a->d.xd_tab && (size_t)a->d.xd_d1_end * 4 + 64 <= XD_SMEM_MAX &&
 		    !(getenv("ACM_DENSE_KERNEL") && !atoi(getenv("ACM_DENSE_KERNEL")));
-		CUDA_TRY(launch_dep(k_resolve_queue, dim3((unsigned)blocks * (S4_THREADS / 32)), dim3(RQ_THREADS), 0, st, a->d, Eq,
-		    (const uint8_t *)d_data, n, limit, vec_lo, (uint32_t)a->d.sample_stride, dense_kernel ? 0u : 1u));
+		CUDA_TRY(launch_dep(dense_kernel ? k_resolve_queue<false> : k_resolve_queue<true>,
+		    dim3((unsigned)blocks * (S4_THREADS / 32)), dim3(RQ_THREADS), 0, st, a->d, Eq,
+		    (const uint8_t *)d_data, n, limit, vec_lo, (uint32_t)a->d.sample_stride));
 		*launches += 1;
 		if (dense_kernel) {
 			uint32_t slots = a->d.xd_len < XD_SMEM_DEFAULT / 4 ? a->d.xd_len : XD_SMEM_DEFAULT / 4;

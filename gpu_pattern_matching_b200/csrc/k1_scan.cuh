@@ -911,9 +911,12 @@ __device__ __forceinline__ bool rq_candidate(const AutDev &A, const EmitCtx &E, 
 	return (c.w & ACM_CAND_LAST) != 0;
 }
 
+/* DENSE: this kernel also walks the region's dense chunks (automata without a row-displaced table;
+ * the usual instantiation carries none of that code and none of its register pressure) */
+template <bool DENSE>
 __global__ void __launch_bounds__(RQ_THREADS, RQ_MINB)
 k_resolve_queue(const __grid_constant__ AutDev A, const __grid_constant__ EmitCtx E,
-    const uint8_t *__restrict__ data, uint64_t n, uint64_t limit, uint64_t vec_lo, uint32_t stride, uint32_t walk_dense)
+    const uint8_t *__restrict__ data, uint64_t n, uint64_t limit, uint64_t vec_lo, uint32_t stride)
 {
 	pdl_wait();               /* the queues of k_scan_sampled */
 	/* k_dense_walk, launched behind this kernel as its programmatic dependent, needs nothing from it,
@@ -922,7 +925,7 @@ k_resolve_queue(const __grid_constant__ AutDev A, const __grid_constant__ EmitCt
 	pdl_trigger();
 	/* the region's dense chunks first (usually none), when k_dense_walk cannot take them (no
 	 * row-displaced table): one thread per slice, table entries through L1 */
-	if (walk_dense) {
+	if (DENSE) {
 		const uint32_t nd = min(E.dq_count[blockIdx.x], E.dq_cap);
 		const uint32_t *dl = E.dq + (size_t)blockIdx.x * E.dq_cap;
 		const uint32_t per = nd >= 96 ? 1u : (nd >= 48 ? 2u : (nd >= 24 ? 4u : 8u));   /* slices per chunk */

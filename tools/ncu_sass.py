@@ -1,13 +1,19 @@
 """Summarise `ncu -i X.ncu-rep --page source --csv`: per-SASS-instruction executed counts,
-stall samples and shared-memory conflicts.  usage: ncu_sass.py src.csv [top]"""
+stall samples and shared-memory conflicts.  usage: ncu_sass.py src.csv [top] [all|hot] [kernel name substring]"""
 import csv
 import sys
 
 rows = list(csv.reader(open(sys.argv[1])))
 top = int(sys.argv[2]) if len(sys.argv) > 2 else 40
-hdr = rows[1]
+# a report with several kernels has one section per kernel: "Kernel Name",<name> / header / instructions
+starts = [i for i, r in enumerate(rows) if r and r[0] == "Kernel Name"]
+want = sys.argv[4] if len(sys.argv) > 4 else None
+pick = [i for i in starts if want is None or want in rows[i][1]][-1]
+end = min([i for i in starts if i > pick] + [len(rows)])
+print(f"kernel: {rows[pick][1]}")
+hdr = rows[pick + 1]
 ci = {h: i for i, h in enumerate(hdr)}
-body = [r for r in rows[2:] if len(r) >= len(hdr) - 2]
+body = [r for r in rows[pick + 2:end] if len(r) >= len(hdr) - 2]
 tot_ex = sum(int(r[ci["Instructions Executed"]]) for r in body)
 tot_s = sum(int(r[ci["# Samples"]]) for r in body)
 print(f"instructions: {len(body)} SASS, {tot_ex} warp-level executed, {tot_s} samples")
