@@ -970,6 +970,37 @@ build_b3(const struct acm_core *c)
 	return b3;
 }
 
+/*
+ * How common a 4-byte window is in the data a scanner meets, whatever the signature set says: a
+ * window the filter indexes is a window whose every occurrence in the input costs an exact-table
+ * probe and a candidate compare.  Added to the gram's popularity among the signatures when the
+ * indexed window of a (pattern, alignment) is chosen, so that a signature is found through a
+ * window of machine code or binary structure rather than through its run of zeros, its UTF-16
+ * string or its English words when it has the choice (10 000 ClamAV signatures: true gram hits on
+ * English text 9.5 % -> 0.8 % of the aligned windows, on a corpus of shared libraries 0.87 % ->
+ * 0.18 %; tools/density_sweep.py).
+ */
+static uint32_t
+gram_background(uint32_t g)
+{
+	const unsigned b[4] = {g & 255u, (g >> 8) & 255u, (g >> 16) & 255u, g >> 24};
+	unsigned zeros = 0, texty = 0, k;
+
+	if (b[0] == b[1] && b[1] == b[2] && b[2] == b[3])
+		return 1000;                      /* runs: zero pages, erased flash, blanks, NOP sleds */
+	for (k = 0; k < 4; k++) {
+		zeros += b[k] == 0;
+		texty += (b[k] >= 'a' && b[k] <= 'z') || (b[k] >= 'A' && b[k] <= 'Z') || (b[k] >= '0' && b[k] <= '9') ||
+		    b[k] == ' ' || b[k] == '.' || b[k] == ',' || b[k] == '\n' || b[k] == '\r' || b[k] == '-' || b[k] == '_' ||
+		    b[k] == '/';
+	}
+	if (zeros >= 2)
+		return 200;                       /* small little-endian integers, UTF-16 text, padding */
+	if (texty == 4)
+		return 100;                       /* words */
+	return 0;
+}
+
 static int
 build_filters(struct acm_core *c)
 {
@@ -1144,13 +1175,19 @@ build_filters(struct acm_core *c)
 					uint32_t best;
 					const uint32_t g0 = (uint32_t)p[j] | ((uint32_t)p[j + 1] << 8) | ((uint32_t)p[j + 2] << 16) |
 					    ((uint32_t)p[j + 3] << 24);
-					POP_OF(g0, best);
+					uint32_t pop0;
+					POP_OF(g0, pop0);
+					best = pop0 + gram_background(g0);
 					if (best > ACM_CAND_POPULAR) {
 						for (uint32_t o2 = j + S; o2 + 4 <= n && o2 <= ACM_CAND_O_MAX; o2 += S) {
 							uint32_t pc;
 							const uint32_t g2 = (uint32_t)p[o2] | ((uint32_t)p[o2 + 1] << 8) |
 							    ((uint32_t)p[o2 + 2] << 16) | ((uint32_t)p[o2 + 3] << 24);
 							POP_OF(g2, pc);
+							/* never into a longer candidate list than the one it leaves (or a short one) */
+							if (pc > pop0 && pc > ACM_CAND_POPULAR)
+								continue;
+							pc += gram_background(g2);
 							if (pc < best) {
 								best = pc;
 								o = o2;

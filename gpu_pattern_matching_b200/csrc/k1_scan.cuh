@@ -1317,13 +1317,16 @@ __device__ __noinline__ void xd_report(const AutDev *__restrict__ Ap, const Emit
 }
 
 /*
- * The same for a dense chunk of the sampled filter (k_dense_walk): of the patterns that end here only
- * the occurrences whose INDEXED window lies in [lo, lo + len) are this walk's (s4_dense_chunk tells why).
+ * The same for a slice of a dense chunk of the sampled filter (k_dense_walk).  The CHUNK owns the
+ * occurrences whose INDEXED window lies in it (s4_dense_chunk tells why); among the chunk's slices an
+ * occurrence belongs to the one it STARTS in, those that start in front of the chunk to slice 0 -- so
+ * only slice 0 needs the cold start in front of it.  lo / len: the slice; chunk_off = lo - chunk start.
  */
 __device__ __noinline__ void xd_report_win(const AutDev *__restrict__ Ap, const EmitCtx *__restrict__ Ep, uint32_t os,
-    uint64_t pos, uint64_t lo, uint32_t len, uint32_t stride)
+    uint64_t pos, uint64_t lo, uint32_t len, uint32_t stride, uint32_t chunk_off)
 {
 	const AutDev &A = *Ap;
+	const uint64_t chunk_lo = lo - chunk_off, chunk_hi = chunk_lo + 32u * S4_UNROLL * 16u;
 	for (uint32_t v = __ldg(A.xd_sid + os); v; v = __ldg(&A.olink[v])) {
 		const uint32_t b = __ldg(&A.own_begin[v]), t = __ldg(&A.own_begin[v + 1]);
 		for (uint32_t k = b; k < t; ++k) {
@@ -1333,8 +1336,10 @@ __device__ __noinline__ void xd_report_win(const AutDev *__restrict__ Ap, const 
 			if (plen < A.split_len || pos + 1 < plen)
 				continue;
 			const uint64_t s = pos + 1 - plen;
+			if (s >= lo + len || (s < lo && chunk_off != 0))
+				continue;
 			const uint64_t w = s + __ldg(&A.pat_win[(size_t)pid * 8 + ((stride - (uint32_t)(s % stride)) % stride)]);
-			if (s >= Ep->valid_lo && w >= lo && w < lo + len)
+			if (s >= Ep->valid_lo && w >= chunk_lo && w < chunk_hi)
 				emit_record(*Ep, pos, pid);
 		}
 	}
@@ -1352,8 +1357,8 @@ struct XdState {
  * of the previous symbol (x is g then).
  */
 template <bool WIN = false>
-__device__ __forceinline__ void xd_step(const AutDev &A, const EmitCtx &E, const XdLook &L, XdState &S, uint32_t c,
-    uint64_t pos, uint64_t a, uint32_t win_len = 0, uint32_t stride = 0)
+__device__ __forceinline__ bool xd_step(const AutDev &A, const EmitCtx &E, const XdLook &L, XdState &S, uint32_t c,
+    uint64_t pos, uint64_t a, uint32_t win_len = 0, uint32_t stride = 0, uint32_t chunk_off = 0)
 {
 	uint32_t r, g, x;
 	asm("ld.shared.u32 %0, [%1];" : "=r"(r) : "r"(L.tab_sa + c * 4));
@@ -1376,12 +1381,14 @@ __device__ __forceinline__ void xd_step(const AutDev &A, const EmitCtx &E, const
 	const uint32_t nx = okx ? x : (okg ? g : r);
 	S.os = nx >> L.base_shift;
 	S.ob = r >> L.base_shift;
-	if (((nx >> (L.base_shift - 1)) & 1u) && pos >= a) {
+	const bool any = ((nx >> (L.base_shift - 1)) & 1u) != 0;
+	if (any && pos >= a) {
 		if (WIN)
-			xd_report_win(&A, &E, S.os, pos, a, win_len, stride);
+			xd_report_win(&A, &E, S.os, pos, a, win_len, stride, chunk_off);
 		else
 			xd_report(&A, &E, S.os, pos);
 	}
+	return any;
 }
 
 template <typename SYM>
@@ -1508,12 +1515,13 @@ k_scan_xd(const __grid_constant__ AutDev A, const __grid_constant__ EmitCtx E, c
  * lists only, and those are complete before k_resolve_queue starts), so its launch and the empty
  * check hide behind that kernel's last wave; griddepcontrol.wait before the exit keeps "this grid
  * done" meaning "k_resolve_queue done" for what follows in the stream.
- * Otherwise the T chunks are cut into `per` slices each, 1 <= per <= 8, so that every thread has up to
+ * Otherwise the T chunks are cut into `per` slices each, 1 <= per <= 16, so that every thread has up to
  * two walks in lockstep (a handful of zero pages in a buffer must not become a handful of 2 KiB walks on
- * one lane each); a slice is never shorter than the cold start in front of it.  A walk: cold start
- * max_win bytes before the slice (nothing that starts earlier can have its indexed window inside),
- * report the occurrences whose indexed window lies in the slice, and run on behind it until no
- * occurrence that began inside can still be open.
+ * one lane each: with six warps on an SM every step is a bare latency chain).  The chunk owns the
+ * occurrences whose indexed window lies in it; a slice reports those of them that START in it, the
+ * chunk's first slice also those that start in front of the chunk.  So a walk starts at its slice --
+ * the first one max_win bytes early: nothing that starts earlier can have its window in the chunk --
+ * and runs on behind it until no occurrence that began inside can still be open.
  */
 __global__ void __launch_bounds__(XD_THREADS, 1)
 k_dense_walk(const __grid_constant__ AutDev A, const __grid_constant__ EmitCtx E, const uint8_t *__restrict__ data,
@@ -1561,13 +1569,14 @@ k_dense_walk(const __grid_constant__ AutDev A, const __grid_constant__ EmitCtx E
 
 	constexpr uint32_t CHUNK = 32u * S4_UNROLL * 16u;
 	uint32_t per_log = 0;
-	while (per_log < 3 && (T << per_log) < 2 * XD_THREADS && (CHUNK >> (per_log + 1)) >= A.max_win)
+	while (per_log < 4 && (T << per_log) < 2 * XD_THREADS)
 		++per_log;
 	const uint32_t slice = CHUNK >> per_log;
 	const uint32_t items = T << per_log, half = (items + 1) / 2;
 
 	for (uint32_t u = threadIdx.x; u < half; u += XD_THREADS) {
 		uint64_t a[2], b[2], pos[2];
+		uint32_t co[2] = {0u, 0u};                       /* slice start - chunk start */
 		XdState S[2] = {{0u, 0u}, {0u, 0u}};
 #pragma unroll
 		for (int q = 0; q < 2; ++q) {
@@ -1582,13 +1591,17 @@ k_dense_walk(const __grid_constant__ AutDev A, const __grid_constant__ EmitCtx E
 				if (pre[r + st] <= ci)
 					r += st;
 			const uint32_t first = E.dq[(size_t)(blockIdx.x * rpc + r) * E.dq_cap + (ci - pre[r])];
-			a[q] = (vec_lo + first) * 16 + (uint64_t)(item & ((1u << per_log) - 1u)) * slice;
+			co[q] = (item & ((1u << per_log) - 1u)) * slice;
+			a[q] = (vec_lo + first) * 16 + co[q];
 			b[q] = a[q] + slice < limit ? a[q] + slice : limit;
 			if (a[q] >= b[q]) {
 				a[q] = b[q] = 0;
 				continue;
 			}
-			pos[q] = a[q] > A.max_win ? a[q] - A.max_win : 0;
+			/* the chunk's first slice also owns what starts in front of the chunk: cold start there */
+			pos[q] = a[q];
+			if (co[q] == 0)
+				pos[q] = a[q] > A.max_win ? a[q] - A.max_win : 0;
 			if (pos[q] < E.valid_lo)
 				pos[q] = E.valid_lo;
 			/* head: byte by byte up to the next 16-byte boundary */
@@ -1596,17 +1609,35 @@ k_dense_walk(const __grid_constant__ AutDev A, const __grid_constant__ EmitCtx E
 			if (head_end > b[q])
 				head_end = b[q];
 			for (; pos[q] < head_end; ++pos[q])
-				xd_step<true>(A, E, L, S[q], data[pos[q]], pos[q], a[q], slice, stride);
+				xd_step<true>(A, E, L, S[q], data[pos[q]], pos[q], a[q], slice, stride, co[q]);
 		}
-		/* body: whole vectors of both slices in lockstep */
+		/*
+		 * body: whole vectors of both slices in lockstep.  Sixteen equal bytes (zero pages, padding,
+		 * erased flash: most of what makes a chunk dense) whose first step leaves the walk where it
+		 * was, in a state that reports nothing: the other fifteen steps would do the same -- the
+		 * transition depends on (state, byte) only -- and are skipped.
+		 */
+		auto constant = [](const uint4 &v) {
+			const uint32_t rep = (v.x & 0xFFu) * 0x01010101u;
+			return v.x == rep && v.y == rep && v.z == rep && v.w == rep;
+		};
 		while (pos[0] + 16 <= b[0] && pos[1] + 16 <= b[1]) {
 			const uint4 v0 = __ldg(reinterpret_cast<const uint4 *>(data + pos[0]));
 			const uint4 v1 = __ldg(reinterpret_cast<const uint4 *>(data + pos[1]));
 			const uint32_t w0[4] = {v0.x, v0.y, v0.z, v0.w}, w1[4] = {v1.x, v1.y, v1.z, v1.w};
+			const XdState P0 = S[0], P1 = S[1];
+			const bool r0 = xd_step<true>(A, E, L, S[0], w0[0] & 0xFFu, pos[0], a[0], slice, stride, co[0]);
+			const bool r1 = xd_step<true>(A, E, L, S[1], w1[0] & 0xFFu, pos[1], a[1], slice, stride, co[1]);
+			const bool skip0 = !r0 && S[0].os == P0.os && S[0].ob == P0.ob && constant(v0);
+			const bool skip1 = !r1 && S[1].os == P1.os && S[1].ob == P1.ob && constant(v1);
+			if (!(skip0 && skip1)) {
 #pragma unroll
-			for (uint32_t k = 0; k < 16; ++k) {
-				xd_step<true>(A, E, L, S[0], (w0[k / 4] >> ((k % 4) * 8)) & 0xFFu, pos[0] + k, a[0], slice, stride);
-				xd_step<true>(A, E, L, S[1], (w1[k / 4] >> ((k % 4) * 8)) & 0xFFu, pos[1] + k, a[1], slice, stride);
+				for (uint32_t k = 1; k < 16; ++k) {
+					if (!skip0)
+						xd_step<true>(A, E, L, S[0], (w0[k / 4] >> ((k % 4) * 8)) & 0xFFu, pos[0] + k, a[0], slice, stride, co[0]);
+					if (!skip1)
+						xd_step<true>(A, E, L, S[1], (w1[k / 4] >> ((k % 4) * 8)) & 0xFFu, pos[1] + k, a[1], slice, stride, co[1]);
+				}
 			}
 			pos[0] += 16;
 			pos[1] += 16;
@@ -1616,18 +1647,36 @@ k_dense_walk(const __grid_constant__ AutDev A, const __grid_constant__ EmitCtx E
 			for (; pos[q] + 16 <= b[q]; pos[q] += 16) {
 				const uint4 v = __ldg(reinterpret_cast<const uint4 *>(data + pos[q]));
 				const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+				const XdState P = S[q];
+				if (!xd_step<true>(A, E, L, S[q], w[0] & 0xFFu, pos[q], a[q], slice, stride, co[q]) && S[q].os == P.os &&
+				    S[q].ob == P.ob && constant(v))
+					continue;
 #pragma unroll
-				for (uint32_t k = 0; k < 16; ++k)
-					xd_step<true>(A, E, L, S[q], (w[k / 4] >> ((k % 4) * 8)) & 0xFFu, pos[q] + k, a[q], slice, stride);
+				for (uint32_t k = 1; k < 16; ++k)
+					xd_step<true>(A, E, L, S[q], (w[k / 4] >> ((k % 4) * 8)) & 0xFFu, pos[q] + k, a[q], slice, stride, co[q]);
 			}
 			for (; pos[q] < b[q]; ++pos[q])
-				xd_step<true>(A, E, L, S[q], data[pos[q]], pos[q], a[q], slice, stride);
-			/* behind the slice: until the longest open prefix began behind it */
+				xd_step<true>(A, E, L, S[q], data[pos[q]], pos[q], a[q], slice, stride, co[q]);
+			/* behind the slice: until the longest open prefix began behind it (d bytes read beyond the
+			 * slice, state shallower than d + 1).  Inside a run of equal bytes the state sits at a fixed
+			 * point as deep as the longest signature prefix made of that byte -- a hundred and more
+			 * zeros -- so the run is skipped a vector at a time here as well; testing the depth only
+			 * after a skipped vector can overshoot by 15 steps, which report nothing they do not own. */
 			if (a[q] < b[q]) {
 				const uint64_t end = b[q] + (uint64_t)A.max_len < limit ? b[q] + (uint64_t)A.max_len : limit;
-				for (; pos[q] < end; ++pos[q]) {
-					xd_step<true>(A, E, L, S[q], data[pos[q]], pos[q], a[q], slice, stride);
-					const uint64_t d = pos[q] - b[q] + 1;
+				while (pos[q] < end) {
+					bool skipped = false;
+					if ((pos[q] & 15) == 0 && pos[q] + 16 <= end) {
+						const uint4 v = __ldg(reinterpret_cast<const uint4 *>(data + pos[q]));
+						const XdState P = S[q];
+						const bool r = xd_step<true>(A, E, L, S[q], v.x & 0xFFu, pos[q], a[q], slice, stride, co[q]);
+						skipped = !r && S[q].os == P.os && S[q].ob == P.ob && constant(v);
+						pos[q] += skipped ? 16 : 1;
+					} else {
+						xd_step<true>(A, E, L, S[q], data[pos[q]], pos[q], a[q], slice, stride, co[q]);
+						++pos[q];
+					}
+					const uint64_t d = pos[q] - b[q];
 					if (__ldg(A.xd_sid + S[q].os) < __ldg(&A.level_start[d + 1 <= (uint64_t)A.max_len ? d + 1 : (uint64_t)A.max_len]))
 						break;
 				}

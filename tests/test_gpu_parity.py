@@ -254,6 +254,35 @@ def test_dense_chunks_next_to_filter_chunks_own_by_indexed_window(device, dq_cap
     assert_same(off, pat, eo, ep, f"mixed dense / filter chunks, stride 4, dq_cap {dq_cap}")
 
 
+def test_constant_runs_in_dense_chunks(device):
+    """The dense walk skips the rest of a 16-byte vector of equal bytes once a step has left it in the
+    same silent state.  Runs of 0x00, 0xFF and 0x90 with signatures that ARE such runs (every position
+    of a long enough run reports), that end in one, and that begin with one: the oracle's list."""
+    base = clamav_pats(10000)
+    extra = [b"\0" * 12, b"\xff" * 16, b"\0" * 11 + b"\x01", b"\x02" + b"\0" * 13, b"\x90" * 10 + b"\xcc\xcc",
+             b"\xff" * 9 + b"\0" * 9]
+    pats = base + [(p, len(base) + i) for i, p in enumerate(extra)]
+    o, a = build_oracle(pats), build_product(pats)
+    n = 4 << 20
+    buf = synth.stream(n, 5)
+    v = buf.reshape(-1, 64 << 10)
+    v[0::4, :5000] = 0
+    v[1::4, 100:4200] = 0xFF
+    v[2::4, 7:2300] = 0x90
+    v[3::4, 2048:6144] = 0
+    v[3::4, 4000] = 1                       # 0...0 01 inside a zero run
+    v[2::4, 2300:2302] = 0xCC
+    v[1::4, 4200:4212] = 0                  # ff..ff 00..00
+    v[0::4, 6000] = 2
+    v[0::4, 6001:6030] = 0                  # 02 00..00 behind a chunk border
+    eo, ep, _, _ = o.search(buf)
+    assert eo.size > 100000
+    off, pat, res = gpu_scan(device, a, buf, g.MODE_SAMPLED4)
+    assert_same(off, pat, eo, ep, "constant runs")
+    off, pat, res = gpu_scan(device, a, buf, g.MODE_DFA)
+    assert_same(off, pat, eo, ep, "constant runs, dfa")
+
+
 @pytest.mark.parametrize("cap", [1, 3, 16])
 def test_resolve_queue_overflow_takes_inline_path(device, cap, monkeypatch):
     """The sampled kernel queues its filter survivors for k_resolve_queue; when a warp's region is
