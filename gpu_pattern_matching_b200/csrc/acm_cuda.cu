@@ -1167,8 +1167,10 @@ launch_k1(struct acm_scanner *s, cudaStream_t st, const void *d_data, uint64_t n
 			slots &= ~3u;
 			if (slots < ((a->d.xd_d1_end + 3) & ~3u))
 				slots = (a->d.xd_d1_end + 3) & ~3u;
-			CUDA_TRY(launch_dep(k_dense_walk, dim3((unsigned)blocks), dim3(XD_THREADS), (size_t)slots * 4 + 64, st, a->d, Eq,
-			    (const uint8_t *)d_data, limit, vec_lo, (uint32_t)a->d.sample_stride, (uint32_t)(S4_THREADS / 32), slots));
+			const uint32_t nreg = (uint32_t)blocks * (S4_THREADS / 32);
+			CUDA_TRY(launch_dep(k_dense_walk, dim3((unsigned)blocks), dim3(XD_THREADS),
+			    (size_t)slots * 4 + 16 + ((size_t)nreg + 1) * 4 + 64, st, a->d, Eq,
+			    (const uint8_t *)d_data, limit, vec_lo, (uint32_t)a->d.sample_stride, nreg, slots));
 			*launches += 1;
 		}
 		if (a->d.split_len) {

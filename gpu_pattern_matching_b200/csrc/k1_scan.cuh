@@ -331,6 +331,7 @@ __device__ __forceinline__ uint4 load_vec(const uint8_t *__restrict__ data, uint
 #define S4_INTERLEAVE 0                  /* 1: the 32 runs of a block are interleaved chunk by chunk */
 #endif
 #define S4_BLOCK_RUNS 32                 /* runs per block = warps per CTA */
+#define DQ_ANY_WORD 10                   /* flags[10]: some warp queued a dense chunk this step */
 #define S4_SLOTS 4                       /* published blocks per CTA (ring) */
 #ifndef S4_PF_DIST
 #define S4_PF_DIST 1                     /* L2 prefetch distance in chunks (1 .. S4_UNIT_CHUNKS) */
@@ -693,8 +694,11 @@ k_scan_sampled(const __grid_constant__ AutDev A, const __grid_constant__ EmitCtx
 		if (__reduce_add_sync(FULL_MASK, (uint32_t)__popc(hits)) >= NW * 32 / 4) {
 			/* dense: queue the chunk for k_resolve_queue (a full list: walk it here, one lane, slowly) */
 			if (lane == 0) {
-				if (dq_n < E.dq_cap)
+				if (dq_n < E.dq_cap) {
+					if (dq_n == 0)
+						E.overflow[DQ_ANY_WORD] = 1u;
 					dq_mine[dq_n++] = (uint32_t)(cur_first - vec_lo);
+				}
 				else
 					s4_dense_chunk(&A, &E, data, cur_first * 16, cur_first * 16 + chunk_vecs * 16, limit, STRIDE);
 			}
@@ -1509,8 +1513,9 @@ k_scan_xd(const __grid_constant__ AutDev A, const __grid_constant__ EmitCtx E, c
  * walked out of the row-displaced table with its hot rows in shared memory, the way k_scan_xd walks a
  * whole buffer.
  *
- * CTA b takes the lists of scanning CTA b's warps (`rpc` regions).  No dense chunk -- random-looking
- * input, the usual case: the CTA is done after reading its `rpc` counters, before anything is staged.
+ * The slices of all queued chunks form one list that the grid shares out thread by thread.  No dense
+ * chunk -- random-looking input, the usual case: a CTA is done after reading one word (flags[10], set by
+ * the scanning warp that queues its first chunk), before anything is staged.
  * The kernel is launched as the programmatic dependent of k_resolve_queue (it needs k_scan_sampled's
  * lists only, and those are complete before k_resolve_queue starts), so its launch and the empty
  * check hide behind that kernel's last wave; griddepcontrol.wait before the exit keeps "this grid
@@ -1525,30 +1530,18 @@ k_scan_xd(const __grid_constant__ AutDev A, const __grid_constant__ EmitCtx E, c
  */
 __global__ void __launch_bounds__(XD_THREADS, 1)
 k_dense_walk(const __grid_constant__ AutDev A, const __grid_constant__ EmitCtx E, const uint8_t *__restrict__ data,
-    uint64_t limit, uint64_t vec_lo, uint32_t stride, uint32_t rpc, uint32_t smem_slots)
+    uint64_t limit, uint64_t vec_lo, uint32_t stride, uint32_t nreg, uint32_t smem_slots)
 {
 	extern __shared__ __align__(128) uint32_t xd_smem[];
-	__shared__ uint32_t pre[33];                     /* chunks in the regions before region r of this CTA */
-	if (threadIdx.x < 32) {
-		uint32_t sum = threadIdx.x < rpc ? min(E.dq_count[blockIdx.x * rpc + threadIdx.x], E.dq_cap) : 0u;
-#pragma unroll
-		for (int d = 1; d < 32; d <<= 1) {
-			const uint32_t t = __shfl_up_sync(FULL_MASK, sum, d);
-			if ((int)threadIdx.x >= d)
-				sum += t;
-		}
-		pre[threadIdx.x + 1] = sum;
-		if (threadIdx.x == 0)
-			pre[0] = 0;
-	}
-	__syncthreads();
-	const uint32_t T = pre[32];
+	__shared__ uint32_t s_warp[XD_THREADS / 32];
+	/* nothing queued anywhere (random-looking input, the usual case): one word read, done */
 	pdl_trigger();
-	if (T == 0) {
+	if (((volatile uint32_t *)E.overflow)[DQ_ANY_WORD] == 0) {
 		pdl_wait();
 		return;
 	}
 	uint64_t *bar = reinterpret_cast<uint64_t *>(xd_smem + smem_slots);
+	uint32_t *pre = reinterpret_cast<uint32_t *>(bar + 2);     /* [nreg + 1]: chunks queued in the regions before r */
 	if (threadIdx.x == 0) {
 		const uint32_t bytes = smem_slots * 4;
 		mbar_init(bar, 1);
@@ -1557,7 +1550,40 @@ k_dense_walk(const __grid_constant__ AutDev A, const __grid_constant__ EmitCtx E
 			bulk_g2s(reinterpret_cast<uint8_t *>(xd_smem) + off, reinterpret_cast<const uint8_t *>(A.xd_tab) + off,
 			    min(bytes - off, 16384u), bar);
 	}
+	/* exclusive prefix sum over ALL regions' counts, the same in every CTA: the slices of all dense chunks
+	 * are one list that the whole grid shares out, thread by thread (a few dense chunks in a buffer --
+	 * real files: padding, a zero page here and there -- used to be walked by the six warps of the CTA
+	 * whose scanning twin had met them while the other SMs had nothing to do) */
+	{
+		const uint32_t per_t = (nreg + XD_THREADS - 1) / XD_THREADS;
+		const uint32_t r0 = threadIdx.x * per_t;
+		uint32_t sum = 0;
+		for (uint32_t k = 0; k < per_t; ++k)
+			if (r0 + k < nreg)
+				sum += min(E.dq_count[r0 + k], E.dq_cap);
+		uint32_t inc = sum;
+#pragma unroll
+		for (int d = 1; d < 32; d <<= 1) {
+			const uint32_t t = __shfl_up_sync(FULL_MASK, inc, d);
+			if ((int)(threadIdx.x & 31) >= d)
+				inc += t;
+		}
+		if ((threadIdx.x & 31) == 31)
+			s_warp[threadIdx.x >> 5] = inc;
+		__syncthreads();
+		uint32_t run = inc - sum;
+		for (uint32_t w = 0; w < (threadIdx.x >> 5); ++w)
+			run += s_warp[w];
+		for (uint32_t k = 0; k < per_t; ++k)
+			if (r0 + k < nreg) {
+				pre[r0 + k] = run;
+				run += min(E.dq_count[r0 + k], E.dq_cap);
+			}
+		if (r0 < nreg && r0 + per_t >= nreg)
+			pre[nreg] = run;
+	}
 	__syncthreads();
+	const uint32_t T = pre[nreg];
 	mbar_wait(bar, 0);
 
 	XdLook L;
@@ -1569,29 +1595,35 @@ k_dense_walk(const __grid_constant__ AutDev A, const __grid_constant__ EmitCtx E
 
 	constexpr uint32_t CHUNK = 32u * S4_UNROLL * 16u;
 	uint32_t per_log = 0;
-	while (per_log < 4 && (T << per_log) < 2 * XD_THREADS)
+	const uint32_t G = gridDim.x * XD_THREADS;       /* walkers in the grid, two walks each at a time */
+	while (per_log < 4 && ((uint64_t)T << per_log) < 2ull * G)
 		++per_log;
 	const uint32_t slice = CHUNK >> per_log;
-	const uint32_t items = T << per_log, half = (items + 1) / 2;
+	const uint64_t items = (uint64_t)T << per_log;
 
-	for (uint32_t u = threadIdx.x; u < half; u += XD_THREADS) {
+	/* consecutive threads take consecutive slices (neighbours share lines of text and of the table) */
+	for (uint64_t u = (uint64_t)blockIdx.x * XD_THREADS + threadIdx.x; u < items; u += 2ull * G) {
 		uint64_t a[2], b[2], pos[2];
 		uint32_t co[2] = {0u, 0u};                       /* slice start - chunk start */
 		XdState S[2] = {{0u, 0u}, {0u, 0u}};
 #pragma unroll
 		for (int q = 0; q < 2; ++q) {
-			const uint32_t item = u + q * half;
+			const uint64_t item = u + (uint64_t)q * G;
 			a[q] = b[q] = pos[q] = 0;
 			if (item >= items)
 				continue;
-			const uint32_t ci = item >> per_log;
-			uint32_t r = 0;
-#pragma unroll
-			for (uint32_t st = 16; st; st >>= 1)
-				if (pre[r + st] <= ci)
-					r += st;
-			const uint32_t first = E.dq[(size_t)(blockIdx.x * rpc + r) * E.dq_cap + (ci - pre[r])];
-			co[q] = (item & ((1u << per_log) - 1u)) * slice;
+			const uint32_t ci = (uint32_t)(item >> per_log);
+			/* the region r with pre[r] <= ci < pre[r + 1] */
+			uint32_t r = 0, hi = nreg;
+			while (hi - r > 1) {
+				const uint32_t mid = (r + hi) >> 1;
+				if (pre[mid] <= ci)
+					r = mid;
+				else
+					hi = mid;
+			}
+			const uint32_t first = E.dq[(size_t)r * E.dq_cap + (ci - pre[r])];
+			co[q] = ((uint32_t)item & ((1u << per_log) - 1u)) * slice;
 			a[q] = (vec_lo + first) * 16 + co[q];
 			b[q] = a[q] + slice < limit ? a[q] + slice : limit;
 			if (a[q] >= b[q]) {
@@ -1658,23 +1690,30 @@ k_dense_walk(const __grid_constant__ AutDev A, const __grid_constant__ EmitCtx E
 			for (; pos[q] < b[q]; ++pos[q])
 				xd_step<true>(A, E, L, S[q], data[pos[q]], pos[q], a[q], slice, stride, co[q]);
 			/* behind the slice: until the longest open prefix began behind it (d bytes read beyond the
-			 * slice, state shallower than d + 1).  Inside a run of equal bytes the state sits at a fixed
-			 * point as deep as the longest signature prefix made of that byte -- a hundred and more
-			 * zeros -- so the run is skipped a vector at a time here as well; testing the depth only
-			 * after a skipped vector can overshoot by 15 steps, which report nothing they do not own. */
+			 * slice, state shallower than d + 1).  The test costs two dependent global loads (state id,
+			 * level table), so it is made once per 16-byte vector, not per byte: running up to 15 steps
+			 * too far reports nothing the slice does not own.  Inside a run of equal bytes the state sits
+			 * at a fixed point as deep as the longest signature prefix made of that byte -- a hundred
+			 * and more zeros -- and the run is skipped a vector at a time here as well. */
 			if (a[q] < b[q]) {
 				const uint64_t end = b[q] + (uint64_t)A.max_len < limit ? b[q] + (uint64_t)A.max_len : limit;
 				while (pos[q] < end) {
-					bool skipped = false;
 					if ((pos[q] & 15) == 0 && pos[q] + 16 <= end) {
 						const uint4 v = __ldg(reinterpret_cast<const uint4 *>(data + pos[q]));
+						const uint32_t w[4] = {v.x, v.y, v.z, v.w};
 						const XdState P = S[q];
-						const bool r = xd_step<true>(A, E, L, S[q], v.x & 0xFFu, pos[q], a[q], slice, stride, co[q]);
-						skipped = !r && S[q].os == P.os && S[q].ob == P.ob && constant(v);
-						pos[q] += skipped ? 16 : 1;
+						const bool r = xd_step<true>(A, E, L, S[q], w[0] & 0xFFu, pos[q], a[q], slice, stride, co[q]);
+						if (r || S[q].os != P.os || S[q].ob != P.ob || !constant(v)) {
+#pragma unroll
+							for (uint32_t k = 1; k < 16; ++k)
+								xd_step<true>(A, E, L, S[q], (w[k / 4] >> ((k % 4) * 8)) & 0xFFu, pos[q] + k, a[q], slice, stride, co[q]);
+						}
+						pos[q] += 16;
 					} else {
 						xd_step<true>(A, E, L, S[q], data[pos[q]], pos[q], a[q], slice, stride, co[q]);
 						++pos[q];
+						if ((pos[q] & 15) != 0 && pos[q] < end)
+							continue;
 					}
 					const uint64_t d = pos[q] - b[q];
 					if (__ldg(A.xd_sid + S[q].os) < __ldg(&A.level_start[d + 1 <= (uint64_t)A.max_len ? d + 1 : (uint64_t)A.max_len]))
