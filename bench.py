@@ -19,9 +19,11 @@ match, so parity and emission would be vacuous).  At N GPUs the stream is N GiB,
   e2e_databuf  the same through the reference-shaped entry points, one 128 MiB databuf at a time:
              databuf_copy_host_to_device -> ocl_aho_match -> databuf_copy_device_to_host ->
              databuf_process_results (reference ocl_aho_grep.c:116-137)
-  roofline   the scan stage alone (CUDA events inside the library around the scan kernels) against
-             the measured HBM copy bandwidth in MEASURED_PEAKS.json; algorithmic traffic = 1 B per
-             input byte
+  roofline   the dominant kernel, k_scan_sampled<8>, alone (timing mode 3: the library's own CUDA
+             events around that launch) against the measured HBM copy bandwidth in
+             MEASURED_PEAKS.json; algorithmic traffic = 1 B per input byte; traffic = that kernel's
+             DRAM bytes per launch from the committed ncu capture of the same config
+             (profiles/traffic.json); whole_step_frac = the step as the caller sees it
   parity     checked IN THIS RUN, at every N, on the gathered list of the last timed step: strictly
              sorted; every planted (end offset, pattern) present; the matches inside a window that
              straddles the first shard cut (the whole stream at N = 1) counted by the reference CPU
