@@ -172,7 +172,10 @@ class Scanner:
 
     def close(self):
         if self._h:
-            self.L.acm_scanner_free(self._h)
+            # acm_scanner_free uses the device (ordinal, streams): after Device.close() that handle is
+            # freed memory, so the scanner is abandoned instead (its buffers stay until the process ends)
+            if getattr(self.device, "_h", None):
+                self.L.acm_scanner_free(self._h)
             self._h = None
 
     def __del__(self):
