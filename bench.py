@@ -375,11 +375,13 @@ def run_stream_config(ctx, nsigs, per, seed, steps, warmup, tail_for_clocks=Fals
     emit_lo = lo - read_lo
     key_add = read_lo << sharded.KEY_PAT_BITS
     cap_keys = max(1 << 21, int(2.5 * PLANTS_PER_GIB * per / GIB))
-    # two scanners, one stream: every kernel of a step is the programmatic dependent of the one before
-    # it (launch set-up and CTA residency under the predecessor's tail); timing 3 = events around the
-    # streaming kernel alone.  BENCH_OWN_STREAMS=1: a stream per scanner instead (measured: no gain --
-    # the small kernels of step i only take from the streaming kernel of step i + 1 what they use)
-    own = os.environ.get("BENCH_OWN_STREAMS", "0") != "0"
+    # two scanners, each on its own stream: the scan stage of step i + 1 waits for the scan stage of
+    # step i only, so the prefix sum / compaction / status kernels of step i run under the streaming
+    # kernel of step i + 1, on the 8 SMs that kernel leaves free (acm_cuda.cu: reserve_sms); within a
+    # step every kernel is the programmatic dependent of the one before it; timing 3 = events around
+    # the streaming kernel alone.  BENCH_OWN_STREAMS=0: both scanners on one stream (0.215 against
+    # 0.204 ms per 1 GiB step)
+    own = os.environ.get("BENCH_OWN_STREAMS", "1") != "0"
     pipe = sharded.StepPipeline(dev, acsm.automaton, hi - lo, cap_keys, rank, world,
                                 scanner_kwargs={"timing": 0 if os.environ.get("BENCH_NO_KERNEL_TIMING") else
                                                 int(os.environ.get("BENCH_TIMING", "3")), "own_stream": own})
@@ -469,7 +471,9 @@ def run_stream_config(ctx, nsigs, per, seed, steps, warmup, tail_for_clocks=Fals
         "launches": launches, "k1_ms": k1_avg, "k1_stats": step_stats(k1_ms), "achieved": achieved, "peak": peak,
         "peak_src": peak_src, "clocks": clocks, "parity": parity, "e2e": e2e, "e2e_databuf": e2e_db,
         "kernel": "k_scan_" + g.MODE_NAMES[mode] + (
-            f"<{stride}>" + (" (the streaming kernel alone: its event pair)"
+            f"<{stride}>" + (" (the streaming kernel alone: its event pair" +
+                             ("; the other scanner's prefix sum / compaction run beside it on 8 SMs it leaves free)"
+                              if own else ")")
                              if os.environ.get("BENCH_TIMING", "3") == "3" else
                              " + k_resolve_queue (scan stage: both launches inside one event pair)") if mode == 1 else ""),
     }

@@ -38,6 +38,11 @@ struct acm_device {
 	cudaStream_t stream;        /* own_stream or an adopted one */
 	cudaStream_t copy_stream;   /* H2D staging for acm_scan_host, side D2H */
 	cudaEvent_t  side_ev;
+	/* scanners with their own streams (acm_scan_params.own_stream): the scan stage of a step waits
+	 * for the scan stage of the step launched before it on ANOTHER scanner, not for that step's
+	 * post-pass -- k1_ev is that scanner's event, recorded behind its scan-stage kernels */
+	cudaEvent_t  k1_ev;
+	struct acm_scanner *k1_owner;
 	/* scratch for the stand-alone scan / sort entry points */
 	uint64_t    *tile_state;
 	uint32_t    *tile_counter;
@@ -115,6 +120,8 @@ struct acm_scanner {
 	cudaEvent_t ev_done;
 	cudaStream_t own_stream;    /* acm_scan_params.own_stream: this scanner's scans run here, not on the device's stream */
 	cudaEvent_t  ev_dep;        /* orders a scan on own_stream behind what the device's stream held at launch */
+	cudaEvent_t  ev_k1;         /* own_stream: recorded behind the scan-stage kernels of a step (acm_device.k1_ev) */
+	uint32_t     reserve_sms;   /* own_stream: SMs the persistent scan kernel leaves to the other scanner's post-pass */
 };
 
 /* ------------------------------------------------------------------------- */
@@ -813,6 +820,13 @@ acm_scanner_free(struct acm_scanner *s)
 	}
 	if (s->ev_dep)
 		cudaEventDestroy(s->ev_dep);
+	if (s->ev_k1) {
+		if (s->dev->k1_owner == s) {
+			s->dev->k1_owner = NULL;
+			s->dev->k1_ev = NULL;
+		}
+		cudaEventDestroy(s->ev_k1);
+	}
 	cudaFree(s->buckets); cudaFree(s->scratch); cudaFree(s->offsets);
 	cudaFree(s->tile_state); cudaFree(s->out); cudaFree(s->tmp); cudaFree(s->hist);
 	cudaFree(s->stage[0]); cudaFree(s->stage[1]); cudaFree(s->trace);
@@ -1056,7 +1070,17 @@ acm_scanner_create(struct acm_device *dev, struct acm_automaton *aut, uint64_t m
 		cudaEventCreate(&s->ev[i]);
 	cudaEventCreateWithFlags(&s->ev_done, cudaEventDisableTiming);
 	if (s->p.own_stream) {
+		/* ACM_RESERVE_SMS (default 8 of 148): the scan kernel is persistent, one CTA per SM, and takes
+		 * the whole SM; the few it leaves free are where the prefix sum / compaction / status kernels
+		 * of the step before run, under this step's scan.  The scan kernel is bound by HBM, not by
+		 * SM count: 140 CTAs stream the GiB in 0.167 ms, 148 in 0.162.  Measured 1 GiB step: 0.2153 ms
+		 * on one stream; own streams with 0 / 2 / 4 / 8 / 12 / 16 / 24 SMs left free: 0.2068 / 0.2047 /
+		 * 0.2045 / 0.2037 / 0.2056 / 0.2072 / 0.2155 */
+		s->reserve_sms = getenv("ACM_RESERVE_SMS") ? (uint32_t)atoi(getenv("ACM_RESERVE_SMS")) : 8u;
+		if (s->reserve_sms >= (uint32_t)dev->sm_count)
+			s->reserve_sms = 0;
 		if (cudaStreamCreateWithFlags(&s->own_stream, cudaStreamNonBlocking) != cudaSuccess ||
+		    cudaEventCreateWithFlags(&s->ev_k1, cudaEventDisableTiming) != cudaSuccess ||
 		    cudaEventCreateWithFlags(&s->ev_dep, cudaEventDisableTiming) != cudaSuccess) {
 			acm_set_error("scanner_create: cannot create the scanner's stream");
 			acm_scanner_free(s);
@@ -1133,8 +1157,17 @@ launch_k1(struct acm_scanner *s, cudaStream_t st, const void *d_data, uint64_t n
 		 * from the block; then the queued candidates are compared in full, one CTA per scanning warp */
 		const uint64_t unit = 32ull * S4_UNROLL * S4_UNIT_CHUNKS * (S4_THREADS / 32);
 		uint64_t blocks = (vec_hi - vec_lo + unit - 1) / unit;
-		if (blocks > (uint64_t)s->dev->sm_count)
-			blocks = s->dev->sm_count;
+		/* the SMs left to the other scanner's post-pass: that work has a whole scan to hide under, so
+		 * the longer the scan, the fewer it needs (8 for 1 GiB, 2 from 4 GiB on) */
+		uint32_t reserve = s->reserve_sms;
+		const uint64_t span_bytes = (vec_hi - vec_lo) * 16;
+		if (reserve > 2 && span_bytes > (1ull << 30)) {
+			reserve = (uint32_t)((uint64_t)reserve * (1ull << 30) / span_bytes);
+			if (reserve < 2)
+				reserve = 2;
+		}
+		if (blocks > (uint64_t)s->dev->sm_count - reserve)
+			blocks = (uint64_t)s->dev->sm_count - reserve;
 		if (zero_work_counter)
 			CUDA_TRY(cudaMemsetAsync(s->flags + 6, 0, 8, st));
 		EmitCtx Eq = E;
@@ -1391,11 +1424,18 @@ scan_launch(struct acm_scanner *s, cudaStream_t st, const void *d_data, uint64_t
 	/* flags (incl. the K1 work counters and the scan's tile counter), tile states, counts (k_scan_rd
 	 * writes every chunk's count and every region's log length itself) */
 	CUDA_TRY(cudaMemsetAsync(s->scratch, 0, 64 + (size_t)s->n_bucket_tiles * 8 + (s->rd ? 0 : (size_t)nb * 4), st));
+	if (s->own_stream && st == s->own_stream && s->dev->k1_owner && s->dev->k1_owner != s)
+		CUDA_TRY(cudaStreamWaitEvent(st, s->dev->k1_ev, 0));
 	if (timing)
 		CUDA_TRY(cudaEventRecord(s->ev[0], st));
 	if ((rc = launch_k1(s, st, d_data, n, E, 0, &launches)) != ACM_OK)
 		return rc;
 	launches++;
+	if (s->own_stream && st == s->own_stream) {
+		CUDA_TRY(cudaEventRecord(s->ev_k1, st));
+		s->dev->k1_ev = s->ev_k1;
+		s->dev->k1_owner = s;
+	}
 	if (timing && !(timing == 3 && s->p.mode == ACM_MODE_SAMPLED4))
 		CUDA_TRY(cudaEventRecord(s->ev[1], st));
 	const int cdfa = s->p.mode == ACM_MODE_CDFA;

@@ -100,8 +100,12 @@ def _worker(rank, world, port, total, outdir):
     dist.destroy_process_group()
 
 
-def test_step_pipeline_single_rank(tmp_path):
-    """world == 1: same pipeline, no torch.distributed, list checked against the oracle."""
+@pytest.mark.parametrize("own_stream", [False, True])
+def test_step_pipeline_single_rank(tmp_path, own_stream):
+    """world == 1: same pipeline, no torch.distributed, list checked against the oracle.  own_stream:
+    every scanner on its own stream -- the scan stage of a step waits for the scan stage of the step
+    before it (the other scanner's), whose post-pass then runs under it on the SMs the persistent
+    scan kernel leaves free; different input every step, so a stale list would show."""
     if not torch.cuda.is_available():
         pytest.fail("gpu test selected but no CUDA device is visible")
     import gpu_pattern_matching_b200 as g
@@ -114,18 +118,27 @@ def test_step_pipeline_single_rank(tmp_path):
     dev = g.Device(0)
     d = dev.alloc(buf.size + 64)
     dev.h2d(d, buf)
-    pipe = sharded.StepPipeline(dev, a.automaton, buf.size, 1 << 14)
+    # a second, different buffer: steps alternate between the two
+    buf2, _ = planted_stream(pats, buf.size, seed=10, plants=300)
+    eo2, ep2, _, _ = o.search(buf2)
+    d2 = dev.alloc(buf2.size + 64)
+    dev.h2d(d2, buf2)
+    dev.sync()
+    pipe = sharded.StepPipeline(dev, a.automaton, buf.size, 1 << 14, scanner_kwargs={"own_stream": own_stream})
     got = []
-    for it in range(6):
-        pipe.submit(d, buf.size, 0, buf.size, 0)
+    for it in range(8):
+        pipe.submit(d2 if it % 2 else d, buf.size, 0, buf.size, 0)
         if it > 0:
             got.append(pipe.complete())
     got.append(pipe.complete())
-    for res, tot, keys in got:
+    assert len(got) == 8
+    for it, (res, tot, keys) in enumerate(got):
         goff, gpat = sharded.unpack_keys(np.array(keys, copy=True))
-        assert tot == eo.size and np.array_equal(goff, eo) and np.array_equal(gpat, ep)
+        wo, wp = (eo2, ep2) if it % 2 else (eo, ep)
+        assert tot == wo.size and np.array_equal(goff, wo) and np.array_equal(gpat, wp), f"step {it}"
     pipe.close()
     dev.free(d)
+    dev.free(d2)
     dev.close()
 
 
