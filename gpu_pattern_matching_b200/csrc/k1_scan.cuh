@@ -860,8 +860,10 @@ k_scan_sampled(const __grid_constant__ AutDev A, const __grid_constant__ EmitCtx
  */
 #define RQ_THREADS 128
 #ifndef RQ_MINB
-#define RQ_MINB 10                          /* <= 51 registers: the (rare, out-of-line) dense-chunk walk may spill, the resolve phases must not grow */
+#define RQ_MINB 12                          /* the usual instantiation: 40 registers, no spills, 12 CTAs per SM (10 / 11 / 12 / 16:
+                                             * 1 GiB step 0.2038 / 0.2011 / 0.2014 / 0.2035 ms -- at 16 the 32 registers spill) */
 #endif
+#define RQ_MINB_DENSE 10                    /* <= 51 registers: the (rare, out-of-line) dense-chunk walk may spill, the resolve phases must not grow */
 #define RQ_WORK    512                      /* candidate work items per CTA round */
 #define RQ_LIST    (2 * RQ_THREADS)         /* candidates awaiting the full compare: one batch of 1b + overflow of 1a */
 
@@ -918,7 +920,7 @@ __device__ __forceinline__ bool rq_candidate(const AutDev &A, const EmitCtx &E, 
 /* DENSE: this kernel also walks the region's dense chunks (automata without a row-displaced table;
  * the usual instantiation carries none of that code and none of its register pressure) */
 template <bool DENSE>
-__global__ void __launch_bounds__(RQ_THREADS, RQ_MINB)
+__global__ void __launch_bounds__(RQ_THREADS, DENSE ? RQ_MINB_DENSE : RQ_MINB)
 k_resolve_queue(const __grid_constant__ AutDev A, const __grid_constant__ EmitCtx E,
     const uint8_t *__restrict__ data, uint64_t n, uint64_t limit, uint64_t vec_lo, uint32_t stride)
 {
