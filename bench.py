@@ -384,7 +384,8 @@ def run_stream_config(ctx, nsigs, per, seed, steps, warmup, tail_for_clocks=Fals
     own = os.environ.get("BENCH_OWN_STREAMS", "1") != "0"
     pipe = sharded.StepPipeline(dev, acsm.automaton, hi - lo, cap_keys, rank, world,
                                 scanner_kwargs={"timing": 0 if os.environ.get("BENCH_NO_KERNEL_TIMING") else
-                                                int(os.environ.get("BENCH_TIMING", "3")), "own_stream": own})
+                                                int(os.environ.get("BENCH_TIMING", "3")), "own_stream": own},
+                                lazy_keys=os.environ.get("BENCH_LAZY_KEYS", "1") != "0")
     step_streams = {}
     k1_ms, stats = [], {"launches": 0, "fallback": 0, "matches": 0, "mode": 0, "list_bytes": 0, "keys": None}
 
@@ -411,6 +412,7 @@ def run_stream_config(ctx, nsigs, per, seed, steps, warmup, tail_for_clocks=Fals
                 note(pipe.complete())
         if k > 0:
             note(pipe.complete())
+        pipe.sync_keys()             # the host copy of the last list (the others were waited for a step later)
 
     run_steps(warmup)
     k1_ms.clear()

@@ -118,6 +118,7 @@ SIGNATURES = {
     "acm_memcpy_d2h_side": (C.c_int, [vp, vp, vp, C.c_size_t]),
     "acm_side_sync": (C.c_int, [vp]),
     "acm_memcpy_d2h_segments": (C.c_int, [vp, vp, C.POINTER(vp), u64p, C.c_uint32]),
+    "acm_memcpy_d2h_segments_async": (C.c_int, [vp, vp, C.POINTER(vp), u64p, C.c_uint32]),
     "acm_automaton_upload": (C.c_int, [vp, vp, C.POINTER(vp)]),
     "acm_automaton_free": (None, [vp]),
     "acm_automaton_states": (C.c_uint32, [vp]),

@@ -442,6 +442,23 @@ acm_memcpy_d2h_segments(struct acm_device *d, void *h_dst, const void *const *d_
 	return ACM_OK;
 }
 
+/* the same without the wait: the copies are complete after the next acm_side_sync() */
+extern "C" int
+acm_memcpy_d2h_segments_async(struct acm_device *d, void *h_dst, const void *const *d_src, const uint64_t *bytes,
+    uint32_t nseg)
+{
+	uint8_t *dst = (uint8_t *)h_dst;
+
+	CUDA_TRY(cudaSetDevice(d->ordinal));
+	for (uint32_t i = 0; i < nseg; i++) {
+		if (!bytes[i])
+			continue;
+		CUDA_TRY(cudaMemcpyAsync(dst, d_src[i], bytes[i], cudaMemcpyDeviceToHost, d->copy_stream));
+		dst += bytes[i];
+	}
+	return ACM_OK;
+}
+
 extern "C" int
 acm_side_sync(struct acm_device *d)
 {

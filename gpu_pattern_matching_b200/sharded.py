@@ -270,11 +270,16 @@ class StepPipeline:
     disjoint and ordered).  world == 1 needs no torch.distributed.
 
     Usage per rank:  submit(step 1); submit(2); complete() -> step 1; submit(3); complete() -> 2 ...
+
+    lazy_keys: rank 0's copy of a step's gathered list to the host is issued by complete() but not
+    waited for -- the keys it returns are valid after sync_keys() or after the NEXT complete() has
+    returned.  At 8 GPUs the copy of a step is 8 regions, ~130 us of a 200-us step: waiting for it
+    inside complete() made rank 0's host thread the slowest part of the job.
     """
     DEPTH = 4
 
     def __init__(self, device, automaton, max_bytes, cap_keys, rank=0, world=1, scanner_kwargs=None,
-                 timeout_s=60.0):
+                 timeout_s=60.0, lazy_keys=False):
         import ctypes as C
         import os
         import tempfile
@@ -286,6 +291,7 @@ class StepPipeline:
         self.timeout = timeout_s
         self.scanners = [Scanner(device, automaton, max_bytes, **(scanner_kwargs or {})) for _ in range(2)]
         self.launched = self.finished = 0
+        self.lazy_keys = bool(lazy_keys)
         self.results = {}
         rows = self.DEPTH + 2
         box = [None, None]
@@ -370,17 +376,33 @@ class StepPipeline:
             self._lens[r] = c * 8
             total += c
         hbase = (s & 1) * self.world * self.cap
+        if self.lazy_keys:
+            # the copies of step s - 1 were issued a whole step ago: this wait is over at once, and its
+            # regions may be overwritten from now on
+            self.check(self.L.acm_side_sync(self.device.handle), "acm_side_sync")
+            self.shm[self.ROW_CONSUMED, 0] = s - 1
+            self.check(self.L.acm_memcpy_d2h_segments_async(
+                self.device.handle, self.C.c_void_p(self.host.ctypes.data + hbase * 8), self._srcs, self._lens,
+                self.world), "acm_memcpy_d2h_segments_async")
+            return res, total, self.host[hbase:hbase + total]
         self.check(self.L.acm_memcpy_d2h_segments(
             self.device.handle, self.C.c_void_p(self.host.ctypes.data + hbase * 8), self._srcs, self._lens,
             self.world), "acm_memcpy_d2h_segments")
         self.shm[self.ROW_CONSUMED, 0] = s
         return res, total, self.host[hbase:hbase + total]
 
+    def sync_keys(self):
+        """lazy_keys: wait for the host copy of every completed step's list (rank 0; no-op elsewhere)."""
+        if self.rank == 0 and self.lazy_keys:
+            self.check(self.L.acm_side_sync(self.device.handle), "acm_side_sync")
+            self.shm[self.ROW_CONSUMED, 0] = self.finished
+
     def close(self):
         import os
         try:
             while self.finished < self.launched:
                 self.complete()
+            self.sync_keys()
             if self.world > 1:
                 dist.barrier()
             for sc in self.scanners:

@@ -74,6 +74,9 @@ int   acm_side_sync(struct acm_device *);
  * against the main stream (for data already known to be complete); waits for the copies */
 int   acm_memcpy_d2h_segments(struct acm_device *, void *h_dst, const void *const *d_src,
           const uint64_t *bytes, uint32_t nseg);
+/* the same, not waited for: complete after the next acm_side_sync() */
+int   acm_memcpy_d2h_segments_async(struct acm_device *, void *h_dst, const void *const *d_src,
+          const uint64_t *bytes, uint32_t nseg);
 
 /* ---- automaton ---- */
 int   acm_automaton_upload(struct acm_device *, const struct acm_tables *, struct acm_automaton **out);

@@ -124,16 +124,29 @@ def test_step_pipeline_single_rank(tmp_path, own_stream):
     d2 = dev.alloc(buf2.size + 64)
     dev.h2d(d2, buf2)
     dev.sync()
-    pipe = sharded.StepPipeline(dev, a.automaton, buf.size, 1 << 14, scanner_kwargs={"own_stream": own_stream})
-    got = []
+    # own streams also run with the host copy of a step's list left in flight (lazy_keys): a list is
+    # read only after the next complete() / sync_keys()
+    pipe = sharded.StepPipeline(dev, a.automaton, buf.size, 1 << 14, scanner_kwargs={"own_stream": own_stream},
+                                lazy_keys=own_stream)
+    got, pending = [], None
+
+    def take(out):
+        nonlocal pending
+        if pending is not None:                 # the previous step's copy is complete now
+            res, tot, keys = pending
+            got.append((res, tot, np.array(keys, copy=True)))
+        pending = out
+
     for it in range(8):
         pipe.submit(d2 if it % 2 else d, buf.size, 0, buf.size, 0)
         if it > 0:
-            got.append(pipe.complete())
-    got.append(pipe.complete())
+            take(pipe.complete())
+    take(pipe.complete())
+    pipe.sync_keys()
+    take(None)
     assert len(got) == 8
     for it, (res, tot, keys) in enumerate(got):
-        goff, gpat = sharded.unpack_keys(np.array(keys, copy=True))
+        goff, gpat = sharded.unpack_keys(keys)
         wo, wp = (eo2, ep2) if it % 2 else (eo, ep)
         assert tot == wo.size and np.array_equal(goff, wo) and np.array_equal(gpat, wp), f"step {it}"
     pipe.close()
