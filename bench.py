@@ -7,6 +7,9 @@
 
 A step = one pass of the hot path (scan -> prefix sum -> compaction + sort -> push of the sorted
 keys into rank 0's gather buffer -> D2H of the gathered list) over one batch of synthetic input.
+Steps are pipelined two deep on two scanners with their own streams (BENCH_OWN_STREAMS=0: one
+stream); rank 0 waits for the host copy of a step's list one step later, the last one inside the
+timed region (BENCH_LAZY_KEYS=0: inside the step itself).
 Headline workload per GPU (BASELINE.json configs[1]): ClamAV 10000 signatures over a 1 GiB seeded
 random byte stream with ~10^5 signatures planted (pure random bytes contain no
 match, so parity and emission would be vacuous).  At N GPUs the stream is N GiB, rank r holds bytes
@@ -885,7 +888,10 @@ def main():
                    "step": ("scan + prefix sum + compaction/sort + push of the sorted keys into rank 0's gather "
                             "buffer (NVLink IPC stores at N > 1) + D2H of the gathered list to pinned host "
                             "memory, every step; steps are queued two deep (acm_scan_device_async / "
-                            "acm_scan_finish), so the host round trip overlaps the next step's scan"),
+                            "acm_scan_finish) on two scanners with their own streams, so the host round trip "
+                            "and the post-pass of a step overlap the next step's scan; the host copy of a "
+                            "step's list is issued in that step and waited for one step later (the last one "
+                            "inside the timed region)"),
                    "list_d2h_bytes_per_step": r["list_bytes"]},
         "roofline": {"bound": "hbm", "achieved": r["achieved"], "peak": r["peak"], "unit": "GB/s",
                      "frac": r["achieved"] / r["peak"], "traffic": traffic, "traffic_source": traffic_src,
